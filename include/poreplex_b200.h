@@ -1,0 +1,216 @@
+/*
+ * poreplex_b200.h -- C ABI of the B200-native Poreplex signal path.
+ *
+ * One shared library (poreplex_b200/libporeplex_b200.so, sm_100a) replaces the
+ * numeric work behind the reference's per-batch entry point
+ *
+ *     poreplex/signal_analyzer.py:46   process_batch(batchid, reads, config)
+ *     poreplex/signal_analyzer.py:82   SignalAnalyzer.process(reads)
+ *
+ * i.e. the calls that the reference makes into numpy / TensorFlow / pomegranate /
+ * its csupport extension for every read.  Each entry point below names the
+ * reference interface it stands in for.  Plain pointers and sizes only; no Python,
+ * torch or CUDA types appear in the signatures (a stream is passed as void*).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PB2_E* code otherwise;
+ *     pb2_last_error() gives a message.  Per-read problems are NOT errors: they are
+ *     reported as per-read status codes (PB2_ST_*), exactly as the reference turns
+ *     them into result-dict statuses (io.py:245-260).
+ *   - "dev" pointers are device pointers on the context's GPU; "host" pointers are
+ *     host memory (pinned memory makes the copies asynchronous).
+ *   - HMM states are always indexed in pomegranate's baked order (sorted by name).
+ */
+#ifndef POREPLEX_B200_H
+#define POREPLEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_ABI_VERSION 1
+
+#define PB2_MAX_STATES 8
+#define PB2_MAX_COMP 4
+#define PB2_MAX_EDGES 64
+#define PB2_MAX_CLASSES 8
+#define PB2_MAX_CALIB 64
+#define PB2_WINDOW_MAX 512
+
+/* error codes */
+#define PB2_OK 0
+#define PB2_EINVAL (-1)
+#define PB2_ECUDA (-2)
+#define PB2_ENOMEM (-3)
+#define PB2_ESTATE (-4)      /* parameters not set yet */
+#define PB2_EUNSUPPORTED (-5)
+
+/* per-read status codes: poreplex/io.py:245-260 */
+enum {
+    PB2_ST_OKAY = 0, PB2_ST_DISAPPEARED = 1, PB2_ST_IRREGULAR_FAST5 = 2,
+    PB2_ST_SCALER_SIGNAL_TOO_SHORT = 3, PB2_ST_SCALING_QC_FAIL = 4,
+    PB2_ST_ADAPTER_NOT_DETECTED = 5, PB2_ST_NOT_BASECALLED = 6,
+    PB2_ST_BASECALL_TABLE_INCOMPLETE = 7, PB2_ST_UNSPLIT_READ = 8,
+    PB2_ST_SEQUENCE_TOO_SHORT = 9, PB2_ST_UNKNOWN_ERROR = 10, PB2_N_STATUS = 11
+};
+
+/* labels (signal_analyzer.py:281-286); PB2_LABEL_NONE = read stopped before stage C */
+enum { PB2_LABEL_PASS = 0, PB2_LABEL_FAIL = 1, PB2_LABEL_ARTIFACT = 2, PB2_LABEL_NONE = 3,
+       PB2_N_LABEL = 4 };
+#define PB2_N_BARCODE_SLOTS 5   /* undetermined + 4 barcodes (io.py:269-278) */
+
+/* switches: commandline.py:279-291 */
+#define PB2_FLAG_BARCODING 1u        /* --barcoding      config['barcoding']            */
+#define PB2_FLAG_KEEP_POOLED 2u      /* also return the scaled pooled signal            */
+
+typedef struct pb2_context pb2_context;
+
+/* One Keras LSTM / LSTMCell (gate blocks i|f|c|o).  Host pointers, copied. */
+typedef struct {
+    int32_t in_dim, units;
+    int32_t implementation;          /* Keras `implementation`: 1 or 2 (bias order) */
+    const float *kernel;             /* [in_dim][4*units] */
+    const float *recurrent;          /* [units][4*units]  */
+    const float *bias;               /* [4*units]         */
+} pb2_lstm_weights;
+
+/* SignalLoader.load_scaler_model (signal_loader.py:49-75): network + input_defs +
+ * output_transform + QC bounds (norm.ppf of scaler_qc_threshold, computed by caller). */
+typedef struct {
+    pb2_lstm_weights l1, l2;
+    const float *dense_kernel;       /* [units][2] */
+    const float *dense_bias;         /* [2] */
+    int32_t stride;                  /* rough_signal_stride (15)   */
+    int32_t length;                  /* input_defs.length (30000)  */
+    int32_t min_length;              /* input_defs.min_length (9000) */
+    double scale_std, scale_mean, shift_std, shift_mean;
+    double qc_scale_lo, qc_scale_hi, qc_shift_lo, qc_shift_hi;
+} pb2_scaler_params;
+
+/* load_segmentation_model + bake() (worker_persistence.py:95-121), log space */
+typedef struct {
+    int32_t n_states;
+    int32_t n_comp[PB2_MAX_STATES];
+    double mu[PB2_MAX_STATES][PB2_MAX_COMP];
+    double log_norm[PB2_MAX_STATES][PB2_MAX_COMP];     /* -log(sigma*SQRT_2_PI) */
+    double inv_two_var[PB2_MAX_STATES][PB2_MAX_COMP];  /* 1/(2 sigma^2)        */
+    double log_weight[PB2_MAX_STATES][PB2_MAX_COMP];
+    double log_start[PB2_MAX_STATES];                  /* -inf: no start edge   */
+    int32_t in_begin[PB2_MAX_STATES + 1];              /* CSR by destination    */
+    int32_t in_src[PB2_MAX_EDGES];
+    double in_logp[PB2_MAX_EDGES];
+} pb2_hmm_params;
+
+/* BarcodeDemultiplexer.__init__/load_model (barcoding.py:34-70) + config['demultiplexing'] */
+typedef struct {
+    pb2_lstm_weights fwd, bwd, l2;
+    const float *dense_kernel;       /* [l2.units][n_classes] */
+    const float *dense_bias;         /* [n_classes] */
+    int32_t n_classes;
+    int32_t n_decoy;                 /* number_of_decoy_labels */
+    int32_t min_length, max_length;  /* minimum/maximum_dna_length (pooled samples) */
+    int32_t trim_length;             /* signal_trim_length (300) */
+    float pad_value;                 /* PAD_FILLER (-1000) */
+    int32_t n_calibration;
+    const double *calibration;       /* pred_score[phred] */
+    double score_threshold;          /* calibration[barcoding_quality_filter] */
+} pb2_demux_params;
+
+/* A batch of reads: ragged int16 DAC samples + per-read calibration
+ * (Fast5Reader.get_raw_data, fast5_file.py:122-131).  raw_offsets[i] is the element
+ * offset of read i in `raw` and must be a multiple of 8 (16-byte aligned reads). */
+typedef struct {
+    int64_t n_reads;
+    int64_t n_raw_total;             /* number of int16 elements in `raw` */
+    int64_t max_raw_length;          /* max(raw_lengths) if known on the host, else 0 */
+    const int16_t *raw;
+    const int64_t *raw_offsets;      /* [n_reads] */
+    const int64_t *raw_lengths;      /* [n_reads] samples per read (= Raw.duration) */
+    const double *range;             /* [n_reads] channel_id attrs */
+    const double *digitisation;      /* [n_reads] */
+    const double *offset;            /* [n_reads] */
+} pb2_batch;
+
+/* Per-read results (any pointer may be NULL = not wanted). */
+typedef struct {
+    int32_t *status;                 /* [n] PB2_ST_*                                   */
+    int32_t *label;                  /* [n] PB2_LABEL_*                                */
+    float *scale_shift;              /* [n][2]  NanoporeRead.scaling_params            */
+    int32_t *segments;               /* [n][PB2_MAX_STATES][2] first,last (pooled idx) */
+    int32_t *barcode;                /* [n] -1 = None          set_barcode(...)        */
+    int32_t *barcode_guess;          /* [n] argmax - decoys; INT32_MIN = not classified */
+    int32_t *barcode_score;          /* [n] calibrated phred;  -1 = not classified     */
+    float *class_probs;              /* [n][PB2_MAX_CLASSES] softmax output            */
+    float *pooled;                   /* scaled pooled signal, ragged; read i starts at
+                                        element (raw_offsets[i] + stride-1) / stride   */
+    int64_t *counts;                 /* [PB2_N_LABEL][PB2_N_BARCODE_SLOTS][PB2_N_STATUS]
+                                        FinalSummaryTracker.counts (io.py:269-278)     */
+} pb2_results;
+
+/* ---- life cycle --------------------------------------------------------- */
+int pb2_abi_version(void);
+/* WorkerPersistenceStorage.init_persistence_objects (worker_persistence.py:60-90) */
+int pb2_create(int device, pb2_context **out);
+void pb2_destroy(pb2_context *ctx);
+const char *pb2_last_error(const pb2_context *ctx);
+
+int pb2_set_scaler(pb2_context *ctx, const pb2_scaler_params *p);
+/* scan_limit_pooled = segmentation_scan_limit // stride (signal_analyzer.py:347) */
+int pb2_set_segmentation_hmm(pb2_context *ctx, const pb2_hmm_params *p,
+                             int32_t scan_limit_pooled, int32_t adapter_state);
+int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p);
+
+/* ---- whole path --------------------------------------------------------- */
+/* SignalAnalyzer.process stages A-D for the numeric outputs (signal_analyzer.py:82-134):
+ * load_padded_signal_head -> fit_scalers -> load_signal(pool) -> detect_segments ->
+ * [push_barcode_signal -> demuxer.predict] -> counts.  `batch`/`res` hold DEVICE
+ * pointers; work is enqueued on `stream` (a cudaStream_t) and not synchronised. */
+int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                       uint32_t flags, void *stream);
+/* Same with HOST buffers: copies in, runs, copies out, synchronises. */
+int pb2_analyze_host(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                     uint32_t flags);
+
+/* ---- single stages over device buffers (parity tests, partial pipelines) -- */
+/* fast5_file.py:122-131 + signal_loader.py:224-225,244-247: int16 -> pA -> mean-pool.
+ * pooled[pooled_offset(i) + t], t < raw_lengths[i] / stride (unscaled). */
+int pb2_pool_signal(pb2_context *ctx, const pb2_batch *batch, float *pooled, void *stream);
+/* signal_loader.py:89-109: scaler network on the left-zero-padded pooled head.
+ * z_out (optional) receives the raw network outputs [n][2]. */
+int pb2_fit_scalers(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                    int32_t *status, float *scale_shift, float *z_out, void *stream);
+/* signal_loader.py:258-262 + signal_analyzer.py:346-364 */
+int pb2_detect_segments(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                        const float *scale_shift, int32_t *status, int32_t *segments,
+                        float *pooled_scaled_out, void *stream);
+/* generic Viterbi over dense float rows (pomegranate HiddenMarkovModel.viterbi):
+ * x[n][ld], lengths[n] -> path[n][ld] (baked state indices), logp[n].
+ * which = 0 segmentation model. */
+int pb2_viterbi_paths(pb2_context *ctx, int which, const float *x, const int32_t *lengths,
+                      int64_t n, int32_t ld, int32_t *path, double *logp, void *stream);
+/* barcoding.py:83-101: windows[n][trim_length], pushed[n] */
+int pb2_barcode_windows(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                        const float *scale_shift, const int32_t *status,
+                        const int32_t *segments, float *windows, int32_t *pushed,
+                        void *stream);
+/* barcoding.py:103-118 on explicit windows[n][trim_length] */
+int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pushed,
+                      int64_t n, float *class_probs, int32_t *barcode, int32_t *guess,
+                      int32_t *score, void *stream);
+/* scaler network on explicit heads[n][length/stride] (keras predict) */
+int pb2_scaler_predict(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
+                       void *stream);
+/* io.py:274-278 */
+int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
+                      const int32_t *barcode, int64_t n, int64_t *counts, void *stream);
+
+/* number of kernel launches issued through this context so far */
+int64_t pb2_kernel_launches(const pb2_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POREPLEX_B200_H */

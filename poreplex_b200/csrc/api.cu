@@ -1,0 +1,467 @@
+// api.cu -- the extern "C" boundary declared in include/poreplex_b200.h:
+// context life cycle, parameter upload, stage entry points and the whole-path
+// pipeline (device-resident and host-buffer variants).
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "pb_internal.h"
+
+namespace pb {
+
+int fail(pb2_context *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+int check_cuda(pb2_context *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return PB2_OK;
+    return fail(ctx, PB2_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+void *ws_get(pb2_context *ctx, Workspace &w, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (w.bytes >= bytes) return w.ptr;
+    if (w.ptr) { cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+    // grow with some slack so that slightly larger batches do not reallocate
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&w.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&w.ptr, want);
+    }
+    if (e != cudaSuccess) {
+        w.ptr = nullptr;
+        fail(ctx, PB2_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return nullptr;
+    }
+    w.bytes = want;
+    return w.ptr;
+}
+
+static void ws_free(Workspace &w)
+{
+    if (w.ptr) cudaFree(w.ptr);
+    w.ptr = nullptr;
+    w.bytes = 0;
+}
+
+static int upload(pb2_context *ctx, const float *host, size_t n, float **dev)
+{
+    if (*dev) { cudaFree(*dev); *dev = nullptr; }
+    if (!host) return fail(ctx, PB2_EINVAL, "null weight pointer");
+    PB_CUDA(ctx, cudaMalloc(dev, sizeof(float) * n));
+    PB_CUDA(ctx, cudaMemcpy(*dev, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+    return PB2_OK;
+}
+
+static int upload_lstm(pb2_context *ctx, const pb2_lstm_weights &w, LstmDev &d)
+{
+    if (w.units <= 0 || w.in_dim <= 0 || (w.implementation != 1 && w.implementation != 2))
+        return fail(ctx, PB2_EINVAL, "bad LSTM description");
+    d.in_dim = w.in_dim; d.units = w.units; d.impl = w.implementation;
+    int rc;
+    if ((rc = upload(ctx, w.kernel, (size_t)w.in_dim * 4 * w.units, &d.kernel))) return rc;
+    if ((rc = upload(ctx, w.recurrent, (size_t)w.units * 4 * w.units, &d.recurrent))) return rc;
+    if ((rc = upload(ctx, w.bias, (size_t)4 * w.units, &d.bias))) return rc;
+    return PB2_OK;
+}
+
+static void free_lstm(LstmDev &d)
+{
+    cudaFree(d.kernel); cudaFree(d.recurrent); cudaFree(d.bias);
+    d.kernel = d.recurrent = d.bias = nullptr;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb2_abi_version(void) { return PB2_ABI_VERSION; }
+
+int pb2_create(int device, pb2_context **out)
+{
+    if (!out) return PB2_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return PB2_ECUDA;          // no GPU: the product path has no CPU fallback
+    }
+    pb2_context *ctx = new (std::nothrow) pb2_context();
+    if (!ctx) return PB2_ENOMEM;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return PB2_ECUDA;
+    }
+    *out = ctx;
+    return PB2_OK;
+}
+
+void pb2_destroy(pb2_context *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    free_lstm(ctx->scaler.l1); free_lstm(ctx->scaler.l2);
+    cudaFree(ctx->scaler.dense_kernel); cudaFree(ctx->scaler.dense_bias);
+    cudaFree(ctx->scaler.zero_prefix);
+    free_lstm(ctx->demux.fwd); free_lstm(ctx->demux.bwd); free_lstm(ctx->demux.l2);
+    cudaFree(ctx->demux.dense_kernel); cudaFree(ctx->demux.dense_bias);
+    Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
+                        &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
+                        &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
+                        &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads};
+    for (Workspace *w : all) ws_free(*w);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    delete ctx;
+}
+
+const char *pb2_last_error(const pb2_context *ctx)
+{
+    return ctx ? ctx->error.c_str() : "no context (CUDA device unavailable?)";
+}
+
+int64_t pb2_kernel_launches(const pb2_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int pb2_set_scaler(pb2_context *ctx, const pb2_scaler_params *p)
+{
+    if (!ctx || !p) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    ScalerDev &S = ctx->scaler;
+    S.set = false;
+    if (p->stride <= 0 || p->length <= 0 || p->length % p->stride != 0)
+        return fail(ctx, PB2_EINVAL, "scaler length must be a positive multiple of stride");
+    int rc;
+    if ((rc = upload_lstm(ctx, p->l1, S.l1))) return rc;
+    if ((rc = upload_lstm(ctx, p->l2, S.l2))) return rc;
+    if ((rc = upload(ctx, p->dense_kernel, (size_t)p->l2.units * 2, &S.dense_kernel))) return rc;
+    if ((rc = upload(ctx, p->dense_bias, 2, &S.dense_bias))) return rc;
+    S.stride = p->stride; S.length = p->length; S.min_length = p->min_length;
+    S.scale_std = p->scale_std; S.scale_mean = p->scale_mean;
+    S.shift_std = p->shift_std; S.shift_mean = p->shift_mean;
+    S.qc_scale_lo = p->qc_scale_lo; S.qc_scale_hi = p->qc_scale_hi;
+    S.qc_shift_lo = p->qc_shift_lo; S.qc_shift_hi = p->qc_shift_hi;
+    if ((rc = build_zero_prefix(ctx))) return rc;
+    S.set = true;
+    return PB2_OK;
+}
+
+int pb2_set_segmentation_hmm(pb2_context *ctx, const pb2_hmm_params *p,
+                             int32_t scan_limit_pooled, int32_t adapter_state)
+{
+    if (!ctx || !p) return PB2_EINVAL;
+    if (p->n_states <= 0 || p->n_states > PB2_MAX_STATES - 1)
+        return fail(ctx, PB2_EINVAL, "HMM must have 1..%d states", PB2_MAX_STATES - 1);
+    if (adapter_state < 0 || adapter_state >= p->n_states || scan_limit_pooled <= 0)
+        return fail(ctx, PB2_EINVAL, "bad adapter state / scan limit");
+    for (int s = 0; s < p->n_states; s++)
+        if (p->n_comp[s] < 1 || p->n_comp[s] > PB2_MAX_COMP)
+            return fail(ctx, PB2_EINVAL, "bad mixture size for state %d", s);
+    if (p->in_begin[p->n_states] > PB2_MAX_EDGES)
+        return fail(ctx, PB2_EINVAL, "too many HMM edges");
+    static_assert(sizeof(HmmDev) == sizeof(pb2_hmm_params), "HmmDev must mirror pb2_hmm_params");
+    memcpy(&ctx->seg_hmm, p, sizeof(HmmDev));
+    ctx->scan_limit_pooled = scan_limit_pooled;
+    ctx->adapter_state = adapter_state;
+    ctx->seg_set = true;
+    return PB2_OK;
+}
+
+int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p)
+{
+    if (!ctx || !p) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    DemuxDev &D = ctx->demux;
+    D.set = false;
+    if (p->n_classes < 1 || p->n_classes > PB2_MAX_CLASSES || p->n_calibration < 1 ||
+        p->n_calibration > PB2_MAX_CALIB || !p->calibration)
+        return fail(ctx, PB2_EINVAL, "bad demux class / calibration sizes");
+    if (p->trim_length < 1 || p->trim_length > PB2_WINDOW_MAX)
+        return fail(ctx, PB2_EINVAL, "signal_trim_length out of range");
+    int rc;
+    if ((rc = upload_lstm(ctx, p->fwd, D.fwd))) return rc;
+    if ((rc = upload_lstm(ctx, p->bwd, D.bwd))) return rc;
+    if ((rc = upload_lstm(ctx, p->l2, D.l2))) return rc;
+    if ((rc = upload(ctx, p->dense_kernel, (size_t)p->l2.units * p->n_classes, &D.dense_kernel))) return rc;
+    if ((rc = upload(ctx, p->dense_bias, p->n_classes, &D.dense_bias))) return rc;
+    D.n_classes = p->n_classes; D.n_decoy = p->n_decoy;
+    D.min_length = p->min_length; D.max_length = p->max_length;
+    D.trim_length = p->trim_length; D.pad_value = p->pad_value;
+    D.n_calibration = p->n_calibration;
+    for (int i = 0; i < PB2_MAX_CALIB; i++)
+        D.calibration[i] = i < p->n_calibration ? p->calibration[i] : INFINITY;
+    D.score_threshold = p->score_threshold;
+    D.set = true;
+    return PB2_OK;
+}
+
+// ---- single stages ----------------------------------------------------------
+static int check_batch(pb2_context *ctx, const pb2_batch *b)
+{
+    if (!ctx || !b) return PB2_EINVAL;
+    if (b->n_reads < 0) return fail(ctx, PB2_EINVAL, "negative read count");
+    if (b->n_reads > 0 && (!b->raw || !b->raw_offsets || !b->raw_lengths || !b->range ||
+                           !b->digitisation || !b->offset))
+        return fail(ctx, PB2_EINVAL, "null batch pointer");
+    return PB2_OK;
+}
+
+int pb2_pool_signal(pb2_context *ctx, const pb2_batch *batch, float *pooled, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->scaler.set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "parameters not set");
+    DeviceGuard g(ctx->device);
+    return launch_pool(ctx, *batch, ctx->scaler.stride, pooled, (cudaStream_t)stream);
+}
+
+int pb2_fit_scalers(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                    int32_t *status, float *scale_shift, float *z_out, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->scaler.set) return fail(ctx, PB2_ESTATE, "scaler not set");
+    DeviceGuard g(ctx->device);
+    return launch_scaler(ctx, *batch, pooled, status, scale_shift, z_out, (cudaStream_t)stream);
+}
+
+int pb2_scaler_predict(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
+                       void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (!ctx->scaler.set) return fail(ctx, PB2_ESTATE, "scaler not set");
+    DeviceGuard g(ctx->device);
+    return launch_scaler_heads(ctx, heads, n, z_out, (cudaStream_t)stream);
+}
+
+int pb2_detect_segments(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                        const float *scale_shift, int32_t *status, int32_t *segments,
+                        float *pooled_scaled_out, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->seg_set || !ctx->scaler.set) return fail(ctx, PB2_ESTATE, "parameters not set");
+    DeviceGuard g(ctx->device);
+    return launch_segment(ctx, *batch, pooled, scale_shift, status, segments,
+                          pooled_scaled_out, (cudaStream_t)stream);
+}
+
+int pb2_viterbi_paths(pb2_context *ctx, int which, const float *x, const int32_t *lengths,
+                      int64_t n, int32_t ld, int32_t *path, double *logp, void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (which != 0) return fail(ctx, PB2_EUNSUPPORTED, "only the segmentation model is loaded");
+    if (!ctx->seg_set) return fail(ctx, PB2_ESTATE, "segmentation HMM not set");
+    DeviceGuard g(ctx->device);
+    return launch_viterbi_paths(ctx, ctx->seg_hmm, x, lengths, n, ld, path, logp,
+                                (cudaStream_t)stream);
+}
+
+int pb2_barcode_windows(pb2_context *ctx, const pb2_batch *batch, const float *pooled,
+                        const float *scale_shift, const int32_t *status,
+                        const int32_t *segments, float *windows, int32_t *pushed, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->demux.set || !ctx->scaler.set || !ctx->seg_set)
+        return fail(ctx, PB2_ESTATE, "parameters not set");
+    DeviceGuard g(ctx->device);
+    return launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows, pushed,
+                          (cudaStream_t)stream);
+}
+
+int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                      float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                      void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
+    DeviceGuard g(ctx->device);
+    return launch_demux(ctx, windows, pushed, n, class_probs, barcode, guess, score,
+                        (cudaStream_t)stream);
+}
+
+int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
+                      const int32_t *barcode, int64_t n, int64_t *counts, void *stream)
+{
+    if (!ctx || !counts) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    return launch_counts(ctx, status, label, barcode, n, counts, (cudaStream_t)stream);
+}
+
+// ---- whole path -------------------------------------------------------------
+#define WS_OR(user, ws, type, count)                                                        \
+    ((user) ? (user) : (type *)ws_get(ctx, ctx->ws, sizeof(type) * (size_t)(count)))
+
+int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                       uint32_t flags, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!res) return PB2_EINVAL;
+    if (!ctx->scaler.set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "parameters not set");
+    if ((flags & PB2_FLAG_BARCODING) && !ctx->demux.set)
+        return fail(ctx, PB2_ESTATE, "barcoding requested but demux not set");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = batch->n_reads;
+    if (n == 0) {
+        if (res->counts)
+            PB_CUDA(ctx, cudaMemsetAsync(res->counts, 0, sizeof(int64_t) * PB2_N_LABEL *
+                                         PB2_N_BARCODE_SLOTS * PB2_N_STATUS, st));
+        return PB2_OK;
+    }
+    const int stride = ctx->scaler.stride;
+    const size_t n_pooled = (size_t)(batch->n_raw_total / stride) + 2;
+
+    float *pooled = (float *)ws_get(ctx, ctx->ws_pooled, sizeof(float) * n_pooled);
+    int32_t *status = WS_OR(res->status, ws_status, int32_t, n);
+    int32_t *label = WS_OR(res->label, ws_label, int32_t, n);
+    float *scale_shift = WS_OR(res->scale_shift, ws_scale, float, 2 * n);
+    int32_t *segments = WS_OR(res->segments, ws_seg, int32_t, 2 * PB2_MAX_STATES * n);
+    if (!pooled || !status || !label || !scale_shift || !segments) return PB2_ENOMEM;
+    float *pooled_out = (flags & PB2_FLAG_KEEP_POOLED) ? res->pooled : nullptr;
+
+    if ((rc = launch_pool(ctx, *batch, stride, pooled, st))) return rc;
+    if ((rc = launch_scaler(ctx, *batch, pooled, status, scale_shift, nullptr, st))) return rc;
+    if ((rc = launch_segment(ctx, *batch, pooled, scale_shift, status, segments, pooled_out, st)))
+        return rc;
+
+    int32_t *barcode = nullptr, *guess = nullptr, *score = nullptr;
+    if (flags & PB2_FLAG_BARCODING) {
+        const int T = ctx->demux.trim_length;
+        float *windows = (float *)ws_get(ctx, ctx->ws_win, sizeof(float) * (size_t)n * T);
+        int32_t *pushed = (int32_t *)ws_get(ctx, ctx->ws_pushed, sizeof(int32_t) * (size_t)n);
+        barcode = WS_OR(res->barcode, ws_bc, int32_t, n);
+        guess = WS_OR(res->barcode_guess, ws_guess, int32_t, n);
+        score = WS_OR(res->barcode_score, ws_score, int32_t, n);
+        if (!windows || !pushed || !barcode || !guess || !score) return PB2_ENOMEM;
+        if (res->class_probs)
+            PB_CUDA(ctx, cudaMemsetAsync(res->class_probs, 0,
+                                         sizeof(float) * PB2_MAX_CLASSES * (size_t)n, st));
+        if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows,
+                                 pushed, st))) return rc;
+        if ((rc = launch_demux(ctx, windows, pushed, n, res->class_probs, barcode, guess, score,
+                               st))) return rc;
+    } else {
+        barcode = res->barcode; guess = res->barcode_guess; score = res->barcode_score;
+    }
+    if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;
+    if (res->counts)
+        if ((rc = launch_counts(ctx, status, label, barcode, n, res->counts, st))) return rc;
+    return PB2_OK;
+}
+
+int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr, uint32_t flags)
+{
+    int rc = check_batch(ctx, hb);
+    if (rc) return rc;
+    if (!hr) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->host_stream;
+    const int64_t n = hb->n_reads;
+    const int stride = ctx->scaler.stride > 0 ? ctx->scaler.stride : 15;
+    const size_t n_pooled = (size_t)(hb->n_raw_total / stride) + 2;
+    const int n_bins = PB2_N_LABEL * PB2_N_BARCODE_SLOTS * PB2_N_STATUS;
+
+    // one device arena for inputs and outputs of this call
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align(bytes); return o; };
+    const size_t o_raw = take(sizeof(int16_t) * (size_t)hb->n_raw_total + 16);
+    const size_t o_off = take(sizeof(int64_t) * n), o_len = take(sizeof(int64_t) * n);
+    const size_t o_rng = take(sizeof(double) * n), o_dig = take(sizeof(double) * n);
+    const size_t o_ofs = take(sizeof(double) * n);
+    const size_t o_status = take(sizeof(int32_t) * n), o_label = take(sizeof(int32_t) * n);
+    const size_t o_ss = take(sizeof(float) * 2 * n);
+    const size_t o_seg = take(sizeof(int32_t) * 2 * PB2_MAX_STATES * n);
+    const size_t o_bc = take(sizeof(int32_t) * n), o_gs = take(sizeof(int32_t) * n);
+    const size_t o_sc = take(sizeof(int32_t) * n);
+    const size_t o_pr = take(sizeof(float) * PB2_MAX_CLASSES * n);
+    const size_t o_cnt = take(sizeof(int64_t) * n_bins);
+    const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
+    const size_t o_pool = take(keep ? sizeof(float) * n_pooled : 16);
+    char *base = (char *)ws_get(ctx, ctx->ws_batch, off);
+    if (!base) return PB2_ENOMEM;
+
+    pb2_batch db = *hb;
+    db.raw = (const int16_t *)(base + o_raw);
+    db.raw_offsets = (const int64_t *)(base + o_off);
+    db.raw_lengths = (const int64_t *)(base + o_len);
+    db.range = (const double *)(base + o_rng);
+    db.digitisation = (const double *)(base + o_dig);
+    db.offset = (const double *)(base + o_ofs);
+    if (db.max_raw_length <= 0)
+        for (int64_t i = 0; i < n; i++)
+            if (hb->raw_lengths[i] > db.max_raw_length) db.max_raw_length = hb->raw_lengths[i];
+    if (n > 0) {
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw, hb->raw, sizeof(int16_t) * (size_t)hb->n_raw_total,
+                                     cudaMemcpyHostToDevice, st));
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw_offsets, hb->raw_offsets, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw_lengths, hb->raw_lengths, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.range, hb->range, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.digitisation, hb->digitisation, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.offset, hb->offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    }
+    pb2_results dr = {};
+    dr.status = (int32_t *)(base + o_status);
+    dr.label = (int32_t *)(base + o_label);
+    dr.scale_shift = (float *)(base + o_ss);
+    dr.segments = (int32_t *)(base + o_seg);
+    dr.barcode = (int32_t *)(base + o_bc);
+    dr.barcode_guess = (int32_t *)(base + o_gs);
+    dr.barcode_score = (int32_t *)(base + o_sc);
+    dr.class_probs = (float *)(base + o_pr);
+    dr.counts = (int64_t *)(base + o_cnt);
+    dr.pooled = keep ? (float *)(base + o_pool) : nullptr;
+    if (keep) PB_CUDA(ctx, cudaMemsetAsync(dr.pooled, 0, sizeof(float) * n_pooled, st));
+    if (!(flags & PB2_FLAG_BARCODING) && n > 0) {
+        PB_CUDA(ctx, cudaMemsetAsync(dr.barcode, 0xFF, sizeof(int32_t) * n, st));
+        PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_guess, 0xFF, sizeof(int32_t) * n, st));
+        PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_score, 0xFF, sizeof(int32_t) * n, st));
+        PB_CUDA(ctx, cudaMemsetAsync(dr.class_probs, 0, sizeof(float) * PB2_MAX_CLASSES * n, st));
+    }
+    if ((rc = pb2_analyze_device(ctx, &db, &dr, flags, st))) return rc;
+
+#define PB_D2H(field, bytes)                                                                 \
+    if (hr->field && (bytes) > 0)                                                            \
+        PB_CUDA(ctx, cudaMemcpyAsync(hr->field, dr.field, (bytes), cudaMemcpyDeviceToHost, st))
+    PB_D2H(status, sizeof(int32_t) * n);
+    PB_D2H(label, sizeof(int32_t) * n);
+    PB_D2H(scale_shift, sizeof(float) * 2 * n);
+    PB_D2H(segments, sizeof(int32_t) * 2 * PB2_MAX_STATES * n);
+    PB_D2H(barcode, sizeof(int32_t) * n);
+    PB_D2H(barcode_guess, sizeof(int32_t) * n);
+    PB_D2H(barcode_score, sizeof(int32_t) * n);
+    PB_D2H(class_probs, sizeof(float) * PB2_MAX_CLASSES * n);
+    PB_D2H(counts, sizeof(int64_t) * n_bins);
+    if (keep) PB_D2H(pooled, sizeof(float) * n_pooled);
+#undef PB_D2H
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+// kernels_lstm.cu -- exact-f32 LSTM inference for the scaler (A3) and the barcode
+// demultiplexer (A7).
+//
+// Reference: keras Model.predict at signal_loader.py:96-97 and barcoding.py:106-107
+// (TensorFlow is not vendored; cell equations and activation kernels restated in
+// oracle/pb_oracle.c).  Bit-exact contract: every pre-activation is an fmaf chain
+// from 0 with k ascending per K.dot(), combined in Keras' order for the layer's
+// `implementation`; activations are pb::sigmoid_eigen / pb::tanh_eigen.
+//
+// Work decomposition (all kernels): a CTA owns a tile of TB = 32 reads and steps them
+// through time together.  A thread owns one UNIT PAIR (2 hidden units x 4 gates) for
+// RG = 4 reads: 32 independent fma chains, fed per k by one 16-byte load of the 4
+// reads' h[k] (smem, k-major) and two 16-byte loads of its 8 weights (smem, re-laid
+// out as [k][unit_pair][gate][2]).  The chains use packed f32x2 FMAs (FFMA2 on
+// sm_100), each half being an IEEE fma identical to the scalar one.  The cell state
+// c lives in registers of the owning thread; h goes through double-buffered shared
+// memory with ONE block barrier per time step.
+#include "pb_internal.h"
+#include "pb_math.cuh"
+
+namespace pb {
+
+constexpr int TB = 32;            // reads per CTA tile
+constexpr int RG = 4;             // reads per thread
+constexpr int NRG = TB / RG;      // read groups per tile (8)
+
+// ---- packed helpers ---------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    return __ffma2_rn(a, b, c);
+}
+
+struct Acc {                       // z[r][gate] for units (2up, 2up+1)
+    float2 v[RG][4];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int r = 0; r < RG; r++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) v[r][g] = make_float2(0.f, 0.f);
+    }
+};
+
+// acc[r][g] = fma chain over k = 0..K-1 of h[k][r] * W[k][g][unit]   (from 0)
+//   Wt : smem, [K][NUP][4][2] floats        hs : smem, [K][TB] floats
+template <int K, int NUP>
+__device__ __forceinline__ void dot_tile(const float *__restrict__ Wt,
+                                         const float *__restrict__ hs, int up, int rg,
+                                         Acc &acc)
+{
+    acc.zero();
+    const float4 *w = reinterpret_cast<const float4 *>(Wt) + up * 2;
+    const float4 *h = reinterpret_cast<const float4 *>(hs) + rg;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const float4 hv = h[k * (TB / 4)];
+        const float4 w0 = w[k * NUP * 2];
+        const float4 w1 = w[k * NUP * 2 + 1];
+        const float2 wi = make_float2(w0.x, w0.y), wf = make_float2(w0.z, w0.w);
+        const float2 wc = make_float2(w1.x, w1.y), wo = make_float2(w1.z, w1.w);
+        const float hr[RG] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            const float2 hh = make_float2(hr[r], hr[r]);
+            acc.v[r][0] = ffma2(hh, wi, acc.v[r][0]);
+            acc.v[r][1] = ffma2(hh, wf, acc.v[r][1]);
+            acc.v[r][2] = ffma2(hh, wc, acc.v[r][2]);
+            acc.v[r][3] = ffma2(hh, wo, acc.v[r][3]);
+        }
+    }
+}
+
+// re-layout a [K][4H] row-major Keras matrix into smem [K][NUP][4][2]
+template <int K, int H>
+__device__ __forceinline__ void load_weights(const float *__restrict__ g, float *Wt)
+{
+    constexpr int NUP = H / 2;
+    for (int idx = threadIdx.x; idx < K * 4 * H; idx += blockDim.x) {
+        const int k = idx / (4 * H), col = idx % (4 * H);
+        const int gate = col / H, u = col % H;
+        Wt[((k * NUP + (u >> 1)) * 4 + gate) * 2 + (u & 1)] = g[idx];
+    }
+}
+
+// gate bias / input-kernel values of this thread's unit pair: [gate] -> (u0, u1)
+template <int H>
+__device__ __forceinline__ void load_pair(const float *__restrict__ v, int up, float2 (&out)[4])
+{
+#pragma unroll
+    for (int g = 0; g < 4; g++) out[g] = make_float2(v[g * H + 2 * up], v[g * H + 2 * up + 1]);
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    return make_float2(pb::fadd(a.x, b.x), pb::fadd(a.y, b.y));
+}
+__device__ __forceinline__ float2 fmul2s(float s, float2 b) {
+    return make_float2(pb::fmul(s, b.x), pb::fmul(s, b.y));
+}
+
+// cell update for both units of the pair, one read; returns h
+__device__ __forceinline__ float2 cell_pair(const float2 (&z)[4], float2 &c)
+{
+    float2 h;
+    pb::lstm_cell(z[0].x, z[1].x, z[2].x, z[3].x, c.x, h.x);
+    pb::lstm_cell(z[0].y, z[1].y, z[2].y, z[3].y, c.y, h.y);
+    return h;
+}
+
+// store this thread's new h for its unit pair and 4 reads: hs[k = unit][read]
+__device__ __forceinline__ void store_h(float *hs, int up, int rg, const float2 (&h)[RG])
+{
+    *reinterpret_cast<float4 *>(hs + (2 * up) * TB + rg * RG) =
+        make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
+    *reinterpret_cast<float4 *>(hs + (2 * up + 1) * TB + rg * RG) =
+        make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+}
+
+// ============================================================================
+// Scaler: LSTM(H, seq, impl 1) -> LSTM(H, last, impl 1) -> Dense(2)
+// ============================================================================
+struct ScalerArgs {
+    const float *x;                // float buffer holding the (unscaled) pooled signals
+    const int64_t *xoff;           // [n] element offset of each read's first real sample
+    const int32_t *nreal;          // [n] real head samples (0 = skip read)
+    int64_t n;
+    int thead;                     // time steps including the left zero padding
+    const float *W1, *U1, *b1, *W2, *U2, *b2, *Wd, *bd;
+    const float *zero_prefix;      // [thead+1][4][H] or nullptr
+    float *prefix_dump;            // when set: record the state of read 0 after each step
+    float *z_out;                  // [n][2] raw network outputs (optional)
+    // output transform + QC (signal_loader.py:98-109)
+    double scale_std, scale_mean, shift_std, shift_mean;
+    double qc_scale_lo, qc_scale_hi, qc_shift_lo, qc_shift_hi;
+    int32_t *status;               // may be nullptr (heads API)
+    float *scale_shift;            // may be nullptr
+};
+
+template <int H>
+__global__ void __launch_bounds__((H / 2) * NRG, 1)
+k_scaler_lstm(const ScalerArgs A)
+{
+    constexpr int NUP = H / 2;
+    extern __shared__ __align__(16) float smem[];
+    float *U1t = smem;                        // [H][NUP][4][2]
+    float *W2t = U1t + H * 4 * H;
+    float *U2t = W2t + H * 4 * H;
+    float *h1s = U2t + H * 4 * H;             // [2][H][TB]
+    float *h2s = h1s + 2 * H * TB;            // [2][H][TB]
+    __shared__ int s_nreal[TB];
+    __shared__ int s_maxreal;
+
+    const int tid = threadIdx.x;
+    const int rg = tid % NRG, up = tid / NRG;
+    const int64_t tile0 = (int64_t)blockIdx.x * TB;
+
+    load_weights<H, H>(A.U1, U1t);
+    load_weights<H, H>(A.W2, W2t);
+    load_weights<H, H>(A.U2, U2t);
+    if (tid == 0) s_maxreal = 0;
+    __syncthreads();
+    if (tid < TB) {
+        const int64_t r = tile0 + tid;
+        const int nr = (r < A.n) ? A.nreal[r] : 0;
+        s_nreal[tid] = nr;
+        atomicMax(&s_maxreal, nr);
+    }
+    __syncthreads();
+    const int t_start = A.zero_prefix ? (A.thead - s_maxreal) : 0;
+
+    // per-thread constants
+    float2 w1[4], b1[4], b2[4];
+    load_pair<H>(A.W1, up, w1);
+    load_pair<H>(A.b1, up, b1);
+    load_pair<H>(A.b2, up, b2);
+    // per-read input addressing
+    const float *xp[RG];
+    int pad[RG];
+#pragma unroll
+    for (int r = 0; r < RG; r++) {
+        const int64_t rd = tile0 + rg * RG + r;
+        const int nr = s_nreal[rg * RG + r];
+        pad[r] = A.thead - nr;
+        xp[r] = A.x + ((rd < A.n && nr > 0) ? A.xoff[rd] : 0) - pad[r];
+    }
+
+    // initial state: zeros, or the tabulated state after t_start zero-input steps
+    float2 c1[RG], c2[RG];
+    {
+        float2 c1i = make_float2(0.f, 0.f), c2i = c1i, h1i = c1i, h2i = c1i;
+        if (A.zero_prefix && t_start > 0) {
+            const float *tb = A.zero_prefix + (size_t)t_start * 4 * H;
+            h1i = make_float2(tb[0 * H + 2 * up], tb[0 * H + 2 * up + 1]);
+            c1i = make_float2(tb[1 * H + 2 * up], tb[1 * H + 2 * up + 1]);
+            h2i = make_float2(tb[2 * H + 2 * up], tb[2 * H + 2 * up + 1]);
+            c2i = make_float2(tb[3 * H + 2 * up], tb[3 * H + 2 * up + 1]);
+        }
+        float2 h1v[RG], h2v[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) { c1[r] = c1i; c2[r] = c2i; h1v[r] = h1i; h2v[r] = h2i; }
+        store_h(h1s, up, rg, h1v);
+        store_h(h2s, up, rg, h2v);
+    }
+    __syncthreads();
+
+    int cur1 = 0, cur2 = 0;
+    Acc acc;
+    for (int t = t_start; t < A.thead; t++) {
+        // ---- layer 1, step t: z = ((x*W1 + b1) + h1.U1)
+        float xv[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) xv[r] = (t >= pad[r]) ? __ldg(xp[r] + t) : 0.0f;
+        dot_tile<H, NUP>(U1t, h1s + cur1 * H * TB, up, rg, acc);
+        float2 hn[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            float2 z[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                z[g] = fadd2(fadd2(fmul2s(xv[r], w1[g]), b1[g]), acc.v[r][g]);
+            hn[r] = cell_pair(z, c1[r]);
+        }
+        store_h(h1s + (cur1 ^ 1) * H * TB, up, rg, hn);
+        cur1 ^= 1;
+        __syncthreads();
+        // ---- layer 2, step t: z = ((h1.W2 + b2) + h2.U2)
+        dot_tile<H, NUP>(W2t, h1s + cur1 * H * TB, up, rg, acc);
+        float2 zx[RG][4];
+#pragma unroll
+        for (int r = 0; r < RG; r++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) zx[r][g] = fadd2(acc.v[r][g], b2[g]);
+        dot_tile<H, NUP>(U2t, h2s + cur2 * H * TB, up, rg, acc);
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            float2 z[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) z[g] = fadd2(zx[r][g], acc.v[r][g]);
+            hn[r] = cell_pair(z, c2[r]);
+        }
+        store_h(h2s + (cur2 ^ 1) * H * TB, up, rg, hn);
+        cur2 ^= 1;
+        if (A.prefix_dump && blockIdx.x == 0 && rg == 0) {
+            // state of read 0 after t + 1 steps; h1 was stored above into buffer cur1
+            float *tb = A.prefix_dump + (size_t)(t + 1) * 4 * H;
+            const float *h1n = h1s + cur1 * H * TB;
+            tb[0 * H + 2 * up] = h1n[(2 * up) * TB];
+            tb[0 * H + 2 * up + 1] = h1n[(2 * up + 1) * TB];
+            tb[1 * H + 2 * up] = c1[0].x;  tb[1 * H + 2 * up + 1] = c1[0].y;
+            tb[2 * H + 2 * up] = hn[0].x;  tb[2 * H + 2 * up + 1] = hn[0].y;
+            tb[3 * H + 2 * up] = c2[0].x;  tb[3 * H + 2 * up + 1] = c2[0].y;
+        }
+        // no barrier needed here: the next writers of h1 target the buffer last read
+        // before the barrier above, and h2's new buffer is read only after the next one
+    }
+    __syncthreads();
+
+    // ---- Dense(2) + output transform + QC, one thread per read
+    if (tid < TB) {
+        const int64_t r = tile0 + tid;
+        if (r < A.n && s_nreal[tid] > 0) {
+            const float *h2f = h2s + cur2 * H * TB;
+            float z0 = 0.f, z1 = 0.f;
+            for (int k = 0; k < H; k++) {
+                const float hk = h2f[k * TB + tid];
+                z0 = pb::ffma(hk, A.Wd[2 * k], z0);
+                z1 = pb::ffma(hk, A.Wd[2 * k + 1], z1);
+            }
+            z0 = pb::fadd(z0, A.bd[0]);
+            z1 = pb::fadd(z1, A.bd[1]);
+            if (A.z_out) { A.z_out[2 * r] = z0; A.z_out[2 * r + 1] = z1; }
+            if (A.scale_shift) {
+                // poly1d([std, mean])(z) promotes to fp64 under numpy 2
+                const double sc = pb::dadd(pb::dmul(A.scale_std, (double)z0), A.scale_mean);
+                const double sh = pb::dadd(pb::dmul(A.shift_std, (double)z1), A.shift_mean);
+                A.scale_shift[2 * r] = (float)sc;
+                A.scale_shift[2 * r + 1] = (float)sh;
+                const bool ok = sc >= A.qc_scale_lo && sc <= A.qc_scale_hi &&
+                                sh >= A.qc_shift_lo && sh <= A.qc_shift_hi;
+                if (A.status && !ok) A.status[r] = PB2_ST_SCALING_QC_FAIL;
+            }
+        }
+    }
+}
+
+// load_padded_signal_head bookkeeping (signal_loader.py:212-222): how many pooled
+// samples feed the scaler, or scaler_signal_too_short.
+__global__ void k_scaler_prepare(const int64_t *__restrict__ raw_offsets,
+                                 const int64_t *__restrict__ raw_lengths, int64_t n, int stride,
+                                 int length, int min_length, int32_t *__restrict__ status,
+                                 int64_t *__restrict__ xoff, int32_t *__restrict__ nreal,
+                                 float *__restrict__ scale_shift)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t sl = raw_lengths[i] < length ? raw_lengths[i] : length;
+    sl -= sl % stride;
+    xoff[i] = pooled_offset(raw_offsets[i], stride);
+    scale_shift[2 * i] = 0.f;
+    scale_shift[2 * i + 1] = 0.f;
+    if (sl < min_length || sl <= 0) {
+        status[i] = PB2_ST_SCALER_SIGNAL_TOO_SHORT;
+        nreal[i] = 0;
+    } else {
+        status[i] = PB2_ST_OKAY;
+        nreal[i] = (int32_t)(sl / stride);
+    }
+}
+
+template <int H>
+static size_t scaler_smem() { return sizeof(float) * (3 * H * 4 * H + 4 * H * TB); }
+
+static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st)
+{
+    const ScalerDev &S = ctx->scaler;
+    if (S.l1.units != 48 || S.l2.units != 48 || S.l1.in_dim != 1 || S.l2.in_dim != 48 ||
+        S.l1.impl != 1 || S.l2.impl != 1)
+        return fail(ctx, PB2_EUNSUPPORTED, "scaler network shape not built "
+                    "(LSTM(48,impl1) x2 expected)");
+    A.W1 = S.l1.kernel; A.U1 = S.l1.recurrent; A.b1 = S.l1.bias;
+    A.W2 = S.l2.kernel; A.U2 = S.l2.recurrent; A.b2 = S.l2.bias;
+    A.Wd = S.dense_kernel; A.bd = S.dense_bias;
+    A.scale_std = S.scale_std; A.scale_mean = S.scale_mean;
+    A.shift_std = S.shift_std; A.shift_mean = S.shift_mean;
+    A.qc_scale_lo = S.qc_scale_lo; A.qc_scale_hi = S.qc_scale_hi;
+    A.qc_shift_lo = S.qc_shift_lo; A.qc_shift_hi = S.qc_shift_hi;
+    const size_t smem = scaler_smem<48>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const unsigned grid = (unsigned)((A.n + TB - 1) / TB);
+    k_scaler_lstm<48><<<grid, 24 * NRG, smem, st>>>(A);
+    PB_LAUNCH_CHECK(ctx, "k_scaler_lstm");
+    return PB2_OK;
+}
+
+int build_zero_prefix(pb2_context *ctx)
+{
+    ScalerDev &S = ctx->scaler;
+    const int thead = S.length / S.stride;
+    const int H = S.l1.units;
+    const size_t bytes = sizeof(float) * (size_t)(thead + 1) * 4 * H;
+    if (S.zero_prefix) cudaFree(S.zero_prefix);
+    S.zero_prefix = nullptr;
+    float *table = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&table, bytes));
+    PB_CUDA(ctx, cudaMemset(table, 0, bytes));
+    float *zeros = nullptr;
+    int64_t *xoff = nullptr;
+    int32_t *nreal = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&zeros, sizeof(float) * thead));
+    PB_CUDA(ctx, cudaMemset(zeros, 0, sizeof(float) * thead));
+    PB_CUDA(ctx, cudaMalloc(&xoff, sizeof(int64_t)));
+    PB_CUDA(ctx, cudaMemset(xoff, 0, sizeof(int64_t)));
+    PB_CUDA(ctx, cudaMalloc(&nreal, sizeof(int32_t)));
+    PB_CUDA(ctx, cudaMemcpy(nreal, &thead, sizeof(int32_t), cudaMemcpyHostToDevice));
+    ScalerArgs A = {};
+    A.x = zeros; A.xoff = xoff; A.nreal = nreal; A.n = 1; A.thead = thead;
+    A.zero_prefix = nullptr; A.prefix_dump = table;
+    int rc = run_scaler(ctx, A, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(zeros); cudaFree(xoff); cudaFree(nreal);
+    if (rc != PB2_OK) { cudaFree(table); return rc; }
+    if (e != cudaSuccess) { cudaFree(table); return check_cuda(ctx, e, "zero-prefix build"); }
+    S.zero_prefix = table;
+    S.zero_prefix_steps = thead;
+    return PB2_OK;
+}
+
+int launch_scaler(pb2_context *ctx, const pb2_batch &b, const float *pooled, int32_t *status,
+                  float *scale_shift, float *z_out, cudaStream_t st)
+{
+    if (b.n_reads <= 0) return PB2_OK;
+    const ScalerDev &S = ctx->scaler;
+    int64_t *xoff = (int64_t *)ws_get(ctx, ctx->ws_misc, (size_t)b.n_reads * 12);
+    if (!xoff) return PB2_ENOMEM;
+    int32_t *nreal = (int32_t *)(xoff + b.n_reads);
+    k_scaler_prepare<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, st>>>(
+        b.raw_offsets, b.raw_lengths, b.n_reads, S.stride, S.length, S.min_length, status, xoff,
+        nreal, scale_shift);
+    PB_LAUNCH_CHECK(ctx, "k_scaler_prepare");
+    ScalerArgs A = {};
+    A.x = pooled; A.xoff = xoff; A.nreal = nreal; A.n = b.n_reads;
+    A.thead = S.length / S.stride;
+    A.zero_prefix = S.zero_prefix; A.prefix_dump = nullptr; A.z_out = z_out;
+    A.status = status; A.scale_shift = scale_shift;
+    return run_scaler(ctx, A, st);
+}
+
+__global__ void k_iota_heads(int64_t n, int thead, int64_t *xoff, int32_t *nreal)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { xoff[i] = i * thead; nreal[i] = thead; }
+}
+
+int launch_scaler_heads(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
+                        cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    const ScalerDev &S = ctx->scaler;
+    int64_t *xoff = (int64_t *)ws_get(ctx, ctx->ws_misc, (size_t)n * 12);
+    if (!xoff) return PB2_ENOMEM;
+    int32_t *nreal = (int32_t *)(xoff + n);
+    const int thead = S.length / S.stride;
+    k_iota_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, thead, xoff, nreal);
+    PB_LAUNCH_CHECK(ctx, "k_iota_heads");
+    ScalerArgs A = {};
+    A.x = heads; A.xoff = xoff; A.nreal = nreal; A.n = n; A.thead = thead;
+    A.zero_prefix = nullptr;       // explicit heads: run every step as keras does
+    A.z_out = z_out;
+    return run_scaler(ctx, A, st);
+}
+
+// ============================================================================
+// Demultiplexer, layer 1: Bidirectional(LSTMCell(H1, impl 2)); one direction per
+// blockIdx.y.  Output h(t) of both directions goes to a scratch laid out for layer 2:
+//   G[tile][t][dir*H1 + unit][TB]
+// ============================================================================
+struct DemuxArgs {
+    const float *windows;          // [n][T]
+    int64_t n;
+    int T;
+    const float *Wf, *Uf, *bf, *Wb, *Ub, *bb;     // layer 1 (fwd, bwd)
+    const float *W2, *U2, *b2;                    // layer 2
+    const float *Wd, *bd;                         // dense
+    float *G;                                     // layer-1 outputs
+    const int32_t *pushed;                        // may be nullptr
+    int n_classes, n_decoy;
+    int n_calibration;
+    double score_threshold;
+    float *class_probs; int32_t *barcode, *guess, *score;
+};
+
+__constant__ double c_calibration[PB2_MAX_CALIB];
+
+template <int H1>
+__global__ void __launch_bounds__((H1 / 2) * NRG)
+k_demux_l1(const DemuxArgs A)
+{
+    constexpr int NUP = H1 / 2;
+    extern __shared__ __align__(16) float smem[];
+    float *Ut = smem;                         // [H1][NUP][4][2]
+    float *hs = Ut + H1 * 4 * H1;             // [2][H1][TB]
+    const int tid = threadIdx.x;
+    const int rg = tid % NRG, up = tid / NRG;
+    const int dir = blockIdx.y;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TB;
+    const float *W = dir ? A.Wb : A.Wf, *U = dir ? A.Ub : A.Uf, *bias = dir ? A.bb : A.bf;
+
+    load_weights<H1, H1>(U, Ut);
+    float2 w[4], b[4];
+    load_pair<H1>(W, up, w);
+    load_pair<H1>(bias, up, b);
+    const float *xp[RG];
+#pragma unroll
+    for (int r = 0; r < RG; r++) {
+        int64_t rd = tile0 + rg * RG + r;
+        if (rd >= A.n) rd = A.n - 1;
+        xp[r] = A.windows + rd * A.T;
+    }
+    float2 c[RG], hz[RG];
+#pragma unroll
+    for (int r = 0; r < RG; r++) { c[r] = make_float2(0.f, 0.f); hz[r] = c[r]; }
+    store_h(hs, up, rg, hz);
+    __syncthreads();
+
+    float *Gt = A.G + (size_t)tile * A.T * (2 * H1) * TB;
+    int cur = 0;
+    Acc acc;
+    for (int s = 0; s < A.T; s++) {
+        const int t = dir ? (A.T - 1 - s) : s;
+        float xv[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) xv[r] = __ldg(xp[r] + t);
+        dot_tile<H1, NUP>(Ut, hs + cur * H1 * TB, up, rg, acc);
+        float2 hn[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            float2 z[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++)       // implementation 2: ((x.W + h.U) + b)
+                z[g] = fadd2(fadd2(fmul2s(xv[r], w[g]), acc.v[r][g]), b[g]);
+            hn[r] = cell_pair(z, c[r]);
+        }
+        store_h(hs + (cur ^ 1) * H1 * TB, up, rg, hn);
+        store_h(Gt + ((size_t)t * 2 * H1 + dir * H1) * TB, up, rg, hn);
+        cur ^= 1;
+        __syncthreads();
+    }
+}
+
+// ============================================================================
+// Demultiplexer, layer 2: LSTMCell(H2, impl 2) over concat(fwd, bwd), then
+// Dense(n_classes) + softmax + the decision rule of barcoding.py:108-118.
+// ============================================================================
+template <int H1, int H2>
+__global__ void __launch_bounds__((H2 / 2) * NRG, 1)
+k_demux_l2(const DemuxArgs A)
+{
+    constexpr int NUP = H2 / 2;
+    constexpr int KX = 2 * H1;
+    extern __shared__ __align__(16) float smem[];
+    float *Wt = smem;                         // [KX][NUP][4][2]
+    float *Ut = Wt + KX * 4 * H2;             // [H2][NUP][4][2]
+    float *hs = Ut + H2 * 4 * H2;             // [2][H2][TB]
+    float *xs = hs + 2 * H2 * TB;             // [KX][TB]
+    const int tid = threadIdx.x;
+    const int rg = tid % NRG, up = tid / NRG;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TB;
+
+    load_weights<KX, H2>(A.W2, Wt);
+    load_weights<H2, H2>(A.U2, Ut);
+    float2 b[4];
+    load_pair<H2>(A.b2, up, b);
+    float2 c[RG], hz[RG];
+#pragma unroll
+    for (int r = 0; r < RG; r++) { c[r] = make_float2(0.f, 0.f); hz[r] = c[r]; }
+    store_h(hs, up, rg, hz);
+
+    const float *Gt = A.G + (size_t)tile * A.T * KX * TB;
+    int cur = 0;
+    Acc acc;
+    for (int t = 0; t < A.T; t++) {
+        __syncthreads();                      // xs free (and h stores of step t-1 visible)
+        const float4 *src = reinterpret_cast<const float4 *>(Gt + (size_t)t * KX * TB);
+        for (int i = tid; i < KX * TB / 4; i += blockDim.x)
+            reinterpret_cast<float4 *>(xs)[i] = __ldg(src + i);
+        __syncthreads();
+        dot_tile<KX, NUP>(Wt, xs, up, rg, acc);
+        float2 zx[RG][4];
+#pragma unroll
+        for (int r = 0; r < RG; r++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) zx[r][g] = acc.v[r][g];
+        dot_tile<H2, NUP>(Ut, hs + cur * H2 * TB, up, rg, acc);
+        float2 hn[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            float2 z[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) z[g] = fadd2(fadd2(zx[r][g], acc.v[r][g]), b[g]);
+            hn[r] = cell_pair(z, c[r]);
+        }
+        store_h(hs + (cur ^ 1) * H2 * TB, up, rg, hn);
+        cur ^= 1;
+    }
+    __syncthreads();
+
+    if (tid < TB) {
+        const int64_t r = tile0 + tid;
+        if (r < A.n && (A.pushed == nullptr || A.pushed[r])) {
+            const float *hf = hs + cur * H2 * TB;
+            const int nc = A.n_classes;
+            float logit[PB2_MAX_CLASSES], e[PB2_MAX_CLASSES];
+#pragma unroll
+            for (int j = 0; j < PB2_MAX_CLASSES; j++) logit[j] = 0.f;
+            for (int k = 0; k < H2; k++) {
+                const float hk = hf[k * TB + tid];
+#pragma unroll
+                for (int j = 0; j < PB2_MAX_CLASSES; j++)
+                    if (j < nc) logit[j] = pb::ffma(hk, A.Wd[k * nc + j], logit[j]);
+            }
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < PB2_MAX_CLASSES; j++)
+                if (j < nc) { logit[j] = pb::fadd(logit[j], A.bd[j]); m = fmaxf(m, logit[j]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < PB2_MAX_CLASSES; j++)
+                if (j < nc) { e[j] = pb::exp_eigen(pb::fsub(logit[j], m)); sum = pb::fadd(sum, e[j]); }
+            const float rs = pb::fdiv(1.0f, sum);
+            int arg = 0;
+            float best = -1.f;
+#pragma unroll
+            for (int j = 0; j < PB2_MAX_CLASSES; j++) {
+                float p = 0.f;
+                if (j < nc) {
+                    p = pb::fmul(e[j], rs);
+                    if (p > best) { best = p; arg = j; }
+                }
+                if (A.class_probs) A.class_probs[r * PB2_MAX_CLASSES + j] = p;
+            }
+            // barcoding.py:108-118
+            const int bcid = arg - A.n_decoy;
+            const double sc = (double)best;
+            if (A.barcode) A.barcode[r] = (bcid >= 0 && sc >= A.score_threshold) ? bcid : -1;
+            if (A.guess) A.guess[r] = bcid;
+            if (A.score) {
+                int lo = 0;
+                if (sc > 0.0) {                 // bisect_right(calibration, score)
+                    int hi = A.n_calibration;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sc < c_calibration[mid]) hi = mid; else lo = mid + 1;
+                    }
+                }
+                A.score[r] = lo;
+            }
+        }
+    }
+}
+
+int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                 float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                 cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    const DemuxDev &D = ctx->demux;
+    if (D.fwd.units != 48 || D.bwd.units != 48 || D.l2.units != 64 || D.fwd.in_dim != 1 ||
+        D.l2.in_dim != 96 || D.fwd.impl != 2 || D.bwd.impl != 2 || D.l2.impl != 2)
+        return fail(ctx, PB2_EUNSUPPORTED, "demux network shape not built "
+                    "(Bidirectional(LSTMCell 48) -> LSTMCell 64, impl 2 expected)");
+    constexpr int H1 = 48, H2 = 64;
+    const int T = D.trim_length;
+    const int64_t tiles = (n + TB - 1) / TB;
+    // layer-1 scratch is tiles*T*96*32 floats (~3.5 MiB per tile at T=300): bound it
+    const size_t per_tile = sizeof(float) * (size_t)T * 2 * H1 * TB;
+    int64_t tiles_per_pass = (int64_t)(((size_t)4 << 30) / per_tile);
+    if (tiles_per_pass > tiles) tiles_per_pass = tiles;
+    float *G = (float *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
+    if (!G) return PB2_ENOMEM;
+
+    static bool attr_done = false;
+    const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
+    const size_t smem2 = sizeof(float) * (2 * H1 * 4 * H2 + H2 * 4 * H2 + 2 * H2 * TB + 2 * H1 * TB);
+    if (!attr_done) {
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr_done = true;
+    }
+    PB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_calibration, D.calibration,
+                                         sizeof(double) * PB2_MAX_CALIB, 0,
+                                         cudaMemcpyHostToDevice, st));
+    for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
+        const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
+        const int64_t r0 = t0 * TB;
+        DemuxArgs A = {};
+        A.windows = windows + r0 * T;
+        A.n = (n - r0 < nt * TB) ? n - r0 : nt * TB;
+        A.T = T;
+        A.Wf = D.fwd.kernel; A.Uf = D.fwd.recurrent; A.bf = D.fwd.bias;
+        A.Wb = D.bwd.kernel; A.Ub = D.bwd.recurrent; A.bb = D.bwd.bias;
+        A.W2 = D.l2.kernel; A.U2 = D.l2.recurrent; A.b2 = D.l2.bias;
+        A.Wd = D.dense_kernel; A.bd = D.dense_bias;
+        A.G = G;
+        A.pushed = pushed ? pushed + r0 : nullptr;
+        A.n_classes = D.n_classes; A.n_decoy = D.n_decoy;
+        A.n_calibration = D.n_calibration; A.score_threshold = D.score_threshold;
+        A.class_probs = class_probs ? class_probs + r0 * PB2_MAX_CLASSES : nullptr;
+        A.barcode = barcode ? barcode + r0 : nullptr;
+        A.guess = guess ? guess + r0 : nullptr;
+        A.score = score ? score + r0 : nullptr;
+        k_demux_l1<H1><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A);
+        PB_LAUNCH_CHECK(ctx, "k_demux_l1");
+        k_demux_l2<H1, H2><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A);
+        PB_LAUNCH_CHECK(ctx, "k_demux_l2");
+    }
+    return PB2_OK;
+}
+
+}  // namespace pb

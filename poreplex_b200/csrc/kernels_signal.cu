@@ -1,0 +1,274 @@
+// kernels_signal.cu -- HBM-bound element kernels of the signal path:
+//   k_pool      int16 DAC -> pA (fp64 affine) -> mean-pool by `stride`   (A1, A2/A4)
+//   k_windows   adapter slice -> median/MAD normalised barcode window    (A6)
+//   k_finalize  per-read label / default barcode fields                  (A13)
+//   k_counts    (label, barcode, status) histogram                       (io.py:274-278)
+#include "pb_internal.h"
+#include "pb_math.cuh"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------
+// k_pool: one warp produces 32 pooled samples per iteration.
+//   raw tile   32*stride int16 staged in shared memory with 16-byte loads
+//              (reads start 16-byte aligned; a tile is 32*stride*2 bytes which is a
+//              multiple of 16 for every stride)
+//   lane l     converts its `stride` samples in fp64 (fast5_file.py:130-131), sums
+//              them in numpy's pairwise order (signal_loader.py:224-225) and stores
+//              one f32 -- 128-byte coalesced store per warp.
+// grid.x covers reads (one warp per read), grid.y covers chunks of POOL_CHUNK pooled
+// samples so that long reads are spread over many warps.
+// ---------------------------------------------------------------------------
+constexpr int POOL_WARPS = 8;
+constexpr int POOL_CHUNK = 256;         // pooled samples per (warp, blockIdx.y)
+constexpr int POOL_MAX_STRIDE = 32;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(POOL_WARPS * 32)
+k_pool(const int16_t *__restrict__ raw, const int64_t *__restrict__ raw_offsets,
+       const int64_t *__restrict__ raw_lengths, const double *__restrict__ range,
+       const double *__restrict__ digitisation, const double *__restrict__ offset,
+       int64_t n_reads, int64_t n_raw_total, int limit_pooled, float *__restrict__ pooled)
+{
+    constexpr int TILE = 32 * STRIDE;                 // int16 elements per warp tile
+    constexpr int NVEC = TILE / 8;                    // 16-byte vectors per tile
+    __shared__ __align__(16) int16_t stage[POOL_WARPS][TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * POOL_WARPS + warp;
+    if (r >= n_reads) return;
+    const int64_t roff = raw_offsets[r];
+    const int64_t rlen = raw_lengths[r];
+    int64_t T = rlen / STRIDE;
+    if (T > limit_pooled) T = limit_pooled;
+    const int64_t t_begin = (int64_t)blockIdx.y * POOL_CHUNK;
+    if (t_begin >= T) return;
+    const int64_t t_end = (t_begin + POOL_CHUNK < T) ? t_begin + POOL_CHUNK : T;
+    const double gain = pb::ddiv(range[r], digitisation[r]);   // range / digitisation
+    const double off = offset[r];
+    const int64_t pout = pooled_offset(roff, STRIDE);
+    int16_t *mine = stage[warp];
+
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += 32) {
+        const int64_t e0 = roff + t0 * STRIDE;          // first raw element of the tile
+#pragma unroll
+        for (int v = lane; v < NVEC; v += 32) {
+            const int64_t e = e0 + (int64_t)v * 8;
+            if (e + 8 <= n_raw_total) {
+                *reinterpret_cast<int4 *>(mine + v * 8) =
+                    __ldg(reinterpret_cast<const int4 *>(raw + e));
+            } else {
+                for (int j = 0; j < 8; j++)
+                    mine[v * 8 + j] = (e + j < n_raw_total) ? raw[e + j] : (int16_t)0;
+            }
+        }
+        __syncwarp();
+        const int64_t t = t0 + lane;
+        if (t < t_end) {
+            float a[STRIDE];
+#pragma unroll
+            for (int j = 0; j < STRIDE; j++)
+                a[j] = pb::dac_to_pa((int)mine[lane * STRIDE + j], gain, off);
+            pooled[pout + t] = pb::pool_mean<STRIDE>(a);
+        }
+        __syncwarp();
+    }
+}
+
+int launch_pool(pb2_context *ctx, const pb2_batch &b, int stride, float *pooled,
+                cudaStream_t st)
+{
+    if (b.n_reads <= 0) return PB2_OK;
+    if (stride != 15)
+        return fail(ctx, PB2_EUNSUPPORTED, "pooling stride %d not built (15 only)", stride);
+    const int limit = ctx->scan_limit_pooled > ctx->scaler.length / stride
+                          ? ctx->scan_limit_pooled : ctx->scaler.length / stride;
+    // without a host-side maximum, cover the whole scan limit
+    int64_t maxT = limit;
+    if (b.max_raw_length > 0 && b.max_raw_length / stride < maxT) maxT = b.max_raw_length / stride;
+    if (maxT < 1) maxT = 1;
+    dim3 grid((unsigned)((b.n_reads + POOL_WARPS - 1) / POOL_WARPS),
+              (unsigned)((maxT + POOL_CHUNK - 1) / POOL_CHUNK));
+    k_pool<15><<<grid, POOL_WARPS * 32, 0, st>>>(b.raw, b.raw_offsets, b.raw_lengths, b.range,
+                                                 b.digitisation, b.offset, b.n_reads,
+                                                 b.n_raw_total, limit, pooled);
+    PB_LAUNCH_CHECK(ctx, "k_pool");
+    return PB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k_windows: BarcodeDemultiplexer.push (barcoding.py:77-101).  One warp per read.
+// The <= trim_length samples of the adapter tail are scaled (unfused mul, add),
+// held in shared memory, and both medians are found by exact rank counting
+// (rank = #smaller + #equal-with-lower-index), which reproduces np.median's
+// order statistics without sorting.
+// ---------------------------------------------------------------------------
+constexpr int WIN_WARPS = 4;
+
+__device__ __forceinline__ float warp_median(const float *v, int n, int lane,
+                                              float *slot /* [2] shared, per warp */)
+{
+    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
+    for (int i = lane; i < n; i += 32) {
+        const float x = v[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const float y = v[j];
+            rank += (y < x) || (y == x && j < i);
+        }
+        if (rank == k_lo) slot[0] = x;
+        if (rank == k_hi) slot[1] = x;
+    }
+    __syncwarp();
+    const float lo = slot[0], hi = slot[1];
+    __syncwarp();
+    if (n & 1) return hi;
+    return pb::fdiv(pb::fadd(lo, hi), 2.0f);        // np.mean of the two middle values
+}
+
+__global__ void __launch_bounds__(WIN_WARPS * 32)
+k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ pooled,
+          const float *__restrict__ scale_shift, const int32_t *__restrict__ status,
+          const int32_t *__restrict__ segments, int64_t n_reads, int stride,
+          int adapter_state, int min_len, int max_len, int trim_len, float pad_value,
+          float *__restrict__ windows, int32_t *__restrict__ pushed)
+{
+    __shared__ float sx[WIN_WARPS][PB2_WINDOW_MAX];
+    __shared__ float sd[WIN_WARPS][PB2_WINDOW_MAX];
+    __shared__ float slot[WIN_WARPS][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * WIN_WARPS + warp;
+    if (r >= n_reads) return;
+    float *out = windows + r * trim_len;
+    int ok = 0;
+    int a0 = -1, a1 = -1;
+    if (status[r] == PB2_ST_OKAY) {
+        a0 = segments[(r * PB2_MAX_STATES + adapter_state) * 2 + 0];
+        a1 = segments[(r * PB2_MAX_STATES + adapter_state) * 2 + 1];
+        const int len = a1 - a0 + 1;
+        ok = (a0 >= 0) && (len > 0) && (min_len <= len) && (len <= max_len);
+    }
+    if (!ok) {
+        if (lane == 0) pushed[r] = 0;
+        for (int i = lane; i < trim_len; i += 32) out[i] = 0.0f;
+        return;
+    }
+    const int len = a1 - a0 + 1;
+    const int n = len > trim_len ? trim_len : len;
+    const int first = a1 - n + 1;
+    const float scale = scale_shift[2 * r], shift = scale_shift[2 * r + 1];
+    const float *src = pooled + pooled_offset(raw_offsets[r], stride) + first;
+    float *x = sx[warp], *d = sd[warp];
+    for (int i = lane; i < n; i += 32) x[i] = pb::fadd(pb::fmul(scale, src[i]), shift);
+    __syncwarp();
+    const float med = warp_median(x, n, lane, slot[warp]);
+    for (int i = lane; i < n; i += 32) d[i] = fabsf(pb::fsub(x[i], med));
+    __syncwarp();
+    const float mad = warp_median(d, n, lane, slot[warp]);
+    const float scaled = pb::fmul(mad, 1.4826f);
+    const float div = scaled > 0.01f ? scaled : 0.01f;
+    const int npad = trim_len - n;
+    for (int i = lane; i < npad; i += 32) out[i] = pad_value;
+    for (int i = lane; i < n; i += 32) out[npad + i] = pb::fdiv(pb::fsub(x[i], med), div);
+    if (lane == 0) pushed[r] = 1;
+}
+
+int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                   const float *scale_shift, const int32_t *status, const int32_t *segments,
+                   float *windows, int32_t *pushed, cudaStream_t st)
+{
+    if (b.n_reads <= 0) return PB2_OK;
+    const DemuxDev &d = ctx->demux;
+    if (d.trim_length > PB2_WINDOW_MAX)
+        return fail(ctx, PB2_EUNSUPPORTED, "signal_trim_length %d > %d", d.trim_length,
+                    PB2_WINDOW_MAX);
+    const unsigned grid = (unsigned)((b.n_reads + WIN_WARPS - 1) / WIN_WARPS);
+    k_windows<<<grid, WIN_WARPS * 32, 0, st>>>(b.raw_offsets, pooled, scale_shift, status,
+                                               segments, b.n_reads, ctx->scaler.stride,
+                                               ctx->adapter_state, d.min_length, d.max_length,
+                                               d.trim_length, d.pad_value, windows, pushed);
+    PB_LAUNCH_CHECK(ctx, "k_windows");
+    return PB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k_finalize: label per read (signal_analyzer.py:281-286; a read stopped before
+// stage C keeps label None) and "not classified" defaults for the barcode fields.
+// ---------------------------------------------------------------------------
+__global__ void k_finalize(int64_t n, const int32_t *__restrict__ status,
+                           const int32_t *__restrict__ pushed, int32_t *__restrict__ label,
+                           int32_t *__restrict__ barcode, int32_t *__restrict__ guess,
+                           int32_t *__restrict__ score)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = status[i];
+    int lab;
+    if (s == PB2_ST_OKAY) lab = PB2_LABEL_PASS;
+    else if (s == PB2_ST_UNSPLIT_READ) lab = PB2_LABEL_ARTIFACT;
+    else if (s == PB2_ST_SCALER_SIGNAL_TOO_SHORT || s == PB2_ST_SCALING_QC_FAIL ||
+             s == PB2_ST_UNKNOWN_ERROR || s == PB2_ST_DISAPPEARED ||
+             s == PB2_ST_IRREGULAR_FAST5) lab = PB2_LABEL_NONE;
+    else lab = PB2_LABEL_FAIL;
+    if (label) label[i] = lab;
+    if (barcode && (pushed == nullptr || !pushed[i])) {
+        barcode[i] = -1;
+        if (guess) guess[i] = INT32_MIN;
+        if (score) score[i] = -1;
+    }
+}
+
+int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
+                    int32_t *label, int32_t *barcode, int32_t *guess, int32_t *score,
+                    cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    const int32_t *pushed = (flags & PB2_FLAG_BARCODING) ? (const int32_t *)ctx->ws_pushed.ptr
+                                                          : nullptr;
+    k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, status, pushed, label, barcode,
+                                                           guess, score);
+    PB_LAUNCH_CHECK(ctx, "k_finalize");
+    return PB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k_counts: FinalSummaryTracker.feed_results (io.py:274-278) as a histogram.
+// Shared-memory bins per block, one global atomic per non-empty bin.
+// ---------------------------------------------------------------------------
+constexpr int N_BINS = PB2_N_LABEL * PB2_N_BARCODE_SLOTS * PB2_N_STATUS;
+
+__global__ void __launch_bounds__(256)
+k_counts(const int32_t *__restrict__ status, const int32_t *__restrict__ label,
+         const int32_t *__restrict__ barcode, int64_t n, unsigned long long *counts)
+{
+    __shared__ unsigned int bins[N_BINS];
+    for (int i = threadIdx.x; i < N_BINS; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = status[i];
+        const int l = label[i];
+        const int b = barcode ? barcode[i] : -1;
+        if (s < 0 || s >= PB2_N_STATUS || l < 0 || l >= PB2_N_LABEL) continue;
+        const int slot = (b >= 0 && b < PB2_N_BARCODE_SLOTS - 1) ? b + 1 : 0;
+        atomicAdd(&bins[(l * PB2_N_BARCODE_SLOTS + slot) * PB2_N_STATUS + s], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N_BINS; i += blockDim.x)
+        if (bins[i]) atomicAdd(&counts[i], (unsigned long long)bins[i]);
+}
+
+int launch_counts(pb2_context *ctx, const int32_t *status, const int32_t *label,
+                  const int32_t *barcode, int64_t n, int64_t *counts, cudaStream_t st)
+{
+    PB_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int64_t) * N_BINS, st));
+    if (n <= 0) return PB2_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_counts<<<(unsigned)blocks, 256, 0, st>>>(status, label, barcode, n,
+                                               reinterpret_cast<unsigned long long *>(counts));
+    PB_LAUNCH_CHECK(ctx, "k_counts");
+    return PB2_OK;
+}
+
+}  // namespace pb

@@ -1,0 +1,263 @@
+// kernels_viterbi.cu -- HMM Viterbi segmentation (A5).
+//
+// Reference: SignalAnalysis.detect_segments (signal_analyzer.py:346-364) calling
+// pomegranate's HiddenMarkovModel.viterbi (restated in oracle/pb_oracle.c
+// orc_viterbi).  fp64 log space, candidates evaluated as
+// ((v[src] + logT) + e[dst]) in baked source order, strict '>' (first maximum wins),
+// final state = first argmax.
+//
+// Mapping: one thread per read.  The recurrence is strictly sequential in time and
+// every read is independent, so a batch of 10^5..10^6 reads fills the machine with
+// the oracle's exact operation order intact (no re-association).  Each thread streams
+// its pooled samples, keeps the 8 state scores in registers, and writes one packed
+// back-pointer word per time step to a [t][read] scratch matrix (coalesced across the
+// warp); the traceback walks that matrix backwards and emits run-length segments.
+#include "pb_internal.h"
+#include "pb_math.cuh"
+
+namespace pb {
+
+constexpr int VT_THREADS = 128;
+
+struct HmmMask {
+    // has_edge[dst] bit src ; has_start bit s
+    uint32_t edge[PB2_MAX_STATES];
+    double logp[PB2_MAX_STATES][PB2_MAX_STATES];   // [dst][src]
+};
+
+__device__ __forceinline__ void hmm_emissions(const HmmDev &M, double x,
+                                              double (&e)[PB2_MAX_STATES])
+{
+#pragma unroll
+    for (int s = 0; s < PB2_MAX_STATES; s++) {
+        e[s] = 0.0;
+        if (s < M.n_states) {
+            const int nc = M.n_comp[s];
+            if (nc == 1) {
+                const double d = pb::dsub(x, M.mu[s][0]);
+                e[s] = pb::dsub(M.log_norm[s][0], pb::dmul(pb::dmul(d, d), M.inv_two_var[s][0]));
+            } else {
+                double acc = pb::neg_inf();
+#pragma unroll
+                for (int j = 0; j < PB2_MAX_COMP; j++) {
+                    if (j < nc) {
+                        const double d = pb::dsub(x, M.mu[s][j]);
+                        const double lp = pb::dsub(M.log_norm[s][j],
+                                                   pb::dmul(pb::dmul(d, d), M.inv_two_var[s][j]));
+                        acc = pb::pair_lse(acc, pb::dadd(lp, M.log_weight[s][j]));
+                    }
+                }
+                e[s] = acc;
+            }
+        }
+    }
+}
+
+// One Viterbi time step.  Returns the packed back-pointer word (3 bits per state,
+// 7 = no predecessor).
+__device__ __forceinline__ uint32_t viterbi_step(const HmmDev &M, const HmmMask &K,
+                                                 double (&v)[PB2_MAX_STATES],
+                                                 const double (&e)[PB2_MAX_STATES])
+{
+    double nv[PB2_MAX_STATES];
+    uint32_t bp = 0;
+#pragma unroll
+    for (int l = 0; l < PB2_MAX_STATES; l++) {
+        double best = pb::neg_inf();
+        uint32_t arg = 7;
+        if (l < M.n_states) {
+#pragma unroll
+            for (int src = 0; src < PB2_MAX_STATES; src++) {
+                if (K.edge[l] & (1u << src)) {
+                    const double cand = pb::dadd(pb::dadd(v[src], K.logp[l][src]), e[l]);
+                    if (cand > best) { best = cand; arg = src; }
+                }
+            }
+        }
+        nv[l] = best;
+        bp |= arg << (3 * l);
+    }
+#pragma unroll
+    for (int l = 0; l < PB2_MAX_STATES; l++) v[l] = nv[l];
+    return bp;
+}
+
+__device__ __forceinline__ void viterbi_init(const HmmDev &M, double (&v)[PB2_MAX_STATES],
+                                             const double (&e)[PB2_MAX_STATES])
+{
+#pragma unroll
+    for (int s = 0; s < PB2_MAX_STATES; s++) {
+        v[s] = pb::neg_inf();
+        if (s < M.n_states && M.log_start[s] > pb::neg_inf()) {
+            const double cand = pb::dadd(pb::dadd(0.0, M.log_start[s]), e[s]);
+            if (cand > v[s]) v[s] = cand;
+        }
+    }
+}
+
+__device__ __forceinline__ int viterbi_end(const HmmDev &M, const double (&v)[PB2_MAX_STATES],
+                                           double &best)
+{
+    int end = 0;
+    best = v[0];
+#pragma unroll
+    for (int s = 1; s < PB2_MAX_STATES; s++)
+        if (s < M.n_states && v[s] > best) { best = v[s]; end = s; }
+    return end;
+}
+
+// ---------------------------------------------------------------------------
+// k_segment: scale (signal_loader.py:262, unfused) + Viterbi + run-length segments
+// (signal_analyzer.py:355-362: a later run of a state overwrites an earlier one).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(VT_THREADS)
+k_segment(const HmmDev M, const HmmMask K, const int64_t *__restrict__ raw_offsets,
+          const int64_t *__restrict__ raw_lengths, const float *__restrict__ pooled,
+          const float *__restrict__ scale_shift, int64_t r0, int64_t n_chunk, int stride,
+          int scan_limit, int adapter_state, uint32_t *__restrict__ bp, int32_t *status,
+          int32_t *__restrict__ segments, float *__restrict__ pooled_scaled_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunk) return;
+    const int64_t r = r0 + i;
+    int32_t *seg = segments + r * PB2_MAX_STATES * 2;
+#pragma unroll
+    for (int s = 0; s < PB2_MAX_STATES * 2; s++) seg[s] = -1;
+    if (status[r] != PB2_ST_OKAY) return;
+    int64_t T64 = raw_lengths[r] / stride;
+    const int T = (int)(T64 > scan_limit ? scan_limit : T64);
+    if (T <= 0) { status[r] = PB2_ST_UNKNOWN_ERROR; return; }
+    const float scale = scale_shift[2 * r], shift = scale_shift[2 * r + 1];
+    const int64_t po = pooled_offset(raw_offsets[r], stride);
+    const float *x = pooled + po;
+
+    double v[PB2_MAX_STATES], e[PB2_MAX_STATES];
+    {
+        const float y = pb::fadd(pb::fmul(scale, x[0]), shift);
+        if (pooled_scaled_out) pooled_scaled_out[po] = y;
+        hmm_emissions(M, (double)y, e);
+        viterbi_init(M, v, e);
+    }
+    for (int t = 1; t < T; t++) {
+        const float y = pb::fadd(pb::fmul(scale, x[t]), shift);
+        if (pooled_scaled_out) pooled_scaled_out[po + t] = y;
+        hmm_emissions(M, (double)y, e);
+        bp[(int64_t)t * n_chunk + i] = viterbi_step(M, K, v, e);
+    }
+    double best;
+    int cur = viterbi_end(M, v, best);
+    if (best == pb::neg_inf()) { status[r] = PB2_ST_UNKNOWN_ERROR; return; }
+
+    // traceback: emit (first, last) of the LAST run of every state
+    uint32_t seen = 0;
+    int run_last = T - 1;
+    for (int t = T - 1; t >= 0; t--) {
+        int prev = -1;
+        if (t > 0) prev = (bp[(int64_t)t * n_chunk + i] >> (3 * cur)) & 7;
+        if (t == 0 || prev != cur) {
+            if (!(seen & (1u << cur))) {
+                seen |= 1u << cur;
+                seg[2 * cur] = t;
+                seg[2 * cur + 1] = run_last;
+            }
+            run_last = t - 1;
+            cur = prev;
+        }
+    }
+    if (!(seen & (1u << adapter_state))) status[r] = PB2_ST_ADAPTER_NOT_DETECTED;
+}
+
+static void make_mask(const HmmDev &M, HmmMask &K)
+{
+    for (int l = 0; l < PB2_MAX_STATES; l++) {
+        K.edge[l] = 0;
+        for (int s = 0; s < PB2_MAX_STATES; s++) K.logp[l][s] = -INFINITY;
+        if (l < M.n_states)
+            for (int k = M.in_begin[l]; k < M.in_begin[l + 1]; k++) {
+                K.edge[l] |= 1u << M.in_src[k];
+                K.logp[l][M.in_src[k]] = M.in_logp[k];
+            }
+    }
+}
+
+int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                   const float *scale_shift, int32_t *status, int32_t *segments,
+                   float *pooled_scaled_out, cudaStream_t st)
+{
+    if (b.n_reads <= 0) return PB2_OK;
+    HmmMask K;
+    make_mask(ctx->seg_hmm, K);
+    int64_t Tmax = ctx->scan_limit_pooled;
+    if (b.max_raw_length > 0 && b.max_raw_length / ctx->scaler.stride < Tmax)
+        Tmax = b.max_raw_length / ctx->scaler.stride;
+    if (Tmax < 1) Tmax = 1;
+    // back-pointer scratch is [Tmax][chunk] words; bound it to ~2 GiB per launch
+    int64_t chunk = ((int64_t)2 << 30) / (Tmax * 4);
+    chunk = (chunk / VT_THREADS) * VT_THREADS;
+    if (chunk < VT_THREADS) chunk = VT_THREADS;
+    if (chunk > b.n_reads) chunk = b.n_reads;
+    uint32_t *bp = (uint32_t *)ws_get(ctx, ctx->ws_bp, (size_t)chunk * Tmax * 4);
+    if (!bp) return PB2_ENOMEM;
+    for (int64_t r0 = 0; r0 < b.n_reads; r0 += chunk) {
+        const int64_t nc = (b.n_reads - r0 < chunk) ? b.n_reads - r0 : chunk;
+        k_segment<<<(unsigned)((nc + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
+            ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
+            ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
+            pooled_scaled_out);
+        PB_LAUNCH_CHECK(ctx, "k_segment");
+    }
+    return PB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k_viterbi_paths: HiddenMarkovModel.viterbi over dense rows, full state path out.
+// Used by the parity tests and by windowed decoding (unsplit-read model).
+// The path buffer itself doubles as back-pointer storage: path[r][t] first holds the
+// packed word of step t, then is overwritten by the decoded state during traceback.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(VT_THREADS)
+k_viterbi_paths(const HmmDev M, const HmmMask K, const float *__restrict__ x,
+                const int32_t *__restrict__ lengths, int64_t n, int ld,
+                int32_t *__restrict__ path, double *__restrict__ logp)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int T = lengths[r] < ld ? lengths[r] : ld;
+    const float *xr = x + r * ld;
+    int32_t *pr = path + r * ld;
+    if (T <= 0) { if (logp) logp[r] = pb::neg_inf(); return; }
+    double v[PB2_MAX_STATES], e[PB2_MAX_STATES];
+    hmm_emissions(M, (double)xr[0], e);
+    viterbi_init(M, v, e);
+    for (int t = 1; t < T; t++) {
+        hmm_emissions(M, (double)xr[t], e);
+        pr[t] = (int32_t)viterbi_step(M, K, v, e);
+    }
+    double best;
+    int cur = viterbi_end(M, v, best);
+    if (logp) logp[r] = best;
+    if (best == pb::neg_inf()) {
+        for (int t = 0; t < T; t++) pr[t] = -1;
+        return;
+    }
+    for (int t = T - 1; t >= 0; t--) {
+        const uint32_t w = (uint32_t)pr[t];
+        pr[t] = cur;
+        if (t > 0) cur = (w >> (3 * cur)) & 7;
+    }
+}
+
+int launch_viterbi_paths(pb2_context *ctx, const HmmDev &hmm, const float *x,
+                         const int32_t *lengths, int64_t n, int32_t ld, int32_t *path,
+                         double *logp, cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    HmmMask K;
+    make_mask(hmm, K);
+    k_viterbi_paths<<<(unsigned)((n + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
+        hmm, K, x, lengths, n, ld, path, logp);
+    PB_LAUNCH_CHECK(ctx, "k_viterbi_paths");
+    return PB2_OK;
+}
+
+}  // namespace pb

@@ -1,0 +1,134 @@
+// pb_internal.h -- context and kernel-launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/poreplex_b200.h"
+
+namespace pb {
+
+// ---- device-side parameter blocks ------------------------------------------
+struct HmmDev {                       // lives in __constant__ memory per kernel launch arg
+    int32_t n_states;
+    int32_t n_comp[PB2_MAX_STATES];
+    double mu[PB2_MAX_STATES][PB2_MAX_COMP];
+    double log_norm[PB2_MAX_STATES][PB2_MAX_COMP];
+    double inv_two_var[PB2_MAX_STATES][PB2_MAX_COMP];
+    double log_weight[PB2_MAX_STATES][PB2_MAX_COMP];
+    double log_start[PB2_MAX_STATES];
+    int32_t in_begin[PB2_MAX_STATES + 1];
+    int32_t in_src[PB2_MAX_EDGES];
+    double in_logp[PB2_MAX_EDGES];
+};
+
+struct LstmDev {                      // device copies of one layer's weights
+    int in_dim = 0, units = 0, impl = 0;
+    float *kernel = nullptr;          // [in_dim][4H]  as given (row-major)
+    float *recurrent = nullptr;       // [H][4H]
+    float *bias = nullptr;            // [4H]
+};
+
+struct ScalerDev {
+    bool set = false;
+    LstmDev l1, l2;
+    float *dense_kernel = nullptr, *dense_bias = nullptr;
+    int stride = 15, length = 30000, min_length = 9000;
+    double scale_std = 0, scale_mean = 0, shift_std = 0, shift_mean = 0;
+    double qc_scale_lo = 0, qc_scale_hi = 0, qc_shift_lo = 0, qc_shift_hi = 0;
+    // state of both layers after n all-zero input steps: [steps+1][4][units]
+    // (h1, c1, h2, c2); lets fit_scalers skip the left zero padding bit-exactly
+    float *zero_prefix = nullptr;
+    int zero_prefix_steps = 0;
+};
+
+struct DemuxDev {
+    bool set = false;
+    LstmDev fwd, bwd, l2;
+    float *dense_kernel = nullptr, *dense_bias = nullptr;
+    int n_classes = 0, n_decoy = 0, min_length = 0, max_length = 0, trim_length = 0;
+    float pad_value = -1000.f;
+    int n_calibration = 0;
+    double calibration[PB2_MAX_CALIB];
+    double score_threshold = 0;
+};
+
+struct Workspace {                    // grow-only device scratch
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace pb
+
+struct pb2_context {
+    int device = 0;
+    std::string error;
+    int64_t launches = 0;
+    int sm_count = 148;
+    pb::ScalerDev scaler;
+    pb::DemuxDev demux;
+    pb::HmmDev seg_hmm;
+    bool seg_set = false;
+    int scan_limit_pooled = 6666;
+    int adapter_state = 0;
+    // scratch
+    pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
+        ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
+        ws_heads;
+    // host staging for pb2_analyze_host
+    cudaStream_t host_stream = nullptr;
+};
+
+namespace pb {
+
+int fail(pb2_context *ctx, int code, const char *fmt, ...);
+int check_cuda(pb2_context *ctx, cudaError_t e, const char *what);
+void *ws_get(pb2_context *ctx, Workspace &w, size_t bytes);   // nullptr on failure
+
+#define PB_CUDA(ctx, call)                                               \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return pb::check_cuda(ctx, _e, #call);    \
+    } while (0)
+
+#define PB_LAUNCH_CHECK(ctx, name)                                       \
+    do {                                                                 \
+        (ctx)->launches++;                                               \
+        cudaError_t _e = cudaGetLastError();                             \
+        if (_e != cudaSuccess) return pb::check_cuda(ctx, _e, name);     \
+    } while (0)
+
+// pooled element offset of a read whose raw data starts at element `raw_off`
+__host__ __device__ inline int64_t pooled_offset(int64_t raw_off, int stride) {
+    return (raw_off + stride - 1) / stride;
+}
+
+// ---- kernel launchers (defined in the kernels_*.cu files) ------------------
+int launch_pool(pb2_context *ctx, const pb2_batch &b, int stride, float *pooled,
+                cudaStream_t st);
+int launch_scaler(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                  int32_t *status, float *scale_shift, float *z_out, cudaStream_t st);
+int launch_scaler_heads(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
+                        cudaStream_t st);
+int build_zero_prefix(pb2_context *ctx);
+int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                   const float *scale_shift, int32_t *status, int32_t *segments,
+                   float *pooled_scaled_out, cudaStream_t st);
+int launch_viterbi_paths(pb2_context *ctx, const HmmDev &hmm, const float *x,
+                         const int32_t *lengths, int64_t n, int32_t ld, int32_t *path,
+                         double *logp, cudaStream_t st);
+int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                   const float *scale_shift, const int32_t *status, const int32_t *segments,
+                   float *windows, int32_t *pushed, cudaStream_t st);
+int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                 float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                 cudaStream_t st);
+int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
+                    int32_t *label, int32_t *barcode, int32_t *guess, int32_t *score,
+                    cudaStream_t st);
+int launch_counts(pb2_context *ctx, const int32_t *status, const int32_t *label,
+                  const int32_t *barcode, int64_t n, int64_t *counts, cudaStream_t st);
+
+}  // namespace pb

@@ -1,0 +1,384 @@
+"""SignalEngine: the per-process GPU state behind ``SignalAnalyzer``.
+
+Plays the role of the objects the reference keeps alive per worker process in
+``WorkerPersistenceStorage`` (worker_persistence.py:35-90): the segmentation HMM, the
+scaler network (``SignalLoader``) and the barcode demultiplexer
+(``BarcodeDemultiplexer``), here as one native context holding their parameters in
+HBM.  Every numeric stage is a call through the C ABI (include/poreplex_b200.h);
+torch is used only to own device buffers / streams in the device-resident API.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import params as P
+
+__all__ = ['SignalEngine', 'get_engine']
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _lstm_struct(layer, keep):
+    W = np.ascontiguousarray(layer.kernel, np.float32)
+    U = np.ascontiguousarray(layer.recurrent, np.float32)
+    b = np.ascontiguousarray(layer.bias, np.float32)
+    keep += [W, U, b]
+    fp = C.POINTER(C.c_float)
+    return N.LstmWeights(layer.in_dim, layer.units, layer.implementation,
+                         W.ctypes.data_as(fp), U.ctypes.data_as(fp), b.ctypes.data_as(fp))
+
+
+def _hmm_struct(tables):
+    h = N.HmmParams()
+    h.n_states = tables.n_states
+    for s in range(N.MAX_STATES):
+        h.n_comp[s] = int(tables.n_comp[s])
+        h.log_start[s] = float(tables.log_start[s])
+        for j in range(N.MAX_COMP):
+            h.mu[s][j] = float(tables.mu[s, j])
+            h.log_norm[s][j] = float(tables.lsp[s, j])
+            h.inv_two_var[s][j] = float(tables.inv2s2[s, j])
+            h.log_weight[s][j] = float(tables.logw[s, j])
+    for i in range(N.MAX_STATES + 1):
+        h.in_begin[i] = int(tables.in_begin[i])
+    for k in range(N.MAX_EDGES):
+        h.in_src[k] = int(tables.in_src[k])
+        h.in_logp[k] = float(tables.in_logp[k])
+    return h
+
+
+class SignalEngine:
+    """One native context configured from the reference's flat ``config`` dict
+    (commandline.py:268-296) or from a preset dict (params.load_preset())."""
+
+    def __init__(self, config, device=0, barcoding=None, barcoding_quality_filter=None):
+        from scipy.stats import norm
+        self.lib = N.load()
+        self.config = config
+        self._keep = []
+        handle = C.c_void_p()
+        rc = self.lib.pb2_create(int(device), C.byref(handle))
+        if rc != 0 or not handle.value:
+            raise N.NativeError('poreplex_b200: cannot open CUDA device %d (rc=%d); this '
+                                'path has no CPU fallback' % (device, rc))
+        self.handle = handle
+        self.device = int(device)
+
+        sp = config['signal_processing']
+        self.stride = int(sp['rough_signal_stride'])
+        # --- scaler: SignalLoader.load_scaler_model (signal_loader.py:49-75)
+        self.scaler_model = sm = P.load_scaler_model(sp['scaler_model'])
+        idef, xf = sm.input_defs, sm.output_transform
+        if idef['stride'] != self.stride:
+            raise ValueError('scaler stride differs from rough_signal_stride')
+        q = sp['scaler_qc_threshold']
+        qs = norm.ppf([q, 1 - q], xf['scale_mean'], xf['scale_std'])
+        qh = norm.ppf([q, 1 - q], xf['shift_mean'], xf['shift_std'])
+        self.scaler_length = int(idef['length'])
+        self.scaler_min_length = int(sp.get('scaler_min_length_override', idef['min_length']))
+        fp = C.POINTER(C.c_float)
+        dk = np.ascontiguousarray(sm.dense_kernel, np.float32)
+        db = np.ascontiguousarray(sm.dense_bias, np.float32)
+        self._keep += [dk, db]
+        spar = N.ScalerParams(_lstm_struct(sm.l1, self._keep), _lstm_struct(sm.l2, self._keep),
+                              dk.ctypes.data_as(fp), db.ctypes.data_as(fp), self.stride,
+                              self.scaler_length, self.scaler_min_length,
+                              xf['scale_std'], xf['scale_mean'], xf['shift_std'],
+                              xf['shift_mean'], qs[0], qs[1], qh[0], qh[1])
+        self._check(self.lib.pb2_set_scaler(self.handle, C.byref(spar)))
+
+        # --- segmentation HMM: load_segmentation_model (worker_persistence.py:95-121)
+        self.seg_tables = st = P.HmmTables(config['segmentation_model'])
+        self.state_names = st.names
+        self.scan_limit_pooled = int(config['segmentation']['segmentation_scan_limit']) // self.stride
+        self.adapter_state = st.index_of('adapter')
+        if self.adapter_state < 0:
+            raise ValueError("segmentation model has no 'adapter' state")
+        hs = _hmm_struct(st)
+        self._check(self.lib.pb2_set_segmentation_hmm(self.handle, C.byref(hs),
+                                                      self.scan_limit_pooled, self.adapter_state))
+
+        # --- demultiplexer: BarcodeDemultiplexer (barcoding.py:34-70)
+        if barcoding is None:
+            barcoding = bool(config.get('barcoding', True))
+        self.barcoding = barcoding
+        self.demux_model = None
+        if barcoding:
+            if barcoding_quality_filter is None:
+                barcoding_quality_filter = config.get('barcoding_quality_filter', 18)
+            dc = config['demultiplexing']
+            self.demux_model = dm = P.load_demux_model(dc['demux_model'])
+            calib = np.ascontiguousarray(dm.calibration, np.float64)
+            if len(calib) - 1 < barcoding_quality_filter:       # barcoding.py:41-45
+                raise ValueError('The current demultiplexer does not support calibrated score '
+                                 'of {}. Consider lowering --barcoding-quality-filter value.'
+                                 .format(barcoding_quality_filter))
+            if dm.n_classes != dc['number_of_decoy_labels'] + dc['number_of_barcodes']:
+                raise ValueError('demux model classes do not match the preset')
+            dk2 = np.ascontiguousarray(dm.dense_kernel, np.float32)
+            db2 = np.ascontiguousarray(dm.dense_bias, np.float32)
+            self._keep += [dk2, db2, calib]
+            self.trim_length = int(dc['signal_trim_length'])
+            dpar = N.DemuxParams(_lstm_struct(dm.fwd, self._keep), _lstm_struct(dm.bwd, self._keep),
+                                 _lstm_struct(dm.l2, self._keep), dk2.ctypes.data_as(fp),
+                                 db2.ctypes.data_as(fp), dm.n_classes,
+                                 int(dc['number_of_decoy_labels']),
+                                 int(dc['minimum_dna_length']), int(dc['maximum_dna_length']),
+                                 self.trim_length, -1000.0, len(calib),
+                                 calib.ctypes.data_as(C.POINTER(C.c_double)),
+                                 float(calib[barcoding_quality_filter]))
+            self._check(self.lib.pb2_set_demux(self.handle, C.byref(dpar)))
+
+    # ------------------------------------------------------------------ util
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.pb2_last_error(self.handle)
+            raise N.NativeError('poreplex_b200 native error %d: %s'
+                                % (rc, msg.decode() if msg else '?'))
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle.value:
+            self.lib.pb2_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.pb2_kernel_launches(self.handle))
+
+    def pooled_offsets(self, raw_offsets):
+        """Element offset of each read inside a pooled buffer (same rule as the kernels)."""
+        return (np.asarray(raw_offsets, np.int64) + self.stride - 1) // self.stride
+
+    # -------------------------------------------------------- host-buffer API
+    @staticmethod
+    def pack_reads(signals):
+        """Concatenate int16 signals with every read 16-byte aligned.
+        Returns (raw, offsets, lengths)."""
+        lengths = np.array([len(s) for s in signals], np.int64)
+        padded = (lengths + 7) // 8 * 8
+        offsets = np.zeros(len(signals), np.int64)
+        if len(signals):
+            offsets[1:] = np.cumsum(padded)[:-1]
+        raw = np.zeros(int(padded.sum()) + 8, np.int16)
+        for s, o, n in zip(signals, offsets, lengths):
+            raw[o:o + n] = s
+        return raw, offsets, lengths
+
+    def analyze_host(self, raw, offsets, lengths, rng, digitisation, offset, barcoding=None,
+                     keep_pooled=False):
+        """SignalAnalyzer.process stages A-D over HOST numpy buffers (H2D, kernels, D2H).
+
+        Returns a dict of numpy arrays: status, label, scale_shift [n,2], segments
+        [n,8,2] (baked state order = ``state_names``), barcode, barcode_guess,
+        barcode_score, class_probs [n,8], counts [4,5,11], and ``pooled`` when asked.
+        """
+        if barcoding is None:
+            barcoding = self.barcoding
+        if barcoding and self.demux_model is None:
+            raise ValueError('engine was created without the demultiplexer')
+        raw = np.ascontiguousarray(raw, np.int16).reshape(-1)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        lengths = np.ascontiguousarray(lengths, np.int64)
+        rng = np.ascontiguousarray(rng, np.float64)
+        digitisation = np.ascontiguousarray(digitisation, np.float64)
+        offset = np.ascontiguousarray(offset, np.float64)
+        n = len(lengths)
+        if np.any(offsets % 8):
+            raise ValueError('raw_offsets must be multiples of 8 samples (see pack_reads)')
+        if n and int((offsets + lengths).max()) > raw.size:
+            raise ValueError('read extends past the raw buffer')
+        out = {
+            'status': np.empty(n, np.int32), 'label': np.empty(n, np.int32),
+            'scale_shift': np.zeros((n, 2), np.float32),
+            'segments': np.empty((n, N.MAX_STATES, 2), np.int32),
+            'barcode': np.empty(n, np.int32), 'barcode_guess': np.empty(n, np.int32),
+            'barcode_score': np.empty(n, np.int32),
+            'class_probs': np.zeros((n, N.MAX_CLASSES), np.float32),
+            'counts': np.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), np.int64),
+        }
+        if keep_pooled:
+            out['pooled'] = np.zeros(raw.size // self.stride + 2, np.float32)
+        b = N.Batch(n, raw.size, int(lengths.max()) if n else 0, _np_ptr(raw), _np_ptr(offsets),
+                    _np_ptr(lengths), _np_ptr(rng), _np_ptr(digitisation), _np_ptr(offset))
+        r = N.Results(_np_ptr(out['status']), _np_ptr(out['label']), _np_ptr(out['scale_shift']),
+                      _np_ptr(out['segments']), _np_ptr(out['barcode']),
+                      _np_ptr(out['barcode_guess']), _np_ptr(out['barcode_score']),
+                      _np_ptr(out['class_probs']),
+                      _np_ptr(out['pooled']) if keep_pooled else None, _np_ptr(out['counts']))
+        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0)
+        self._check(self.lib.pb2_analyze_host(self.handle, C.byref(b), C.byref(r), flags))
+        return out
+
+    # ----------------------------------------------------- device-resident API
+    def _batch_from_tensors(self, raw, offsets, lengths, rng, digitisation, offset,
+                            max_raw_length=0):
+        return N.Batch(int(lengths.numel()), int(raw.numel()), int(max_raw_length),
+                       raw.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), rng.data_ptr(),
+                       digitisation.data_ptr(), offset.data_ptr())
+
+    def alloc_results(self, n, n_raw_total=0, keep_pooled=False):
+        import torch
+        dev = torch.device('cuda', self.device)
+        out = {
+            'status': torch.empty(n, dtype=torch.int32, device=dev),
+            'label': torch.empty(n, dtype=torch.int32, device=dev),
+            'scale_shift': torch.zeros((n, 2), dtype=torch.float32, device=dev),
+            'segments': torch.empty((n, N.MAX_STATES, 2), dtype=torch.int32, device=dev),
+            'barcode': torch.full((n,), -1, dtype=torch.int32, device=dev),
+            'barcode_guess': torch.full((n,), -1, dtype=torch.int32, device=dev),
+            'barcode_score': torch.full((n,), -1, dtype=torch.int32, device=dev),
+            'class_probs': torch.zeros((n, N.MAX_CLASSES), dtype=torch.float32, device=dev),
+            'counts': torch.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS),
+                                  dtype=torch.int64, device=dev),
+        }
+        if keep_pooled:
+            out['pooled'] = torch.zeros(n_raw_total // self.stride + 2, dtype=torch.float32,
+                                        device=dev)
+        return out
+
+    def analyze_device(self, raw, offsets, lengths, rng, digitisation, offset, out=None,
+                       barcoding=None, keep_pooled=False, max_raw_length=0, stream=None):
+        """Same path over tensors already resident in HBM; enqueued on ``stream`` (default:
+        torch's current stream), not synchronised."""
+        import torch
+        if barcoding is None:
+            barcoding = self.barcoding
+        n = int(lengths.numel())
+        if out is None:
+            out = self.alloc_results(n, int(raw.numel()), keep_pooled)
+        b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset,
+                                     max_raw_length)
+        r = N.Results(out['status'].data_ptr(), out['label'].data_ptr(),
+                      out['scale_shift'].data_ptr(), out['segments'].data_ptr(),
+                      out['barcode'].data_ptr(), out['barcode_guess'].data_ptr(),
+                      out['barcode_score'].data_ptr(), out['class_probs'].data_ptr(),
+                      out['pooled'].data_ptr() if keep_pooled else None,
+                      out['counts'].data_ptr())
+        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._check(self.lib.pb2_analyze_device(self.handle, C.byref(b), C.byref(r), flags,
+                                                C.c_void_p(st.cuda_stream)))
+        return out
+
+    # ------------------------------------------------ single stages (tensors)
+    def _stream(self, stream):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(st.cuda_stream)
+
+    def pool_signal(self, raw, offsets, lengths, rng, digitisation, offset, max_raw_length=0,
+                    stream=None):
+        import torch
+        pooled = torch.zeros(int(raw.numel()) // self.stride + 2, dtype=torch.float32,
+                             device=raw.device)
+        b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset,
+                                     max_raw_length)
+        self._check(self.lib.pb2_pool_signal(self.handle, C.byref(b), pooled.data_ptr(),
+                                             self._stream(stream)))
+        return pooled
+
+    def fit_scalers(self, raw, offsets, lengths, rng, digitisation, offset, pooled, stream=None):
+        import torch
+        n = int(lengths.numel())
+        status = torch.empty(n, dtype=torch.int32, device=raw.device)
+        ss = torch.zeros((n, 2), dtype=torch.float32, device=raw.device)
+        z = torch.zeros((n, 2), dtype=torch.float32, device=raw.device)
+        b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset)
+        self._check(self.lib.pb2_fit_scalers(self.handle, C.byref(b), pooled.data_ptr(),
+                                             status.data_ptr(), ss.data_ptr(), z.data_ptr(),
+                                             self._stream(stream)))
+        return status, ss, z
+
+    def detect_segments(self, raw, offsets, lengths, rng, digitisation, offset, pooled,
+                        scale_shift, status, keep_pooled=False, max_raw_length=0, stream=None):
+        import torch
+        n = int(lengths.numel())
+        seg = torch.empty((n, N.MAX_STATES, 2), dtype=torch.int32, device=raw.device)
+        scaled = torch.zeros_like(pooled) if keep_pooled else None
+        b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset,
+                                     max_raw_length)
+        self._check(self.lib.pb2_detect_segments(
+            self.handle, C.byref(b), pooled.data_ptr(), scale_shift.data_ptr(),
+            status.data_ptr(), seg.data_ptr(), scaled.data_ptr() if keep_pooled else None,
+            self._stream(stream)))
+        return seg, scaled
+
+    def viterbi_paths(self, x, lengths, stream=None):
+        import torch
+        n, ld = x.shape
+        path = torch.full((n, ld), -1, dtype=torch.int32, device=x.device)
+        logp = torch.empty(n, dtype=torch.float64, device=x.device)
+        self._check(self.lib.pb2_viterbi_paths(self.handle, 0, x.data_ptr(), lengths.data_ptr(),
+                                               n, ld, path.data_ptr(), logp.data_ptr(),
+                                               self._stream(stream)))
+        return path, logp
+
+    def barcode_windows(self, raw, offsets, lengths, rng, digitisation, offset, pooled,
+                        scale_shift, status, segments, stream=None):
+        import torch
+        n = int(lengths.numel())
+        win = torch.zeros((n, self.trim_length), dtype=torch.float32, device=raw.device)
+        pushed = torch.zeros(n, dtype=torch.int32, device=raw.device)
+        b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset)
+        self._check(self.lib.pb2_barcode_windows(
+            self.handle, C.byref(b), pooled.data_ptr(), scale_shift.data_ptr(),
+            status.data_ptr(), segments.data_ptr(), win.data_ptr(), pushed.data_ptr(),
+            self._stream(stream)))
+        return win, pushed
+
+    def demux_predict(self, windows, pushed=None, stream=None):
+        import torch
+        n = windows.shape[0]
+        dev = windows.device
+        probs = torch.zeros((n, N.MAX_CLASSES), dtype=torch.float32, device=dev)
+        bc = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        guess = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        score = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        self._check(self.lib.pb2_demux_predict(
+            self.handle, windows.data_ptr(), pushed.data_ptr() if pushed is not None else None,
+            n, probs.data_ptr(), bc.data_ptr(), guess.data_ptr(), score.data_ptr(),
+            self._stream(stream)))
+        return probs, bc, guess, score
+
+    def scaler_predict(self, heads, stream=None):
+        import torch
+        n = heads.shape[0]
+        z = torch.zeros((n, 2), dtype=torch.float32, device=heads.device)
+        self._check(self.lib.pb2_scaler_predict(self.handle, heads.data_ptr(), n, z.data_ptr(),
+                                                self._stream(stream)))
+        return z
+
+    def count_results(self, status, label, barcode, stream=None):
+        import torch
+        counts = torch.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), dtype=torch.int64,
+                             device=status.device)
+        self._check(self.lib.pb2_count_results(
+            self.handle, status.data_ptr(), label.data_ptr(),
+            barcode.data_ptr() if barcode is not None else None, int(status.numel()),
+            counts.data_ptr(), self._stream(stream)))
+        return counts
+
+
+_engines = {}
+
+
+def get_engine(config, device=0):
+    """Process-lifetime engine cache, the analogue of the reference's
+    ``sys.modules['__poreplex_persistence']`` singleton (worker_persistence.py:46-58)."""
+    key = (id(config.get('segmentation_model')), device, bool(config.get('barcoding')),
+           config.get('barcoding_quality_filter', 18),
+           config['signal_processing'].get('scaler_min_length_override'),
+           config.get('demultiplexing', {}).get('minimum_dna_length'))
+    eng = _engines.get(key)
+    if eng is None:
+        eng = _engines[key] = SignalEngine(config, device=device)
+    return eng

@@ -1,0 +1,399 @@
+"""Minimal read-only HDF5 walker for Keras 2.2.4 weight files.
+
+The reference opens its two model files with h5py (``signal_loader.py:49-75``,
+``barcoding.py:51-70``).  h5py/libhdf5 do not exist in this image, so this module
+understands exactly the subset of the HDF5 file format those two files use:
+
+* superblock version 0, 8-byte offsets/lengths
+* version-1 object headers (with continuation blocks)
+* "old style" groups: symbol-table message -> v1 B-tree -> SNOD nodes + local heap
+* contiguous (and compact) unfiltered datasets of fixed-point / IEEE-float / compound type
+* version 1..3 attribute messages holding fixed- or variable-length strings and
+  numeric scalars/arrays (vlen data lives in global heap collections)
+
+Anything else raises ``Hdf5FormatError`` instead of guessing.
+"""
+import struct
+
+import numpy as np
+
+__all__ = ['Hdf5File', 'Hdf5FormatError']
+
+_SIGNATURE = b'\x89HDF\r\n\x1a\n'
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class Hdf5FormatError(Exception):
+    pass
+
+
+def _pad8(n):
+    return (n + 7) & ~7
+
+
+class _Datatype:
+    """Decoded datatype message."""
+
+    def __init__(self, cls, size, dtype=None, vlen_string=False, consumed=0):
+        self.cls = cls
+        self.size = size
+        self.dtype = dtype            # numpy dtype for fixed-size types
+        self.vlen_string = vlen_string
+        self.consumed = consumed      # bytes of the message that were parsed
+
+
+def _parse_datatype(buf, pos):
+    b0 = buf[pos]
+    version, cls = b0 >> 4, b0 & 0x0F
+    bits = buf[pos + 1] | (buf[pos + 2] << 8) | (buf[pos + 3] << 16)
+    size = struct.unpack_from('<I', buf, pos + 4)[0]
+    p = pos + 8
+    if cls == 0:      # fixed point
+        endian = '>' if bits & 1 else '<'
+        signed = bool(bits & 8)
+        dt = np.dtype('%s%s%d' % (endian, 'i' if signed else 'u', size))
+        return _Datatype(cls, size, dt, consumed=p + 4 - pos)
+    if cls == 1:      # IEEE float
+        endian = '>' if bits & 1 else '<'
+        dt = np.dtype('%sf%d' % (endian, size))
+        return _Datatype(cls, size, dt, consumed=p + 12 - pos)
+    if cls == 3:      # fixed-length string
+        return _Datatype(cls, size, np.dtype('S%d' % size), consumed=p - pos)
+    if cls == 6:      # compound
+        nmemb = bits & 0xFFFF
+        names, formats, offsets = [], [], []
+        for _ in range(nmemb):
+            end = buf.index(b'\0', p)
+            name = buf[p:end].decode()
+            if version < 3:
+                p += _pad8(end - p + 1)
+            else:
+                p = end + 1
+            if version == 1:
+                off = struct.unpack_from('<I', buf, p)[0]
+                p += 4 + 1 + 3 + 4 + 4 + 16
+            elif version == 2:
+                off = struct.unpack_from('<I', buf, p)[0]
+                p += 4
+            else:
+                nb = 1
+                while (1 << (8 * nb)) <= size:
+                    nb += 1
+                off = int.from_bytes(buf[p:p + nb], 'little')
+                p += nb
+            sub = _parse_datatype(buf, p)
+            if sub.dtype is None:
+                raise Hdf5FormatError('unsupported compound member type')
+            p += sub.consumed
+            names.append(name)
+            formats.append(sub.dtype)
+            offsets.append(off)
+        dt = np.dtype({'names': names, 'formats': formats, 'offsets': offsets,
+                       'itemsize': size})
+        return _Datatype(cls, size, dt, consumed=p - pos)
+    if cls == 9:      # variable length
+        is_string = (bits & 0x0F) == 1
+        base = _parse_datatype(buf, p)
+        return _Datatype(cls, size, None, vlen_string=is_string,
+                         consumed=p + base.consumed - pos)
+    raise Hdf5FormatError('unsupported datatype class %d' % cls)
+
+
+def _parse_dataspace(buf, pos):
+    version = buf[pos]
+    rank = buf[pos + 1]
+    flags = buf[pos + 2]
+    if version == 1:
+        p = pos + 8
+    elif version == 2:
+        p = pos + 4
+    else:
+        raise Hdf5FormatError('unsupported dataspace version %d' % version)
+    dims = struct.unpack_from('<%dQ' % rank, buf, p) if rank else ()
+    p += 8 * rank
+    if flags & 1:
+        p += 8 * rank
+    return tuple(int(d) for d in dims), p - pos
+
+
+class _Attrs(dict):
+    pass
+
+
+class _Node:
+    def __init__(self, h5, addr, name):
+        self._h5 = h5
+        self._addr = addr
+        self.name = name
+        self._msgs = h5._read_object_header(addr)
+        self.attrs = _Attrs()
+        for mtype, mbuf in self._msgs:
+            if mtype == 0x000C:
+                k, v = h5._parse_attribute(mbuf)
+                self.attrs[k] = v
+
+
+class Hdf5Dataset(_Node):
+    def __init__(self, h5, addr, name):
+        super().__init__(h5, addr, name)
+        self.shape = self._dtype = self._data_addr = self._compact = None
+        for mtype, mbuf in self._msgs:
+            if mtype == 0x0001:
+                self.shape, _ = _parse_dataspace(mbuf, 0)
+            elif mtype == 0x0003:
+                dt = _parse_datatype(mbuf, 0)
+                if dt.dtype is None:
+                    raise Hdf5FormatError('unsupported dataset datatype')
+                self._dtype = dt.dtype
+            elif mtype == 0x0008:
+                self._parse_layout(mbuf)
+            elif mtype == 0x000B:
+                raise Hdf5FormatError('filtered datasets are not supported')
+        if self.shape is None or self._dtype is None:
+            raise Hdf5FormatError('not a dataset: ' + name)
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def file_offset(self):
+        """Absolute byte offset of the contiguous data (None if compact)."""
+        return self._data_addr
+
+    def _parse_layout(self, mbuf):
+        version = mbuf[0]
+        if version == 3:
+            lclass = mbuf[1]
+            if lclass == 1:
+                self._data_addr, _size = struct.unpack_from('<QQ', mbuf, 2)
+            elif lclass == 0:
+                size = struct.unpack_from('<H', mbuf, 2)[0]
+                self._compact = bytes(mbuf[4:4 + size])
+            else:
+                raise Hdf5FormatError('chunked layout is not supported')
+        elif version in (1, 2):
+            rank, lclass = mbuf[1], mbuf[2]
+            if lclass != 1:
+                raise Hdf5FormatError('only contiguous v1/v2 layouts are supported')
+            self._data_addr = struct.unpack_from('<Q', mbuf, 8)[0]
+        else:
+            raise Hdf5FormatError('unsupported layout version %d' % version)
+
+    def read(self):
+        n = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        nbytes = n * self._dtype.itemsize
+        if self._compact is not None:
+            raw = self._compact[:nbytes]
+        else:
+            if self._data_addr == _UNDEF:
+                return np.zeros(self.shape, self._dtype)
+            raw = self._h5._buf[self._data_addr:self._data_addr + nbytes]
+        return np.frombuffer(raw, self._dtype, count=n).reshape(self.shape).copy()
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        arr = self.read()
+        if isinstance(key, tuple) and key == ():
+            return arr if arr.shape else arr[()]
+        return arr[key]
+
+
+class Hdf5Group(_Node):
+    def __init__(self, h5, addr, name):
+        super().__init__(h5, addr, name)
+        self._children = None
+        self._stab = None
+        for mtype, mbuf in self._msgs:
+            if mtype == 0x0011:
+                self._stab = struct.unpack_from('<QQ', mbuf, 0)
+        if self._stab is None:
+            raise Hdf5FormatError('not an old-style group: ' + name)
+
+    def _load(self):
+        if self._children is None:
+            self._children = dict(self._h5._walk_group(*self._stab))
+        return self._children
+
+    def keys(self):
+        return list(self._load().keys())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __contains__(self, path):
+        try:
+            self[path]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, path):
+        node = self
+        for part in [p for p in path.split('/') if p]:
+            if not isinstance(node, Hdf5Group):
+                raise KeyError(path)
+            children = node._load()
+            if part not in children:
+                raise KeyError(path)
+            node = node._h5._open(children[part],
+                                  (node.name.rstrip('/') + '/' + part))
+        return node
+
+    def visit_datasets(self, prefix=''):
+        """Yield (path, Hdf5Dataset) for every dataset below this group."""
+        for k in self.keys():
+            child = self[k]
+            p = prefix + k
+            if isinstance(child, Hdf5Group):
+                yield from child.visit_datasets(p + '/')
+            else:
+                yield p, child
+
+
+class Hdf5File(Hdf5Group):
+    def __init__(self, path):
+        with open(path, 'rb') as f:
+            self._buf = f.read()
+        buf = self._buf
+        if buf[:8] != _SIGNATURE:
+            raise Hdf5FormatError('not an HDF5 file: ' + path)
+        if buf[8] != 0:
+            raise Hdf5FormatError('unsupported superblock version %d' % buf[8])
+        if buf[13] != 8 or buf[14] != 8:
+            raise Hdf5FormatError('only 8-byte offsets/lengths are supported')
+        base = struct.unpack_from('<Q', buf, 24)[0]
+        if base != 0:
+            raise Hdf5FormatError('non-zero base address')
+        # root symbol table entry follows the four addresses at byte 24
+        root_entry = 24 + 4 * 8
+        _name_off, ohdr = struct.unpack_from('<QQ', buf, root_entry)
+        self._cache = {}
+        Hdf5Group.__init__(self, self, ohdr, '/')
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- low level ---------------------------------------------------------
+    def _open(self, addr, name):
+        if addr not in self._cache:
+            msgs = self._read_object_header(addr)
+            types = {t for t, _ in msgs}
+            cls = Hdf5Group if 0x0011 in types else Hdf5Dataset
+            self._cache[addr] = cls(self, addr, name)
+        return self._cache[addr]
+
+    def _read_object_header(self, addr):
+        buf = self._buf
+        if buf[addr] != 1:
+            raise Hdf5FormatError('only version-1 object headers are supported')
+        nmsgs = struct.unpack_from('<H', buf, addr + 2)[0]
+        hsize = struct.unpack_from('<I', buf, addr + 8)[0]
+        blocks = [(addr + 16, hsize)]
+        msgs = []
+        while blocks and len(msgs) < nmsgs:
+            p, remaining = blocks.pop(0)
+            end = p + remaining
+            while p + 8 <= end and len(msgs) < nmsgs:
+                mtype, msize, _flags = struct.unpack_from('<HHB', buf, p)
+                body = buf[p + 8:p + 8 + msize]
+                p += 8 + msize
+                if mtype == 0x0010:
+                    coff, clen = struct.unpack_from('<QQ', body, 0)
+                    blocks.append((coff, clen))
+                msgs.append((mtype, body))
+        return msgs
+
+    def _walk_group(self, btree_addr, heap_addr):
+        buf = self._buf
+        if buf[heap_addr:heap_addr + 4] != b'HEAP':
+            raise Hdf5FormatError('bad local heap signature')
+        heap_data = struct.unpack_from('<Q', buf, heap_addr + 24)[0]
+
+        def heap_string(off):
+            start = heap_data + off
+            return buf[start:buf.index(b'\0', start)].decode()
+
+        def walk(node):
+            if buf[node:node + 4] == b'TREE':
+                level = buf[node + 5]
+                used = struct.unpack_from('<H', buf, node + 6)[0]
+                p = node + 8 + 16
+                for i in range(used):
+                    child = struct.unpack_from('<Q', buf, p + 8)[0]
+                    p += 16
+                    yield from walk(child)
+                del level
+            elif buf[node:node + 4] == b'SNOD':
+                nsym = struct.unpack_from('<H', buf, node + 6)[0]
+                p = node + 8
+                for _ in range(nsym):
+                    name_off, ohdr = struct.unpack_from('<QQ', buf, p)
+                    yield heap_string(name_off), ohdr
+                    p += 40
+            else:
+                raise Hdf5FormatError('bad group node signature')
+
+        yield from walk(btree_addr)
+
+    def _global_heap_object(self, coll_addr, index):
+        buf = self._buf
+        if buf[coll_addr:coll_addr + 4] != b'GCOL':
+            raise Hdf5FormatError('bad global heap signature')
+        csize = struct.unpack_from('<Q', buf, coll_addr + 8)[0]
+        p = coll_addr + 16
+        end = coll_addr + csize
+        while p + 16 <= end:
+            idx, _ref, _res, osize = struct.unpack_from('<HHIQ', buf, p)
+            if idx == 0:
+                break
+            if idx == index:
+                return buf[p + 16:p + 16 + osize]
+            p += 16 + _pad8(osize)
+        raise Hdf5FormatError('global heap object not found')
+
+    def _parse_attribute(self, mbuf):
+        version = mbuf[0]
+        if version == 1:
+            nsize, tsize, ssize = struct.unpack_from('<HHH', mbuf, 2)
+            p = 8
+            name = mbuf[p:p + nsize].split(b'\0')[0].decode()
+            p += _pad8(nsize)
+            dt = _parse_datatype(mbuf, p)
+            p += _pad8(tsize)
+            shape, _ = _parse_dataspace(mbuf, p)
+            p += _pad8(ssize)
+        elif version in (2, 3):
+            nsize, tsize, ssize = struct.unpack_from('<HHH', mbuf, 2)
+            p = 8 if version == 2 else 9
+            name = mbuf[p:p + nsize].split(b'\0')[0].decode()
+            p += nsize
+            dt = _parse_datatype(mbuf, p)
+            p += tsize
+            shape, _ = _parse_dataspace(mbuf, p)
+            p += ssize
+        else:
+            raise Hdf5FormatError('unsupported attribute version %d' % version)
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        if dt.vlen_string:
+            vals = []
+            for i in range(n):
+                _length, coll, idx = struct.unpack_from('<IQI', mbuf, p + 16 * i)
+                vals.append(bytes(self._global_heap_object(coll, idx)))
+            value = vals[0] if not shape else np.array(vals, dtype=object).reshape(shape)
+        elif dt.dtype is not None:
+            arr = np.frombuffer(mbuf[p:p + n * dt.dtype.itemsize], dt.dtype, count=n)
+            if dt.cls == 3:
+                arr = np.array([s.rstrip(b'\0') for s in arr], dtype=object)
+            value = arr[0] if not shape else arr.reshape(shape).copy()
+        else:
+            raise Hdf5FormatError('unsupported attribute datatype')
+        return name, value

@@ -1,0 +1,148 @@
+"""Seeded synthetic direct-RNA reads for benchmarks and parity tests.
+
+Reads are sampled from the preset's own segmentation HMM emissions
+(presets/rna-r941.cfg:61-101 in the reference) at the pooled rate, up-sampled by the
+pooling stride with per-sample noise, pushed through the inverse of a planted
+(scale, shift) and quantised to int16 DAC counts with typical MinION calibration.
+The recipe follows SURVEY.md section 8(d) "Generator calibration": the scaled-space
+signal is compressed about 100 pA by ``k`` before the planted transform is inverted,
+otherwise the scaler network sends most reads to ``scaling_qc_fail``.
+
+Written with torch ops only so the same code fills a CUDA buffer in the benchmark
+(torch is plumbing here: RNG + device memory) and a small CPU batch in the tests.
+"""
+import numpy as np
+import torch
+
+__all__ = ['SynthSpec', 'generate_reads']
+
+# state order used by the generator (time order of a direct-RNA read)
+_ORDER = ['pre-leader', 'leader-low', 'leader-high', 'adapter', 'polya-tail', 'transcript']
+
+
+class SynthSpec:
+    def __init__(self, read_length=4000, adapter_pooled=(110, 190), polya_pooled=(8, 40),
+                 lead_pooled=((4, 12), (6, 14), (6, 14)), compress=0.78,
+                 scale_dist=(0.955, 0.05), shift_dist=(5.5, 4.0), sample_noise=1.5,
+                 frac_no_adapter=0.01, frac_qc_fail=0.01, stride=15):
+        self.read_length = read_length
+        self.adapter_pooled = adapter_pooled
+        self.polya_pooled = polya_pooled
+        self.lead_pooled = lead_pooled
+        self.compress = compress
+        self.scale_dist = scale_dist
+        self.shift_dist = shift_dist
+        self.sample_noise = sample_noise
+        self.frac_no_adapter = frac_no_adapter
+        self.frac_qc_fail = frac_qc_fail
+        self.stride = stride
+
+    @classmethod
+    def for_length(cls, L, **kw):
+        """Sensible segment dwell ranges for read length L (raw samples)."""
+        T = L // 15
+        if T >= 700:                       # stock preset: adapter must be 260..3000 pooled
+            a = (270, min(600, T // 2))
+        elif T >= 200:                     # bench-short: 100..3000 pooled
+            a = (110, min(190, T - 70))
+        else:                              # too short for demux under any preset
+            a = (max(8, T // 3), max(10, T // 2))
+        return cls(read_length=L, adapter_pooled=a, **kw)
+
+
+def _emission_table(preset):
+    by_name = {s['name']: s for s in preset['segmentation_model']}
+    mu = torch.zeros(len(_ORDER), 2)
+    sd = torch.zeros(len(_ORDER), 2)
+    w0 = torch.ones(len(_ORDER))
+    for i, n in enumerate(_ORDER):
+        em = by_name[n]['emission']
+        mu[i, 0], sd[i, 0] = em[0][0], em[0][1]
+        if len(em) > 1:
+            mu[i, 1], sd[i, 1] = em[1][0], em[1][1]
+            w0[i] = em[0][2] / (em[0][2] + em[1][2])
+        else:
+            mu[i, 1], sd[i, 1] = em[0][0], em[0][1]
+    return mu, sd, w0
+
+
+def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
+    """Return a dict of tensors on ``device``:
+
+    ``raw`` int16 [n, L]; ``range``/``digitisation``/``offset`` f64 [n] (channel_id
+    attributes); ``gain`` f64 [n] (= range / digitisation, fast5_file.py:130);
+    ``sampling_rate`` f64 [n]; ``planted`` dict with the planted scale/shift and the
+    pooled segment boundaries (for diagnostics only -- never used by the kernels).
+    """
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    L, st = spec.read_length, spec.stride
+    T = L // st
+    mu, sd, w0 = (t.to(dev) for t in _emission_table(preset))
+
+    raw = torch.empty((n, L), dtype=torch.int16, device=dev)
+    gain = torch.empty(n, dtype=torch.float64, device=dev)
+    rng_pa = torch.empty(n, dtype=torch.float64, device=dev)
+    offset = torch.empty(n, dtype=torch.float64, device=dev)
+    p_scale = torch.empty(n, dtype=torch.float32, device=dev)
+    p_shift = torch.empty(n, dtype=torch.float32, device=dev)
+    bounds = torch.empty((n, 5), dtype=torch.int32, device=dev)
+
+    def randint(lo, hi, m):
+        return torch.randint(int(lo), int(hi) + 1, (m,), generator=g, device=dev)
+
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        # segment boundaries in pooled samples
+        d = [randint(lo, hi, m) for lo, hi in spec.lead_pooled]
+        d.append(randint(*spec.adapter_pooled, m))
+        d.append(randint(*spec.polya_pooled, m))
+        b = torch.cumsum(torch.stack(d, dim=1), dim=1)              # [m, 5]
+        # reads with no adapter: leader-high never ends
+        no_ad = torch.rand(m, generator=g, device=dev) < spec.frac_no_adapter
+        b = torch.where(no_ad[:, None] & (torch.arange(5, device=dev)[None, :] >= 2),
+                        torch.full_like(b, T + 1), b)
+        t = torch.arange(T, device=dev)[None, :]
+        state = (t[:, :, None] >= b[:, None, :]).sum(dim=2)         # [m, T] in 0..5
+        comp = (torch.rand((m, T), generator=g, device=dev) >= w0[state]).long()
+        level = mu[state, comp] + sd[state, comp] * torch.randn((m, T), generator=g, device=dev)
+        # up-sample to the raw rate (+ remainder) and add per-sample noise
+        sig = level.repeat_interleave(st, dim=1)
+        if L > T * st:
+            sig = torch.cat([sig, sig[:, -1:].expand(m, L - T * st)], dim=1)
+        sig = sig + spec.sample_noise * torch.randn((m, L), generator=g, device=dev)
+        sig = 100.0 + spec.compress * (sig - 100.0)
+        sc = spec.scale_dist[0] + spec.scale_dist[1] * torch.randn(m, generator=g, device=dev)
+        sh = spec.shift_dist[0] + spec.shift_dist[1] * torch.randn(m, generator=g, device=dev)
+        qc_fail = torch.rand(m, generator=g, device=dev) < spec.frac_qc_fail
+        sh = torch.where(qc_fail, sh + 60.0, sh)
+        pa = (sig - sh[:, None]) / sc[:, None]
+        rng = 1180.0 + 290.0 * torch.rand(m, generator=g, device=dev, dtype=torch.float64)
+        gn = rng / 8192.0
+        off = randint(0, 20, m).to(torch.float64)
+        dac = torch.round(pa.to(torch.float64) / gn[:, None] - off[:, None])
+        raw[c0:c0 + m] = dac.clamp_(-32768, 32767).to(torch.int16)
+        gain[c0:c0 + m] = gn
+        rng_pa[c0:c0 + m] = rng
+        offset[c0:c0 + m] = off
+        p_scale[c0:c0 + m] = sc
+        p_shift[c0:c0 + m] = sh
+        bounds[c0:c0 + m] = b.to(torch.int32)
+        del sig, pa, dac, level, state, comp
+    return {
+        'raw': raw, 'gain': gain, 'offset': offset, 'range': rng_pa,
+        'digitisation': torch.full((n,), 8192.0, dtype=torch.float64, device=dev),
+        'sampling_rate': torch.full((n,), 3012.0, dtype=torch.float64, device=dev),
+        'planted': {'scale': p_scale, 'shift': p_shift, 'bounds': bounds},
+    }
+
+
+def to_numpy(reads):
+    out = {}
+    for k, v in reads.items():
+        if isinstance(v, dict):
+            out[k] = to_numpy(v)
+        else:
+            out[k] = v.detach().cpu().numpy()
+    return out

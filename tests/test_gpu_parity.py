@@ -1,0 +1,180 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs.  Integer outputs (status, segment indices, barcode
+calls, phred bins, counts) must be bit-exact; float outputs are compared bit-exact too
+where the arithmetic contract promises it, and within 1e-5 relative otherwise (the
+tolerance BASELINE.json's north_star states for the normalised signal)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+def _reads(preset, n, L, seed, **kw):
+    from poreplex_b200 import synth
+    spec = synth.SynthSpec.for_length(L, **kw)
+    return synth.to_numpy(synth.generate_reads(n, spec, preset, seed=seed))
+
+
+def _dense_batch(rd):
+    n, L = rd['raw'].shape
+    return rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64)
+
+
+def _oracle_batch(orc, raw, offsets, lengths, rd, barcoding=True):
+    return orc.process_batch(raw, offsets, lengths, rd['range'] / rd['digitisation'],
+                             rd['offset'], barcoding=barcoding)
+
+
+def _compare(out, ref, n_states=6, check_probs=True):
+    assert np.array_equal(out['status'], ref['status'])
+    okay_like = np.isin(ref['status'], [0, 5])       # scale/shift defined
+    ss_ref = np.stack([ref['scale'], ref['shift']], axis=1)
+    has_ss = ref['status'] != 3
+    assert np.array_equal(out['scale_shift'][has_ss].view(np.uint32),
+                          ss_ref[has_ss].view(np.uint32)), 'scale/shift not bit-exact'
+    seg_ok = okay_like
+    assert np.array_equal(out['segments'][seg_ok][:, :n_states], ref['seg'][seg_ok][:, :n_states])
+    pushed = ref['pushed'] == 1
+    assert np.array_equal(out['barcode'][pushed], ref['barcode'][pushed])
+    assert np.array_equal(out['barcode_guess'][pushed], ref['guess'][pushed])
+    assert np.array_equal(out['barcode_score'][pushed], ref['phred'][pushed])
+    assert np.all(out['barcode'][~pushed] == -1)
+    assert np.all(out['barcode_score'][~pushed] == -1)
+    if check_probs:
+        assert np.array_equal(out['class_probs'][pushed][:, :5].view(np.uint32),
+                              ref['probs'][pushed][:, :5].view(np.uint32)), 'softmax not bit-exact'
+
+
+def test_whole_path_short_reads(eng_short, orc_short, preset_short):
+    rd = _reads(preset_short, 200, 4000, seed=11, frac_no_adapter=0.05, frac_qc_fail=0.05)
+    raw, off, ln = _dense_batch(rd)
+    out = eng_short.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
+    ref = _oracle_batch(orc_short, raw, off, ln, rd)
+    _compare(out, ref)
+    assert (ref['status'] == 0).sum() > 150 and (ref['pushed'] == 1).sum() > 100
+    assert set(np.unique(ref['status'])) >= {0, 4, 5}
+
+
+def test_whole_path_stock_16k(eng_stock, orc_stock, preset):
+    rd = _reads(preset, 64, 16000, seed=12)
+    raw, off, ln = _dense_batch(rd)
+    out = eng_stock.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
+    ref = _oracle_batch(orc_stock, raw, off, ln, rd)
+    _compare(out, ref)
+    assert (ref['pushed'] == 1).sum() > 40
+
+
+def test_ragged_lengths_and_exit_paths(eng_stock, orc_stock, preset):
+    """G1-G4: too-short reads, heads shorter/longer than 30000, L % 15 != 0, a read past
+    the 100000-sample scan limit; ragged packing with 16-byte aligned reads."""
+    lengths = [5000, 8999, 9000, 9001, 9014, 12345, 16000, 29999, 30000, 30001, 45007,
+               100000, 100010, 120000, 0, 14, 15]
+    sigs, rngs, digs, offs = [], [], [], []
+    for i, L in enumerate(lengths):
+        Lgen = max(L, 9000)
+        rd = _reads(preset, 1, Lgen, seed=100 + i)
+        sigs.append(rd['raw'][0][:L])
+        rngs.append(rd['range'][0]); digs.append(rd['digitisation'][0]); offs.append(rd['offset'][0])
+    raw, off, ln = eng_stock.pack_reads(sigs)
+    rd = {'range': np.array(rngs), 'digitisation': np.array(digs), 'offset': np.array(offs)}
+    out = eng_stock.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'],
+                                 keep_pooled=True)
+    ref = _oracle_batch(orc_stock, raw, off, ln, rd)
+    _compare(out, ref)
+    assert (ref['status'] == 3).sum() == 5
+    # normalised pooled signal of an okay read, against the oracle's element kernels
+    i = lengths.index(45007)
+    pa = orc_stock.dac_to_pa(sigs[i], rngs[i] / digs[i], offs[i])
+    T = len(pa) // 15
+    want = orc_stock.scale(orc_stock.pool_mean(pa[:T * 15]), ref['scale'][i], ref['shift'][i])
+    po = eng_stock.pooled_offsets(off)[i]
+    got = out['pooled'][po:po + T]
+    np.testing.assert_allclose(got, want, rtol=REL_TOL, atol=0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_stage_pool_and_scaler(eng_short, orc_short, preset_short):
+    import torch
+    rd = _reads(preset_short, 40, 4000, seed=13)
+    raw, off, ln = _dense_batch(rd)
+    dev = torch.device('cuda', 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (t(raw), t(off), t(ln), t(rd['range']), t(rd['digitisation']), t(rd['offset']))
+    pooled = eng_short.pool_signal(*args, max_raw_length=4000)
+    status, ss, z = eng_short.fit_scalers(*args, pooled)
+    torch.cuda.synchronize()
+    pooled = pooled.cpu().numpy(); z = z.cpu().numpy()
+    po = eng_short.pooled_offsets(off)
+    heads = np.zeros((40, 2000), np.float32)
+    for i in range(40):
+        pa = orc_short.dac_to_pa(rd['raw'][i], rd['range'][i] / rd['digitisation'][i], rd['offset'][i])
+        want = orc_short.pool_mean(pa[:266 * 15])
+        assert np.array_equal(pooled[po[i]:po[i] + 266].view(np.uint32), want.view(np.uint32))
+        heads[i, 2000 - 266:] = want
+    zref = orc_short.scaler_predict(heads)
+    assert np.array_equal(z.view(np.uint32), zref.view(np.uint32))
+    # explicit heads (no zero-prefix skipping) must give the same bits
+    z2 = eng_short.scaler_predict(t(heads)).cpu().numpy()
+    assert np.array_equal(z2.view(np.uint32), zref.view(np.uint32))
+
+
+def test_stage_viterbi_paths(eng_stock, orc_stock):
+    import torch
+    rng = np.random.default_rng(5)
+    n, ld = 64, 700
+    x = np.empty((n, ld), np.float32)
+    lengths = rng.integers(1, ld + 1, n).astype(np.int32)
+    lengths[:3] = [1, 2, ld]
+    levels = np.array([71.5, 102.0, 112.0, 80.5, 109.0, 95.0])
+    for i in range(n):
+        segs = np.sort(rng.integers(0, ld, 5))
+        st = np.searchsorted(segs, np.arange(ld), side='right')
+        x[i] = levels[st] + rng.normal(0, 4.0, ld)
+    dev = torch.device('cuda', 0)
+    path, logp = eng_stock.viterbi_paths(torch.from_numpy(x).to(dev),
+                                         torch.from_numpy(lengths).to(dev))
+    torch.cuda.synchronize()
+    path = path.cpu().numpy(); logp = logp.cpu().numpy()
+    for i in range(n):
+        lp, p = orc_stock.viterbi(x[i, :lengths[i]])
+        assert lp == logp[i]
+        assert np.array_equal(p, path[i, :lengths[i]])
+
+
+def test_stage_windows_and_demux(eng_stock, orc_stock):
+    """G8-G11: window lengths around the 260/300/3000 limits, flat windows (MAD = 0),
+    even/odd medians, decisions on arbitrary windows."""
+    import torch
+    rng = np.random.default_rng(7)
+    dev = torch.device('cuda', 0)
+    n = 96
+    win = rng.normal(0, 1.2, (n, 300)).astype(np.float32)
+    npad = rng.integers(0, 41, n)
+    for i in range(n):
+        win[i, :npad[i]] = -1000.0
+    win[0] = 0.0
+    probs, bc, guess, score = eng_stock.demux_predict(torch.from_numpy(win).to(dev))
+    torch.cuda.synchronize()
+    pref = orc_stock.demux_predict(win)
+    assert np.array_equal(probs.cpu().numpy()[:, :5].view(np.uint32), pref.view(np.uint32))
+    for i in range(n):
+        b, g, p = orc_stock.barcode_decide(pref[i])
+        assert (bc[i].item(), guess[i].item(), score[i].item()) == (-1 if b is None else b, g, p)
+
+
+def test_counts(eng_short):
+    import torch
+    rng = np.random.default_rng(9)
+    n = 100000
+    status = rng.integers(0, 11, n).astype(np.int32)
+    label = rng.integers(0, 4, n).astype(np.int32)
+    barcode = rng.integers(-1, 4, n).astype(np.int32)
+    dev = torch.device('cuda', 0)
+    c = eng_short.count_results(torch.from_numpy(status).to(dev), torch.from_numpy(label).to(dev),
+                                torch.from_numpy(barcode).to(dev)).cpu().numpy()
+    want = np.zeros((4, 5, 11), np.int64)
+    np.add.at(want, (label, barcode + 1, status), 1)
+    assert np.array_equal(c, want)
+    assert c.sum() == n
