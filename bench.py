@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/sec of the adapter-segmentation + 4-way barcode-demux hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+One "step" = one pass of SignalAnalyzer.process stages A-D (int16 -> pA -> pool ->
+scaler network -> scale -> Viterbi segmentation -> barcode window -> demux network ->
+decision -> counts) over one batch of synthetic reads.  Workload at every N: BASELINE
+configs[1]+[2] -- `--reads` (default 1,000,000) synthetic 4000-sample int16 reads per
+GPU under the `bench-short` preset, weak scaling, one
+all-reduce of the per-(label, barcode, status) counts per step when N > 1.
+
+Prints ONE JSON line (rank 0).  `value` is measured with the batch resident in HBM
+(CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
+pb2_analyze_host with pinned HOST buffers, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'reads/sec (adapter segment + 4-way barcode demux)'
+UNIT = 'reads/s'
+
+# algorithmic work per read (DESIGN.md "Kernels"); T = L // 15 pooled samples
+def algorithmic(L, stride=15, trim=300, scaler_len=30000):
+    T = min(L, 100000) // stride
+    H = min(L, scaler_len) // stride
+    return {
+        # bytes: int16 in + 3 f64 calibration, pooled f32 out
+        'k_pool': ('hbm', 2 * T * stride + 24 + 4 * T),
+        # pooled in + scale/shift in; segments + status out
+        'k_segment': ('hbm', 4 * T + 8 + 48 + 4),
+        'k_windows': ('hbm', 4 * min(T, trim) + 8 + 4 * trim + 4),
+        # FLOPs (2 per multiply-add): LSTM(1->48)+LSTM(48->48), zero padding skipped
+        'k_scaler_lstm': ('tensor', 2 * (192 + 48 * 192 + 2 * 48 * 192) * H),
+        'k_demux_l1': ('tensor', 2 * 2 * (192 + 48 * 192) * trim),
+        'k_demux_l2': ('tensor', 2 * (96 * 256 + 64 * 256) * trim + 2 * 64 * 5),
+    }
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'tensor_tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'tensor_tflops_burst': d['bf16_tflops'], 'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tensor_tflops': 1400.0, 'tensor_tflops_burst': 1590.0,
+            'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_workload(args, device, seed):
+    """Synthetic reads generated straight into HBM (torch RNG on the device)."""
+    import torch
+    from poreplex_b200 import params, synth
+    preset = params.bench_short_preset(params.load_preset()) if args.preset == 'bench-short' \
+        else params.load_preset()
+    spec = synth.SynthSpec.for_length(args.length)
+    rd = synth.generate_reads(args.reads, spec, preset, seed=seed, device=device)
+    n, L = rd['raw'].shape
+    Lp = (L + 7) // 8 * 8                      # keep every read 16-byte aligned
+    if Lp != L:
+        raw = torch.zeros((n, Lp), dtype=torch.int16, device=device)
+        raw[:, :L] = rd['raw']
+    else:
+        raw = rd['raw']
+    offsets = torch.arange(n, dtype=torch.int64, device=device) * Lp
+    lengths = torch.full((n,), L, dtype=torch.int64, device=device)
+    return preset, {'raw': raw.reshape(-1), 'offsets': offsets, 'lengths': lengths,
+                    'range': rd['range'], 'digitisation': rd['digitisation'],
+                    'offset': rd['offset']}
+
+
+def cpu_reference_rate(preset_name, sample, threads, barcoding=True, repeats=1):
+    """Time the CPU oracle (C restatement of the reference path, OpenMP over reads)."""
+    from oracle import oracle as O
+    orc = O.default_oracle(bench_short=(preset_name == 'bench-short'))
+    raw, off, ln, rng, dig, ofs = sample
+    gain = rng / dig
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        res = orc.process_batch(raw, off, ln, gain, ofs, barcoding=barcoding, nthreads=threads)
+    dt = (time.perf_counter() - t0) / repeats
+    return len(ln) / dt, dt, res
+
+
+def host_sample(work, n):
+    n = min(n, int(work['lengths'].numel()))
+    stride = int(work['offsets'][1].item()) if work['offsets'].numel() > 1 else int(work['raw'].numel())
+    raw = work['raw'][:n * stride].cpu().numpy()
+    return (raw, work['offsets'][:n].cpu().numpy(), work['lengths'][:n].cpu().numpy(),
+            work['range'][:n].cpu().numpy(), work['digitisation'][:n].cpu().numpy(),
+            work['offset'][:n].cpu().numpy())
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port --
+    its TensorFlow / pomegranate dependencies cannot be installed here) on all host
+    cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from poreplex_b200 import params, synth
+    preset = params.bench_short_preset(params.load_preset()) if args.preset == 'bench-short' \
+        else params.load_preset()
+    threads = os.cpu_count() or 1
+    n = args.ref_reads
+    rd = synth.to_numpy(synth.generate_reads(n, synth.SynthSpec.for_length(args.length), preset,
+                                             seed=args.seed, device='cpu'))
+    L = rd['raw'].shape[1]
+    sample = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64),
+              rd['range'], rd['digitisation'], rd['offset'])
+    nw = min(n, 8 * threads)                  # warm-up: page in the library and weights
+    cpu_reference_rate(args.preset, (sample[0][:nw * L], sample[1][:nw], sample[2][:nw],
+                                     sample[3][:nw], sample[4][:nw], sample[5][:nw]), threads)
+    times = []
+    for _ in range(args.steps):
+        rate, dt, _ = cpu_reference_rate(args.preset, sample, threads)
+        times.append(dt)
+    dt = float(np.mean(times))
+    value = n / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32+f64',
+        'data': 'synthetic',
+        'config': {'workload': '%d synthetic %d-sample int16 reads per step (bounded sample of '
+                               'the GPU workload), preset %s, barcoding on' % (n, args.length, args.preset),
+                   'read_length': args.length, 'preset': args.preset},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d reads per step; C restatement of the reference path '
+                                   '(oracle/pb_oracle.c, OpenMP, AVX2+FMA)' % n},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--reads', type=int, default=1000000, help='reads per GPU per step')
+    ap.add_argument('--length', type=int, default=4000, help='raw samples per read')
+    ap.add_argument('--preset', default='bench-short', choices=['bench-short', 'stock'])
+    ap.add_argument('--seed', type=int, default=20261017)
+    ap.add_argument('--ref-reads', type=int, default=8192, help='reads per step of the CPU arm')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target CPU-baseline time')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    from poreplex_b200 import _native
+    from poreplex_b200.engine import SignalEngine
+    if _native.needs_build() and rank == 0:
+        _native.build()
+    if world > 1:
+        dist.barrier()
+
+    preset, work = make_workload(args, device, args.seed + rank)
+    cfg = dict(preset)
+    cfg['barcoding'] = True
+    eng = SignalEngine(cfg, device=local_rank)
+    n = args.reads
+    out = eng.alloc_results(n)
+    torch.cuda.synchronize()
+
+    def step():
+        eng.analyze_device(work['raw'], work['offsets'], work['lengths'], work['range'],
+                           work['digitisation'], work['offset'], out=out, barcoding=True,
+                           max_raw_length=args.length)
+        if world > 1:
+            dist.all_reduce(out['counts'])        # the one collective of the path
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = eng.kernel_launches
+    eng.profile_enable(True)
+    eng.profile_read()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    launches = eng.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n / (ms_per_step / 1e3)
+
+    # status mix of the workload (from the last step)
+    status = out['status'].cpu().numpy()
+    from poreplex_b200.params import STATUS_NAMES
+    mix = {STATUS_NAMES[s]: int(c) for s, c in zip(*np.unique(status, return_counts=True))}
+    classified = int((out['barcode_score'] >= 0).sum().item())
+
+    # ---- roofline of every kernel, dominant one on top ------------------------
+    peaks = load_peaks()
+    alg = algorithmic(args.length)
+    kernels = []
+    total_kernel_ms = sum(ms for ms, _ in prof.values()) or 1.0
+    n_classified = max(classified, 1)
+    for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        per_step_ms = ms / args.steps
+        ent = {'kernel': name, 'ms_per_step': per_step_ms, 'launches_per_step': cnt / args.steps,
+               'share': ms / total_kernel_ms}
+        if name in alg:
+            bound, per_read = alg[name]
+            units = n           # every read goes through the kernel (no compaction yet)
+            if bound == 'hbm':
+                ach = per_read * units / (per_step_ms / 1e3) / 1e9
+                ent.update({'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'],
+                            'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                            'algorithmic_bytes_per_read': per_read})
+            else:
+                ach = per_read * units / (per_step_ms / 1e3) / 1e12
+                fp32_peak = 148 * 128 * 2 * (clocks.get('sm_mhz') or 1965.0) * 1e6 / 1e12
+                ent.update({'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_tflops'],
+                            'unit': 'TFLOP/s', 'frac': ach / peaks['tensor_tflops'],
+                            'algorithmic_flops_per_read': per_read,
+                            'fp32_simt_peak_tflops_at_clock': fp32_peak,
+                            'frac_of_fp32_simt': ach / fp32_peak})
+        kernels.append(ent)
+    dom = kernels[0] if kernels else {}
+    roofline = {k: dom.get(k) for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
+    roofline.update({'kernel': dom.get('kernel'), 'traffic': None, 'peak_source': peaks['source'],
+                     'share_of_step': dom.get('share'),
+                     'note': 'exact-f32 SIMT LSTM (packed FFMA2) kept bit-identical to the CPU '
+                             'oracle; the tensor pipe is not used by this kernel, so frac is '
+                             'quoted against the measured bf16 peak only because the contract '
+                             'asks for hbm|tensor -- see frac_of_fp32_simt in `kernels`'})
+    if 'frac_of_fp32_simt' in dom:
+        roofline['frac_of_fp32_simt'] = dom['frac_of_fp32_simt']
+
+    result = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (LSTM) + f64 (Viterbi)',
+        'data': 'synthetic',
+        'config': {'workload': '%d synthetic %d-sample int16 reads per GPU per step, adapter '
+                               'segmentation + 4-way barcode demux (BASELINE configs[1]+[2]), '
+                               'preset %s' % (n, args.length, args.preset),
+                   'reads_per_gpu': n, 'read_length': args.length, 'preset': args.preset,
+                   'l2_policy': 'inputs (%.1f GB per GPU) larger than L2' % (n * args.length * 2 / 1e9),
+                   'status_mix': mix, 'classified_reads': classified,
+                   'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)'},
+        'clocks': clocks, 'gpu_launches': launches,
+        'roofline': roofline, 'kernels': kernels,
+    }
+
+    # ---- e2e: host buffers through pb2_analyze_host ---------------------------
+    if not args.no_e2e:
+        hn = n
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        h = {k: pin(v) for k, v in work.items()}
+        hnp = {k: v.numpy() for k, v in h.items()}
+        torch.cuda.synchronize()
+        eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
+                         hnp['digitisation'], hnp['offset'], barcoding=True)      # warm-up
+        if world > 1:
+            dist.barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
+                                   hnp['digitisation'], hnp['offset'], barcoding=True)
+            if world > 1:
+                c = torch.from_numpy(res['counts']).to(device)
+                dist.all_reduce(c)
+                c.cpu()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(v.numel() * v.element_size() for v in h.values())
+        d2h = sum(v.nbytes for v in res.values())
+        result['e2e'] = {'value': world * hn / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+                         'api': 'pb2_analyze_host (pinned host buffers, synchronous)'}
+        assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        probe = host_sample(work, 16 * threads)
+        rate, _, _ = cpu_reference_rate(args.preset, probe, threads)
+        ns = int(min(max(rate * args.cpu_seconds, 256), 65536, n))
+        sample = host_sample(work, ns)
+        rate, dt, ref = cpu_reference_rate(args.preset, sample, threads)
+        same = bool(np.array_equal(ref['status'], status[:ns]) and
+                    np.array_equal(ref['seg'][:, :6][np.isin(ref['status'], [0, 5])],
+                                   out['segments'][:ns].cpu().numpy()[:, :6][np.isin(ref['status'], [0, 5])]))
+        result['cpu_baseline'] = {
+            'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': 'first %d reads of the same workload, %.1f s; C restatement of the '
+                      'reference path (oracle/pb_oracle.c, OpenMP over reads, AVX2+FMA) -- '
+                      'faster than the real Python/TF/pomegranate stack' % (ns, dt),
+            'outputs_match_gpu': same}
+
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

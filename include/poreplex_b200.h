@@ -210,6 +210,15 @@ int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *la
 /* number of kernel launches issued through this context so far */
 int64_t pb2_kernel_launches(const pb2_context *ctx);
 
+/* ---- measurement ----------------------------------------------------------
+ * With profiling on, every kernel launch is bracketed by CUDA events on its own
+ * stream.  pb2_profile_read synchronises the device, adds the elapsed times up per
+ * kernel and resets the event list.  Kernel ids: 0..pb2_profile_kernel_count()-1. */
+int pb2_profile_enable(pb2_context *ctx, int on);
+int pb2_profile_kernel_count(void);
+const char *pb2_profile_kernel_name(int kernel_id);
+int pb2_profile_read(pb2_context *ctx, double *total_ms, int64_t *launches, int n_kernels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,7 +84,9 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_set_segmentation_hmm', 'pb2_set_demux', 'pb2_analyze_device',
            'pb2_analyze_host', 'pb2_pool_signal', 'pb2_fit_scalers', 'pb2_detect_segments',
            'pb2_viterbi_paths', 'pb2_barcode_windows', 'pb2_demux_predict',
-           'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches']
+           'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches',
+           'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
+           'pb2_profile_read']
 
 
 def sources():
@@ -145,6 +147,11 @@ def load():
     L.pb2_count_results.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp]
     L.pb2_kernel_launches.argtypes = [vp]
     L.pb2_kernel_launches.restype = C.c_int64
+    L.pb2_profile_enable.argtypes = [vp, C.c_int]
+    L.pb2_profile_kernel_count.restype = C.c_int
+    L.pb2_profile_kernel_name.argtypes = [C.c_int]
+    L.pb2_profile_kernel_name.restype = C.c_char_p
+    L.pb2_profile_read.argtypes = [vp, _dp, _i64p, C.c_int]
     if L.pb2_abi_version() != 1:
         raise RuntimeError('poreplex_b200: ABI version mismatch')
     _lib = L

@@ -48,6 +48,34 @@ void *ws_get(pb2_context *ctx, Workspace &w, size_t bytes)
     return w.ptr;
 }
 
+static cudaEvent_t prof_event(pb2_context *ctx)
+{
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(pb2_context *ctx, int id, cudaStream_t st)
+{
+    ProfEvent pe{id, prof_event(ctx), prof_event(ctx)};
+    cudaEventRecord(pe.a, st);
+    ctx->prof_events.push_back(pe);
+}
+
+void prof_end(pb2_context *ctx, cudaStream_t st)
+{
+    if (!ctx->prof_events.empty()) cudaEventRecord(ctx->prof_events.back().b, st);
+}
+
+static const char *const kKernelNames[K_NUM] = {
+    "k_pool", "k_scaler_prepare", "k_scaler_lstm", "k_segment", "k_viterbi_paths",
+    "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc"};
+
 static void ws_free(Workspace &w)
 {
     if (w.ptr) cudaFree(w.ptr);
@@ -135,6 +163,8 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads};
     for (Workspace *w : all) ws_free(*w);
+    for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
     delete ctx;
 }
@@ -145,6 +175,37 @@ const char *pb2_last_error(const pb2_context *ctx)
 }
 
 int64_t pb2_kernel_launches(const pb2_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int pb2_profile_enable(pb2_context *ctx, int on)
+{
+    if (!ctx) return PB2_EINVAL;
+    ctx->profiling = on != 0;
+    return PB2_OK;
+}
+
+int pb2_profile_kernel_count(void) { return K_NUM; }
+
+const char *pb2_profile_kernel_name(int id) { return (id >= 0 && id < K_NUM) ? kKernelNames[id] : ""; }
+
+int pb2_profile_read(pb2_context *ctx, double *total_ms, int64_t *launches, int n_kernels)
+{
+    if (!ctx || !total_ms || !launches) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    PB_CUDA(ctx, cudaDeviceSynchronize());
+    for (int i = 0; i < n_kernels; i++) { total_ms[i] = 0; launches[i] = 0; }
+    for (const ProfEvent &pe : ctx->prof_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess && pe.id < n_kernels) {
+            total_ms[pe.id] += ms;
+            launches[pe.id] += 1;
+        }
+        ctx->prof_pool.push_back(pe.a);
+        ctx->prof_pool.push_back(pe.b);
+    }
+    ctx->prof_events.clear();
+    cudaGetLastError();
+    return PB2_OK;
+}
 
 int pb2_set_scaler(pb2_context *ctx, const pb2_scaler_params *p)
 {

@@ -329,8 +329,8 @@ static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st)
         attr_done = true;
     }
     const unsigned grid = (unsigned)((A.n + TB - 1) / TB);
-    k_scaler_lstm<48><<<grid, 24 * NRG, smem, st>>>(A);
-    PB_LAUNCH_CHECK(ctx, "k_scaler_lstm");
+    PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm", st,
+        k_scaler_lstm<48><<<grid, 24 * NRG, smem, st>>>(A));
     return PB2_OK;
 }
 
@@ -375,10 +375,10 @@ int launch_scaler(pb2_context *ctx, const pb2_batch &b, const float *pooled, int
     int64_t *xoff = (int64_t *)ws_get(ctx, ctx->ws_misc, (size_t)b.n_reads * 12);
     if (!xoff) return PB2_ENOMEM;
     int32_t *nreal = (int32_t *)(xoff + b.n_reads);
-    k_scaler_prepare<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, st>>>(
+    PB_LAUNCH(ctx, K_SCALER_PREPARE, "k_scaler_prepare", st,
+        k_scaler_prepare<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, st>>>(
         b.raw_offsets, b.raw_lengths, b.n_reads, S.stride, S.length, S.min_length, status, xoff,
-        nreal, scale_shift);
-    PB_LAUNCH_CHECK(ctx, "k_scaler_prepare");
+        nreal, scale_shift));
     ScalerArgs A = {};
     A.x = pooled; A.xoff = xoff; A.nreal = nreal; A.n = b.n_reads;
     A.thead = S.length / S.stride;
@@ -402,8 +402,8 @@ int launch_scaler_heads(pb2_context *ctx, const float *heads, int64_t n, float *
     if (!xoff) return PB2_ENOMEM;
     int32_t *nreal = (int32_t *)(xoff + n);
     const int thead = S.length / S.stride;
-    k_iota_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, thead, xoff, nreal);
-    PB_LAUNCH_CHECK(ctx, "k_iota_heads");
+    PB_LAUNCH(ctx, K_MISC, "k_iota_heads", st,
+        k_iota_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, thead, xoff, nreal));
     ScalerArgs A = {};
     A.x = heads; A.xoff = xoff; A.nreal = nreal; A.n = n; A.thead = thead;
     A.zero_prefix = nullptr;       // explicit heads: run every step as keras does
@@ -654,10 +654,10 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
         A.barcode = barcode ? barcode + r0 : nullptr;
         A.guess = guess ? guess + r0 : nullptr;
         A.score = score ? score + r0 : nullptr;
-        k_demux_l1<H1><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A);
-        PB_LAUNCH_CHECK(ctx, "k_demux_l1");
-        k_demux_l2<H1, H2><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A);
-        PB_LAUNCH_CHECK(ctx, "k_demux_l2");
+        PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1", st,
+            k_demux_l1<H1><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
+        PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2", st,
+            k_demux_l2<H1, H2><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
     }
     return PB2_OK;
 }

@@ -88,10 +88,10 @@ int launch_pool(pb2_context *ctx, const pb2_batch &b, int stride, float *pooled,
     if (maxT < 1) maxT = 1;
     dim3 grid((unsigned)((b.n_reads + POOL_WARPS - 1) / POOL_WARPS),
               (unsigned)((maxT + POOL_CHUNK - 1) / POOL_CHUNK));
-    k_pool<15><<<grid, POOL_WARPS * 32, 0, st>>>(b.raw, b.raw_offsets, b.raw_lengths, b.range,
+    PB_LAUNCH(ctx, K_POOL, "k_pool", st,
+        k_pool<15><<<grid, POOL_WARPS * 32, 0, st>>>(b.raw, b.raw_offsets, b.raw_lengths, b.range,
                                                  b.digitisation, b.offset, b.n_reads,
-                                                 b.n_raw_total, limit, pooled);
-    PB_LAUNCH_CHECK(ctx, "k_pool");
+                                                 b.n_raw_total, limit, pooled));
     return PB2_OK;
 }
 
@@ -182,11 +182,11 @@ int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
         return fail(ctx, PB2_EUNSUPPORTED, "signal_trim_length %d > %d", d.trim_length,
                     PB2_WINDOW_MAX);
     const unsigned grid = (unsigned)((b.n_reads + WIN_WARPS - 1) / WIN_WARPS);
-    k_windows<<<grid, WIN_WARPS * 32, 0, st>>>(b.raw_offsets, pooled, scale_shift, status,
+    PB_LAUNCH(ctx, K_WINDOWS, "k_windows", st,
+        k_windows<<<grid, WIN_WARPS * 32, 0, st>>>(b.raw_offsets, pooled, scale_shift, status,
                                                segments, b.n_reads, ctx->scaler.stride,
                                                ctx->adapter_state, d.min_length, d.max_length,
-                                               d.trim_length, d.pad_value, windows, pushed);
-    PB_LAUNCH_CHECK(ctx, "k_windows");
+                                               d.trim_length, d.pad_value, windows, pushed));
     return PB2_OK;
 }
 
@@ -224,9 +224,9 @@ int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status
     if (n <= 0) return PB2_OK;
     const int32_t *pushed = (flags & PB2_FLAG_BARCODING) ? (const int32_t *)ctx->ws_pushed.ptr
                                                           : nullptr;
-    k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, status, pushed, label, barcode,
-                                                           guess, score);
-    PB_LAUNCH_CHECK(ctx, "k_finalize");
+    PB_LAUNCH(ctx, K_FINALIZE, "k_finalize", st,
+        k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, status, pushed, label, barcode,
+                                                           guess, score));
     return PB2_OK;
 }
 
@@ -265,9 +265,9 @@ int launch_counts(pb2_context *ctx, const int32_t *status, const int32_t *label,
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    k_counts<<<(unsigned)blocks, 256, 0, st>>>(status, label, barcode, n,
-                                               reinterpret_cast<unsigned long long *>(counts));
-    PB_LAUNCH_CHECK(ctx, "k_counts");
+    PB_LAUNCH(ctx, K_COUNTS, "k_counts", st,
+        k_counts<<<(unsigned)blocks, 256, 0, st>>>(status, label, barcode, n,
+                                               reinterpret_cast<unsigned long long *>(counts)));
     return PB2_OK;
 }
 

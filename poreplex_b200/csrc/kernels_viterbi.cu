@@ -200,11 +200,11 @@ int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
     if (!bp) return PB2_ENOMEM;
     for (int64_t r0 = 0; r0 < b.n_reads; r0 += chunk) {
         const int64_t nc = (b.n_reads - r0 < chunk) ? b.n_reads - r0 : chunk;
-        k_segment<<<(unsigned)((nc + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
+        PB_LAUNCH(ctx, K_SEGMENT, "k_segment", st,
+            k_segment<<<(unsigned)((nc + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
             ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
             ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
-            pooled_scaled_out);
-        PB_LAUNCH_CHECK(ctx, "k_segment");
+            pooled_scaled_out));
     }
     return PB2_OK;
 }
@@ -254,9 +254,9 @@ int launch_viterbi_paths(pb2_context *ctx, const HmmDev &hmm, const float *x,
     if (n <= 0) return PB2_OK;
     HmmMask K;
     make_mask(hmm, K);
-    k_viterbi_paths<<<(unsigned)((n + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
-        hmm, K, x, lengths, n, ld, path, logp);
-    PB_LAUNCH_CHECK(ctx, "k_viterbi_paths");
+    PB_LAUNCH(ctx, K_VITERBI_PATHS, "k_viterbi_paths", st,
+        k_viterbi_paths<<<(unsigned)((n + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
+        hmm, K, x, lengths, n, ld, path, logp));
     return PB2_OK;
 }
 

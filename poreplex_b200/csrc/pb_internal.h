@@ -62,8 +62,17 @@ struct Workspace {                    // grow-only device scratch
 
 }  // namespace pb
 
+namespace pb {
+enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
+                K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_NUM };
+struct ProfEvent { int id; cudaEvent_t a, b; };
+}
+
 struct pb2_context {
     int device = 0;
+    bool profiling = false;
+    std::vector<pb::ProfEvent> prof_events;
+    std::vector<cudaEvent_t> prof_pool;
     std::string error;
     int64_t launches = 0;
     int sm_count = 148;
@@ -98,6 +107,18 @@ void *ws_get(pb2_context *ctx, Workspace &w, size_t bytes);   // nullptr on fail
         (ctx)->launches++;                                               \
         cudaError_t _e = cudaGetLastError();                             \
         if (_e != cudaSuccess) return pb::check_cuda(ctx, _e, name);     \
+    } while (0)
+
+void prof_begin(pb2_context *ctx, int id, cudaStream_t st);
+void prof_end(pb2_context *ctx, cudaStream_t st);
+
+// launch `...` (a <<<>>> expression) as kernel `id`, timed when profiling is on
+#define PB_LAUNCH(ctx, id, name, st, ...)                                \
+    do {                                                                 \
+        if ((ctx)->profiling) pb::prof_begin(ctx, id, st);               \
+        __VA_ARGS__;                                                     \
+        if ((ctx)->profiling) pb::prof_end(ctx, st);                     \
+        PB_LAUNCH_CHECK(ctx, name);                                      \
     } while (0)
 
 // pooled element offset of a read whose raw data starts at element `raw_off`

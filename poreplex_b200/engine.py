@@ -154,6 +154,18 @@ class SignalEngine:
     def kernel_launches(self):
         return int(self.lib.pb2_kernel_launches(self.handle))
 
+    def profile_enable(self, on=True):
+        self._check(self.lib.pb2_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (total_ms, launches)} since the last read (synchronises)."""
+        k = self.lib.pb2_profile_kernel_count()
+        ms = (C.c_double * k)()
+        cnt = (C.c_int64 * k)()
+        self._check(self.lib.pb2_profile_read(self.handle, ms, cnt, k))
+        return {self.lib.pb2_profile_kernel_name(i).decode(): (ms[i], int(cnt[i]))
+                for i in range(k) if cnt[i]}
+
     def pooled_offsets(self, raw_offsets):
         """Element offset of each read inside a pooled buffer (same rule as the kernels)."""
         return (np.asarray(raw_offsets, np.int64) + self.stride - 1) // self.stride

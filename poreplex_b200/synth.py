@@ -116,8 +116,10 @@ def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
         sc = spec.scale_dist[0] + spec.scale_dist[1] * torch.randn(m, generator=g, device=dev)
         sh = spec.shift_dist[0] + spec.shift_dist[1] * torch.randn(m, generator=g, device=dev)
         qc_fail = torch.rand(m, generator=g, device=dev) < spec.frac_qc_fail
-        sh = torch.where(qc_fail, sh + 60.0, sh)
         pa = (sig - sh[:, None]) / sc[:, None]
+        # deliberately failing stratum: a 2.2x amplitude error drives the predicted
+        # scale below the QC window (signal_loader.py:100-109)
+        pa = torch.where(qc_fail[:, None], pa * 2.2, pa)
         rng = 1180.0 + 290.0 * torch.rand(m, generator=g, device=dev, dtype=torch.float64)
         gn = rng / 8192.0
         off = randint(0, 20, m).to(torch.float64)
