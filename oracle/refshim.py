@@ -333,6 +333,16 @@ def _stub(name, **attrs):
     return m
 
 
+def install_fake_h5py():
+    """Only the in-memory h5py (what the GPU-box tests need to feed FAST5 trees to the
+    product's process_batch; no reference tree required)."""
+    if 'h5py' not in sys.modules or not hasattr(sys.modules['h5py'], '__oracle_shim__'):
+        m = make_h5py()
+        m.__oracle_shim__ = True
+        sys.modules['h5py'] = m
+    return sys.modules['h5py']
+
+
 _installed = False
 
 
@@ -343,7 +353,7 @@ def install():
         return
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, 'poreplex')):
         raise RuntimeError('reference tree not found at ' + REFERENCE_ROOT)
-    sys.modules['h5py'] = make_h5py()
+    install_fake_h5py()
     sys.modules['pomegranate'] = make_pomegranate()
     sys.modules.update(make_tensorflow())
     sys.modules.setdefault('pysam', _stub('pysam', BGZFile=None, FUNMAP=4))

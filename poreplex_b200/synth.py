@@ -24,7 +24,7 @@ class SynthSpec:
     def __init__(self, read_length=4000, adapter_pooled=(110, 190), polya_pooled=(8, 40),
                  lead_pooled=((4, 12), (6, 14), (6, 14)), compress=0.78,
                  scale_dist=(0.955, 0.05), shift_dist=(5.5, 4.0), sample_noise=1.5,
-                 frac_no_adapter=0.01, frac_qc_fail=0.01, stride=15):
+                 frac_no_adapter=0.01, frac_qc_fail=0.01, stride=15, transcript_level=None):
         self.read_length = read_length
         self.adapter_pooled = adapter_pooled
         self.polya_pooled = polya_pooled
@@ -36,21 +36,31 @@ class SynthSpec:
         self.frac_no_adapter = frac_no_adapter
         self.frac_qc_fail = frac_qc_fail
         self.stride = stride
+        # (mean, sd) of a single-Gaussian transcript level, or None to sample the
+        # preset's two-component transcript mixture
+        self.transcript_level = transcript_level
 
     @classmethod
     def for_length(cls, L, **kw):
         """Sensible segment dwell ranges for read length L (raw samples)."""
         T = L // 15
+        # Shape parameters were calibrated against the scaler network with the CPU
+        # oracle (DESIGN.md "Synthetic reads"): they are the values for which >= 95 %
+        # of reads come back `okay` with the planted adapter boundaries recovered.
         if T >= 700:                       # stock preset: adapter must be 260..3000 pooled
-            a = (270, min(600, T // 2))
+            d = dict(adapter_pooled=(270, min(330, T // 3)), polya_pooled=(20, 60),
+                     compress=1.0, transcript_level=(105.0, 12.0))
         elif T >= 200:                     # bench-short: 100..3000 pooled
-            a = (110, min(190, T - 70))
+            d = dict(adapter_pooled=(105, min(135, T - 110)), polya_pooled=(20, 50),
+                     compress=0.85, transcript_level=(112.0, 8.0))
         else:                              # too short for demux under any preset
-            a = (max(8, T // 3), max(10, T // 2))
-        return cls(read_length=L, adapter_pooled=a, **kw)
+            d = dict(adapter_pooled=(max(8, T // 3), max(10, T // 2)),
+                     polya_pooled=(4, max(5, T // 8)))
+        d.update(kw)
+        return cls(read_length=L, **d)
 
 
-def _emission_table(preset):
+def _emission_table(preset, transcript_level=None):
     by_name = {s['name']: s for s in preset['segmentation_model']}
     mu = torch.zeros(len(_ORDER), 2)
     sd = torch.zeros(len(_ORDER), 2)
@@ -63,6 +73,11 @@ def _emission_table(preset):
             w0[i] = em[0][2] / (em[0][2] + em[1][2])
         else:
             mu[i, 1], sd[i, 1] = em[0][0], em[0][1]
+    if transcript_level is not None:
+        i = _ORDER.index('transcript')
+        mu[i, :] = transcript_level[0]
+        sd[i, :] = transcript_level[1]
+        w0[i] = 1.0
     return mu, sd, w0
 
 
@@ -79,7 +94,7 @@ def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
     g.manual_seed(int(seed))
     L, st = spec.read_length, spec.stride
     T = L // st
-    mu, sd, w0 = (t.to(dev) for t in _emission_table(preset))
+    mu, sd, w0 = (t.to(dev) for t in _emission_table(preset, spec.transcript_level))
 
     raw = torch.empty((n, L), dtype=torch.int16, device=dev)
     gain = torch.empty(n, dtype=torch.float64, device=dev)
