@@ -210,6 +210,10 @@ int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *la
 /* number of kernel launches issued through this context so far */
 int64_t pb2_kernel_launches(const pb2_context *ctx);
 
+/* Verification switch: run the LSTM kernels with IEEE __fdiv_rn instead of the
+ * branch-free Newton division (identical outputs, slower; see csrc/pb_math.cuh). */
+int pb2_set_exact_division(pb2_context *ctx, int on);
+
 /* ---- measurement ----------------------------------------------------------
  * With profiling on, every kernel launch is bracketed by CUDA events on its own
  * stream.  pb2_profile_read synchronises the device, adds the elapsed times up per

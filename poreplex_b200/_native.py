@@ -86,7 +86,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_viterbi_paths', 'pb2_barcode_windows', 'pb2_demux_predict',
            'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches',
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
-           'pb2_profile_read']
+           'pb2_profile_read', 'pb2_set_exact_division']
 
 
 def sources():
@@ -147,6 +147,7 @@ def load():
     L.pb2_count_results.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp]
     L.pb2_kernel_launches.argtypes = [vp]
     L.pb2_kernel_launches.restype = C.c_int64
+    L.pb2_set_exact_division.argtypes = [vp, C.c_int]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

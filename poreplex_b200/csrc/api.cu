@@ -161,7 +161,8 @@ void pb2_destroy(pb2_context *ctx)
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
-                        &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads};
+                        &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
+                        &ctx->ws_flags};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -180,6 +181,13 @@ int pb2_profile_enable(pb2_context *ctx, int on)
 {
     if (!ctx) return PB2_EINVAL;
     ctx->profiling = on != 0;
+    return PB2_OK;
+}
+
+int pb2_set_exact_division(pb2_context *ctx, int on)
+{
+    if (!ctx) return PB2_EINVAL;
+    ctx->exact_division = on != 0;
     return PB2_OK;
 }
 

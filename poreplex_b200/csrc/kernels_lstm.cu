@@ -96,11 +96,12 @@ __device__ __forceinline__ float2 fmul2s(float s, float2 b) {
 }
 
 // cell update for both units of the pair, one read; returns h
-__device__ __forceinline__ float2 cell_pair(const float2 (&z)[4], float2 &c)
+template <bool EXACT>
+__device__ __forceinline__ float2 cell_pair(const float2 (&z)[4], float2 &c, bool &risk)
 {
     float2 h;
-    pb::lstm_cell(z[0].x, z[1].x, z[2].x, z[3].x, c.x, h.x);
-    pb::lstm_cell(z[0].y, z[1].y, z[2].y, z[3].y, c.y, h.y);
+    pb::lstm_cell<EXACT>(z[0].x, z[1].x, z[2].x, z[3].x, c.x, h.x, risk);
+    pb::lstm_cell<EXACT>(z[0].y, z[1].y, z[2].y, z[3].y, c.y, h.y, risk);
     return h;
 }
 
@@ -133,11 +134,14 @@ struct ScalerArgs {
     float *scale_shift;            // may be nullptr
 };
 
-template <int H>
+// EXACT = false: branch-free divisions (pb::div_posq); EXACT = true: IEEE __fdiv_rn
+// everywhere (verification mode, pb2_set_exact_division, and the zero-prefix table).
+template <int H, bool EXACT>
 __global__ void __launch_bounds__((H / 2) * NRG, 1)
 k_scaler_lstm(const ScalerArgs A)
 {
     constexpr int NUP = H / 2;
+    bool risk = false;
     extern __shared__ __align__(16) float smem[];
     float *U1t = smem;                        // [H][NUP][4][2]
     float *W2t = U1t + H * 4 * H;
@@ -215,7 +219,7 @@ k_scaler_lstm(const ScalerArgs A)
 #pragma unroll
             for (int g = 0; g < 4; g++)
                 z[g] = fadd2(fadd2(fmul2s(xv[r], w1[g]), b1[g]), acc.v[r][g]);
-            hn[r] = cell_pair(z, c1[r]);
+            hn[r] = cell_pair<EXACT>(z, c1[r], risk);
         }
         store_h(h1s + (cur1 ^ 1) * H * TB, up, rg, hn);
         cur1 ^= 1;
@@ -233,7 +237,7 @@ k_scaler_lstm(const ScalerArgs A)
             float2 z[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) z[g] = fadd2(zx[r][g], acc.v[r][g]);
-            hn[r] = cell_pair(z, c2[r]);
+            hn[r] = cell_pair<EXACT>(z, c2[r], risk);
         }
         store_h(h2s + (cur2 ^ 1) * H * TB, up, rg, hn);
         cur2 ^= 1;
@@ -274,10 +278,11 @@ k_scaler_lstm(const ScalerArgs A)
                 A.scale_shift[2 * r + 1] = (float)sh;
                 const bool ok = sc >= A.qc_scale_lo && sc <= A.qc_scale_hi &&
                                 sh >= A.qc_shift_lo && sh <= A.qc_shift_hi;
-                if (A.status && !ok) A.status[r] = PB2_ST_SCALING_QC_FAIL;
+                if (A.status) A.status[r] = ok ? PB2_ST_OKAY : PB2_ST_SCALING_QC_FAIL;
             }
         }
     }
+    (void)risk;
 }
 
 // load_padded_signal_head bookkeeping (signal_loader.py:212-222): how many pooled
@@ -307,7 +312,7 @@ __global__ void k_scaler_prepare(const int64_t *__restrict__ raw_offsets,
 template <int H>
 static size_t scaler_smem() { return sizeof(float) * (3 * H * 4 * H + 4 * H * TB); }
 
-static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st)
+static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st, bool exact_only = false)
 {
     const ScalerDev &S = ctx->scaler;
     if (S.l1.units != 48 || S.l2.units != 48 || S.l1.in_dim != 1 || S.l2.in_dim != 48 ||
@@ -324,13 +329,20 @@ static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st)
     const size_t smem = scaler_smem<48>();
     static bool attr_done = false;
     if (!attr_done) {
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const unsigned grid = (unsigned)((A.n + TB - 1) / TB);
-    PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm", st,
-        k_scaler_lstm<48><<<grid, 24 * NRG, smem, st>>>(A));
+    if (exact_only || ctx->exact_division) {
+        PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm<exact>", st,
+            k_scaler_lstm<48, true><<<grid, 24 * NRG, smem, st>>>(A));
+    } else {
+        PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm", st,
+            k_scaler_lstm<48, false><<<grid, 24 * NRG, smem, st>>>(A));
+    }
     return PB2_OK;
 }
 
@@ -357,7 +369,7 @@ int build_zero_prefix(pb2_context *ctx)
     ScalerArgs A = {};
     A.x = zeros; A.xoff = xoff; A.nreal = nreal; A.n = 1; A.thead = thead;
     A.zero_prefix = nullptr; A.prefix_dump = table;
-    int rc = run_scaler(ctx, A, 0);
+    int rc = run_scaler(ctx, A, 0, /*exact_only=*/true);
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(zeros); cudaFree(xoff); cudaFree(nreal);
     if (rc != PB2_OK) { cudaFree(table); return rc; }
@@ -433,11 +445,12 @@ struct DemuxArgs {
 
 __constant__ double c_calibration[PB2_MAX_CALIB];
 
-template <int H1>
-__global__ void __launch_bounds__((H1 / 2) * NRG)
+template <int H1, bool EXACT>
+__global__ void __launch_bounds__((H1 / 2) * NRG, 3)
 k_demux_l1(const DemuxArgs A)
 {
     constexpr int NUP = H1 / 2;
+    bool risk = false;
     extern __shared__ __align__(16) float smem[];
     float *Ut = smem;                         // [H1][NUP][4][2]
     float *hs = Ut + H1 * 4 * H1;             // [2][H1][TB]
@@ -481,24 +494,26 @@ k_demux_l1(const DemuxArgs A)
 #pragma unroll
             for (int g = 0; g < 4; g++)       // implementation 2: ((x.W + h.U) + b)
                 z[g] = fadd2(fadd2(fmul2s(xv[r], w[g]), acc.v[r][g]), b[g]);
-            hn[r] = cell_pair(z, c[r]);
+            hn[r] = cell_pair<EXACT>(z, c[r], risk);
         }
         store_h(hs + (cur ^ 1) * H1 * TB, up, rg, hn);
         store_h(Gt + ((size_t)t * 2 * H1 + dir * H1) * TB, up, rg, hn);
         cur ^= 1;
         __syncthreads();
     }
+    (void)risk;
 }
 
 // ============================================================================
 // Demultiplexer, layer 2: LSTMCell(H2, impl 2) over concat(fwd, bwd), then
 // Dense(n_classes) + softmax + the decision rule of barcoding.py:108-118.
 // ============================================================================
-template <int H1, int H2>
+template <int H1, int H2, bool EXACT>
 __global__ void __launch_bounds__((H2 / 2) * NRG, 1)
 k_demux_l2(const DemuxArgs A)
 {
     constexpr int NUP = H2 / 2;
+    bool risk = false;
     constexpr int KX = 2 * H1;
     extern __shared__ __align__(16) float smem[];
     float *Wt = smem;                         // [KX][NUP][4][2]
@@ -541,11 +556,12 @@ k_demux_l2(const DemuxArgs A)
             float2 z[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) z[g] = fadd2(fadd2(zx[r][g], acc.v[r][g]), b[g]);
-            hn[r] = cell_pair(z, c[r]);
+            hn[r] = cell_pair<EXACT>(z, c[r], risk);
         }
         store_h(hs + (cur ^ 1) * H2 * TB, up, rg, hn);
         cur ^= 1;
     }
+    (void)risk;
     __syncthreads();
 
     if (tid < TB) {
@@ -626,9 +642,13 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
     const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
     const size_t smem2 = sizeof(float) * (2 * H1 * 4 * H2 + H2 * 4 * H2 + 2 * H2 * TB + 2 * H1 * TB);
     if (!attr_done) {
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         attr_done = true;
     }
@@ -654,10 +674,17 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
         A.barcode = barcode ? barcode + r0 : nullptr;
         A.guess = guess ? guess + r0 : nullptr;
         A.score = score ? score + r0 : nullptr;
-        PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1", st,
-            k_demux_l1<H1><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
-        PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2", st,
-            k_demux_l2<H1, H2><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
+        if (ctx->exact_division) {
+            PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1<exact>", st,
+                k_demux_l1<H1, true><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
+            PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2<exact>", st,
+                k_demux_l2<H1, H2, true><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
+        } else {
+            PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1", st,
+                k_demux_l1<H1, false><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
+            PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2", st,
+                k_demux_l2<H1, H2, false><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
+        }
     }
     return PB2_OK;
 }

@@ -71,6 +71,7 @@ struct ProfEvent { int id; cudaEvent_t a, b; };
 struct pb2_context {
     int device = 0;
     bool profiling = false;
+    bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
     std::vector<pb::ProfEvent> prof_events;
     std::vector<cudaEvent_t> prof_pool;
     std::string error;
@@ -85,7 +86,7 @@ struct pb2_context {
     // scratch
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
-        ws_heads;
+        ws_heads, ws_flags;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
 };

@@ -154,6 +154,10 @@ class SignalEngine:
     def kernel_launches(self):
         return int(self.lib.pb2_kernel_launches(self.handle))
 
+    def set_exact_division(self, on=True):
+        """Verification mode: IEEE division in the LSTM kernels (same outputs, slower)."""
+        self._check(self.lib.pb2_set_exact_division(self.handle, 1 if on else 0))
+
     def profile_enable(self, on=True):
         self._check(self.lib.pb2_profile_enable(self.handle, 1 if on else 0))
 

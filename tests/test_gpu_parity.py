@@ -178,3 +178,23 @@ def test_counts(eng_short):
     np.add.at(want, (label, barcode + 1, status), 1)
     assert np.array_equal(c, want)
     assert c.sum() == n
+
+
+def test_fast_division_equals_ieee_division(eng_short, preset_short):
+    """The LSTM kernels' branch-free Newton division vs the verification mode that uses
+    IEEE __fdiv_rn everywhere: every output identical (incl. long -1000 pad regions where
+    cell states decay towards zero)."""
+    rd = _reads(preset_short, 160, 4000, seed=21)
+    raw, off, ln = _dense_batch(rd)
+    args = (raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
+    fast = eng_short.analyze_host(*args)
+    eng_short.set_exact_division(True)
+    try:
+        exact = eng_short.analyze_host(*args)
+    finally:
+        eng_short.set_exact_division(False)
+    for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts'):
+        assert np.array_equal(fast[k], exact[k]), k
+    assert np.array_equal(fast['scale_shift'].view(np.uint32), exact['scale_shift'].view(np.uint32))
+    assert np.array_equal(fast['class_probs'].view(np.uint32), exact['class_probs'].view(np.uint32))
+    assert (fast['barcode_score'] >= 0).sum() > 100
