@@ -24,6 +24,15 @@ constexpr int TB = 32;            // reads per CTA tile
 constexpr int RG = 4;             // reads per thread
 constexpr int NRG = TB / RG;      // read groups per tile (8)
 
+// ---- read groups --------------------------------------------------------------
+// A CTA holds GROUPS independent tiles ("read groups") that share the weight matrices in
+// shared memory but step through time on their own: each group synchronises with a
+// named barrier of its own, so while one group is in its activation phase (scalar FMA /
+// MUFU / ALU pipes) another is in its dot-product phase (packed FFMA2 pipe).
+__device__ __forceinline__ void group_sync(int group, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(nthreads) : "memory");
+}
+
 // ---- packed helpers ---------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return __ffma2_rn(a, b, c);
@@ -136,38 +145,45 @@ struct ScalerArgs {
 
 // EXACT = false: branch-free divisions (pb::div_posq); EXACT = true: IEEE __fdiv_rn
 // everywhere (verification mode, pb2_set_exact_division, and the zero-prefix table).
-template <int H, bool EXACT>
-__global__ void __launch_bounds__((H / 2) * NRG, 1)
+constexpr int SCALER_GROUPS = 2;
+
+template <int H, int GROUPS, bool EXACT>
+__global__ void __launch_bounds__(GROUPS * (H / 2) * NRG, 1)
 k_scaler_lstm(const ScalerArgs A)
 {
     constexpr int NUP = H / 2;
+    constexpr int GT = NUP * NRG;             // threads per read group
     bool risk = false;
     extern __shared__ __align__(16) float smem[];
     float *U1t = smem;                        // [H][NUP][4][2]
     float *W2t = U1t + H * 4 * H;
     float *U2t = W2t + H * 4 * H;
-    float *h1s = U2t + H * 4 * H;             // [2][H][TB]
-    float *h2s = h1s + 2 * H * TB;            // [2][H][TB]
-    __shared__ int s_nreal[TB];
-    __shared__ int s_maxreal;
+    __shared__ int s_nreal_all[GROUPS][TB];
+    __shared__ int s_maxreal_all[GROUPS];
 
-    const int tid = threadIdx.x;
+    const int group = threadIdx.x / GT;
+    const int tid = threadIdx.x % GT;
     const int rg = tid % NRG, up = tid / NRG;
-    const int64_t tile0 = (int64_t)blockIdx.x * TB;
+    float *h1s = U2t + H * 4 * H + group * (4 * H * TB);   // [2][H][TB]
+    float *h2s = h1s + 2 * H * TB;                         // [2][H][TB]
+    int *s_nreal = s_nreal_all[group];
+    const int64_t tile = (int64_t)blockIdx.x * GROUPS + group;
+    const int64_t tile0 = tile * TB;
 
     load_weights<H, H>(A.U1, U1t);
     load_weights<H, H>(A.W2, W2t);
     load_weights<H, H>(A.U2, U2t);
-    if (tid == 0) s_maxreal = 0;
+    if (tid == 0) s_maxreal_all[group] = 0;
     __syncthreads();
+    if (tile0 >= A.n) return;                 // whole group past the end (never syncs again)
     if (tid < TB) {
         const int64_t r = tile0 + tid;
         const int nr = (r < A.n) ? A.nreal[r] : 0;
         s_nreal[tid] = nr;
-        atomicMax(&s_maxreal, nr);
+        atomicMax(&s_maxreal_all[group], nr);
     }
-    __syncthreads();
-    const int t_start = A.zero_prefix ? (A.thead - s_maxreal) : 0;
+    group_sync(group, GT);
+    const int t_start = A.zero_prefix ? (A.thead - s_maxreal_all[group]) : 0;
 
     // per-thread constants
     float2 w1[4], b1[4], b2[4];
@@ -202,7 +218,7 @@ k_scaler_lstm(const ScalerArgs A)
         store_h(h1s, up, rg, h1v);
         store_h(h2s, up, rg, h2v);
     }
-    __syncthreads();
+    group_sync(group, GT);
 
     int cur1 = 0, cur2 = 0;
     Acc acc;
@@ -223,7 +239,7 @@ k_scaler_lstm(const ScalerArgs A)
         }
         store_h(h1s + (cur1 ^ 1) * H * TB, up, rg, hn);
         cur1 ^= 1;
-        __syncthreads();
+        group_sync(group, GT);
         // ---- layer 2, step t: z = ((h1.W2 + b2) + h2.U2)
         dot_tile<H, NUP>(W2t, h1s + cur1 * H * TB, up, rg, acc);
         float2 zx[RG][4];
@@ -241,7 +257,7 @@ k_scaler_lstm(const ScalerArgs A)
         }
         store_h(h2s + (cur2 ^ 1) * H * TB, up, rg, hn);
         cur2 ^= 1;
-        if (A.prefix_dump && blockIdx.x == 0 && rg == 0) {
+        if (A.prefix_dump && tile == 0 && rg == 0) {
             // state of read 0 after t + 1 steps; h1 was stored above into buffer cur1
             float *tb = A.prefix_dump + (size_t)(t + 1) * 4 * H;
             const float *h1n = h1s + cur1 * H * TB;
@@ -254,7 +270,7 @@ k_scaler_lstm(const ScalerArgs A)
         // no barrier needed here: the next writers of h1 target the buffer last read
         // before the barrier above, and h2's new buffer is read only after the next one
     }
-    __syncthreads();
+    group_sync(group, GT);
 
     // ---- Dense(2) + output transform + QC, one thread per read
     if (tid < TB) {
@@ -309,8 +325,8 @@ __global__ void k_scaler_prepare(const int64_t *__restrict__ raw_offsets,
     }
 }
 
-template <int H>
-static size_t scaler_smem() { return sizeof(float) * (3 * H * 4 * H + 4 * H * TB); }
+template <int H, int GROUPS>
+static size_t scaler_smem() { return sizeof(float) * (3 * H * 4 * H + GROUPS * 4 * H * TB); }
 
 static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st, bool exact_only = false)
 {
@@ -326,22 +342,24 @@ static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st, bool exa
     A.shift_std = S.shift_std; A.shift_mean = S.shift_mean;
     A.qc_scale_lo = S.qc_scale_lo; A.qc_scale_hi = S.qc_scale_hi;
     A.qc_shift_lo = S.qc_shift_lo; A.qc_shift_hi = S.qc_shift_hi;
-    const size_t smem = scaler_smem<48>();
+    constexpr int G = SCALER_GROUPS;
+    const size_t smem = scaler_smem<48, G>();
     static bool attr_done = false;
     if (!attr_done) {
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, false>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, G, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, true>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, G, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    const unsigned grid = (unsigned)((A.n + TB - 1) / TB);
+    const int64_t tiles = (A.n + TB - 1) / TB;
+    const unsigned grid = (unsigned)((tiles + G - 1) / G);
     if (exact_only || ctx->exact_division) {
         PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm<exact>", st,
-            k_scaler_lstm<48, true><<<grid, 24 * NRG, smem, st>>>(A));
+            k_scaler_lstm<48, G, true><<<grid, G * 24 * NRG, smem, st>>>(A));
     } else {
         PB_LAUNCH(ctx, K_SCALER_LSTM, "k_scaler_lstm", st,
-            k_scaler_lstm<48, false><<<grid, 24 * NRG, smem, st>>>(A));
+            k_scaler_lstm<48, G, false><<<grid, G * 24 * NRG, smem, st>>>(A));
     }
     return PB2_OK;
 }
@@ -508,25 +526,31 @@ k_demux_l1(const DemuxArgs A)
 // Demultiplexer, layer 2: LSTMCell(H2, impl 2) over concat(fwd, bwd), then
 // Dense(n_classes) + softmax + the decision rule of barcoding.py:108-118.
 // ============================================================================
-template <int H1, int H2, bool EXACT>
-__global__ void __launch_bounds__((H2 / 2) * NRG, 1)
+constexpr int DEMUX_L2_GROUPS = 2;
+
+template <int H1, int H2, int GROUPS, bool EXACT>
+__global__ void __launch_bounds__(GROUPS * (H2 / 2) * NRG, 1)
 k_demux_l2(const DemuxArgs A)
 {
     constexpr int NUP = H2 / 2;
+    constexpr int GT = NUP * NRG;             // threads per read group
     bool risk = false;
     constexpr int KX = 2 * H1;
     extern __shared__ __align__(16) float smem[];
     float *Wt = smem;                         // [KX][NUP][4][2]
     float *Ut = Wt + KX * 4 * H2;             // [H2][NUP][4][2]
-    float *hs = Ut + H2 * 4 * H2;             // [2][H2][TB]
+    const int group = threadIdx.x / GT;
+    const int tid = threadIdx.x % GT;
+    float *hs = Ut + H2 * 4 * H2 + group * (2 * H2 * TB + KX * TB);   // [2][H2][TB]
     float *xs = hs + 2 * H2 * TB;             // [KX][TB]
-    const int tid = threadIdx.x;
     const int rg = tid % NRG, up = tid / NRG;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = (int64_t)blockIdx.x * GROUPS + group;
     const int64_t tile0 = tile * TB;
 
     load_weights<KX, H2>(A.W2, Wt);
     load_weights<H2, H2>(A.U2, Ut);
+    __syncthreads();
+    if (tile0 >= A.n) return;
     float2 b[4];
     load_pair<H2>(A.b2, up, b);
     float2 c[RG], hz[RG];
@@ -538,11 +562,11 @@ k_demux_l2(const DemuxArgs A)
     int cur = 0;
     Acc acc;
     for (int t = 0; t < A.T; t++) {
-        __syncthreads();                      // xs free (and h stores of step t-1 visible)
+        group_sync(group, GT);                      // xs free (and h stores of step t-1 visible)
         const float4 *src = reinterpret_cast<const float4 *>(Gt + (size_t)t * KX * TB);
-        for (int i = tid; i < KX * TB / 4; i += blockDim.x)
+        for (int i = tid; i < KX * TB / 4; i += GT)
             reinterpret_cast<float4 *>(xs)[i] = __ldg(src + i);
-        __syncthreads();
+        group_sync(group, GT);
         dot_tile<KX, NUP>(Wt, xs, up, rg, acc);
         float2 zx[RG][4];
 #pragma unroll
@@ -562,7 +586,7 @@ k_demux_l2(const DemuxArgs A)
         cur ^= 1;
     }
     (void)risk;
-    __syncthreads();
+    group_sync(group, GT);
 
     if (tid < TB) {
         const int64_t r = tile0 + tid;
@@ -640,15 +664,17 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
 
     static bool attr_done = false;
     const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
-    const size_t smem2 = sizeof(float) * (2 * H1 * 4 * H2 + H2 * 4 * H2 + 2 * H2 * TB + 2 * H1 * TB);
+    constexpr int G2 = DEMUX_L2_GROUPS;
+    const size_t smem2 = sizeof(float) * (2 * H1 * 4 * H2 + H2 * 4 * H2 +
+                                          G2 * (2 * H2 * TB + 2 * H1 * TB));
     if (!attr_done) {
         PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, false>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, G2, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, true>,
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l2<H1, H2, G2, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         attr_done = true;
     }
@@ -678,12 +704,12 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
             PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1<exact>", st,
                 k_demux_l1<H1, true><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
             PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2<exact>", st,
-                k_demux_l2<H1, H2, true><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
+                k_demux_l2<H1, H2, G2, true><<<(unsigned)((nt + G2 - 1) / G2), G2 * (H2 / 2) * NRG, smem2, st>>>(A));
         } else {
             PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1", st,
                 k_demux_l1<H1, false><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));
             PB_LAUNCH(ctx, K_DEMUX_L2, "k_demux_l2", st,
-                k_demux_l2<H1, H2, false><<<(unsigned)nt, (H2 / 2) * NRG, smem2, st>>>(A));
+                k_demux_l2<H1, H2, G2, false><<<(unsigned)((nt + G2 - 1) / G2), G2 * (H2 / 2) * NRG, smem2, st>>>(A));
         }
     }
     return PB2_OK;
