@@ -162,7 +162,7 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
-                        &ctx->ws_flags};
+                        &ctx->ws_flags, &ctx->ws_slots};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -359,7 +359,7 @@ int pb2_barcode_windows(pb2_context *ctx, const pb2_batch *batch, const float *p
         return fail(ctx, PB2_ESTATE, "parameters not set");
     DeviceGuard g(ctx->device);
     return launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows, pushed,
-                          (cudaStream_t)stream);
+                          nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
@@ -369,8 +369,8 @@ int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pus
     if (!ctx) return PB2_EINVAL;
     if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
     DeviceGuard g(ctx->device);
-    return launch_demux(ctx, windows, pushed, n, class_probs, barcode, guess, score,
-                        (cudaStream_t)stream);
+    return launch_demux(ctx, windows, pushed, n, nullptr, nullptr, class_probs, barcode, guess,
+                        score, (cudaStream_t)stream);
 }
 
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
@@ -427,14 +427,17 @@ int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_resul
         barcode = WS_OR(res->barcode, ws_bc, int32_t, n);
         guess = WS_OR(res->barcode_guess, ws_guess, int32_t, n);
         score = WS_OR(res->barcode_score, ws_score, int32_t, n);
-        if (!windows || !pushed || !barcode || !guess || !score) return PB2_ENOMEM;
+        int32_t *slots = (int32_t *)ws_get(ctx, ctx->ws_slots, sizeof(int32_t) * ((size_t)n + 4));
+        if (!windows || !pushed || !barcode || !guess || !score || !slots) return PB2_ENOMEM;
+        int *slot_count = (int *)slots;           // [0] = number of accepted windows
+        int32_t *slot_read = slots + 4;
         if (res->class_probs)
             PB_CUDA(ctx, cudaMemsetAsync(res->class_probs, 0,
                                          sizeof(float) * PB2_MAX_CLASSES * (size_t)n, st));
         if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows,
-                                 pushed, st))) return rc;
-        if ((rc = launch_demux(ctx, windows, pushed, n, res->class_probs, barcode, guess, score,
-                               st))) return rc;
+                                 pushed, slot_count, slot_read, st))) return rc;
+        if ((rc = launch_demux(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
+                               barcode, guess, score, st))) return rc;
     } else {
         barcode = res->barcode; guess = res->barcode_guess; score = res->barcode_score;
     }

@@ -455,6 +455,9 @@ struct DemuxArgs {
     const float *Wd, *bd;                         // dense
     float *G;                                     // layer-1 outputs
     const int32_t *pushed;                        // may be nullptr
+    const int *slot_count;                        // compacted input: valid rows (or nullptr)
+    const int32_t *slot_read;                     // compacted input: row -> read (or nullptr)
+    int64_t row0;                                 // first row of this pass
     int n_classes, n_decoy;
     int n_calibration;
     double score_threshold;
@@ -477,6 +480,12 @@ k_demux_l1(const DemuxArgs A)
     const int dir = blockIdx.y;
     const int64_t tile = blockIdx.x;
     const int64_t tile0 = tile * TB;
+    int64_t n_eff = A.n;                      // rows of this pass that hold a window
+    if (A.slot_count) {
+        n_eff = (int64_t)*A.slot_count - A.row0;
+        if (n_eff > A.n) n_eff = A.n;
+    }
+    if (tile0 >= n_eff) return;
     const float *W = dir ? A.Wb : A.Wf, *U = dir ? A.Ub : A.Uf, *bias = dir ? A.bb : A.bf;
 
     load_weights<H1, H1>(U, Ut);
@@ -487,7 +496,7 @@ k_demux_l1(const DemuxArgs A)
 #pragma unroll
     for (int r = 0; r < RG; r++) {
         int64_t rd = tile0 + rg * RG + r;
-        if (rd >= A.n) rd = A.n - 1;
+        if (rd >= n_eff) rd = n_eff - 1;
         xp[r] = A.windows + rd * A.T;
     }
     float2 c[RG], hz[RG];
@@ -547,10 +556,16 @@ k_demux_l2(const DemuxArgs A)
     const int64_t tile = (int64_t)blockIdx.x * GROUPS + group;
     const int64_t tile0 = tile * TB;
 
+    int64_t n_eff = A.n;
+    if (A.slot_count) {
+        n_eff = (int64_t)*A.slot_count - A.row0;
+        if (n_eff > A.n) n_eff = A.n;
+    }
+    if ((int64_t)blockIdx.x * GROUPS * TB >= n_eff) return;      // whole CTA idle
     load_weights<KX, H2>(A.W2, Wt);
     load_weights<H2, H2>(A.U2, Ut);
     __syncthreads();
-    if (tile0 >= A.n) return;
+    if (tile0 >= n_eff) return;
     float2 b[4];
     load_pair<H2>(A.b2, up, b);
     float2 c[RG], hz[RG];
@@ -589,8 +604,10 @@ k_demux_l2(const DemuxArgs A)
     group_sync(group, GT);
 
     if (tid < TB) {
-        const int64_t r = tile0 + tid;
-        if (r < A.n && (A.pushed == nullptr || A.pushed[r])) {
+        const int64_t row = tile0 + tid;
+        // results go to the read that owns the row
+        const int64_t r = (row < n_eff && A.slot_read) ? (int64_t)A.slot_read[A.row0 + row] : row;
+        if (row < n_eff && (A.pushed == nullptr || A.pushed[r])) {
             const float *hf = hs + cur * H2 * TB;
             const int nc = A.n_classes;
             float logit[PB2_MAX_CLASSES], e[PB2_MAX_CLASSES];
@@ -643,6 +660,7 @@ k_demux_l2(const DemuxArgs A)
 }
 
 int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                 const int *slot_count, const int32_t *slot_read,
                  float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                  cudaStream_t st)
 {
@@ -693,13 +711,19 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
         A.W2 = D.l2.kernel; A.U2 = D.l2.recurrent; A.b2 = D.l2.bias;
         A.Wd = D.dense_kernel; A.bd = D.dense_bias;
         A.G = G;
-        A.pushed = pushed ? pushed + r0 : nullptr;
+        A.slot_count = slot_count; A.slot_read = slot_read; A.row0 = r0;
         A.n_classes = D.n_classes; A.n_decoy = D.n_decoy;
         A.n_calibration = D.n_calibration; A.score_threshold = D.score_threshold;
-        A.class_probs = class_probs ? class_probs + r0 * PB2_MAX_CLASSES : nullptr;
-        A.barcode = barcode ? barcode + r0 : nullptr;
-        A.guess = guess ? guess + r0 : nullptr;
-        A.score = score ? score + r0 : nullptr;
+        if (slot_read) {                 // outputs are indexed by read, not by row
+            A.pushed = nullptr;
+            A.class_probs = class_probs; A.barcode = barcode; A.guess = guess; A.score = score;
+        } else {
+            A.pushed = pushed ? pushed + r0 : nullptr;
+            A.class_probs = class_probs ? class_probs + r0 * PB2_MAX_CLASSES : nullptr;
+            A.barcode = barcode ? barcode + r0 : nullptr;
+            A.guess = guess ? guess + r0 : nullptr;
+            A.score = score ? score + r0 : nullptr;
+        }
         if (ctx->exact_division) {
             PB_LAUNCH(ctx, K_DEMUX_L1, "k_demux_l1<exact>", st,
                 k_demux_l1<H1, true><<<dim3((unsigned)nt, 2), (H1 / 2) * NRG, smem1, st>>>(A));

@@ -130,7 +130,8 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
           const float *__restrict__ scale_shift, const int32_t *__restrict__ status,
           const int32_t *__restrict__ segments, int64_t n_reads, int stride,
           int adapter_state, int min_len, int max_len, int trim_len, float pad_value,
-          float *__restrict__ windows, int32_t *__restrict__ pushed)
+          float *__restrict__ windows, int32_t *__restrict__ pushed,
+          int *__restrict__ slot_count, int32_t *__restrict__ slot_read)
 {
     __shared__ float sx[WIN_WARPS][PB2_WINDOW_MAX];
     __shared__ float sd[WIN_WARPS][PB2_WINDOW_MAX];
@@ -138,6 +139,7 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * WIN_WARPS + warp;
     if (r >= n_reads) return;
+    const bool compact = slot_count != nullptr;
     float *out = windows + r * trim_len;
     int ok = 0;
     int a0 = -1, a1 = -1;
@@ -149,8 +151,20 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
     }
     if (!ok) {
         if (lane == 0) pushed[r] = 0;
-        for (int i = lane; i < trim_len; i += 32) out[i] = 0.0f;
+        if (!compact)
+            for (int i = lane; i < trim_len; i += 32) out[i] = 0.0f;
         return;
+    }
+    if (compact) {
+        // accepted windows are packed densely (order is irrelevant: every read is
+        // classified independently and results are scattered back through slot_read)
+        int slot = 0;
+        if (lane == 0) {
+            slot = atomicAdd(slot_count, 1);
+            slot_read[slot] = (int32_t)r;
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        out = windows + (int64_t)slot * trim_len;
     }
     const int len = a1 - a0 + 1;
     const int n = len > trim_len ? trim_len : len;
@@ -174,19 +188,22 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
 
 int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
                    const float *scale_shift, const int32_t *status, const int32_t *segments,
-                   float *windows, int32_t *pushed, cudaStream_t st)
+                   float *windows, int32_t *pushed, int *slot_count, int32_t *slot_read,
+                   cudaStream_t st)
 {
     if (b.n_reads <= 0) return PB2_OK;
     const DemuxDev &d = ctx->demux;
     if (d.trim_length > PB2_WINDOW_MAX)
         return fail(ctx, PB2_EUNSUPPORTED, "signal_trim_length %d > %d", d.trim_length,
                     PB2_WINDOW_MAX);
+    if (slot_count) PB_CUDA(ctx, cudaMemsetAsync(slot_count, 0, sizeof(int), st));
     const unsigned grid = (unsigned)((b.n_reads + WIN_WARPS - 1) / WIN_WARPS);
     PB_LAUNCH(ctx, K_WINDOWS, "k_windows", st,
         k_windows<<<grid, WIN_WARPS * 32, 0, st>>>(b.raw_offsets, pooled, scale_shift, status,
                                                segments, b.n_reads, ctx->scaler.stride,
                                                ctx->adapter_state, d.min_length, d.max_length,
-                                               d.trim_length, d.pad_value, windows, pushed));
+                                               d.trim_length, d.pad_value, windows, pushed,
+                                               slot_count, slot_read));
     return PB2_OK;
 }
 

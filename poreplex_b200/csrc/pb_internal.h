@@ -86,7 +86,7 @@ struct pb2_context {
     // scratch
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
-        ws_heads, ws_flags;
+        ws_heads, ws_flags, ws_slots;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
 };
@@ -143,8 +143,12 @@ int launch_viterbi_paths(pb2_context *ctx, const HmmDev &hmm, const float *x,
                          double *logp, cudaStream_t st);
 int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
                    const float *scale_shift, const int32_t *status, const int32_t *segments,
-                   float *windows, int32_t *pushed, cudaStream_t st);
+                   float *windows, int32_t *pushed, int *slot_count, int32_t *slot_read,
+                   cudaStream_t st);
+// slot_count / slot_read: compacted windows (row s belongs to read slot_read[s], *slot_count
+// rows are valid); both nullptr = windows[n] aligned with reads, optional `pushed` mask
 int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                 const int *slot_count, const int32_t *slot_read,
                  float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                  cudaStream_t st);
 int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
