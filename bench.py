@@ -38,7 +38,8 @@ def algorithmic(L, stride=15, trim=300, scaler_len=30000):
     return {
         # bytes: int16 in + 3 f64 calibration, pooled f32 out
         'k_pool': ('hbm', 2 * T * stride + 24 + 4 * T),
-        # pooled in + scale/shift in; segments + status out
+        # pooled in + scale/shift in; segments + status out (time is fp64-compute bound:
+        # ~250 fp64 ops per pooled sample)
         'k_segment': ('hbm', 4 * T + 8 + 48 + 4),
         'k_windows': ('hbm', 4 * min(T, trim) + 8 + 4 * trim + 4),
         # FLOPs (2 per multiply-add): LSTM(1->48)+LSTM(48->48), zero padding skipped
@@ -301,12 +302,19 @@ def main():
                'share': ms / total_kernel_ms}
         if name in alg:
             bound, per_read = alg[name]
-            units = n           # every read goes through the kernel (no compaction yet)
+            # demux kernels only step the compacted, classified reads
+            units = n_classified if name.startswith('k_demux') else n
             if bound == 'hbm':
                 ach = per_read * units / (per_step_ms / 1e3) / 1e9
                 ent.update({'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'],
                             'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
                             'algorithmic_bytes_per_read': per_read})
+                if name == 'k_segment':
+                    T = min(args.length, 100000) // 15
+                    fp64 = 250.0 * T * units / (per_step_ms / 1e3) / 1e12
+                    ent.update({'fp64_tops_estimate': fp64,
+                                'note': 'fp64-compute bound (Gaussian/GMM emissions + DP in '
+                                        'double); ~250 fp64 ops per pooled sample'})
             else:
                 ach = per_read * units / (per_step_ms / 1e3) / 1e12
                 fp32_peak = 148 * 128 * 2 * (clocks.get('sm_mhz') or 1965.0) * 1e6 / 1e12
