@@ -229,6 +229,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout
         dist.init_process_group('nccl', device_id=device)
 
     from poreplex_b200 import _native
