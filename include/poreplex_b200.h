@@ -65,6 +65,7 @@ enum { PB2_LABEL_PASS = 0, PB2_LABEL_FAIL = 1, PB2_LABEL_ARTIFACT = 2, PB2_LABEL
 /* switches: commandline.py:279-291 */
 #define PB2_FLAG_BARCODING 1u        /* --barcoding      config['barcoding']            */
 #define PB2_FLAG_KEEP_POOLED 2u      /* also return the scaled pooled signal            */
+#define PB2_FLAG_POLYA 4u            /* --polya          config['measure_polya']        */
 
 typedef struct pb2_context pb2_context;
 
@@ -119,6 +120,40 @@ typedef struct {
     double score_threshold;          /* calibration[barcoding_quality_filter] */
 } pb2_demux_params;
 
+/* PolyASignalAnalyzer.__init__ (polya.py:39-48) over config['polya_dwell'].  Values
+ * that the reference compares against float32 Series are given as float (NEP 50). */
+typedef struct {
+    int32_t stride;                  /* rough_signal_stride                              */
+    int32_t refinement_expansion;
+    int32_t openend_unit;            /* openend_expansion // stride                      */
+    int32_t max_extension;           /* maximum_openend_extension                        */
+    int32_t window_length1, window_length2;   /* event_detection                         */
+    float threshold1, threshold2, peak_height;
+    float cutoff_lo, cutoff_hi;      /* f32(mean -/+ sd * z_cutoff)                      */
+    float mean_loc;                  /* f32(polya_mean_dist[0])                          */
+    float trigger;                   /* f32(polya_mean_trigger_recalibration * sd)       */
+    float half_range;                /* f32(sd * z_cutoff)                               */
+    float stdv_max;
+    double stdv_lo, stdv_hi;         /* polya_stdv_range                                 */
+    int32_t spike_tolerance;
+    double spike_weight;
+    int32_t recal_max_dist;          /* recalibrate_shifted_signal.*                     */
+    float recal_min_length;
+    float recal_max_stdv;
+} pb2_polya_params;
+
+#define PB2_POLYA_MAX_SPIKES 48
+/* NanoporeRead.set_polya_tail payload (polya.py:116-121) */
+typedef struct {
+    int32_t found;                   /* 0: no poly(A) reported for this read             */
+    int32_t n_spikes;                /* may exceed PB2_POLYA_MAX_SPIKES (list truncated) */
+    int64_t begin, end;              /* raw-sample coordinates                           */
+    int64_t dwell_samples;           /* dwell_time = dwell_samples / sampling_rate       */
+    int32_t extensions;              /* open-end extensions used                         */
+    int32_t flags;
+    float spikes[PB2_POLYA_MAX_SPIKES][4];   /* length, mean[k-1], mean[k], mean[k+1]; NaN = absent */
+} pb2_polya_result;
+
 /* A batch of reads: ragged int16 DAC samples + per-read calibration
  * (Fast5Reader.get_raw_data, fast5_file.py:122-131).  raw_offsets[i] is the element
  * offset of read i in `raw` and must be a multiple of 8 (16-byte aligned reads). */
@@ -148,6 +183,7 @@ typedef struct {
                                         element (raw_offsets[i] + stride-1) / stride   */
     int64_t *counts;                 /* [PB2_N_LABEL][PB2_N_BARCODE_SLOTS][PB2_N_STATUS]
                                         FinalSummaryTracker.counts (io.py:269-278)     */
+    pb2_polya_result *polya;         /* [n] with PB2_FLAG_POLYA                        */
 } pb2_results;
 
 /* ---- life cycle --------------------------------------------------------- */
@@ -162,6 +198,8 @@ int pb2_set_scaler(pb2_context *ctx, const pb2_scaler_params *p);
 int pb2_set_segmentation_hmm(pb2_context *ctx, const pb2_hmm_params *p,
                              int32_t scan_limit_pooled, int32_t adapter_state);
 int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p);
+/* polya_state: baked index of the 'polya-tail' state (-1 if the model has none) */
+int pb2_set_polya(pb2_context *ctx, const pb2_polya_params *p, int32_t polya_state);
 
 /* ---- whole path --------------------------------------------------------- */
 /* SignalAnalyzer.process stages A-D for the numeric outputs (signal_analyzer.py:82-134):
@@ -203,6 +241,10 @@ int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pus
 /* scaler network on explicit heads[n][length/stride] (keras predict) */
 int pb2_scaler_predict(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
                        void *stream);
+/* polya.py:50-187 + csupport.detect_events, for reads whose status is okay */
+int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *scale_shift,
+                      const int32_t *status, const int32_t *segments, pb2_polya_result *out,
+                      void *stream);
 /* io.py:274-278 */
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream);

@@ -16,7 +16,8 @@ HEADER = os.path.join(HERE, '..', 'include', 'poreplex_b200.h')
 
 MAX_STATES, MAX_COMP, MAX_EDGES, MAX_CLASSES, MAX_CALIB = 8, 4, 64, 8, 64
 N_LABEL, N_BARCODE_SLOTS, N_STATUS = 4, 5, 11
-FLAG_BARCODING, FLAG_KEEP_POOLED = 1, 2
+FLAG_BARCODING, FLAG_KEEP_POOLED, FLAG_POLYA = 1, 2, 4
+POLYA_MAX_SPIKES = 48
 LABEL_NAMES = ['pass', 'fail', 'artifact', None]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
@@ -65,6 +66,25 @@ class DemuxParams(C.Structure):
                 ('score_threshold', C.c_double)]
 
 
+class PolyaParams(C.Structure):
+    _fields_ = [('stride', C.c_int32), ('refinement_expansion', C.c_int32),
+                ('openend_unit', C.c_int32), ('max_extension', C.c_int32),
+                ('window_length1', C.c_int32), ('window_length2', C.c_int32),
+                ('threshold1', C.c_float), ('threshold2', C.c_float), ('peak_height', C.c_float),
+                ('cutoff_lo', C.c_float), ('cutoff_hi', C.c_float), ('mean_loc', C.c_float),
+                ('trigger', C.c_float), ('half_range', C.c_float), ('stdv_max', C.c_float),
+                ('stdv_lo', C.c_double), ('stdv_hi', C.c_double),
+                ('spike_tolerance', C.c_int32), ('spike_weight', C.c_double),
+                ('recal_max_dist', C.c_int32), ('recal_min_length', C.c_float),
+                ('recal_max_stdv', C.c_float)]
+
+
+class PolyaResult(C.Structure):
+    _fields_ = [('found', C.c_int32), ('n_spikes', C.c_int32), ('begin', C.c_int64),
+                ('end', C.c_int64), ('dwell_samples', C.c_int64), ('extensions', C.c_int32),
+                ('flags', C.c_int32), ('spikes', (C.c_float * 4) * POLYA_MAX_SPIKES)]
+
+
 class Batch(C.Structure):
     _fields_ = [('n_reads', C.c_int64), ('n_raw_total', C.c_int64),
                 ('max_raw_length', C.c_int64),
@@ -76,7 +96,8 @@ class Results(C.Structure):
     _fields_ = [('status', C.c_void_p), ('label', C.c_void_p), ('scale_shift', C.c_void_p),
                 ('segments', C.c_void_p), ('barcode', C.c_void_p),
                 ('barcode_guess', C.c_void_p), ('barcode_score', C.c_void_p),
-                ('class_probs', C.c_void_p), ('pooled', C.c_void_p), ('counts', C.c_void_p)]
+                ('class_probs', C.c_void_p), ('pooled', C.c_void_p), ('counts', C.c_void_p),
+                ('polya', C.c_void_p)]
 
 
 # every symbol include/poreplex_b200.h declares
@@ -86,7 +107,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_viterbi_paths', 'pb2_barcode_windows', 'pb2_demux_predict',
            'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches',
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
-           'pb2_profile_read', 'pb2_set_exact_division']
+           'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya']
 
 
 def sources():
@@ -148,6 +169,8 @@ def load():
     L.pb2_kernel_launches.argtypes = [vp]
     L.pb2_kernel_launches.restype = C.c_int64
     L.pb2_set_exact_division.argtypes = [vp, C.c_int]
+    L.pb2_set_polya.argtypes = [vp, C.POINTER(PolyaParams), C.c_int32]
+    L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

@@ -74,7 +74,7 @@ void prof_end(pb2_context *ctx, cudaStream_t st)
 
 static const char *const kKernelNames[K_NUM] = {
     "k_pool", "k_scaler_prepare", "k_scaler_lstm", "k_segment", "k_viterbi_paths",
-    "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc"};
+    "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya"};
 
 static void ws_free(Workspace &w)
 {
@@ -162,7 +162,7 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
-                        &ctx->ws_flags, &ctx->ws_slots};
+                        &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -287,6 +287,18 @@ int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p)
     return PB2_OK;
 }
 
+int pb2_set_polya(pb2_context *ctx, const pb2_polya_params *p, int32_t polya_state)
+{
+    if (!ctx || !p) return PB2_EINVAL;
+    if (p->stride <= 0 || p->window_length1 < 2 || p->window_length2 < p->window_length1 ||
+        p->window_length2 > 30)
+        return fail(ctx, PB2_EUNSUPPORTED, "event-detection windows must satisfy 2 <= w1 <= w2 <= 30");
+    ctx->polya = *p;
+    ctx->polya_state = polya_state;
+    ctx->polya_set = true;
+    return PB2_OK;
+}
+
 // ---- single stages ----------------------------------------------------------
 static int check_batch(pb2_context *ctx, const pb2_batch *b)
 {
@@ -373,6 +385,17 @@ int pb2_demux_predict(pb2_context *ctx, const float *windows, const int32_t *pus
                         score, (cudaStream_t)stream);
 }
 
+int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *scale_shift,
+                      const int32_t *status, const int32_t *segments, pb2_polya_result *out,
+                      void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->polya_set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "poly(A) parameters not set");
+    DeviceGuard g(ctx->device);
+    return launch_polya(ctx, *batch, scale_shift, status, segments, out, (cudaStream_t)stream);
+}
+
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream)
 {
@@ -441,6 +464,11 @@ int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_resul
     } else {
         barcode = res->barcode; guess = res->barcode_guess; score = res->barcode_score;
     }
+    if (flags & PB2_FLAG_POLYA) {
+        if (!ctx->polya_set) return fail(ctx, PB2_ESTATE, "poly(A) requested but parameters not set");
+        if (!res->polya) return fail(ctx, PB2_EINVAL, "PB2_FLAG_POLYA needs res->polya");
+        if ((rc = launch_polya(ctx, *batch, scale_shift, status, segments, res->polya, st))) return rc;
+    }
     if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;
     if (res->counts)
         if ((rc = launch_counts(ctx, status, label, barcode, n, res->counts, st))) return rc;
@@ -476,6 +504,8 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     const size_t o_cnt = take(sizeof(int64_t) * n_bins);
     const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
     const size_t o_pool = take(keep ? sizeof(float) * n_pooled : 16);
+    const bool want_polya = (flags & PB2_FLAG_POLYA) && hr->polya;
+    const size_t o_polya = take(want_polya ? sizeof(pb2_polya_result) * (size_t)n : 16);
     char *base = (char *)ws_get(ctx, ctx->ws_batch, off);
     if (!base) return PB2_ENOMEM;
 
@@ -509,6 +539,8 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     dr.class_probs = (float *)(base + o_pr);
     dr.counts = (int64_t *)(base + o_cnt);
     dr.pooled = keep ? (float *)(base + o_pool) : nullptr;
+    dr.polya = want_polya ? (pb2_polya_result *)(base + o_polya) : nullptr;
+    if ((flags & PB2_FLAG_POLYA) && !want_polya) flags &= ~PB2_FLAG_POLYA;
     if (keep) PB_CUDA(ctx, cudaMemsetAsync(dr.pooled, 0, sizeof(float) * n_pooled, st));
     if (!(flags & PB2_FLAG_BARCODING) && n > 0) {
         PB_CUDA(ctx, cudaMemsetAsync(dr.barcode, 0xFF, sizeof(int32_t) * n, st));
@@ -531,6 +563,7 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     PB_D2H(class_probs, sizeof(float) * PB2_MAX_CLASSES * n);
     PB_D2H(counts, sizeof(int64_t) * n_bins);
     if (keep) PB_D2H(pooled, sizeof(float) * n_pooled);
+    if (want_polya) PB_D2H(polya, sizeof(pb2_polya_result) * (size_t)n);
 #undef PB_D2H
     PB_CUDA(ctx, cudaStreamSynchronize(st));
     return PB2_OK;

@@ -14,7 +14,46 @@ import numpy as np
 from . import _native as N
 from . import params as P
 
-__all__ = ['SignalEngine', 'get_engine']
+__all__ = ['SignalEngine', 'get_engine', 'POLYA_DTYPE', 'polya_to_dict']
+
+POLYA_DTYPE = np.dtype([('found', 'i4'), ('n_spikes', 'i4'), ('begin', 'i8'), ('end', 'i8'),
+                        ('dwell_samples', 'i8'), ('extensions', 'i4'), ('flags', 'i4'),
+                        ('spikes', 'f4', (N.POLYA_MAX_SPIKES, 4))])
+assert POLYA_DTYPE.itemsize == C.sizeof(N.PolyaResult)
+
+
+def polya_to_dict(rec, sampling_rate):
+    """pb2_polya_result -> the dict of NanoporeRead.set_polya_tail (polya.py:116-121)."""
+    if not rec['found']:
+        return None
+    spikes = []
+    for k in range(min(int(rec['n_spikes']), N.POLYA_MAX_SPIKES)):
+        row = rec['spikes'][k]
+        vals = [row[0]] + [row[j] for j in (1, 2, 3) if not np.isnan(row[j])]
+        spikes.append(tuple(float(v) for v in vals))
+    return {'begin': int(rec['begin']), 'end': int(rec['end']),
+            'dwell_time': int(rec['dwell_samples']) / sampling_rate, 'spikes': spikes}
+
+
+def polya_params_struct(cfg, stride):
+    """config['polya_dwell'] -> pb2_polya_params, with the reference's rounding
+    (PolyASignalAnalyzer.__init__, polya.py:39-48; float32 where the reference compares
+    against float32 Series)."""
+    f = np.float32
+    loc, sd = cfg['polya_mean_dist']
+    z = cfg['polya_mean_z_cutoff']
+    ed = cfg['event_detection']
+    rc = cfg['recalibrate_shifted_signal']
+    if cfg['median_pre_filter'] != 7:
+        raise ValueError('poly(A) kernel is built for median_pre_filter = 7')
+    return N.PolyaParams(stride, cfg['refinement_expansion'], cfg['openend_expansion'] // stride,
+                         cfg['maximum_openend_extension'], ed['window_length1'],
+                         ed['window_length2'], ed['threshold1'], ed['threshold2'],
+                         ed['peak_height'], f(loc - sd * z), f(loc + sd * z), f(loc),
+                         f(cfg['polya_mean_trigger_recalibration'] * sd), f(sd * z),
+                         f(cfg['polya_stdv_max']), cfg['polya_stdv_range'][0],
+                         cfg['polya_stdv_range'][1], cfg['spike_tolerance'], cfg['spike_weight'],
+                         rc['max_dist_from_adapter'], f(rc['min_length']), f(rc['max_stdv']))
 
 
 def _np_ptr(a):
@@ -100,6 +139,13 @@ class SignalEngine:
         hs = _hmm_struct(st)
         self._check(self.lib.pb2_set_segmentation_hmm(self.handle, C.byref(hs),
                                                       self.scan_limit_pooled, self.adapter_state))
+
+        # --- poly(A) analyzer: PolyASignalAnalyzer.__init__ (polya.py:39-48)
+        self.polya_ready = False
+        if 'polya_dwell' in config:
+            pp = polya_params_struct(config['polya_dwell'], self.stride)
+            self._check(self.lib.pb2_set_polya(self.handle, C.byref(pp), st.index_of('polya-tail')))
+            self.polya_ready = True
 
         # --- demultiplexer: BarcodeDemultiplexer (barcoding.py:34-70)
         if barcoding is None:
@@ -190,7 +236,7 @@ class SignalEngine:
         return raw, offsets, lengths
 
     def analyze_host(self, raw, offsets, lengths, rng, digitisation, offset, barcoding=None,
-                     keep_pooled=False):
+                     keep_pooled=False, polya=False):
         """SignalAnalyzer.process stages A-D over HOST numpy buffers (H2D, kernels, D2H).
 
         Returns a dict of numpy arrays: status, label, scale_shift [n,2], segments
@@ -223,14 +269,20 @@ class SignalEngine:
         }
         if keep_pooled:
             out['pooled'] = np.zeros(raw.size // self.stride + 2, np.float32)
+        if polya:
+            if not self.polya_ready:
+                raise ValueError("config has no 'polya_dwell' section")
+            out['polya'] = np.zeros(n, POLYA_DTYPE)
         b = N.Batch(n, raw.size, int(lengths.max()) if n else 0, _np_ptr(raw), _np_ptr(offsets),
                     _np_ptr(lengths), _np_ptr(rng), _np_ptr(digitisation), _np_ptr(offset))
         r = N.Results(_np_ptr(out['status']), _np_ptr(out['label']), _np_ptr(out['scale_shift']),
                       _np_ptr(out['segments']), _np_ptr(out['barcode']),
                       _np_ptr(out['barcode_guess']), _np_ptr(out['barcode_score']),
                       _np_ptr(out['class_probs']),
-                      _np_ptr(out['pooled']) if keep_pooled else None, _np_ptr(out['counts']))
-        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0)
+                      _np_ptr(out['pooled']) if keep_pooled else None, _np_ptr(out['counts']),
+                      _np_ptr(out['polya']) if polya else None)
+        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0) \
+            | (N.FLAG_POLYA if polya else 0)
         self._check(self.lib.pb2_analyze_host(self.handle, C.byref(b), C.byref(r), flags))
         return out
 
@@ -241,7 +293,7 @@ class SignalEngine:
                        raw.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), rng.data_ptr(),
                        digitisation.data_ptr(), offset.data_ptr())
 
-    def alloc_results(self, n, n_raw_total=0, keep_pooled=False):
+    def alloc_results(self, n, n_raw_total=0, keep_pooled=False, polya=False):
         import torch
         dev = torch.device('cuda', self.device)
         out = {
@@ -259,10 +311,13 @@ class SignalEngine:
         if keep_pooled:
             out['pooled'] = torch.zeros(n_raw_total // self.stride + 2, dtype=torch.float32,
                                         device=dev)
+        if polya:
+            out['polya'] = torch.zeros((n, POLYA_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         return out
 
     def analyze_device(self, raw, offsets, lengths, rng, digitisation, offset, out=None,
-                       barcoding=None, keep_pooled=False, max_raw_length=0, stream=None):
+                       barcoding=None, keep_pooled=False, max_raw_length=0, stream=None,
+                       polya=False):
         """Same path over tensors already resident in HBM; enqueued on ``stream`` (default:
         torch's current stream), not synchronised."""
         import torch
@@ -270,7 +325,7 @@ class SignalEngine:
             barcoding = self.barcoding
         n = int(lengths.numel())
         if out is None:
-            out = self.alloc_results(n, int(raw.numel()), keep_pooled)
+            out = self.alloc_results(n, int(raw.numel()), keep_pooled, polya)
         b = self._batch_from_tensors(raw, offsets, lengths, rng, digitisation, offset,
                                      max_raw_length)
         r = N.Results(out['status'].data_ptr(), out['label'].data_ptr(),
@@ -278,8 +333,9 @@ class SignalEngine:
                       out['barcode'].data_ptr(), out['barcode_guess'].data_ptr(),
                       out['barcode_score'].data_ptr(), out['class_probs'].data_ptr(),
                       out['pooled'].data_ptr() if keep_pooled else None,
-                      out['counts'].data_ptr())
-        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0)
+                      out['counts'].data_ptr(), out['polya'].data_ptr() if polya else None)
+        flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0) \
+            | (N.FLAG_POLYA if polya else 0)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         self._check(self.lib.pb2_analyze_device(self.handle, C.byref(b), C.byref(r), flags,
                                                 C.c_void_p(st.cuda_stream)))

@@ -10,7 +10,7 @@ TensorFlow / pomegranate calls.  ``pipeline.py:204`` can call this ``process_bat
 unchanged.
 
 Switch coverage this round: ``trim_adapter`` (a no-op in the reference at this commit,
-SURVEY.md F6 -- reproduced) and ``barcoding``.  ``measure_polya``,
+SURVEY.md F6 -- reproduced), ``barcoding`` and ``measure_polya``.
 ``filter_unsplit_reads`` and the dump switches raise ``NotImplementedError`` when the
 analyzer is built, which ``process_batch`` reports as a batch-level failure exactly like
 any other unhandled exception -- never a silent CPU fallback.
@@ -23,7 +23,7 @@ from io import StringIO
 import numpy as np
 
 from . import _native as N
-from .engine import get_engine
+from .engine import get_engine, polya_to_dict
 from .fast5_source import Fast5Source
 from .params import STATUS_NAMES
 
@@ -85,6 +85,9 @@ class NanoporeRead:
         self.barcode = newbarcode
         self.barcode_bestguess = guess
         self.barcode_quality = quality
+
+    def set_polya_tail(self, polya_info):
+        self.polya = polya_info
 
     def set_adapter_trimming_length(self, newlength):
         if self.sequence is None:
@@ -157,7 +160,6 @@ class NanoporeRead:
 class SignalAnalyzer:
 
     UNSUPPORTED_SWITCHES = {
-        'measure_polya': 'poly(A) dwell measurement (--polya)',
         'filter_unsplit_reads': 'chimera filter (--filter-chimera)',
         'dump_adapter_signals': 'adapter signal dumps',
         'dump_basecalls': 'basecalled event dumps',
@@ -225,12 +227,15 @@ class SignalAnalyzer:
                 np.array([r.fast5.range for r in loaded], np.float64),
                 np.array([r.fast5.digitization for r in loaded], np.float64),
                 np.array([r.fast5.offset for r in loaded], np.float64),
-                barcoding=bool(self.config['barcoding']))
+                barcoding=bool(self.config['barcoding']),
+                polya=bool(self.config['measure_polya']))
             for i, npread in enumerate(loaded):
                 npread._raw = None
                 npread._gpu = {k: out[k][i] for k in ('status', 'scale_shift', 'segments',
                                                       'barcode', 'barcode_guess',
                                                       'barcode_score')}
+                if 'polya' in out:
+                    npread._gpu['polya'] = out['polya'][i]
                 st = STATUS_NAMES[int(out['status'][i])]
                 if st == 'scaling_qc_fail':            # fit_scalers, signal_loader.py:104-109
                     npread.set_status('scaling_qc_fail', stop=True)
@@ -308,6 +313,11 @@ class SignalAnalysis:
                 bc = int(gpu['barcode'])
                 npread.set_barcode(None if bc < 0 else bc, int(gpu['barcode_guess']),
                                    int(gpu['barcode_score']))
+
+            if self.config['measure_polya']:         # signal_analyzer.py:250-256
+                info = polya_to_dict(gpu['polya'], npread.sampling_rate)
+                if info is not None:
+                    npread.set_polya_tail(info)
 
             events = self.load_events()
 

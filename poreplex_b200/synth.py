@@ -48,7 +48,7 @@ class SynthSpec:
         # oracle (DESIGN.md "Synthetic reads"): they are the values for which >= 95 %
         # of reads come back `okay` with the planted adapter boundaries recovered.
         if T >= 700:                       # stock preset: adapter must be 260..3000 pooled
-            d = dict(adapter_pooled=(270, min(330, T // 3)), polya_pooled=(20, 60),
+            d = dict(adapter_pooled=(270, max(280, min(330, T // 3))), polya_pooled=(20, 60),
                      compress=1.0, transcript_level=(105.0, 12.0))
         elif T >= 200:                     # bench-short: 100..3000 pooled
             d = dict(adapter_pooled=(105, min(135, T - 110)), polya_pooled=(20, 50),

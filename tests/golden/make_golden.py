@@ -155,6 +155,8 @@ def main():
                                            trim_adapter=True, barcoding=True)
         _, res_trim, _ = run_reference(preset, variant, rd, read_ids, basecalls,
                                        trim_adapter=True)
+        _, res_polya, _ = run_reference(preset, variant, rd, read_ids, basecalls,
+                                        trim_adapter=True, barcoding=True, measure_polya=True)
         full = None
         if variant == 'stock':
             _, full, _ = run_reference(preset, variant, rd, read_ids, basecalls,
@@ -181,6 +183,7 @@ def main():
                'reads': [list(r) for r in reads],
                'results_trim_barcoding': jsonable(res_bc),
                'results_trim_only': jsonable(res_trim),
+               'results_trim_barcoding_polya': jsonable(res_polya),
                'segments': cap['segments']}
         if full is not None:
             doc['results_all_switches'] = jsonable(full)

@@ -52,4 +52,9 @@ def normalise_result(r):
         d['error_message'] = True
     if 'sequence' in d:
         d['sequence'] = [d['sequence'][0], d['sequence'][1], int(d['sequence'][2])]
+    if 'polya' in d:
+        p = d['polya']
+        d['polya'] = {'begin': int(p['begin']), 'end': int(p['end']),
+                      'dwell_time': float(p['dwell_time']),
+                      'spikes': [tuple(float(x) for x in s) for s in p['spikes']]}
     return d

@@ -1,0 +1,48 @@
+// hostcheck.cpp -- TEST-ONLY host build of the __host__ __device__ cores in
+// poreplex_b200/csrc (compiled with g++, no CUDA).  Lets the CPU test-suite run the very
+// code the kernels execute against the oracle.  Never used by the product path.
+#include <cstdint>
+#include <cmath>
+#include "../../poreplex_b200/csrc/polya_core.cuh"
+
+extern "C" {
+
+float hc_median7(const float *v) { return pb::median7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]); }
+
+float hc_pairwise_sum(const float *a, int64_t n)
+{
+    pb::PairwiseSum s;
+    s.begin(n);
+    for (int64_t i = 0; i < n; i++) s.push(a[i]);
+    return s.total;
+}
+
+// events of one window into caller arrays; returns the count
+int64_t hc_detect_events(const int16_t *raw, int64_t n, double gain, double offset, float scale,
+                         float shift, const pb::PolyaParams *P, uint64_t *start, float *length,
+                         float *mean, float *stdv, int64_t cap)
+{
+    pb::WindowSource src;
+    src.raw = raw; src.gain = gain; src.offset = offset; src.scale = scale; src.shift = shift;
+    src.w0 = 0; src.n = n;
+    pb::EventStream es;
+    es.begin(src, *P);
+    pb::Event ev;
+    int64_t k = 0;
+    while (es.next(ev)) {
+        if (k < cap) { start[k] = ev.start; length[k] = ev.length; mean[k] = ev.mean; stdv[k] = ev.stdv; }
+        k++;
+    }
+    return k;
+}
+
+void hc_polya(const pb::PolyaParams *P, const int16_t *raw, int64_t full_length, double gain,
+              double offset, float scale, float shift, int32_t rough_begin, int32_t rough_end,
+              pb::PolyaResult *R)
+{
+    pb::polya_analyze(*P, raw, full_length, gain, offset, scale, shift, rough_begin, rough_end, *R);
+}
+
+int hc_sizeof_params(void) { return (int)sizeof(pb::PolyaParams); }
+int hc_sizeof_result(void) { return (int)sizeof(pb::PolyaResult); }
+}

@@ -45,7 +45,9 @@ def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_s
     p = preset_short if doc['preset'] == 'bench-short' else preset
     reads = [tuple(r) for r in doc['reads']]
     for key, sw in (('results_trim_only', dict(trim_adapter=True)),
-                    ('results_trim_barcoding', dict(trim_adapter=True, barcoding=True))):
+                    ('results_trim_barcoding', dict(trim_adapter=True, barcoding=True)),
+                    ('results_trim_barcoding_polya', dict(trim_adapter=True, barcoding=True,
+                                                          measure_polya=True))):
         got = sa.process_batch(0, reads, _config(p, tmp, **sw))
         assert not isinstance(got, tuple), got
         want = doc[key]
@@ -61,7 +63,7 @@ def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_s
 def test_unbuilt_switches_fail_loudly(preset, eng_stock):
     from poreplex_b200 import signal_analyzer as sa
     z, doc, tmp = _serve('stock16k')
-    for sw in ('measure_polya', 'filter_unsplit_reads'):
+    for sw in ('filter_unsplit_reads', 'dump_adapter_signals'):
         res = sa.process_batch(0, [tuple(r) for r in doc['reads']], _config(preset, tmp, **{sw: True}))
         assert isinstance(res, tuple) and res[0] == -1 and 'NotImplementedError' in res[1]
 

@@ -198,3 +198,43 @@ def test_fast_division_equals_ieee_division(eng_short, preset_short):
     assert np.array_equal(fast['scale_shift'].view(np.uint32), exact['scale_shift'].view(np.uint32))
     assert np.array_equal(fast['class_probs'].view(np.uint32), exact['class_probs'].view(np.uint32))
     assert (fast['barcode_score'] >= 0).sum() > 100
+
+
+def test_polya_kernel_matches_host_core(eng_stock, orc_stock, preset):
+    """k_polya (thread per read) against the same core compiled for the host, which the CPU
+    suite ties to the reference's polya.py: found flag, begin/end, dwell, spikes identical."""
+    import ctypes as C
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import hostcheck_util as H
+    from poreplex_b200.engine import polya_to_dict
+    hc = H.load()
+    Pc = H.polya_params(preset['polya_dwell'])
+    found = 0
+    for L, polya_len, seed in ((16000, (20, 60), 31), (24000, (5, 300), 32), (20000, (100, 500), 33)):
+        from poreplex_b200 import synth
+        spec = synth.SynthSpec.for_length(L, frac_no_adapter=0.05, frac_qc_fail=0.05)
+        spec.polya_pooled = polya_len
+        rd = synth.to_numpy(synth.generate_reads(96, spec, preset, seed=seed))
+        raw, off, ln = _dense_batch(rd)
+        out = eng_stock.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'],
+                                     polya=True)
+        names = eng_stock.state_names
+        ia, ip = names.index('adapter'), names.index('polya-tail')
+        for i in range(len(ln)):
+            got = polya_to_dict(out['polya'][i], 3012.0)
+            if out['status'][i] != 0:
+                assert got is None
+                continue
+            seg = out['segments'][i]
+            rb, re = (int(seg[ip, 0]), int(seg[ip, 1])) if seg[ip, 0] >= 0 else (int(seg[ia, 1]) + 1, -1)
+            R = H.PolyaResultC()
+            sig = np.ascontiguousarray(rd['raw'][i])
+            hc.hc_polya(C.byref(Pc), sig.ctypes.data_as(C.c_void_p), C.c_int64(L),
+                        C.c_double(rd['range'][i] / rd['digitisation'][i]), C.c_double(rd['offset'][i]),
+                        C.c_float(out['scale_shift'][i, 0]), C.c_float(out['scale_shift'][i, 1]),
+                        C.c_int32(rb), C.c_int32(re), C.byref(R))
+            want = H.result_to_dict(R, 3012.0)
+            assert want == got, (L, i, want, got)
+            found += got is not None
+    assert found > 150
