@@ -154,6 +154,27 @@ typedef struct {
     float spikes[PB2_POLYA_MAX_SPIKES][4];   /* length, mean[k-1], mean[k], mean[k+1]; NaN = absent */
 } pb2_polya_result;
 
+/* config['unsplit_read_detection'] (rna-r941.cfg:17-27); durations in seconds -- the
+ * kernel applies int(value * sampling_rate) per read (signal_analyzer.py:375-380). */
+typedef struct {
+    double window_size, window_step, strict_duration;
+    double strict_full_length, strict_dna_length, loosen_full_length, loosen_dna_length;
+    double basecount_quality_limit, subread_basecount_limit, subread_baseratio_limit;
+} pb2_unsplit_params;
+
+/* Basecalled event tables of a batch (NanoporeRead.load_fast5_events): ragged, read i owns
+ * rows [event_offsets[i], event_offsets[i+1]); reads without a table have an empty range.
+ * The derived columns of load_events (scaled_mean, pos, end) are computed on the device. */
+typedef struct {
+    int64_t n_events_total;
+    const int64_t *event_offsets;    /* [n_reads + 1]                  */
+    const int64_t *start;            /* [total] raw-sample index       */
+    const float *mean;               /* [total] event mean, pA         */
+    const int32_t *move;             /* [total]                        */
+    const double *p_model_state;     /* [total]                        */
+    const double *sampling_rate;     /* [n_reads]                      */
+} pb2_event_tables;
+
 /* A batch of reads: ragged int16 DAC samples + per-read calibration
  * (Fast5Reader.get_raw_data, fast5_file.py:122-131).  raw_offsets[i] is the element
  * offset of read i in `raw` and must be a multiple of 8 (16-byte aligned reads). */
@@ -200,6 +221,10 @@ int pb2_set_segmentation_hmm(pb2_context *ctx, const pb2_hmm_params *p,
 int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p);
 /* polya_state: baked index of the 'polya-tail' state (-1 if the model has none) */
 int pb2_set_polya(pb2_context *ctx, const pb2_polya_params *p, int32_t polya_state);
+/* unsplit_read_detection_model (baked) + its switches; state indices are baked indices of
+ * 'adapter', 'leader-high', 'leader-low' in THAT model */
+int pb2_set_unsplit(pb2_context *ctx, const pb2_hmm_params *hmm, const pb2_unsplit_params *p,
+                    int32_t adapter_state, int32_t leader_high_state, int32_t leader_low_state);
 
 /* ---- whole path --------------------------------------------------------- */
 /* SignalAnalyzer.process stages A-D for the numeric outputs (signal_analyzer.py:82-134):
@@ -245,6 +270,16 @@ int pb2_scaler_predict(pb2_context *ctx, const float *heads, int64_t n, float *z
 int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *scale_shift,
                       const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                       void *stream);
+/* SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443) for reads whose status is
+ * okay and that have an event table.  flag[i]: 1 unsplit, 0 not, <0 internal overflow/no path.
+ * max_windows >= ceil((last event end - payload start) / window_step) over the batch. */
+int pb2_detect_unsplit(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
+                       const float *scale_shift, const int32_t *status, const int32_t *segments,
+                       int32_t max_windows, int32_t *flag, void *stream);
+/* same with HOST pointers everywhere (copies in, runs, copies flag out, synchronises) */
+int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
+                            const float *scale_shift, const int32_t *status,
+                            const int32_t *segments, int32_t max_windows, int32_t *flag);
 /* io.py:274-278 */
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream);

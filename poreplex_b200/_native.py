@@ -85,6 +85,19 @@ class PolyaResult(C.Structure):
                 ('flags', C.c_int32), ('spikes', (C.c_float * 4) * POLYA_MAX_SPIKES)]
 
 
+class UnsplitParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        'window_size', 'window_step', 'strict_duration', 'strict_full_length',
+        'strict_dna_length', 'loosen_full_length', 'loosen_dna_length',
+        'basecount_quality_limit', 'subread_basecount_limit', 'subread_baseratio_limit')]
+
+
+class EventTables(C.Structure):
+    _fields_ = [('n_events_total', C.c_int64), ('event_offsets', C.c_void_p),
+                ('start', C.c_void_p), ('mean', C.c_void_p), ('move', C.c_void_p),
+                ('p_model_state', C.c_void_p), ('sampling_rate', C.c_void_p)]
+
+
 class Batch(C.Structure):
     _fields_ = [('n_reads', C.c_int64), ('n_raw_total', C.c_int64),
                 ('max_raw_length', C.c_int64),
@@ -107,7 +120,8 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_viterbi_paths', 'pb2_barcode_windows', 'pb2_demux_predict',
            'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches',
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
-           'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya']
+           'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
+           'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host']
 
 
 def sources():
@@ -171,6 +185,12 @@ def load():
     L.pb2_set_exact_division.argtypes = [vp, C.c_int]
     L.pb2_set_polya.argtypes = [vp, C.POINTER(PolyaParams), C.c_int32]
     L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
+    L.pb2_set_unsplit.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(UnsplitParams), C.c_int32,
+                                  C.c_int32, C.c_int32]
+    L.pb2_detect_unsplit.argtypes = [vp, C.POINTER(EventTables), C.c_int64, vp, vp, vp, C.c_int32,
+                                     vp, vp]
+    L.pb2_detect_unsplit_host.argtypes = [vp, C.POINTER(EventTables), C.c_int64, vp, vp, vp,
+                                          C.c_int32, vp]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

@@ -74,7 +74,8 @@ void prof_end(pb2_context *ctx, cudaStream_t st)
 
 static const char *const kKernelNames[K_NUM] = {
     "k_pool", "k_scaler_prepare", "k_scaler_lstm", "k_segment", "k_viterbi_paths",
-    "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya"};
+    "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
+    "k_unsplit_windows", "k_unsplit_decide"};
 
 static void ws_free(Workspace &w)
 {
@@ -162,7 +163,8 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
-                        &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya};
+                        &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
+                        &ctx->ws_unsplit, &ctx->ws_unsplit_host};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -299,6 +301,21 @@ int pb2_set_polya(pb2_context *ctx, const pb2_polya_params *p, int32_t polya_sta
     return PB2_OK;
 }
 
+int pb2_set_unsplit(pb2_context *ctx, const pb2_hmm_params *hmm, const pb2_unsplit_params *p,
+                    int32_t adapter_state, int32_t leader_high_state, int32_t leader_low_state)
+{
+    if (!ctx || !hmm || !p) return PB2_EINVAL;
+    if (hmm->n_states <= 0 || hmm->n_states > PB2_MAX_STATES - 1)
+        return fail(ctx, PB2_EINVAL, "HMM must have 1..%d states", PB2_MAX_STATES - 1);
+    memcpy(&ctx->unsplit_hmm, hmm, sizeof(HmmDev));
+    ctx->unsplit = *p;
+    ctx->unsplit_states[0] = adapter_state;
+    ctx->unsplit_states[1] = leader_high_state;
+    ctx->unsplit_states[2] = leader_low_state;
+    ctx->unsplit_set = true;
+    return PB2_OK;
+}
+
 // ---- single stages ----------------------------------------------------------
 static int check_batch(pb2_context *ctx, const pb2_batch *b)
 {
@@ -394,6 +411,65 @@ int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *sca
     if (!ctx->polya_set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "poly(A) parameters not set");
     DeviceGuard g(ctx->device);
     return launch_polya(ctx, *batch, scale_shift, status, segments, out, (cudaStream_t)stream);
+}
+
+int pb2_detect_unsplit(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
+                       const float *scale_shift, const int32_t *status, const int32_t *segments,
+                       int32_t max_windows, int32_t *flag, void *stream)
+{
+    if (!ctx || !events || !flag) return PB2_EINVAL;
+    if (!ctx->unsplit_set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "unsplit-read model not set");
+    DeviceGuard g(ctx->device);
+    return launch_unsplit(ctx, *events, n_reads, scale_shift, status, segments, max_windows, flag,
+                          (cudaStream_t)stream);
+}
+
+int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *hev, int64_t n,
+                            const float *scale_shift, const int32_t *status,
+                            const int32_t *segments, int32_t max_windows, int32_t *flag)
+{
+    if (!ctx || !hev || !flag) return PB2_EINVAL;
+    if (!ctx->unsplit_set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "unsplit-read model not set");
+    if (n <= 0) return PB2_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->host_stream;
+    const size_t E = (size_t)hev->n_events_total;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align(bytes + 16); return o; };
+    const size_t o_eo = take(sizeof(int64_t) * (n + 1)), o_st = take(sizeof(int64_t) * E);
+    const size_t o_mn = take(sizeof(float) * E), o_mv = take(sizeof(int32_t) * E);
+    const size_t o_ps = take(sizeof(double) * E), o_rt = take(sizeof(double) * n);
+    const size_t o_ss = take(sizeof(float) * 2 * n), o_stat = take(sizeof(int32_t) * n);
+    const size_t o_seg = take(sizeof(int32_t) * 2 * PB2_MAX_STATES * n), o_fl = take(sizeof(int32_t) * n);
+    char *base = (char *)ws_get(ctx, ctx->ws_unsplit_host, off);
+    if (!base) return PB2_ENOMEM;
+#define PB_H2D(o, src, bytes) PB_CUDA(ctx, cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
+    PB_H2D(o_eo, hev->event_offsets, sizeof(int64_t) * (n + 1));
+    if (E) {
+        PB_H2D(o_st, hev->start, sizeof(int64_t) * E);
+        PB_H2D(o_mn, hev->mean, sizeof(float) * E);
+        PB_H2D(o_mv, hev->move, sizeof(int32_t) * E);
+        PB_H2D(o_ps, hev->p_model_state, sizeof(double) * E);
+    }
+    PB_H2D(o_rt, hev->sampling_rate, sizeof(double) * n);
+    PB_H2D(o_ss, scale_shift, sizeof(float) * 2 * n);
+    PB_H2D(o_stat, status, sizeof(int32_t) * n);
+    PB_H2D(o_seg, segments, sizeof(int32_t) * 2 * PB2_MAX_STATES * n);
+#undef PB_H2D
+    pb2_event_tables dev = *hev;
+    dev.event_offsets = (const int64_t *)(base + o_eo);
+    dev.start = (const int64_t *)(base + o_st);
+    dev.mean = (const float *)(base + o_mn);
+    dev.move = (const int32_t *)(base + o_mv);
+    dev.p_model_state = (const double *)(base + o_ps);
+    dev.sampling_rate = (const double *)(base + o_rt);
+    int rc = launch_unsplit(ctx, dev, n, (const float *)(base + o_ss), (const int32_t *)(base + o_stat),
+                            (const int32_t *)(base + o_seg), max_windows, (int32_t *)(base + o_fl), st);
+    if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpyAsync(flag, base + o_fl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
 }
 
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,

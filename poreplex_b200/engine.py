@@ -147,6 +147,23 @@ class SignalEngine:
             self._check(self.lib.pb2_set_polya(self.handle, C.byref(pp), st.index_of('polya-tail')))
             self.polya_ready = True
 
+        # --- unsplit-read (chimera) model + switches (worker_persistence.py:63,
+        #     rna-r941.cfg:17-27,103-151)
+        self.unsplit_ready = False
+        if 'unsplit_read_detection_model' in config and 'unsplit_read_detection' in config:
+            ut = P.HmmTables(config['unsplit_read_detection_model'])
+            uc = config['unsplit_read_detection']
+            self.unsplit_cfg = uc
+            up = N.UnsplitParams(*(float(uc[k]) for k in (
+                'window_size', 'window_step', 'strict_duration', 'strict_full_length',
+                'strict_dna_length', 'loosen_full_length', 'loosen_dna_length',
+                'basecount_quality_limit', 'subread_basecount_limit', 'subread_baseratio_limit')))
+            uh = _hmm_struct(ut)
+            self._check(self.lib.pb2_set_unsplit(self.handle, C.byref(uh), C.byref(up),
+                                                 ut.index_of('adapter'), ut.index_of('leader-high'),
+                                                 ut.index_of('leader-low')))
+            self.unsplit_ready = True
+
         # --- demultiplexer: BarcodeDemultiplexer (barcoding.py:34-70)
         if barcoding is None:
             barcoding = bool(config.get('barcoding', True))
@@ -285,6 +302,47 @@ class SignalEngine:
             | (N.FLAG_POLYA if polya else 0)
         self._check(self.lib.pb2_analyze_host(self.handle, C.byref(b), C.byref(r), flags))
         return out
+
+    def detect_unsplit_host(self, tables, sampling_rate, scale_shift, status, segments):
+        """SignalAnalysis.detect_unsplit_read for a batch (host buffers).
+
+        ``tables``: per read either None or a dict with 'start', 'mean', 'move',
+        'p_model_state' arrays (the reference's event table columns).  Returns int32 flags:
+        1 unsplit, 0 not, < 0 internal error for that read."""
+        if not self.unsplit_ready:
+            raise ValueError('config has no unsplit-read detection model')
+        n = len(tables)
+        counts = np.array([0 if t is None else len(t['start']) for t in tables], np.int64)
+        offs = np.zeros(n + 1, np.int64)
+        offs[1:] = np.cumsum(counts)
+        total = int(offs[-1])
+        cat = lambda key, dt: (np.concatenate([np.asarray(t[key]).astype(dt) for t in tables
+                                               if t is not None and len(t['start'])])
+                               if total else np.zeros(0, dt))
+        start, mean = cat('start', np.int64), cat('mean', np.float32)
+        move, pstate = cat('move', np.int32), cat('p_model_state', np.float64)
+        rate = np.ascontiguousarray(sampling_rate, np.float64)
+        scale_shift = np.ascontiguousarray(scale_shift, np.float32)
+        status = np.ascontiguousarray(status, np.int32)
+        segments = np.ascontiguousarray(segments, np.int32)
+        # windows needed: range(payload_start, last_end, int(window_step * rate))
+        maxw = 1
+        ia = self.adapter_state
+        for i, t in enumerate(tables):
+            if t is None or not len(t['start']):
+                continue
+            step = int(self.unsplit_cfg['window_step'] * rate[i])
+            payload = (int(segments[i, ia, 1]) + 1) * self.stride
+            span = int(t['start'][-1]) + 1 - payload
+            if step > 0 and span > 0:
+                maxw = max(maxw, -(-span // step))
+        ev = N.EventTables(total, _np_ptr(offs), _np_ptr(start), _np_ptr(mean), _np_ptr(move),
+                           _np_ptr(pstate), _np_ptr(rate))
+        flag = np.zeros(n, np.int32)
+        self._check(self.lib.pb2_detect_unsplit_host(
+            self.handle, C.byref(ev), n, _np_ptr(scale_shift), _np_ptr(status), _np_ptr(segments),
+            int(maxw), _np_ptr(flag)))
+        return flag
 
     # ----------------------------------------------------- device-resident API
     def _batch_from_tensors(self, raw, offsets, lengths, rng, digitisation, offset,

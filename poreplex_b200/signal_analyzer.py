@@ -10,8 +10,8 @@ TensorFlow / pomegranate calls.  ``pipeline.py:204`` can call this ``process_bat
 unchanged.
 
 Switch coverage this round: ``trim_adapter`` (a no-op in the reference at this commit,
-SURVEY.md F6 -- reproduced), ``barcoding`` and ``measure_polya``.
-``filter_unsplit_reads`` and the dump switches raise ``NotImplementedError`` when the
+SURVEY.md F6 -- reproduced), ``barcoding``, ``measure_polya`` and
+``filter_unsplit_reads``.  The dump switches and on-the-fly albacore raise ``NotImplementedError`` when the
 analyzer is built, which ``process_batch`` reports as a batch-level failure exactly like
 any other unhandled exception -- never a silent CPU fallback.
 """
@@ -160,7 +160,6 @@ class NanoporeRead:
 class SignalAnalyzer:
 
     UNSUPPORTED_SWITCHES = {
-        'filter_unsplit_reads': 'chimera filter (--filter-chimera)',
         'dump_adapter_signals': 'adapter signal dumps',
         'dump_basecalls': 'basecalled event dumps',
         'albacore_onthefly': 'on-the-fly albacore basecalling',
@@ -242,23 +241,43 @@ class SignalAnalyzer:
                 else:
                     npread.set_scaling_params(np.array(out['scale_shift'][i], dtype=np.float32))
 
-        # STAGE C: per-read bookkeeping in input order (signal_analyzer.py:111-124)
+        # STAGE C: per-read bookkeeping in input order (signal_analyzer.py:111-124); the
+        # chimera filter runs as one batched GPU call between its two halves
+        for phase in (1, 2):
+            for siganal in nextprocs:
+                try:
+                    if not siganal.is_stopped() and not siganal.failed:
+                        siganal.process(phase)
+                except Exception as exc:
+                    f5file = siganal.npread.filename
+                    read_id = siganal.npread.read_id
+                    error = self.pack_unhandled_exception(f5file, read_id, exc, sys.exc_info())
+                    siganal.set_error(error)
+                    siganal.failed = True
+            if phase == 1 and self.config['filter_unsplit_reads']:
+                self.detect_unsplit_reads([s for s in nextprocs
+                                           if not s.is_stopped() and not s.failed])
         for siganal in nextprocs:
-            try:
-                if not siganal.is_stopped():
-                    siganal.process()
-            except Exception as exc:
-                f5file = siganal.npread.filename
-                read_id = siganal.npread.read_id
-                error = self.pack_unhandled_exception(f5file, read_id, exc, sys.exc_info())
-                siganal.set_error(error)
-            finally:
-                siganal.clear_cache()
+            siganal.clear_cache()
 
         # STAGE E
         for npread in loaded:
             results.append(npread.report())
         return results
+
+    def detect_unsplit_reads(self, analyses):
+        """Batched SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443)."""
+        if not analyses:
+            return
+        eng = self.engine
+        flags = eng.detect_unsplit_host(
+            [a.events for a in analyses],
+            np.array([a.npread.sampling_rate for a in analyses], np.float64),
+            np.array([a.npread._gpu['scale_shift'] for a in analyses], np.float32),
+            np.zeros(len(analyses), np.int32),
+            np.array([a.npread._gpu['segments'] for a in analyses], np.int32))
+        for a, f in zip(analyses, flags):
+            a.unsplit_flag = int(f)
 
     def pack_unhandled_exception(self, f5filename, read_id, exc, excinfo):
         exc_type, exc_obj, exc_tb = excinfo
@@ -284,6 +303,9 @@ class SignalAnalysis:
         self.npread = npread
         self.config = analyzer.config
         self.analyzer = analyzer
+        self.failed = False          # an unhandled exception ended this read
+        self.events = None
+        self.unsplit_flag = 0
 
     def set_error(self, error):
         self.npread.set_error(error['status'], error['error_message'])
@@ -294,47 +316,56 @@ class SignalAnalysis:
     def clear_cache(self):
         self.npread.close()
 
-    def process(self):
+    def process(self, phase=None):
         """Consume the GPU results of this read in the reference's order of checks
-        (signal_analyzer.py:230-286)."""
+        (signal_analyzer.py:230-286).  Phase 1 = everything up to load_events, phase 2 =
+        trim / chimera verdict / minimum length; ``phase=None`` runs both."""
         npread = self.npread
         gpu = npread._gpu
         eng = self.analyzer.engine
         try:
-            status = STATUS_NAMES[int(gpu['status'])]
-            if status == 'unknown_error':
-                raise Exception('Viterbi decoding found no path for this read.')
-            segments = self.detect_segments()
-            npread.segments = segments
-            if 'adapter' not in segments:
-                raise SignalAnalysisError('adapter_not_detected')
+            if phase in (None, 1):
+                status = STATUS_NAMES[int(gpu['status'])]
+                if status == 'unknown_error':
+                    raise Exception('Viterbi decoding found no path for this read.')
+                segments = self.detect_segments()
+                npread.segments = segments
+                if 'adapter' not in segments:
+                    raise SignalAnalysisError('adapter_not_detected')
 
-            if self.config['barcoding'] and int(gpu['barcode_score']) >= 0:
-                bc = int(gpu['barcode'])
-                npread.set_barcode(None if bc < 0 else bc, int(gpu['barcode_guess']),
-                                   int(gpu['barcode_score']))
+                if self.config['barcoding'] and int(gpu['barcode_score']) >= 0:
+                    bc = int(gpu['barcode'])
+                    npread.set_barcode(None if bc < 0 else bc, int(gpu['barcode_guess']),
+                                       int(gpu['barcode_score']))
 
-            if self.config['measure_polya']:         # signal_analyzer.py:250-256
-                info = polya_to_dict(gpu['polya'], npread.sampling_rate)
-                if info is not None:
-                    npread.set_polya_tail(info)
+                if self.config['measure_polya']:         # signal_analyzer.py:250-256
+                    info = polya_to_dict(gpu['polya'], npread.sampling_rate)
+                    if info is not None:
+                        npread.set_polya_tail(info)
 
-            events = self.load_events()
+                self.events = self.load_events()
 
-            if self.config['trim_adapter']:
-                self.trim_adapter(events, segments, eng.stride)
+            if phase in (None, 2):
+                if self.config['trim_adapter']:
+                    self.trim_adapter(self.events, npread.segments, eng.stride)
 
-            if npread.sequence is not None:
-                readlength = len(npread.sequence[0]) - npread.sequence[2]
-                if readlength < self.config['minimum_sequence_length']:
-                    raise SignalAnalysisError('sequence_too_short')
+                if self.config['filter_unsplit_reads']:
+                    if self.unsplit_flag < 0:
+                        raise Exception('unsplit-read detection failed on the device '
+                                        '(code {})'.format(self.unsplit_flag))
+                    if self.unsplit_flag:
+                        raise SignalAnalysisError('unsplit_read')
+
+                if npread.sequence is not None:
+                    readlength = len(npread.sequence[0]) - npread.sequence[2]
+                    if readlength < self.config['minimum_sequence_length']:
+                        raise SignalAnalysisError('sequence_too_short')
+                npread.set_label('pass')
 
         except SignalAnalysisError as exc:
             outname = 'artifact' if exc.args[0] in ('unsplit_read',) else 'fail'
             npread.set_status(exc.args[0], stop=True)
             npread.set_label(outname)
-        else:
-            npread.set_label('pass')
 
     def detect_segments(self):
         """{state name: (first, last)} from the kernel's baked-order table
@@ -345,7 +376,8 @@ class SignalAnalysis:
                 for s in range(len(names)) if seg[s, 0] >= 0}
 
     def load_events(self):
-        events = self.npread.load_fast5_events(want_events=False)
+        events = self.npread.load_fast5_events(
+            want_events=bool(self.config['filter_unsplit_reads']))
         if self.npread.scaling_params is None:
             raise Exception('Signal scaling is not available yet.')
         return events

@@ -37,6 +37,8 @@ SETS = {
     # name: (preset variant, read length, reads, seed)
     'stock16k': ('stock', 16000, 40, 101),
     'short4k': ('bench-short', 4000, 88, 202),
+    # long reads, half of them with a second leader+adapter+poly(A) planted in the transcript
+    'chimera40k': ('stock', 40000, 18, 303),
 }
 
 
@@ -66,6 +68,8 @@ def build_inputs(variant, L, n, seed):
         spec.adapter_pooled = (90, 140)      # straddles the bench-short minimum of 100
     rd = synth.to_numpy(synth.generate_reads(n, spec, preset, seed=seed))
     rng = np.random.default_rng(seed)
+    if L >= 30000:
+        plant_chimeras(rd, np.random.default_rng(seed + 1))
     lengths = np.full(n, L, np.int64)
     lengths[0] = 5000 if variant == 'stock' else 700          # scaler_signal_too_short
     lengths[1] = L - 7                                        # L % 15 != 0
@@ -77,6 +81,22 @@ def build_inputs(variant, L, n, seed):
     short = fake_fast5.synth_basecall(int(lengths[3]), rng, p_move=0.0)
     basecalls[3] = short
     return preset, rd, read_ids, basecalls
+
+
+def plant_chimeras(rd, rng, frac=0.6):
+    """Copy a read's own leader+adapter+poly(A) block into its transcript (every other
+    planted block is cut short so that it stays below the duration cut-offs)."""
+    n, L = rd['raw'].shape
+    for i in range(4, n):
+        if rng.random() >= frac:
+            continue
+        b = rd['planted']['bounds'][i]
+        blk0, blk1 = int(b[0]) * 15, int(b[4]) * 15
+        blk = rd['raw'][i, blk0:blk1].copy()
+        if rng.random() < 0.35:
+            blk = blk[:len(blk) // 3]
+        pos = int(rng.integers(blk1 + 1500, L - len(blk) - 3000))
+        rd['raw'][i, pos:pos + len(blk)] = blk
 
 
 def run_reference(preset, variant, rd, read_ids, basecalls, **switches):

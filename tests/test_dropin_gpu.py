@@ -36,7 +36,7 @@ def _serve(name):
     return z, doc, tmp
 
 
-@pytest.mark.parametrize('name', ['stock16k', 'short4k'])
+@pytest.mark.parametrize('name', ['stock16k', 'short4k', 'chimera40k'])
 def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_stock, eng_short):
     import torch
     assert torch.cuda.is_available()
@@ -47,7 +47,11 @@ def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_s
     for key, sw in (('results_trim_only', dict(trim_adapter=True)),
                     ('results_trim_barcoding', dict(trim_adapter=True, barcoding=True)),
                     ('results_trim_barcoding_polya', dict(trim_adapter=True, barcoding=True,
-                                                          measure_polya=True))):
+                                                          measure_polya=True)),
+                    ('results_all_switches', dict(trim_adapter=True, barcoding=True,
+                                                  measure_polya=True, filter_unsplit_reads=True))):
+        if key not in doc:
+            continue
         got = sa.process_batch(0, reads, _config(p, tmp, **sw))
         assert not isinstance(got, tuple), got
         want = doc[key]
@@ -63,7 +67,7 @@ def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_s
 def test_unbuilt_switches_fail_loudly(preset, eng_stock):
     from poreplex_b200 import signal_analyzer as sa
     z, doc, tmp = _serve('stock16k')
-    for sw in ('filter_unsplit_reads', 'dump_adapter_signals'):
+    for sw in ('dump_basecalls', 'dump_adapter_signals'):
         res = sa.process_batch(0, [tuple(r) for r in doc['reads']], _config(preset, tmp, **{sw: True}))
         assert isinstance(res, tuple) and res[0] == -1 and 'NotImplementedError' in res[1]
 

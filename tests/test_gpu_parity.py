@@ -238,3 +238,44 @@ def test_polya_kernel_matches_host_core(eng_stock, orc_stock, preset):
             assert want == got, (L, i, want, got)
             found += got is not None
     assert found > 150
+
+
+def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
+    """k_unsplit_windows / k_unsplit_decide against oracle/unsplit_restated.py (which the CPU
+    suite ties to the reference's detect_unsplit_read) on the chimera fixture's event tables."""
+    import tempfile
+    from golden_util import load_golden, golden_reads, golden_basecalls, pack_golden
+    from oracle import refshim, fake_fast5, unsplit_restated as UR
+    from poreplex_b200.fast5_source import Fast5Source
+    refshim.install_fake_h5py()
+    refshim.clear_fast5()
+    z, doc = load_golden('chimera40k')
+    ids = [str(s) for s in z['read_ids']]
+    tmp = tempfile.mkdtemp()
+    fake_fast5.build_fast5(tmp, 'reads.fast5', golden_reads(z), ids, golden_basecalls(z))
+    raw, off, ln = pack_golden(z)
+    out = eng_stock.analyze_host(raw, off, ln, z['range'], z['digitisation'], z['offset'])
+    tables, rates = [], []
+    for i, rid in enumerate(ids):
+        src = Fast5Source(tmp + '/reads.fast5', rid)
+        bc = src.get_basecall(want_events=True) if out['status'][i] == 0 else None
+        tables.append(None if bc is None else bc['events'])
+        rates.append(src.sampling_rate)
+    status = np.where([t is None for t in tables], 10, out['status']).astype(np.int32)
+    flags = eng_stock.detect_unsplit_host(tables, np.array(rates), out['scale_shift'], status,
+                                          out['segments'])
+    ia = eng_stock.adapter_state
+    n_true = 0
+    for i, t in enumerate(tables):
+        if t is None:
+            assert flags[i] == 0
+            continue
+        scaled, pos, end = UR.derive_event_columns(t['start'], t['mean'], t['move'],
+                                                   out['scale_shift'][i, 0], out['scale_shift'][i, 1])
+        want = UR.detect_unsplit_read(
+            preset['unsplit_read_detection'], lambda x: orc_stock.viterbi(x, 'unsplit')[1],
+            orc_stock.unsplit_names, np.asarray(t['start'], np.int64), end, scaled, pos,
+            np.asarray(t['p_model_state'], np.float64), int(out['segments'][i, ia, 1]), rates[i])
+        assert int(flags[i]) == int(want), (i, flags[i], want)
+        n_true += want
+    assert n_true >= 4

@@ -230,7 +230,7 @@ def test_lstm_networks_against_float64(orc_stock):
     assert abs(pr.sum() - 1) < 1e-5
 
 
-@pytest.mark.parametrize('name', ['stock16k', 'short4k'])
+@pytest.mark.parametrize('name', ['stock16k', 'short4k', 'chimera40k'])
 def test_oracle_pipeline_reproduces_reference_run(oracle_mod, name):
     """The standalone oracle pipeline (orc_process_batch) must reproduce what was captured
     from INSIDE the reference's own Python when it ran over the same reads: scaling
@@ -270,4 +270,58 @@ def test_oracle_pipeline_reproduces_reference_run(oracle_mod, name):
             if bc is not None:
                 assert ref['barcode_guess'] == res['guess'][i] and ref['barcode_score'] == res['phred'][i]
             n_win += 1
-    assert n_seg > 30 and n_win > 15
+    assert n_seg >= 15 and n_win >= 15
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree not present')
+def test_unsplit_restatement_matches_reference(oracle_mod):
+    """oracle/unsplit_restated.py vs SignalAnalysis.load_events + detect_unsplit_read running
+    verbatim on the chimera fixture (event tables served through the fake FAST5)."""
+    import tempfile
+    from golden_util import golden_reads, golden_basecalls
+    from oracle import refshim, fake_fast5, unsplit_restated as UR
+    sa, sl, _, _, _ = refshim.reference_modules()
+    from poreplex import worker_persistence as wp
+    z, doc = load_golden('chimera40k')
+    orc = oracle_mod.default_oracle()
+    preset = orc.preset
+    raw, off, ln = pack_golden(z)
+    res = orc.process_batch(raw, off, ln, z['range'] / z['digitisation'], z['offset'])
+    ids = [str(s) for s in z['read_ids']]
+    tmp = tempfile.mkdtemp()
+    refshim.clear_fast5()
+    fake_fast5.build_fast5(tmp, 'reads.fast5', golden_reads(z), ids, golden_basecalls(z))
+
+    class Analyzer:
+        pass
+    an = Analyzer()
+    an.unsplitmodel = wp.load_segmentation_model(preset['unsplit_read_detection_model'])
+    an.config = dict(preset, albacore_onthefly=False)
+    by_id = {r['read_id']: r for r in doc['results_all_switches'] if 'read_id' in r}
+    n_true = n_false = 0
+    for i, rid in enumerate(ids):
+        if by_id[rid]['status'] not in ('okay', 'unsplit_read'):
+            continue
+        npread = sl.NanoporeRead('reads.fast5', tmp, rid)
+        npread.set_scaling_params(np.array([res['scale'][i], res['shift'][i]], np.float32))
+        s = sa.SignalAnalysis(npread, an)
+        events = s.load_events()
+        seg = {orc.seg_names[k]: (int(res['seg'][i][k][0]), int(res['seg'][i][k][1]))
+               for k in range(6) if res['seg'][i][k][0] >= 0}
+        want = bool(s.detect_unsplit_read(events, seg, 15))
+        scaled, pos, end = UR.derive_event_columns(events['start'].values, events['mean'].values,
+                                                   events['move'].values, res['scale'][i],
+                                                   res['shift'][i])
+        assert np.array_equal(scaled.view(np.uint32),
+                              np.asarray(events['scaled_mean'].values, np.float32).view(np.uint32))
+        assert np.array_equal(pos, events['pos'].values) and np.array_equal(end, events['end'].values)
+        got = UR.detect_unsplit_read(
+            preset['unsplit_read_detection'], lambda x: orc.viterbi(x, 'unsplit')[1],
+            orc.unsplit_names, events['start'].values.astype(np.int64), end, scaled, pos,
+            events['p_model_state'].values.astype(np.float64), seg['adapter'][1],
+            npread.sampling_rate)
+        assert want == got == (by_id[rid]['status'] == 'unsplit_read')
+        n_true += want
+        n_false += not want
+        npread.close()
+    assert n_true >= 4 and n_false >= 6
