@@ -2,6 +2,7 @@
 // context life cycle, parameter upload, stage entry points and the whole-path
 // pipeline (device-resident and host-buffer variants).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -169,6 +170,8 @@ void pb2_destroy(pb2_context *ctx)
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     delete ctx;
 }
 
@@ -551,7 +554,7 @@ int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_resul
     return PB2_OK;
 }
 
-int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr, uint32_t flags)
+static int analyze_host_single(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr, uint32_t flags)
 {
     int rc = check_batch(ctx, hb);
     if (rc) return rc;
@@ -643,6 +646,167 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
 #undef PB_D2H
     PB_CUDA(ctx, cudaStreamSynchronize(st));
     return PB2_OK;
+}
+
+
+// Host-buffer path for large batches: the batch is cut into chunks of reads and run as a
+// three-stage pipeline on three streams -- H2D of chunk c+1 and D2H of chunk c-1 overlap
+// the kernels of chunk c (two device arenas, events for hand-over).  With pinned host
+// buffers the copies disappear behind the compute.
+static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr,
+                                  uint32_t flags, const std::vector<int64_t> &bounds)
+{
+    DeviceGuard g(ctx->device);
+    const int n_bins = PB2_N_LABEL * PB2_N_BARCODE_SLOTS * PB2_N_STATUS;
+    const int nchunks = (int)bounds.size() - 1;
+    if (!ctx->copy_in) PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    cudaStream_t compute = ctx->host_stream;
+    int64_t max_reads = 0, max_span = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t c0 = bounds[c], c1 = bounds[c + 1];
+        const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - hb->raw_offsets[c0];
+        if (c1 - c0 > max_reads) max_reads = c1 - c0;
+        if (span > max_span) max_span = span;
+    }
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t m = (size_t)max_reads;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align(bytes); return o; };
+    const size_t o_raw = take(sizeof(int16_t) * (size_t)max_span + 32);
+    const size_t o_off = take(8 * m), o_len = take(8 * m), o_rng = take(8 * m), o_dig = take(8 * m);
+    const size_t o_ofs = take(8 * m), o_status = take(4 * m), o_label = take(4 * m);
+    const size_t o_ss = take(8 * m), o_seg = take(4 * 2 * PB2_MAX_STATES * m);
+    const size_t o_bc = take(4 * m), o_gs = take(4 * m), o_sc = take(4 * m);
+    const size_t o_pr = take(4 * PB2_MAX_CLASSES * m), o_cnt = take(8 * n_bins);
+    const bool want_polya = (flags & PB2_FLAG_POLYA) && hr->polya;
+    const size_t o_polya = take(want_polya ? sizeof(pb2_polya_result) * m : 16);
+    if ((flags & PB2_FLAG_POLYA) && !want_polya) flags &= ~PB2_FLAG_POLYA;
+    const size_t arena_bytes = off;
+    char *base = (char *)ws_get(ctx, ctx->ws_batch, 2 * arena_bytes);
+    if (!base) return PB2_ENOMEM;
+    int64_t *counts_host = nullptr;
+    PB_CUDA(ctx, cudaMallocHost(&counts_host, sizeof(int64_t) * n_bins * nchunks));
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming);
+    }
+    std::vector<int64_t> rebased[2];
+    int rc = PB2_OK;
+    auto run = [&]() -> int {
+        for (int c = 0; c < nchunks; c++) {
+            const int a = c & 1;
+            char *A = base + (size_t)a * arena_bytes;
+            const int64_t c0 = bounds[c], c1 = bounds[c + 1], nc = c1 - c0;
+            const int64_t roff0 = hb->raw_offsets[c0];
+            const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - roff0;
+            if (c >= 2) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_d2h[a], 0));
+            rebased[a].resize((size_t)nc);
+            int64_t max_len = 0;
+            for (int64_t i = 0; i < nc; i++) {
+                rebased[a][i] = hb->raw_offsets[c0 + i] - roff0;
+                if (hb->raw_lengths[c0 + i] > max_len) max_len = hb->raw_lengths[c0 + i];
+            }
+            cudaStream_t ci = ctx->copy_in;
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_raw, hb->raw + roff0, sizeof(int16_t) * (size_t)span, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_off, rebased[a].data(), 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_len, hb->raw_lengths + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_rng, hb->range + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_dig, hb->digitisation + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_ofs, hb->offset + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaEventRecord(ev_h2d[a], ci));
+
+            pb2_batch db = {};
+            db.n_reads = nc; db.n_raw_total = span; db.max_raw_length = max_len;
+            db.raw = (const int16_t *)(A + o_raw);
+            db.raw_offsets = (const int64_t *)(A + o_off);
+            db.raw_lengths = (const int64_t *)(A + o_len);
+            db.range = (const double *)(A + o_rng);
+            db.digitisation = (const double *)(A + o_dig);
+            db.offset = (const double *)(A + o_ofs);
+            pb2_results dr = {};
+            dr.status = (int32_t *)(A + o_status); dr.label = (int32_t *)(A + o_label);
+            dr.scale_shift = (float *)(A + o_ss); dr.segments = (int32_t *)(A + o_seg);
+            dr.barcode = (int32_t *)(A + o_bc); dr.barcode_guess = (int32_t *)(A + o_gs);
+            dr.barcode_score = (int32_t *)(A + o_sc); dr.class_probs = (float *)(A + o_pr);
+            dr.counts = (int64_t *)(A + o_cnt);
+            dr.polya = want_polya ? (pb2_polya_result *)(A + o_polya) : nullptr;
+            PB_CUDA(ctx, cudaStreamWaitEvent(compute, ev_h2d[a], 0));
+            if (!(flags & PB2_FLAG_BARCODING)) {
+                PB_CUDA(ctx, cudaMemsetAsync(dr.barcode, 0xFF, 4 * (size_t)nc, compute));
+                PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_guess, 0xFF, 4 * (size_t)nc, compute));
+                PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_score, 0xFF, 4 * (size_t)nc, compute));
+                PB_CUDA(ctx, cudaMemsetAsync(dr.class_probs, 0, 4 * PB2_MAX_CLASSES * (size_t)nc, compute));
+            }
+            int r2 = pb2_analyze_device(ctx, &db, &dr, flags & ~PB2_FLAG_KEEP_POOLED, compute);
+            if (r2) return r2;
+            PB_CUDA(ctx, cudaEventRecord(ev_comp[a], compute));
+
+            cudaStream_t co = ctx->copy_out;
+            PB_CUDA(ctx, cudaStreamWaitEvent(co, ev_comp[a], 0));
+#define PB_OUT(field, devp, bytes_per)                                                         \
+            if (hr->field) PB_CUDA(ctx, cudaMemcpyAsync((char *)hr->field + (size_t)c0 * (bytes_per), devp, \
+                                                        (size_t)nc * (bytes_per), cudaMemcpyDeviceToHost, co))
+            PB_OUT(status, dr.status, 4);
+            PB_OUT(label, dr.label, 4);
+            PB_OUT(scale_shift, dr.scale_shift, 8);
+            PB_OUT(segments, dr.segments, 4 * 2 * PB2_MAX_STATES);
+            PB_OUT(barcode, dr.barcode, 4);
+            PB_OUT(barcode_guess, dr.barcode_guess, 4);
+            PB_OUT(barcode_score, dr.barcode_score, 4);
+            PB_OUT(class_probs, dr.class_probs, 4 * PB2_MAX_CLASSES);
+            if (want_polya) PB_OUT(polya, dr.polya, sizeof(pb2_polya_result));
+#undef PB_OUT
+            PB_CUDA(ctx, cudaMemcpyAsync(counts_host + (size_t)c * n_bins, dr.counts, 8 * n_bins,
+                                         cudaMemcpyDeviceToHost, co));
+            PB_CUDA(ctx, cudaEventRecord(ev_d2h[a], co));
+        }
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+        PB_CUDA(ctx, cudaStreamSynchronize(compute));
+        return PB2_OK;
+    };
+    rc = run();
+    if (rc == PB2_OK && hr->counts) {
+        for (int i = 0; i < n_bins; i++) {
+            int64_t t = 0;
+            for (int c = 0; c < nchunks; c++) t += counts_host[(size_t)c * n_bins + i];
+            hr->counts[i] = t;
+        }
+    }
+    if (rc != PB2_OK) cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_d2h[i]); }
+    cudaFreeHost(counts_host);
+    return rc;
+}
+
+int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr, uint32_t flags)
+{
+    int rc = check_batch(ctx, hb);
+    if (rc) return rc;
+    if (!hr) return PB2_EINVAL;
+    // chunking: ~256 MiB of raw samples per chunk, at least 4 chunks, never for small batches
+    const int64_t n = hb->n_reads;
+    int64_t kChunkElems = (int64_t)128 << 20;
+    int64_t min_reads = 32768;
+    if (const char *env = getenv("POREPLEX_B200_HOST_CHUNK_ELEMS")) {     // tests / tuning
+        const long long v = atoll(env);
+        if (v > 0) { kChunkElems = v; min_reads = 2048; }
+    }
+    const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
+    if (n < min_reads || keep || hb->n_raw_total < 2 * kChunkElems)
+        return analyze_host_single(ctx, hb, hr, flags);
+    std::vector<int64_t> bounds;
+    bounds.push_back(0);
+    int64_t start = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t span = hb->raw_offsets[i] + hb->raw_lengths[i] - hb->raw_offsets[start];
+        if (span >= kChunkElems && i + 1 - start >= 1024) { bounds.push_back(i + 1); start = i + 1; }
+    }
+    if (bounds.back() != n) bounds.push_back(n);
+    if (bounds.size() < 3) return analyze_host_single(ctx, hb, hr, flags);
+    return analyze_host_pipelined(ctx, hb, hr, flags, bounds);
 }
 
 }  // extern "C"

@@ -97,6 +97,7 @@ struct pb2_context {
         ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
 };
 
 namespace pb {

@@ -279,3 +279,28 @@ def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
         assert int(flags[i]) == int(want), (i, flags[i], want)
         n_true += want
     assert n_true >= 4
+
+
+def test_pipelined_host_path_equals_single_pass(eng_short, orc_short, preset_short, monkeypatch):
+    """pb2_analyze_host cuts big batches into chunks and overlaps H2D / kernels / D2H on three
+    streams; results must equal the single-pass path read for read (and the oracle on a
+    sample), including poly(A) records and the summed counts."""
+    rd = _reads(preset_short, 6000, 4000, seed=41, frac_no_adapter=0.03, frac_qc_fail=0.03)
+    raw, off, ln = _dense_batch(rd)
+    args = (raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
+    single = eng_short.analyze_host(*args, polya=True)
+    monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(3_000_000))     # -> 8 chunks
+    piped = eng_short.analyze_host(*args, polya=True)
+    monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
+    for k in single:
+        a, b = single[k], piped[k]
+        if a.dtype.fields:
+            assert a.tobytes() == b.tobytes(), k
+        elif a.dtype.kind == 'f':
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
+        else:
+            assert np.array_equal(a, b), k
+    assert piped['counts'].sum() == 6000
+    ref = _oracle_batch(orc_short, raw[:400 * 4000], off[:400], ln[:400],
+                        {k: rd[k][:400] for k in ('range', 'digitisation', 'offset')})
+    _compare({k: v[:400] for k, v in piped.items() if k not in ('counts', 'polya')}, ref)
