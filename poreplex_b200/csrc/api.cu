@@ -786,23 +786,25 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     int rc = check_batch(ctx, hb);
     if (rc) return rc;
     if (!hr) return PB2_EINVAL;
-    // chunking: ~256 MiB of raw samples per chunk, at least 4 chunks, never for small batches
+    // chunking: a few large chunks (small ones lose to wave quantisation in the LSTM
+    // kernels): 4 by default, more only to keep a chunk under ~4 Gi samples
     const int64_t n = hb->n_reads;
-    int64_t kChunkElems = (int64_t)128 << 20;
-    int64_t min_reads = 32768;
+    int64_t min_elems = (int64_t)256 << 20;      // below this the copies are not worth hiding
+    int64_t min_reads = 65536;
+    int64_t nchunks = 4;
     if (const char *env = getenv("POREPLEX_B200_HOST_CHUNK_ELEMS")) {     // tests / tuning
         const long long v = atoll(env);
-        if (v > 0) { kChunkElems = v; min_reads = 2048; }
+        if (v > 0) { min_elems = v; min_reads = 2048; nchunks = (hb->n_raw_total + v - 1) / v; }
     }
+    while (hb->n_raw_total / nchunks > ((int64_t)4 << 30)) nchunks *= 2;
     const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
-    if (n < min_reads || keep || hb->n_raw_total < 2 * kChunkElems)
+    if (n < min_reads || keep || hb->n_raw_total < min_elems || nchunks < 2)
         return analyze_host_single(ctx, hb, hr, flags);
     std::vector<int64_t> bounds;
-    bounds.push_back(0);
-    int64_t start = 0;
-    for (int64_t i = 0; i < n; i++) {
-        const int64_t span = hb->raw_offsets[i] + hb->raw_lengths[i] - hb->raw_offsets[start];
-        if (span >= kChunkElems && i + 1 - start >= 1024) { bounds.push_back(i + 1); start = i + 1; }
+    for (int64_t c = 0; c <= nchunks; c++) {
+        int64_t b = (n * c) / nchunks;
+        if (c < nchunks) b -= b % 64;            // keep chunk starts tile aligned
+        if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
     }
     if (bounds.back() != n) bounds.push_back(n);
     if (bounds.size() < 3) return analyze_host_single(ctx, hb, hr, flags);
