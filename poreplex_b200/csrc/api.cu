@@ -696,6 +696,40 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
     std::vector<int64_t> rebased[2];
     int rc = PB2_OK;
     auto run = [&]() -> int {
+        // results of chunk c leave on the third stream.  Issued one chunk LATE: the caller's
+        // result buffers are usually pageable, which makes these copies block the host, and
+        // the next chunk's H2D and kernels must already be queued when that happens.
+        auto drain = [&](int c) -> int {
+            const int a = c & 1;
+            char *A = base + (size_t)a * arena_bytes;
+            const int64_t c0 = bounds[c], nc = bounds[c + 1] - c0;
+            pb2_results dr = {};
+            dr.status = (int32_t *)(A + o_status); dr.label = (int32_t *)(A + o_label);
+            dr.scale_shift = (float *)(A + o_ss); dr.segments = (int32_t *)(A + o_seg);
+            dr.barcode = (int32_t *)(A + o_bc); dr.barcode_guess = (int32_t *)(A + o_gs);
+            dr.barcode_score = (int32_t *)(A + o_sc); dr.class_probs = (float *)(A + o_pr);
+            dr.counts = (int64_t *)(A + o_cnt);
+            dr.polya = want_polya ? (pb2_polya_result *)(A + o_polya) : nullptr;
+            cudaStream_t co = ctx->copy_out;
+            PB_CUDA(ctx, cudaStreamWaitEvent(co, ev_comp[a], 0));
+#define PB_OUT(field, devp, bytes_per)                                                         \
+            if (hr->field) PB_CUDA(ctx, cudaMemcpyAsync((char *)hr->field + (size_t)c0 * (bytes_per), devp, \
+                                                        (size_t)nc * (bytes_per), cudaMemcpyDeviceToHost, co))
+            PB_OUT(status, dr.status, 4);
+            PB_OUT(label, dr.label, 4);
+            PB_OUT(scale_shift, dr.scale_shift, 8);
+            PB_OUT(segments, dr.segments, 4 * 2 * PB2_MAX_STATES);
+            PB_OUT(barcode, dr.barcode, 4);
+            PB_OUT(barcode_guess, dr.barcode_guess, 4);
+            PB_OUT(barcode_score, dr.barcode_score, 4);
+            PB_OUT(class_probs, dr.class_probs, 4 * PB2_MAX_CLASSES);
+            if (want_polya) PB_OUT(polya, dr.polya, sizeof(pb2_polya_result));
+#undef PB_OUT
+            PB_CUDA(ctx, cudaMemcpyAsync(counts_host + (size_t)c * n_bins, dr.counts, 8 * n_bins,
+                                         cudaMemcpyDeviceToHost, co));
+            PB_CUDA(ctx, cudaEventRecord(ev_d2h[a], co));
+            return PB2_OK;
+        };
         for (int c = 0; c < nchunks; c++) {
             const int a = c & 1;
             char *A = base + (size_t)a * arena_bytes;
@@ -744,25 +778,9 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             if (r2) return r2;
             PB_CUDA(ctx, cudaEventRecord(ev_comp[a], compute));
 
-            cudaStream_t co = ctx->copy_out;
-            PB_CUDA(ctx, cudaStreamWaitEvent(co, ev_comp[a], 0));
-#define PB_OUT(field, devp, bytes_per)                                                         \
-            if (hr->field) PB_CUDA(ctx, cudaMemcpyAsync((char *)hr->field + (size_t)c0 * (bytes_per), devp, \
-                                                        (size_t)nc * (bytes_per), cudaMemcpyDeviceToHost, co))
-            PB_OUT(status, dr.status, 4);
-            PB_OUT(label, dr.label, 4);
-            PB_OUT(scale_shift, dr.scale_shift, 8);
-            PB_OUT(segments, dr.segments, 4 * 2 * PB2_MAX_STATES);
-            PB_OUT(barcode, dr.barcode, 4);
-            PB_OUT(barcode_guess, dr.barcode_guess, 4);
-            PB_OUT(barcode_score, dr.barcode_score, 4);
-            PB_OUT(class_probs, dr.class_probs, 4 * PB2_MAX_CLASSES);
-            if (want_polya) PB_OUT(polya, dr.polya, sizeof(pb2_polya_result));
-#undef PB_OUT
-            PB_CUDA(ctx, cudaMemcpyAsync(counts_host + (size_t)c * n_bins, dr.counts, 8 * n_bins,
-                                         cudaMemcpyDeviceToHost, co));
-            PB_CUDA(ctx, cudaEventRecord(ev_d2h[a], co));
+            if (c >= 1) { int r3 = drain(c - 1); if (r3) return r3; }
         }
+        { int r3 = drain(nchunks - 1); if (r3) return r3; }
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
         PB_CUDA(ctx, cudaStreamSynchronize(compute));
         return PB2_OK;
