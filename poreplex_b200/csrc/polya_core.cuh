@@ -193,7 +193,7 @@ struct EventStream {
     int64_t w[2];
     // event emission
     uint64_t prev_pos; double prevS, prevQ;
-    int64_t pend_pos[2]; double pendS[2], pendQ[2]; int n_pend;
+    Event pend_ev[2]; int n_pend;          // only used by next()
     int64_t n_peaks;
     bool tail_emitted;
 
@@ -264,70 +264,81 @@ struct EventStream {
         ev.stdv = sqrtf(fmaxf(var, 0.0f));
         ev.end = (int64_t)pb::dadd((double)s, (double)ev.length);
     }
-    // next event in table order; false when the table is exhausted
+    PB_HD bool finished() const { return tail_emitted; }
+
+    // Advance by ONE detector index (or, after the last index, emit the closing event).
+    // Writes the 0..2 events completed by this step to out[] in table order and returns
+    // their count.  Stepping sample by sample keeps the 32 reads of a warp in lock step;
+    // the consumers below are written as "for every step, for every event" loops.
+    PB_HD int step(Event *out) {
+        if (det_i >= n) {
+            if (tail_emitted) return 0;
+            tail_emitted = true;
+            fill_to(n);
+            if (n_peaks == 0) {
+                // create_events with no peak: create_event(0, peaks[0] = 0)
+                make_event(0, 0.0, 0.0, 0, 0.0, 0.0, out[0]);
+            } else {
+                make_event(prev_pos, prevS, prevQ, (uint64_t)n, S[n & 63], Q[n & 63], out[0]);
+            }
+            return 1;
+        }
+        // short_long_peak_detector, one index (event_detection.c:124-201)
+        const int64_t i = det_i++;
+        fill_to(i + w[1] + 1);
+        int nout = 0;
+        for (int k = 0; k < 2; k++) {
+            Detector &D = d[k];
+            if (D.masked_to >= i) continue;
+            const float cur = tstat(i, w[k]);
+            if (D.peak_pos == -1) {
+                if (cur < D.peak_value) {
+                    D.peak_value = cur;
+                } else if (pb::fsub(cur, D.peak_value) > peak_height) {
+                    D.peak_value = cur;
+                    D.peak_pos = i;
+                    D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
+                }
+            } else {
+                if (cur > D.peak_value) {
+                    D.peak_value = cur;
+                    D.peak_pos = i;
+                    D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
+                }
+                if (k == 0 && D.peak_value > D.threshold) {
+                    d[1].masked_to = D.peak_pos + D.window;
+                    d[1].peak_pos = -1;
+                    d[1].peak_value = FLT_MAX;
+                    d[1].valid = 0;
+                }
+                if (pb::fsub(D.peak_value, cur) > peak_height && D.peak_value > D.threshold)
+                    D.valid = 1;
+                if (D.valid && (i - D.peak_pos) > D.window / 2) {
+                    make_event(prev_pos, prevS, prevQ, (uint64_t)D.peak_pos, D.snapS, D.snapQ,
+                               out[nout]);
+                    nout++;
+                    prev_pos = (uint64_t)D.peak_pos; prevS = D.snapS; prevQ = D.snapQ;
+                    n_peaks++;
+                    D.peak_pos = -1;
+                    D.peak_value = cur;
+                    D.valid = 0;
+                }
+            }
+        }
+        return nout;
+    }
+
+    // pull-style access (host tests): next event in table order, false when exhausted
     PB_HD bool next(Event &ev) {
         for (;;) {
             if (n_pend > 0) {
-                const int64_t p = pend_pos[0];
-                const double pS = pendS[0], pQ = pendQ[0];
-                pend_pos[0] = pend_pos[1]; pendS[0] = pendS[1]; pendQ[0] = pendQ[1];
+                ev = pend_ev[0];
+                pend_ev[0] = pend_ev[1];
                 n_pend--;
-                make_event(prev_pos, prevS, prevQ, (uint64_t)p, pS, pQ, ev);
-                prev_pos = (uint64_t)p; prevS = pS; prevQ = pQ;
                 return true;
             }
-            if (det_i >= n) {
-                if (tail_emitted) return false;
-                tail_emitted = true;
-                fill_to(n);
-                if (n_peaks == 0) {
-                    // create_events with no peak: create_event(0, peaks[0] = 0)
-                    make_event(0, 0.0, 0.0, 0, 0.0, 0.0, ev);
-                } else {
-                    make_event(prev_pos, prevS, prevQ, (uint64_t)n, S[n & 63], Q[n & 63], ev);
-                }
-                return true;
-            }
-            // short_long_peak_detector, one index (event_detection.c:124-201)
-            const int64_t i = det_i++;
-            fill_to(i + w[1] + 1);
-            for (int k = 0; k < 2; k++) {
-                Detector &D = d[k];
-                if (D.masked_to >= i) continue;
-                const float cur = tstat(i, w[k]);
-                if (D.peak_pos == -1) {
-                    if (cur < D.peak_value) {
-                        D.peak_value = cur;
-                    } else if (pb::fsub(cur, D.peak_value) > peak_height) {
-                        D.peak_value = cur;
-                        D.peak_pos = i;
-                        D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
-                    }
-                } else {
-                    if (cur > D.peak_value) {
-                        D.peak_value = cur;
-                        D.peak_pos = i;
-                        D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
-                    }
-                    if (k == 0 && D.peak_value > D.threshold) {
-                        d[1].masked_to = D.peak_pos + D.window;
-                        d[1].peak_pos = -1;
-                        d[1].peak_value = FLT_MAX;
-                        d[1].valid = 0;
-                    }
-                    if (pb::fsub(D.peak_value, cur) > peak_height && D.peak_value > D.threshold)
-                        D.valid = 1;
-                    if (D.valid && (i - D.peak_pos) > D.window / 2) {
-                        pend_pos[n_pend] = D.peak_pos;
-                        pendS[n_pend] = D.snapS; pendQ[n_pend] = D.snapQ;
-                        n_pend++;
-                        n_peaks++;
-                        D.peak_pos = -1;
-                        D.peak_value = cur;
-                        D.valid = 0;
-                    }
-                }
-            }
+            if (finished()) return false;
+            n_pend = step(pend_ev);
         }
     }
 };
@@ -349,7 +360,7 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
     float lo = P.cutoff_lo, hi = P.cutoff_hi;
     int ext_depth = 0;
     EventStream es;
-    Event ev;
+    Event evs[2];
 
     for (;;) {                                    // one iteration per __call__ (window)
         int64_t rough_end = rough_end_cur;
@@ -376,11 +387,15 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
                 float a_ml[64], a_len[64];
                 int na = 0;
                 es.begin(src, P);
-                while (es.next(ev)) {
-                    if ((int64_t)ev.start <= adapter_end + P.recal_max_dist &&
-                        ev.end > adapter_end && ev.stdv < P.recal_max_stdv) {
-                        if (na < 64) { a_ml[na] = pb::fmul(ev.mean, ev.length); a_len[na] = ev.length; }
-                        na++;
+                while (!es.finished()) {
+                    const int ne = es.step(evs);
+                    for (int q = 0; q < ne; q++) {
+                        const Event &ev = evs[q];
+                        if ((int64_t)ev.start <= adapter_end + P.recal_max_dist &&
+                            ev.end > adapter_end && ev.stdv < P.recal_max_stdv) {
+                            if (na < 64) { a_ml[na] = pb::fmul(ev.mean, ev.length); a_len[na] = ev.length; }
+                            na++;
+                        }
                     }
                 }
                 if (na == 0) return;
@@ -395,11 +410,18 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
                 // events[is_polya]['length'].sum() >= min_length
                 int64_t npol = 0;
                 es.begin(src, P);
-                while (es.next(ev)) npol += between_f32(ev.mean, lo, hi);
+                while (!es.finished()) {
+                    const int ne = es.step(evs);
+                    for (int q = 0; q < ne; q++) npol += between_f32(evs[q].mean, lo, hi);
+                }
                 PairwiseSum sl;
                 sl.begin(npol);
                 es.begin(src, P);
-                while (es.next(ev)) if (between_f32(ev.mean, lo, hi)) sl.push(ev.length);
+                while (!es.finished()) {
+                    const int ne = es.step(evs);
+                    for (int q = 0; q < ne; q++)
+                        if (between_f32(evs[q].mean, lo, hi)) sl.push(evs[q].length);
+                }
                 if (!(sl.total >= P.recal_min_length)) return;
                 recal_mode = false;
             }
@@ -411,7 +433,10 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
                 int64_t Sv = 0, minP = 0, minI = -1, minCnt = 0, Pfx = 0, cnt = 0;
                 es.begin(src, P);
                 int64_t j = 0;
-                while (es.next(ev)) {
+                while (!es.finished()) {
+                  const int ne = es.step(evs);
+                  for (int q = 0; q < ne; q++) {
+                    const Event &ev = evs[q];
                     const bool ip = between_f32(ev.mean, lo, hi);
                     const double L = (double)ev.length;
                     const double v = ip ? L : -L;
@@ -434,6 +459,7 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
                         if (val > best) { best = val; best_i = minI; best_j = j; best_npol = cnt - minCnt; }
                     }
                     j++;
+                  }
                 }
                 n_events = j;
             }
@@ -456,8 +482,12 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
             {
                 es.begin(src, P);
                 int64_t j = 0;
-                while (es.next(ev)) {
-                    if (j > best_j) break;
+                bool stop = false;
+                while (!es.finished() && !stop) {
+                  const int ne = es.step(evs);
+                  for (int q = 0; q < ne; q++) {
+                    const Event &ev = evs[q];
+                    if (j > best_j) { stop = true; break; }
                     if (j >= best_i) {
                         const bool ip = between_f32(ev.mean, lo, hi);
                         s_ml.push(pb::fmul(ev.mean, ev.length));
@@ -484,6 +514,7 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
                         prev_mean = ev.mean;
                     }
                     j++;
+                  }
                 }
             }
             if (!have_range) {
