@@ -20,7 +20,8 @@ k_polya(const PolyaParams P, const int16_t *__restrict__ raw,
         const double *__restrict__ range, const double *__restrict__ digitisation,
         const double *__restrict__ offset, const float *__restrict__ scale_shift,
         const int32_t *__restrict__ status, const int32_t *__restrict__ segments, int64_t n,
-        int adapter_state, int polya_state, PolyaResult *__restrict__ out)
+        int adapter_state, int polya_state, PolyaResult *__restrict__ out,
+        EventCacheSlot *__restrict__ cache, int cache_cap)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -39,8 +40,9 @@ k_polya(const PolyaParams P, const int16_t *__restrict__ raw,
         re = -1;
     }
     const double gain = pb::ddiv(range[r], digitisation[r]);
+    // event replay cache: slot k of read r at cache[k * n + r] (coalesced across the warp)
     polya_analyze(P, raw + raw_offsets[r], raw_lengths[r], gain, offset[r], scale_shift[2 * r],
-                  scale_shift[2 * r + 1], rb, re, R);
+                  scale_shift[2 * r + 1], rb, re, R, cache ? cache + r : nullptr, n, cache_cap);
 }
 
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
@@ -50,11 +52,18 @@ int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
     if (b.n_reads <= 0) return PB2_OK;
     PolyaParams P;
     memcpy(&P, &ctx->polya, sizeof P);
+    // replay cache: up to 192 events per read, bounded to ~3 GiB
+    int cap = 192;
+    while (cap > 0 && (size_t)cap * (size_t)b.n_reads * sizeof(EventCacheSlot) > ((size_t)3 << 30)) cap /= 2;
+    EventCacheSlot *cache = cap >= 16
+        ? (EventCacheSlot *)ws_get(ctx, ctx->ws_polya, (size_t)cap * (size_t)b.n_reads * sizeof(EventCacheSlot))
+        : nullptr;
+    if (!cache) { cap = 0; cudaGetLastError(); }
     PB_LAUNCH(ctx, K_POLYA, "k_polya", st,
         k_polya<<<(unsigned)((b.n_reads + POLYA_THREADS - 1) / POLYA_THREADS), POLYA_THREADS, 0, st>>>(
             P, b.raw, b.raw_offsets, b.raw_lengths, b.range, b.digitisation, b.offset, scale_shift,
             status, segments, b.n_reads, ctx->adapter_state, ctx->polya_state,
-            reinterpret_cast<PolyaResult *>(out)));
+            reinterpret_cast<PolyaResult *>(out), cache, cap));
     return PB2_OK;
 }
 

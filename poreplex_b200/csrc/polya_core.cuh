@@ -343,6 +343,56 @@ struct EventStream {
     }
 };
 
+// ---- event iteration with a replay cache --------------------------------------------
+// The first complete walk over a window records its events (16 bytes each) in a per-read
+// slice of a global scratch; later walks over the same window replay them instead of
+// re-running median filter, prefix sums, t-statistics and the peak detector.  A window
+// with more events than the slice holds simply keeps streaming.
+struct EventCacheSlot { uint32_t start; float length, mean, stdv; };
+
+struct EvIter {
+    EventStream es;
+    EventCacheSlot *cache;        // element k of this read at cache[k * stride]
+    int64_t stride;
+    int cap, count, pos;
+    bool valid, replay, overflow;
+
+    PB_HD void attach(EventCacheSlot *c, int64_t stride_, int cap_) {
+        cache = c; stride = stride_; cap = c ? cap_ : 0; count = 0; valid = false;
+    }
+    PB_HD void invalidate() { valid = false; }
+    PB_HD void begin(const WindowSource &src, const PolyaParams &P) {
+        pos = 0;
+        replay = valid;
+        if (!replay) { es.begin(src, P); count = 0; overflow = (cap == 0); }
+    }
+    PB_HD bool finished() const { return replay ? pos >= count : es.finished(); }
+    PB_HD int step(Event *out) {
+        if (replay) {
+            const EventCacheSlot c = cache[(int64_t)pos * stride];
+            pos++;
+            out[0].start = c.start; out[0].length = c.length; out[0].mean = c.mean;
+            out[0].stdv = c.stdv;
+            out[0].end = (int64_t)pb::dadd((double)c.start, (double)c.length);
+            return 1;
+        }
+        const int k = es.step(out);
+        for (int q = 0; q < k; q++) {
+            if (count < cap) {
+                EventCacheSlot c;
+                c.start = (uint32_t)out[q].start; c.length = out[q].length;
+                c.mean = out[q].mean; c.stdv = out[q].stdv;
+                cache[(int64_t)count * stride] = c;
+            } else {
+                overflow = true;
+            }
+            count++;
+        }
+        if (es.finished()) valid = !overflow;
+        return k;
+    }
+};
+
 PB_HD bool between_f32(float x, float lo, float hi) { return x >= lo && x <= hi; }
 
 // ---- the whole of PolyASignalAnalyzer for one read --------------------------------
@@ -350,7 +400,9 @@ PB_HD bool between_f32(float x, float lo, float hi) { return x >= lo && x <= hi;
 // None: no polya-tail state, polya.py:53-56,69-70).
 PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_length,
                          double gain, double offset, float scale, float shift,
-                         int32_t rough_begin, int32_t rough_end_in, PolyaResult &R)
+                         int32_t rough_begin, int32_t rough_end_in, PolyaResult &R,
+                         EventCacheSlot *cache = nullptr, int64_t cache_stride = 1,
+                         int cache_cap = 0)
 {
     R.found = 0; R.n_spikes = 0; R.begin = 0; R.end = 0; R.dwell_samples = 0;
     R.extensions = 0; R.flags = 0;
@@ -359,7 +411,8 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
     bool have_range = false;
     float lo = P.cutoff_lo, hi = P.cutoff_hi;
     int ext_depth = 0;
-    EventStream es;
+    EvIter es;
+    es.attach(cache, cache_stride, cache_cap);
     Event evs[2];
 
     for (;;) {                                    // one iteration per __call__ (window)
@@ -375,6 +428,7 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
         src.raw = raw; src.gain = gain; src.offset = offset; src.scale = scale; src.shift = shift;
         src.w0 = insp_begin; src.n = insp_end - insp_begin;
         if (src.n <= 0) return;                   // csupport raises on an empty signal
+        es.invalidate();                          // new window: recorded events are stale
         if (!have_range) { lo = P.cutoff_lo; hi = P.cutoff_hi; }
         bool recal_mode = rough_end_cur < 0;
         bool extend = false;

@@ -43,6 +43,17 @@ void hc_polya(const pb::PolyaParams *P, const int16_t *raw, int64_t full_length,
     pb::polya_analyze(*P, raw, full_length, gain, offset, scale, shift, rough_begin, rough_end, *R);
 }
 
+// same, with the event replay cache enabled (capacity `cap` events)
+void hc_polya_cached(const pb::PolyaParams *P, const int16_t *raw, int64_t full_length, double gain,
+                     double offset, float scale, float shift, int32_t rough_begin,
+                     int32_t rough_end, pb::PolyaResult *R, int cap)
+{
+    pb::EventCacheSlot *buf = new pb::EventCacheSlot[cap > 0 ? cap : 1];
+    pb::polya_analyze(*P, raw, full_length, gain, offset, scale, shift, rough_begin, rough_end, *R,
+                      buf, 1, cap);
+    delete[] buf;
+}
+
 int hc_sizeof_params(void) { return (int)sizeof(pb::PolyaParams); }
 int hc_sizeof_result(void) { return (int)sizeof(pb::PolyaResult); }
 }

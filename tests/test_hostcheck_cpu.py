@@ -153,6 +153,14 @@ def test_polya_core_matches_restatement_and_reference(hc, oracle_mod, preset):
                         C.c_int32(rr[0]), C.c_int32(-1 if rr[1] is None else rr[1]), C.byref(R))
             got = H.result_to_dict(R, 3012.0)
             assert _same(want, got), (kind, rep, want, got)
+            for cap in (8, 4096):          # replay cache: overflowing and roomy
+                R2 = H.PolyaResultC()
+                hc.hc_polya_cached(C.byref(Pc), raw.ctypes.data_as(C.c_void_p), C.c_int64(len(raw)),
+                                   C.c_double(gain), C.c_double(off), C.c_float(scale),
+                                   C.c_float(shift), C.c_int32(rr[0]),
+                                   C.c_int32(-1 if rr[1] is None else rr[1]), C.byref(R2),
+                                   C.c_int(cap))
+                assert _same(want, H.result_to_dict(R2, 3012.0)), (kind, rep, cap)
             found += got is not None
             none += got is None
             extended += R.extensions > 0
