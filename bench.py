@@ -381,7 +381,7 @@ def main():
         d2h = sum(v.nbytes for v in res.values())
         result['e2e'] = {'value': world * hn / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
-                         'api': 'pb2_analyze_host (pinned host buffers, synchronous)'}
+                         'api': 'pb2_analyze_host (pinned host buffers; 4-chunk H2D/compute/D2H pipeline)'}
         assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------
