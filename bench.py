@@ -156,7 +156,7 @@ def host_sample(work, n):
             work['offset'][:n].cpu().numpy())
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path (oracle port --
     its TensorFlow / pomegranate dependencies cannot be installed here) on all host
     cores, bounded sample per step."""
@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -218,8 +218,17 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. NCCL's
+    # version banner) is diverted to stderr and the line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + '\n').encode())
+
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -229,7 +238,6 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout
         dist.init_process_group('nccl', device_id=device)
 
     from poreplex_b200 import _native
@@ -403,7 +411,7 @@ def main():
             'outputs_match_gpu': same}
 
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         dist.destroy_process_group()
 

@@ -288,7 +288,8 @@ int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *la
 int64_t pb2_kernel_launches(const pb2_context *ctx);
 
 /* Verification switch: run the LSTM kernels with IEEE __fdiv_rn instead of the
- * branch-free Newton division (identical outputs, slower; see csrc/pb_math.cuh). */
+ * branch-free Newton division and without left-pad skipping in the demultiplexer
+ * (identical outputs, slower; see csrc/pb_math.cuh, kernels_lstm.cu). */
 int pb2_set_exact_division(pb2_context *ctx, int on);
 
 /* ---- measurement ----------------------------------------------------------

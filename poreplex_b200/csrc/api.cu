@@ -160,12 +160,13 @@ void pb2_destroy(pb2_context *ctx)
     cudaFree(ctx->scaler.zero_prefix);
     free_lstm(ctx->demux.fwd); free_lstm(ctx->demux.bwd); free_lstm(ctx->demux.l2);
     cudaFree(ctx->demux.dense_kernel); cudaFree(ctx->demux.dense_bias);
+    cudaFree(ctx->demux.pad_state); cudaFree(ctx->demux.pad_prefix);
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
                         &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
-                        &ctx->ws_unsplit, &ctx->ws_unsplit_host};
+                        &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -193,6 +194,7 @@ int pb2_set_exact_division(pb2_context *ctx, int on)
 {
     if (!ctx) return PB2_EINVAL;
     ctx->exact_division = on != 0;
+    ctx->no_pad_skip = on != 0;        // verification mode also steps every padded position
     return PB2_OK;
 }
 
@@ -288,6 +290,7 @@ int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p)
     for (int i = 0; i < PB2_MAX_CALIB; i++)
         D.calibration[i] = i < p->n_calibration ? p->calibration[i] : INFINITY;
     D.score_threshold = p->score_threshold;
+    if ((rc = build_pad_tables(ctx))) return rc;
     D.set = true;
     return PB2_OK;
 }

@@ -77,6 +77,33 @@ __device__ __forceinline__ void dot_tile(const float *__restrict__ Wt,
     }
 }
 
+// same chain continued: acc keeps its incoming value, k runs over [K0, K1)
+template <int K0, int K1, int NUP>
+__device__ __forceinline__ void dot_tile_range(const float *__restrict__ Wt,
+                                               const float *__restrict__ hs, int up, int rg,
+                                               Acc &acc)
+{
+    const float4 *w = reinterpret_cast<const float4 *>(Wt) + up * 2;
+    const float4 *h = reinterpret_cast<const float4 *>(hs) + rg;
+#pragma unroll 4
+    for (int k = K0; k < K1; k++) {
+        const float4 hv = h[k * (TB / 4)];
+        const float4 w0 = w[k * NUP * 2];
+        const float4 w1 = w[k * NUP * 2 + 1];
+        const float2 wi = make_float2(w0.x, w0.y), wf = make_float2(w0.z, w0.w);
+        const float2 wc = make_float2(w1.x, w1.y), wo = make_float2(w1.z, w1.w);
+        const float hr[RG] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            const float2 hh = make_float2(hr[r], hr[r]);
+            acc.v[r][0] = ffma2(hh, wi, acc.v[r][0]);
+            acc.v[r][1] = ffma2(hh, wf, acc.v[r][1]);
+            acc.v[r][2] = ffma2(hh, wc, acc.v[r][2]);
+            acc.v[r][3] = ffma2(hh, wo, acc.v[r][3]);
+        }
+    }
+}
+
 // re-layout a [K][4H] row-major Keras matrix into smem [K][NUP][4][2]
 template <int K, int H>
 __device__ __forceinline__ void load_weights(const float *__restrict__ g, float *Wt)
@@ -462,6 +489,16 @@ struct DemuxArgs {
     int n_calibration;
     double score_threshold;
     float *class_probs; int32_t *barcode, *guess, *score;
+    // left-pad skipping (all nullptr / 0 = off).  While every read of a tile is still in its
+    // -1000 left padding, the forward layer-1 state is a read-independent function of t:
+    //   pad_state [T+1][2][H1]   h, c after n pad steps (built once by this same kernel)
+    //   pad_prefix[T][H2/2][4][2] layer-2 chain x.W2 over the forward half (k < H1) at pad step t
+    //   tile_tstart[tiles]       per tile: min over its reads of the leading pad count
+    const float *pad_state;
+    const float *pad_prefix;
+    int *tile_tstart;
+    float *pad_dump;               // table construction: record (h, c) of row 0 after each step
+    float pad_value;
 };
 
 __constant__ double c_calibration[PB2_MAX_CALIB];
@@ -499,16 +536,53 @@ k_demux_l1(const DemuxArgs A)
         if (rd >= n_eff) rd = n_eff - 1;
         xp[r] = A.windows + rd * A.T;
     }
+    // forward direction: steps that are left padding for EVERY read of the tile are not
+    // computed -- their (h, c) come from the pad-state table and G is filled from it
+    __shared__ int s_tstart;
+    int t_start = 0;
+    if (dir == 0 && A.pad_state) {
+        if (tid == 0) s_tstart = A.T;
+        __syncthreads();
+        if (tid < TB) {
+            int64_t rd = tile0 + tid;
+            if (rd < n_eff) {
+                const float *row = A.windows + rd * A.T;
+                int np = 0;
+                while (np < A.T && row[np] == A.pad_value) np++;
+                atomicMin(&s_tstart, np);
+            }
+        }
+        __syncthreads();
+        t_start = s_tstart;
+        if (t_start >= A.T) t_start = A.T - 1;      // keep at least the last step live
+        if (tid == 0 && A.tile_tstart) A.tile_tstart[tile] = t_start;
+    }
+    float *Gt = A.G + (size_t)tile * A.T * (2 * H1) * TB;
     float2 c[RG], hz[RG];
+    {
+        float2 h0 = make_float2(0.f, 0.f), c0 = h0;
+        if (t_start > 0) {
+            const float *tb = A.pad_state + (size_t)t_start * 2 * H1;
+            h0 = make_float2(tb[2 * up], tb[2 * up + 1]);
+            c0 = make_float2(tb[H1 + 2 * up], tb[H1 + 2 * up + 1]);
+            for (int t = 0; t < t_start; t++) {     // h after pad step t = table[t + 1]
+                const float *tt = A.pad_state + (size_t)(t + 1) * 2 * H1;
+                const float2 hv = make_float2(tt[2 * up], tt[2 * up + 1]);
+                float2 hq[RG];
 #pragma unroll
-    for (int r = 0; r < RG; r++) { c[r] = make_float2(0.f, 0.f); hz[r] = c[r]; }
+                for (int r = 0; r < RG; r++) hq[r] = hv;
+                store_h(Gt + ((size_t)t * 2 * H1) * TB, up, rg, hq);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RG; r++) { c[r] = c0; hz[r] = h0; }
+    }
     store_h(hs, up, rg, hz);
     __syncthreads();
 
-    float *Gt = A.G + (size_t)tile * A.T * (2 * H1) * TB;
     int cur = 0;
     Acc acc;
-    for (int s = 0; s < A.T; s++) {
+    for (int s = t_start; s < A.T; s++) {
         const int t = dir ? (A.T - 1 - s) : s;
         float xv[RG];
 #pragma unroll
@@ -525,10 +599,31 @@ k_demux_l1(const DemuxArgs A)
         }
         store_h(hs + (cur ^ 1) * H1 * TB, up, rg, hn);
         store_h(Gt + ((size_t)t * 2 * H1 + dir * H1) * TB, up, rg, hn);
+        if (A.pad_dump && dir == 0 && tile == 0 && rg == 0) {
+            float *tt = A.pad_dump + (size_t)(s + 1) * 2 * H1;
+            tt[2 * up] = hn[0].x;  tt[2 * up + 1] = hn[0].y;
+            tt[H1 + 2 * up] = c[0].x;  tt[H1 + 2 * up + 1] = c[0].y;
+        }
         cur ^= 1;
         __syncthreads();
     }
     (void)risk;
+}
+
+// pad_prefix[t][up][gate][2] = fma chain over k < H1 of pad_state[t+1].h[k] * W2[k][col]
+// (exactly the first H1 terms of layer 2's x.W chain at a pad step)
+template <int H1, int H2>
+__global__ void k_pad_prefix(const float *__restrict__ pad_state, const float *__restrict__ W2,
+                             int T, float *__restrict__ prefix)
+{
+    const int t = blockIdx.x;
+    const int col = threadIdx.x;              // 0 .. 4*H2-1
+    if (t >= T || col >= 4 * H2) return;
+    const float *h = pad_state + (size_t)(t + 1) * 2 * H1;
+    float acc = 0.f;
+    for (int k = 0; k < H1; k++) acc = pb::ffma(h[k], W2[(size_t)k * 4 * H2 + col], acc);
+    const int gate = col / H2, u = col % H2;
+    prefix[(((size_t)t * (H2 / 2) + (u >> 1)) * 4 + gate) * 2 + (u & 1)] = acc;
 }
 
 // ============================================================================
@@ -574,6 +669,7 @@ k_demux_l2(const DemuxArgs A)
     store_h(hs, up, rg, hz);
 
     const float *Gt = A.G + (size_t)tile * A.T * KX * TB;
+    const int t_pad = (A.pad_prefix && A.tile_tstart) ? A.tile_tstart[tile] : 0;
     int cur = 0;
     Acc acc;
     for (int t = 0; t < A.T; t++) {
@@ -582,7 +678,21 @@ k_demux_l2(const DemuxArgs A)
         for (int i = tid; i < KX * TB / 4; i += GT)
             reinterpret_cast<float4 *>(xs)[i] = __ldg(src + i);
         group_sync(group, GT);
-        dot_tile<KX, NUP>(Wt, xs, up, rg, acc);
+        if (t < t_pad) {
+            // every read of the tile is in its left padding: the forward half of the input
+            // (k < H1) is the same for all of them, its partial chain is tabulated
+            const float4 *pf = reinterpret_cast<const float4 *>(
+                A.pad_prefix + ((size_t)t * NUP + up) * 8);
+            const float4 p0 = __ldg(pf), p1 = __ldg(pf + 1);
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                acc.v[r][0] = make_float2(p0.x, p0.y); acc.v[r][1] = make_float2(p0.z, p0.w);
+                acc.v[r][2] = make_float2(p1.x, p1.y); acc.v[r][3] = make_float2(p1.z, p1.w);
+            }
+            dot_tile_range<H1, KX, NUP>(Wt, xs, up, rg, acc);
+        } else {
+            dot_tile<KX, NUP>(Wt, xs, up, rg, acc);
+        }
         float2 zx[RG][4];
 #pragma unroll
         for (int r = 0; r < RG; r++)
@@ -696,6 +806,9 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         attr_done = true;
     }
+    const bool use_pad = D.pad_state && D.pad_prefix && !ctx->no_pad_skip;
+    int *tstart = (int *)ws_get(ctx, ctx->ws_tstart, sizeof(int) * (size_t)tiles_per_pass);
+    if (!tstart) return PB2_ENOMEM;
     PB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_calibration, D.calibration,
                                          sizeof(double) * PB2_MAX_CALIB, 0,
                                          cudaMemcpyHostToDevice, st));
@@ -712,6 +825,11 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
         A.Wd = D.dense_kernel; A.bd = D.dense_bias;
         A.G = G;
         A.slot_count = slot_count; A.slot_read = slot_read; A.row0 = r0;
+        A.pad_state = use_pad ? D.pad_state : nullptr;
+        A.pad_prefix = use_pad ? D.pad_prefix : nullptr;
+        A.tile_tstart = use_pad ? tstart : nullptr;
+        A.pad_dump = nullptr;
+        A.pad_value = D.pad_value;
         A.n_classes = D.n_classes; A.n_decoy = D.n_decoy;
         A.n_calibration = D.n_calibration; A.score_threshold = D.score_threshold;
         if (slot_read) {                 // outputs are indexed by read, not by row
@@ -736,6 +854,44 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
                 k_demux_l2<H1, H2, G2, false><<<(unsigned)((nt + G2 - 1) / G2), G2 * (H2 / 2) * NRG, smem2, st>>>(A));
         }
     }
+    return PB2_OK;
+}
+
+// Tables for left-pad skipping, built with the exact kernels themselves: one all-pad window
+// is stepped through the forward layer-1 kernel while its (h, c) are recorded, then the
+// layer-2 chain prefixes are accumulated in the kernel's own fma order.
+int build_pad_tables(pb2_context *ctx)
+{
+    DemuxDev &D = ctx->demux;
+    cudaFree(D.pad_state); cudaFree(D.pad_prefix);
+    D.pad_state = D.pad_prefix = nullptr;
+    if (D.fwd.units != 48 || D.l2.units != 64 || D.fwd.in_dim != 1 || D.l2.in_dim != 96)
+        return PB2_OK;                       // unsupported shape is reported by launch_demux
+    constexpr int H1 = 48, H2 = 64;
+    const int T = D.trim_length;
+    float *state = nullptr, *prefix = nullptr, *win = nullptr, *G = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&state, sizeof(float) * (size_t)(T + 1) * 2 * H1));
+    PB_CUDA(ctx, cudaMemset(state, 0, sizeof(float) * (size_t)(T + 1) * 2 * H1));
+    PB_CUDA(ctx, cudaMalloc(&prefix, sizeof(float) * (size_t)T * 4 * H2));
+    PB_CUDA(ctx, cudaMalloc(&G, sizeof(float) * (size_t)T * 2 * H1 * TB));
+    std::vector<float> hw((size_t)T, D.pad_value);
+    PB_CUDA(ctx, cudaMalloc(&win, sizeof(float) * (size_t)T));
+    PB_CUDA(ctx, cudaMemcpy(win, hw.data(), sizeof(float) * (size_t)T, cudaMemcpyHostToDevice));
+    DemuxArgs A = {};
+    A.windows = win; A.n = 1; A.T = T;
+    A.Wf = D.fwd.kernel; A.Uf = D.fwd.recurrent; A.bf = D.fwd.bias;
+    A.Wb = D.bwd.kernel; A.Ub = D.bwd.recurrent; A.bb = D.bwd.bias;
+    A.G = G; A.pad_dump = state; A.pad_value = D.pad_value;
+    const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    k_demux_l1<H1, true><<<dim3(1, 1), (H1 / 2) * NRG, smem1, 0>>>(A);     // forward only
+    k_pad_prefix<H1, H2><<<T, 4 * H2, 0, 0>>>(state, D.l2.kernel, T, prefix);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(win); cudaFree(G);
+    if (e != cudaSuccess) { cudaFree(state); cudaFree(prefix); return check_cuda(ctx, e, "pad tables"); }
+    D.pad_state = state;
+    D.pad_prefix = prefix;
     return PB2_OK;
 }
 

@@ -53,6 +53,9 @@ struct DemuxDev {
     int n_calibration = 0;
     double calibration[PB2_MAX_CALIB];
     double score_threshold = 0;
+    // left-pad skipping tables (see kernels_lstm.cu DemuxArgs)
+    float *pad_state = nullptr;       // [T+1][2][H1]
+    float *pad_prefix = nullptr;      // [T][H2/2][4][2]
 };
 
 struct Workspace {                    // grow-only device scratch
@@ -72,6 +75,7 @@ struct ProfEvent { int id; cudaEvent_t a, b; };
 struct pb2_context {
     int device = 0;
     bool profiling = false;
+    bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
     std::vector<pb::ProfEvent> prof_events;
     std::vector<cudaEvent_t> prof_pool;
@@ -94,7 +98,7 @@ struct pb2_context {
     // scratch
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
-        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host;
+        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
@@ -144,6 +148,7 @@ int launch_scaler(pb2_context *ctx, const pb2_batch &b, const float *pooled,
 int launch_scaler_heads(pb2_context *ctx, const float *heads, int64_t n, float *z_out,
                         cudaStream_t st);
 int build_zero_prefix(pb2_context *ctx);
+int build_pad_tables(pb2_context *ctx);
 int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
                    const float *scale_shift, int32_t *status, int32_t *segments,
                    float *pooled_scaled_out, cudaStream_t st);
