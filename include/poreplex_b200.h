@@ -169,10 +169,14 @@ typedef struct {
     int64_t n_events_total;
     const int64_t *event_offsets;    /* [n_reads + 1]                  */
     const int64_t *start;            /* [total] raw-sample index       */
-    const float *mean;               /* [total] event mean, pA         */
+    const float *mean;               /* [total] event mean, pA; NULL = derive on the device
+                                        from the raw signal as convert_events_guppy does
+                                        (fast5_file.py:209-230), see first_sample     */
     const int32_t *move;             /* [total]                        */
     const double *p_model_state;     /* [total]                        */
     const double *sampling_rate;     /* [n_reads]                      */
+    const int64_t *first_sample;     /* [n_reads] first_sample_template (mean == NULL) */
+    int32_t block_stride;            /* samples per event row          (mean == NULL) */
 } pb2_event_tables;
 
 /* A batch of reads: ragged int16 DAC samples + per-read calibration
@@ -271,13 +275,16 @@ int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *sca
                       const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                       void *stream);
 /* SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443) for reads whose status is
- * okay and that have an event table.  flag[i]: 1 unsplit, 0 not, <0 internal overflow/no path.
+ * okay and that have an event table.  `batch` (the reads' raw signal, same read order) is only
+ * needed when events->mean is NULL and may be NULL otherwise.  flag[i]: 1 unsplit, 0 not, <0 internal overflow/no path.
  * max_windows >= ceil((last event end - payload start) / window_step) over the batch. */
-int pb2_detect_unsplit(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
+int pb2_detect_unsplit(pb2_context *ctx, const pb2_batch *batch,
+                       const pb2_event_tables *events, int64_t n_reads,
                        const float *scale_shift, const int32_t *status, const int32_t *segments,
                        int32_t max_windows, int32_t *flag, void *stream);
 /* same with HOST pointers everywhere (copies in, runs, copies flag out, synchronises) */
-int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
+int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_batch *batch,
+                            const pb2_event_tables *events, int64_t n_reads,
                             const float *scale_shift, const int32_t *status,
                             const int32_t *segments, int32_t max_windows, int32_t *flag);
 /* io.py:274-278 */

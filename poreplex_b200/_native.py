@@ -95,7 +95,8 @@ class UnsplitParams(C.Structure):
 class EventTables(C.Structure):
     _fields_ = [('n_events_total', C.c_int64), ('event_offsets', C.c_void_p),
                 ('start', C.c_void_p), ('mean', C.c_void_p), ('move', C.c_void_p),
-                ('p_model_state', C.c_void_p), ('sampling_rate', C.c_void_p)]
+                ('p_model_state', C.c_void_p), ('sampling_rate', C.c_void_p),
+                ('first_sample', C.c_void_p), ('block_stride', C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -187,10 +188,10 @@ def load():
     L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
     L.pb2_set_unsplit.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(UnsplitParams), C.c_int32,
                                   C.c_int32, C.c_int32]
-    L.pb2_detect_unsplit.argtypes = [vp, C.POINTER(EventTables), C.c_int64, vp, vp, vp, C.c_int32,
-                                     vp, vp]
-    L.pb2_detect_unsplit_host.argtypes = [vp, C.POINTER(EventTables), C.c_int64, vp, vp, vp,
-                                          C.c_int32, vp]
+    L.pb2_detect_unsplit.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables), C.c_int64, vp,
+                                     vp, vp, C.c_int32, vp, vp]
+    L.pb2_detect_unsplit_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables), C.c_int64,
+                                          vp, vp, vp, C.c_int32, vp]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

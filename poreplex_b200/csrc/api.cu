@@ -76,7 +76,7 @@ void prof_end(pb2_context *ctx, cudaStream_t st)
 static const char *const kKernelNames[K_NUM] = {
     "k_pool", "k_scaler_prepare", "k_scaler_lstm", "k_segment", "k_viterbi_paths",
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
-    "k_unsplit_windows", "k_unsplit_decide"};
+    "k_unsplit_windows", "k_unsplit_decide", "k_event_means"};
 
 static void ws_free(Workspace &w)
 {
@@ -166,7 +166,7 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
                         &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
-                        &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart};
+                        &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -419,19 +419,19 @@ int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *sca
     return launch_polya(ctx, *batch, scale_shift, status, segments, out, (cudaStream_t)stream);
 }
 
-int pb2_detect_unsplit(pb2_context *ctx, const pb2_event_tables *events, int64_t n_reads,
-                       const float *scale_shift, const int32_t *status, const int32_t *segments,
-                       int32_t max_windows, int32_t *flag, void *stream)
+int pb2_detect_unsplit(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tables *events,
+                       int64_t n_reads, const float *scale_shift, const int32_t *status,
+                       const int32_t *segments, int32_t max_windows, int32_t *flag, void *stream)
 {
     if (!ctx || !events || !flag) return PB2_EINVAL;
     if (!ctx->unsplit_set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "unsplit-read model not set");
     DeviceGuard g(ctx->device);
-    return launch_unsplit(ctx, *events, n_reads, scale_shift, status, segments, max_windows, flag,
-                          (cudaStream_t)stream);
+    return launch_unsplit(ctx, batch, *events, n_reads, scale_shift, status, segments, max_windows,
+                          flag, (cudaStream_t)stream);
 }
 
-int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *hev, int64_t n,
-                            const float *scale_shift, const int32_t *status,
+int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_batch *hb, const pb2_event_tables *hev,
+                            int64_t n, const float *scale_shift, const int32_t *status,
                             const int32_t *segments, int32_t max_windows, int32_t *flag)
 {
     if (!ctx || !hev || !flag) return PB2_EINVAL;
@@ -448,13 +448,29 @@ int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *hev, int64
     const size_t o_ps = take(sizeof(double) * E), o_rt = take(sizeof(double) * n);
     const size_t o_ss = take(sizeof(float) * 2 * n), o_stat = take(sizeof(int32_t) * n);
     const size_t o_seg = take(sizeof(int32_t) * 2 * PB2_MAX_STATES * n), o_fl = take(sizeof(int32_t) * n);
+    const bool derive = hev->mean == nullptr;
+    if (derive && (!hb || hb->n_reads != n || !hev->first_sample))
+        return fail(ctx, PB2_EINVAL, "deriving event means needs the batch of the same reads");
+    const size_t R = derive ? (size_t)hb->n_raw_total : 0;
+    const size_t o_raw = take(sizeof(int16_t) * R), o_ro = take(8 * (size_t)n), o_rl = take(8 * (size_t)n);
+    const size_t o_rg = take(8 * (size_t)n), o_dg = take(8 * (size_t)n), o_of = take(8 * (size_t)n);
+    const size_t o_fs = take(8 * (size_t)n);
     char *base = (char *)ws_get(ctx, ctx->ws_unsplit_host, off);
     if (!base) return PB2_ENOMEM;
 #define PB_H2D(o, src, bytes) PB_CUDA(ctx, cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
     PB_H2D(o_eo, hev->event_offsets, sizeof(int64_t) * (n + 1));
+    if (derive) {
+        PB_H2D(o_raw, hb->raw, sizeof(int16_t) * R);
+        PB_H2D(o_ro, hb->raw_offsets, 8 * (size_t)n);
+        PB_H2D(o_rl, hb->raw_lengths, 8 * (size_t)n);
+        PB_H2D(o_rg, hb->range, 8 * (size_t)n);
+        PB_H2D(o_dg, hb->digitisation, 8 * (size_t)n);
+        PB_H2D(o_of, hb->offset, 8 * (size_t)n);
+        PB_H2D(o_fs, hev->first_sample, 8 * (size_t)n);
+    }
     if (E) {
         PB_H2D(o_st, hev->start, sizeof(int64_t) * E);
-        PB_H2D(o_mn, hev->mean, sizeof(float) * E);
+        if (!derive) PB_H2D(o_mn, hev->mean, sizeof(float) * E);
         PB_H2D(o_mv, hev->move, sizeof(int32_t) * E);
         PB_H2D(o_ps, hev->p_model_state, sizeof(double) * E);
     }
@@ -466,11 +482,22 @@ int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_event_tables *hev, int64
     pb2_event_tables dev = *hev;
     dev.event_offsets = (const int64_t *)(base + o_eo);
     dev.start = (const int64_t *)(base + o_st);
-    dev.mean = (const float *)(base + o_mn);
+    dev.mean = derive ? nullptr : (const float *)(base + o_mn);
+    dev.first_sample = (const int64_t *)(base + o_fs);
+    pb2_batch db = {};
+    if (derive) {
+        db = *hb;
+        db.raw = (const int16_t *)(base + o_raw);
+        db.raw_offsets = (const int64_t *)(base + o_ro);
+        db.raw_lengths = (const int64_t *)(base + o_rl);
+        db.range = (const double *)(base + o_rg);
+        db.digitisation = (const double *)(base + o_dg);
+        db.offset = (const double *)(base + o_of);
+    }
     dev.move = (const int32_t *)(base + o_mv);
     dev.p_model_state = (const double *)(base + o_ps);
     dev.sampling_rate = (const double *)(base + o_rt);
-    int rc = launch_unsplit(ctx, dev, n, (const float *)(base + o_ss), (const int32_t *)(base + o_stat),
+    int rc = launch_unsplit(ctx, derive ? &db : nullptr, dev, n, (const float *)(base + o_ss), (const int32_t *)(base + o_stat),
                             (const int32_t *)(base + o_seg), max_windows, (int32_t *)(base + o_fl), st);
     if (rc) return rc;
     PB_CUDA(ctx, cudaMemcpyAsync(flag, base + o_fl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));

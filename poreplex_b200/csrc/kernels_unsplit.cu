@@ -205,12 +205,69 @@ k_unsplit_decide(const UnsplitArgs A)
     A.flag[r] = is_unsplit ? 1 : 0;
 }
 
-int launch_unsplit(pb2_context *ctx, const pb2_event_tables &ev, int64_t n,
-                   const float *scale_shift, const int32_t *status, const int32_t *segments,
-                   int32_t max_windows, int32_t *flag, cudaStream_t st)
+// ---------------------------------------------------------------------------
+// k_event_means: the `mean` column of convert_events_guppy (fast5_file.py:209-230):
+// pA of raw[first : first + stride * E] (clamped to the read), scipy medfilt(5) with zero
+// padding at the ends of THAT slice, NaN padding of a short last block, then the float32
+// pairwise row mean of reshape(E, stride).  One thread per event row.
+// ---------------------------------------------------------------------------
+__global__ void k_event_means(const int16_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
+                              const int64_t *__restrict__ raw_len, const double *__restrict__ range,
+                              const double *__restrict__ digitisation,
+                              const double *__restrict__ offset, const int64_t *__restrict__ ev_off,
+                              const int64_t *__restrict__ first_sample, int stride, int64_t n,
+                              int64_t total, float *__restrict__ mean)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int64_t a = 0, b = n;                      // read r with ev_off[r] <= g < ev_off[r + 1]
+    while (a + 1 < b) { const int64_t m = (a + b) >> 1; if (ev_off[m] <= g) a = m; else b = m; }
+    const int64_t r = a;
+    const int64_t E = ev_off[r + 1] - ev_off[r];
+    const int64_t first = first_sample[r];
+    int64_t end = first + (int64_t)stride * E;
+    if (end > raw_len[r]) end = raw_len[r];
+    const double gain = pb::ddiv(range[r], digitisation[r]);
+    const double off = offset[r];
+    const int16_t *x = raw + raw_off[r];
+    const int64_t base = first + (g - ev_off[r]) * stride;
+    float v[32];
+    for (int j = 0; j < stride; j++) {
+        const int64_t p = base + j;
+        if (p >= end) { v[j] = NAN; continue; }
+        float w[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int64_t pp = p - 2 + q;
+            w[q] = (pp < first || pp >= end) ? 0.0f : pb::dac_to_pa((int)x[pp], gain, off);
+        }
+        v[j] = pb::median5(w[0], w[1], w[2], w[3], w[4]);
+    }
+    mean[g] = pb::pool_mean_generic(v, stride);
+}
+
+int launch_unsplit(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tables &ev_in,
+                   int64_t n, const float *scale_shift, const int32_t *status,
+                   const int32_t *segments, int32_t max_windows, int32_t *flag, cudaStream_t st)
 {
     if (n <= 0) return PB2_OK;
     if (max_windows < 1) max_windows = 1;
+    pb2_event_tables ev = ev_in;
+    if (!ev.mean) {
+        if (!batch || !ev.first_sample || ev.block_stride < 1 || ev.block_stride > 32)
+            return fail(ctx, PB2_EINVAL, "event means missing and cannot be derived "
+                        "(need batch, first_sample and 1 <= block_stride <= 32)");
+        float *m = (float *)ws_get(ctx, ctx->ws_evmean, sizeof(float) * (size_t)(ev.n_events_total + 1));
+        if (!m) return PB2_ENOMEM;
+        if (ev.n_events_total > 0) {
+            PB_LAUNCH(ctx, K_EVENT_MEANS, "k_event_means", st,
+                k_event_means<<<(unsigned)((ev.n_events_total + 127) / 128), 128, 0, st>>>(
+                    batch->raw, batch->raw_offsets, batch->raw_lengths, batch->range,
+                    batch->digitisation, batch->offset, ev.event_offsets, ev.first_sample,
+                    ev.block_stride, n, ev.n_events_total, m));
+        }
+        ev.mean = m;
+    }
     UnsplitArgs A = {};
     A.ev_off = ev.event_offsets; A.start = ev.start; A.mean = ev.mean; A.move = ev.move;
     A.p_state = ev.p_model_state; A.rate = ev.sampling_rate;

@@ -68,7 +68,7 @@ struct Workspace {                    // grow-only device scratch
 namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
-                K_UNSPLIT_DECIDE, K_NUM };
+                K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 
@@ -98,7 +98,7 @@ struct pb2_context {
     // scratch
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
-        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart;
+        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
@@ -168,9 +168,9 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);
-int launch_unsplit(pb2_context *ctx, const pb2_event_tables &ev, int64_t n,
-                   const float *scale_shift, const int32_t *status, const int32_t *segments,
-                   int32_t max_windows, int32_t *flag, cudaStream_t st);
+int launch_unsplit(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tables &ev,
+                   int64_t n, const float *scale_shift, const int32_t *status,
+                   const int32_t *segments, int32_t max_windows, int32_t *flag, cudaStream_t st);
 int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
                     int32_t *label, int32_t *barcode, int32_t *guess, int32_t *score,
                     cudaStream_t st);

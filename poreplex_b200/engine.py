@@ -303,14 +303,30 @@ class SignalEngine:
         self._check(self.lib.pb2_analyze_host(self.handle, C.byref(b), C.byref(r), flags))
         return out
 
-    def detect_unsplit_host(self, tables, sampling_rate, scale_shift, status, segments):
+    def detect_unsplit_host(self, tables, sampling_rate, scale_shift, status, segments,
+                            batch=None):
         """SignalAnalysis.detect_unsplit_read for a batch (host buffers).
 
-        ``tables``: per read either None or a dict with 'start', 'mean', 'move',
-        'p_model_state' arrays (the reference's event table columns).  Returns int32 flags:
+        ``tables``: per read either None or a dict with 'start', 'move', 'p_model_state' and
+        either 'mean' (albacore-style tables) or 'first_sample' + 'block_stride' (guppy Move
+        tables: the means are then derived on the device from ``batch`` = (raw, offsets,
+        lengths, range, digitisation, offset) of the same reads).  Returns int32 flags:
         1 unsplit, 0 not, < 0 internal error for that read."""
         if not self.unsplit_ready:
             raise ValueError('config has no unsplit-read detection model')
+        has = [t is not None and len(t['start']) > 0 for t in tables]
+        with_mean = [h and 'mean' in t for h, t in zip(has, tables)]
+        derived = [h and 'mean' not in t for h, t in zip(has, tables)]
+        flag = np.zeros(len(tables), np.int32)
+        for group in (with_mean, derived):
+            if any(group):
+                sub = [t if g else None for t, g in zip(tables, group)]
+                f = self._detect_unsplit_group(sub, sampling_rate, scale_shift, status, segments,
+                                               batch if group is derived else None)
+                flag = np.where(group, f, flag).astype(np.int32)
+        return flag
+
+    def _detect_unsplit_group(self, tables, sampling_rate, scale_shift, status, segments, batch):
         n = len(tables)
         counts = np.array([0 if t is None else len(t['start']) for t in tables], np.int64)
         offs = np.zeros(n + 1, np.int64)
@@ -319,8 +335,14 @@ class SignalEngine:
         cat = lambda key, dt: (np.concatenate([np.asarray(t[key]).astype(dt) for t in tables
                                                if t is not None and len(t['start'])])
                                if total else np.zeros(0, dt))
-        start, mean = cat('start', np.int64), cat('mean', np.float32)
+        start = cat('start', np.int64)
         move, pstate = cat('move', np.int32), cat('p_model_state', np.float64)
+        derive = batch is not None
+        mean = None if derive else cat('mean', np.float32)
+        first = np.array([0 if t is None else int(t.get('first_sample', 0)) for t in tables], np.int64)
+        strides = {int(t['block_stride']) for t in tables if t is not None and 'block_stride' in t}
+        if derive and len(strides) != 1:
+            raise ValueError('reads of one batch must share block_stride')
         rate = np.ascontiguousarray(sampling_rate, np.float64)
         scale_shift = np.ascontiguousarray(scale_shift, np.float32)
         status = np.ascontiguousarray(status, np.int32)
@@ -336,12 +358,19 @@ class SignalEngine:
             span = int(t['start'][-1]) + 1 - payload
             if step > 0 and span > 0:
                 maxw = max(maxw, -(-span // step))
-        ev = N.EventTables(total, _np_ptr(offs), _np_ptr(start), _np_ptr(mean), _np_ptr(move),
-                           _np_ptr(pstate), _np_ptr(rate))
+        ev = N.EventTables(total, _np_ptr(offs), _np_ptr(start),
+                           None if derive else _np_ptr(mean), _np_ptr(move), _np_ptr(pstate),
+                           _np_ptr(rate), _np_ptr(first), strides.pop() if derive else 0)
+        bptr = None
+        if derive:
+            raw, roff, rlen, rng, dig, off = (np.ascontiguousarray(a) for a in batch)
+            b = N.Batch(n, raw.size, int(rlen.max()) if n else 0, _np_ptr(raw), _np_ptr(roff),
+                        _np_ptr(rlen), _np_ptr(rng), _np_ptr(dig), _np_ptr(off))
+            bptr = C.byref(b)
         flag = np.zeros(n, np.int32)
         self._check(self.lib.pb2_detect_unsplit_host(
-            self.handle, C.byref(ev), n, _np_ptr(scale_shift), _np_ptr(status), _np_ptr(segments),
-            int(maxw), _np_ptr(flag)))
+            self.handle, bptr, C.byref(ev), n, _np_ptr(scale_shift), _np_ptr(status),
+            _np_ptr(segments), int(maxw), _np_ptr(flag)))
         return flag
 
     # ----------------------------------------------------- device-resident API

@@ -144,15 +144,10 @@ class Fast5Source:
         if padded // block_stride != n:
             raise Exception('Numbers of events and raw data strides does not match.')
         if want_events:
-            from scipy.signal import medfilt
-            raw = node[first_sample:end]
-            pa = np.array(self.range / self.digitization * (raw + self.offset), dtype=np.float32)
-            pa = medfilt(pa, self.RAWSIGNAL_PREFILTER_SIZE)
-            if len(pa) % block_stride > 0:
-                pa = np.pad(pa, [0, block_stride - len(pa) % block_stride], 'constant',
-                            constant_values=[np.nan, np.nan])
-            byev = pa.reshape([n, block_stride])
-            cols['mean'] = byev.mean(axis=1)
-            cols['stdv'] = byev.std(axis=1)
+            # the `mean` column (medfilt(5) + per-block mean of the pA signal,
+            # fast5_file.py:217-227) is derived on the GPU from the raw signal
+            # (k_event_means); only its coordinates are recorded here
+            cols['first_sample'] = first_sample
+            cols['block_stride'] = block_stride
         cols['length'] = np.full(n, block_stride)
         return cols

@@ -221,11 +221,12 @@ class SignalAnalyzer:
         # STAGES B-D on the GPU: one batched pass for every loaded read
         if loaded:
             raw, offsets, lengths = eng.pack_reads([r._raw for r in loaded])
+            batch = (raw, offsets, lengths,
+                     np.array([r.fast5.range for r in loaded], np.float64),
+                     np.array([r.fast5.digitization for r in loaded], np.float64),
+                     np.array([r.fast5.offset for r in loaded], np.float64))
             out = eng.analyze_host(
-                raw, offsets, lengths,
-                np.array([r.fast5.range for r in loaded], np.float64),
-                np.array([r.fast5.digitization for r in loaded], np.float64),
-                np.array([r.fast5.offset for r in loaded], np.float64),
+                *batch,
                 barcoding=bool(self.config['barcoding']),
                 polya=bool(self.config['measure_polya']))
             for i, npread in enumerate(loaded):
@@ -254,9 +255,8 @@ class SignalAnalyzer:
                     error = self.pack_unhandled_exception(f5file, read_id, exc, sys.exc_info())
                     siganal.set_error(error)
                     siganal.failed = True
-            if phase == 1 and self.config['filter_unsplit_reads']:
-                self.detect_unsplit_reads([s for s in nextprocs
-                                           if not s.is_stopped() and not s.failed])
+            if phase == 1 and self.config['filter_unsplit_reads'] and loaded:
+                self.detect_unsplit_reads(nextprocs, batch)
         for siganal in nextprocs:
             siganal.clear_cache()
 
@@ -265,17 +265,20 @@ class SignalAnalyzer:
             results.append(npread.report())
         return results
 
-    def detect_unsplit_reads(self, analyses):
-        """Batched SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443)."""
-        if not analyses:
-            return
+    def detect_unsplit_reads(self, analyses, batch):
+        """Batched SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443); `analyses`
+        is aligned with the packed `batch` (one entry per loaded read)."""
         eng = self.engine
+        live = [not (a.is_stopped() or a.failed) and a.events is not None for a in analyses]
+        if not any(live):
+            return
         flags = eng.detect_unsplit_host(
-            [a.events for a in analyses],
+            [a.events if ok else None for a, ok in zip(analyses, live)],
             np.array([a.npread.sampling_rate for a in analyses], np.float64),
             np.array([a.npread._gpu['scale_shift'] for a in analyses], np.float32),
-            np.zeros(len(analyses), np.int32),
-            np.array([a.npread._gpu['segments'] for a in analyses], np.int32))
+            np.array([0 if ok else 10 for ok in live], np.int32),
+            np.array([a.npread._gpu['segments'] for a in analyses], np.int32),
+            batch=batch)
         for a, f in zip(analyses, flags):
             a.unsplit_flag = int(f)
 

@@ -9,6 +9,8 @@ extern "C" {
 
 float hc_median7(const float *v) { return pb::median7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]); }
 
+float hc_median5(const float *v) { return pb::median5(v[0], v[1], v[2], v[3], v[4]); }
+
 float hc_pairwise_sum(const float *a, int64_t n)
 {
     pb::PairwiseSum s;

@@ -58,6 +58,7 @@ def load():
                                '-mavx2', '-mfma', '-o', LIB, src])
     L = C.CDLL(LIB)
     L.hc_median7.restype = C.c_float
+    L.hc_median5.restype = C.c_float
     L.hc_pairwise_sum.restype = C.c_float
     L.hc_detect_events.restype = C.c_int64
     assert L.hc_sizeof_params() == C.sizeof(PolyaParamsC)

@@ -263,14 +263,21 @@ def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
         rates.append(src.sampling_rate)
     status = np.where([t is None for t in tables], 10, out['status']).astype(np.int32)
     flags = eng_stock.detect_unsplit_host(tables, np.array(rates), out['scale_shift'], status,
-                                          out['segments'])
+                                          out['segments'],
+                                          batch=(raw, off, ln, z['range'], z['digitisation'], z['offset']))
+    from scipy.signal import medfilt
     ia = eng_stock.adapter_state
     n_true = 0
     for i, t in enumerate(tables):
         if t is None:
             assert flags[i] == 0
             continue
-        scaled, pos, end = UR.derive_event_columns(t['start'], t['mean'], t['move'],
+        # the reference's own numpy recipe for the mean column (fast5_file.py:217-227)
+        sig = z['raw'][i][:ln[i]]
+        pa = np.array(z['range'][i] / z['digitisation'][i] * (sig + z['offset'][i]), dtype=np.float32)
+        E = len(t['start'])
+        mean = medfilt(pa[t['first_sample']:t['first_sample'] + 15 * E], 5).reshape(E, 15).mean(axis=1)
+        scaled, pos, end = UR.derive_event_columns(t['start'], mean, t['move'],
                                                    out['scale_shift'][i, 0], out['scale_shift'][i, 1])
         want = UR.detect_unsplit_read(
             preset['unsplit_read_detection'], lambda x: orc_stock.viterbi(x, 'unsplit')[1],

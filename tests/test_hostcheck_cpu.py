@@ -29,6 +29,16 @@ def test_median7_network_exhaustive(hc):
         assert hc.hc_median7(v.ctypes.data_as(C.POINTER(C.c_float))) == np.median(v)
 
 
+def test_median5_network_exhaustive(hc):
+    for bits in itertools.product([0.0, 1.0], repeat=5):
+        v = np.array(bits, np.float32)
+        assert hc.hc_median5(v.ctypes.data_as(C.POINTER(C.c_float))) == np.median(v)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        v = rng.normal(0, 1, 5).astype(np.float32)
+        assert hc.hc_median5(v.ctypes.data_as(C.POINTER(C.c_float))) == np.median(v)
+
+
 def test_pairwise_sum_matches_numpy(hc):
     rng = np.random.default_rng(1)
     for n in list(range(0, 20)) + [127, 128, 129, 255, 256, 257, 1000, 4097, 8192, 8193, 70001]:
