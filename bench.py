@@ -335,7 +335,18 @@ def main():
         kernels.append(ent)
     dom = kernels[0] if kernels else {}
     roofline = {k: dom.get(k) for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
-    roofline.update({'kernel': dom.get('kernel'), 'traffic': None, 'peak_source': peaks['source'],
+    # DRAM traffic per launch of the dominant kernel: dram__bytes_read+write per read from the
+    # committed `ncu --set full` capture (profiles/r1_traffic.json) x reads per launch here
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if dom and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        ent = tj.get(dom['kernel'])
+        if ent and dom.get('launches_per_step'):
+            units = n_classified if dom['kernel'].startswith('k_demux') else n
+            traffic = ent['dram_bytes_per_read'] * units / dom['launches_per_step']
+    roofline.update({'kernel': dom.get('kernel'), 'traffic': traffic, 'peak_source': peaks['source'],
                      'share_of_step': dom.get('share'),
                      'note': 'exact-f32 SIMT LSTM (packed FFMA2) kept bit-identical to the CPU '
                              'oracle; the tensor pipe is not used by this kernel, so frac is '

@@ -371,7 +371,7 @@ static int run_scaler(pb2_context *ctx, ScalerArgs &A, cudaStream_t st, bool exa
     A.qc_shift_lo = S.qc_shift_lo; A.qc_shift_hi = S.qc_shift_hi;
     constexpr int G = SCALER_GROUPS;
     const size_t smem = scaler_smem<48, G>();
-    static bool attr_done = false;
+    bool &attr_done = ctx->attr_scaler;      // per context: the attribute is per device
     if (!attr_done) {
         PB_CUDA(ctx, cudaFuncSetAttribute(k_scaler_lstm<48, G, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -790,7 +790,7 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
     float *G = (float *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
     if (!G) return PB2_ENOMEM;
 
-    static bool attr_done = false;
+    bool &attr_done = ctx->attr_demux;
     const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
     constexpr int G2 = DEMUX_L2_GROUPS;
     const size_t smem2 = sizeof(float) * (2 * H1 * 4 * H2 + H2 * 4 * H2 +

@@ -75,6 +75,7 @@ struct ProfEvent { int id; cudaEvent_t a, b; };
 struct pb2_context {
     int device = 0;
     bool profiling = false;
+    bool attr_scaler = false, attr_demux = false;   // max-dynamic-smem attributes set
     bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
     std::vector<pb::ProfEvent> prof_events;

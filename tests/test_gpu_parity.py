@@ -315,3 +315,23 @@ def test_pipelined_host_path_equals_single_pass(eng_short, orc_short, preset_sho
     ref = _oracle_batch(orc_short, raw[:400 * 4000], off[:400], ln[:400],
                         {k: rd[k][:400] for k in ('range', 'digitisation', 'offset')})
     _compare({k: v[:400] for k, v in piped.items() if k not in ('counts', 'polya')}, ref)
+
+
+def test_degenerate_batches(eng_stock, orc_stock, preset):
+    """Empty batch, a batch in which every read is too short, and one very long read
+    (> scan limit, poly(A) on) through the host API."""
+    e = np.zeros(0)
+    out = eng_stock.analyze_host(np.zeros(8, np.int16), e.astype(np.int64), e.astype(np.int64), e, e, e)
+    assert out['status'].shape == (0,) and out['counts'].sum() == 0
+    sigs = [np.full(n, 500, np.int16) for n in (0, 10, 8999)]
+    raw, off, ln = eng_stock.pack_reads(sigs)
+    c = np.array([1400.0] * 3), np.array([8192.0] * 3), np.array([5.0] * 3)
+    out = eng_stock.analyze_host(raw, off, ln, *c, polya=True)
+    assert list(out['status']) == [3, 3, 3] and list(out['label']) == [3, 3, 3]
+    assert out['counts'][3, 0, 3] == 3 and not out['polya']['found'].any()
+    rd = _reads(preset, 2, 150000, seed=77)
+    raw, off, ln = _dense_batch(rd)
+    out = eng_stock.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'], polya=True)
+    ref = _oracle_batch(orc_stock, raw, off, ln, rd)
+    _compare(out, ref)
+    assert out['segments'][:, :6].max() < 6666          # scan limit (signal_analyzer.py:347-349)
