@@ -428,6 +428,25 @@ class SignalEngine:
                                                 C.c_void_p(st.cuda_stream)))
         return out
 
+    def detect_unsplit_device(self, batch, ev_offsets, start, move, p_model_state, sampling_rate,
+                              first_sample, block_stride, scale_shift, status, segments,
+                              max_windows, mean=None, stream=None):
+        """pb2_detect_unsplit over tensors resident in HBM.  ``batch`` = (raw, offsets, lengths,
+        range, digitisation, offset) tensors; ``mean=None`` derives the event means on the
+        device.  Returns an int32 flag tensor."""
+        import torch
+        n = int(sampling_rate.numel())
+        ev = N.EventTables(int(start.numel()), ev_offsets.data_ptr(), start.data_ptr(),
+                           mean.data_ptr() if mean is not None else None, move.data_ptr(),
+                           p_model_state.data_ptr(), sampling_rate.data_ptr(),
+                           first_sample.data_ptr(), int(block_stride))
+        b = self._batch_from_tensors(*batch)
+        flag = torch.zeros(n, dtype=torch.int32, device=status.device)
+        self._check(self.lib.pb2_detect_unsplit(
+            self.handle, C.byref(b), C.byref(ev), n, scale_shift.data_ptr(), status.data_ptr(),
+            segments.data_ptr(), int(max_windows), flag.data_ptr(), self._stream(stream)))
+        return flag
+
     # ------------------------------------------------ single stages (tensors)
     def _stream(self, stream):
         import torch

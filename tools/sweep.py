@@ -69,6 +69,30 @@ def main():
                 if polya:
                     pol = res['polya'].cpu().numpy().view(np.dtype([('found', 'i4'), ('rest', 'V804')]))
                     ent['polya_found'] = int(pol['found'].sum())
+                if polya and eng.unsplit_ready:
+                    # chimera filter on synthetic guppy-style tables: one row per 15 samples,
+                    # random moves / qualities, means derived on the device
+                    E = L // 15
+                    g = torch.Generator(device=dev); g.manual_seed(L)
+                    ev_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * E
+                    start = (torch.arange(E, dtype=torch.int64, device=dev) * 15).repeat(n)
+                    move = (torch.rand(n * E, generator=g, device=dev) < 0.3).to(torch.int32)
+                    pst = torch.rand(n * E, generator=g, device=dev, dtype=torch.float64)
+                    rate = torch.full((n,), 3012.0, dtype=torch.float64, device=dev)
+                    first = torch.zeros(n, dtype=torch.int64, device=dev)
+                    maxw = max(1, -(-L // int(3 * 3012)))
+                    for rep in range(2):
+                        torch.cuda.synchronize()
+                        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        u0.record()
+                        flag = eng.detect_unsplit_device(work, ev_off, start, move, pst, rate, first, 15,
+                                                         res['scale_shift'], res['status'],
+                                                         res['segments'], maxw)
+                        u1.record()
+                        torch.cuda.synchronize()
+                    ent['unsplit_ms'] = u0.elapsed_time(u1)
+                    ent['unsplit_flagged'] = int((flag == 1).sum().item())
+                    ent['unsplit_errors'] = int((flag < 0).sum().item())
                 out.append(ent)
                 print(json.dumps(ent), file=sys.stderr)
             del raw, rd, work
