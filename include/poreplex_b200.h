@@ -299,6 +299,31 @@ int64_t pb2_kernel_launches(const pb2_context *ctx);
  * (identical outputs, slower; see csrc/pb_math.cuh, kernels_lstm.cu). */
 int pb2_set_exact_division(pb2_context *ctx, int on);
 
+/* Tensor-core LSTM path (default on).  The recurrent products of keras predict()
+ * (signal_loader.py:96-97, barcoding.py:106-107) run on tcgen05 tensor cores as split-fp16
+ * GEMMs; every decision taken from those approximate outputs passes a margin test and the
+ * reads that fail it are re-run through the exact f32 kernels, so barcode / guess / score
+ * stay those of the exact path.  The error bound the margin test assumes for a window's class
+ * logits is  demux_margin_delta + demux_probe_gain * s,  s being the shift of the logits
+ * under a deliberately coarse second evaluation of layer 2 (the classifier's second LSTM
+ * amplifies perturbations by orders of magnitude for a small fraction of windows, so the
+ * sensitivity is measured per window).  Pass 0 to keep a value.  on = 0: exact kernels only. */
+int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta,
+                      double demux_probe_gain);
+/* Verification: the tensor-core demultiplexer WITHOUT the exact re-run -- approximate class
+ * probabilities and logits ([n][PB2_MAX_CLASSES]), tentative calls, and the margin-test verdict
+ * per window (unsafe[i] = 1: this window would be re-run; sensitivity[i] = its measured logit
+ * shift).  Device pointers; any may be NULL. */
+int pb2_demux_predict_tc(pb2_context *ctx, const float *windows, int64_t n, float *class_probs,
+                         float *logits, int32_t *barcode, int32_t *guess, int32_t *score,
+                         int32_t *unsafe, float *sensitivity, void *stream);
+/* Verification: layer-1 outputs of the exact kernels, every position stepped:
+ * out[n][signal_trim_length][2 * units] (forward | backward), n <= 4096.  Device pointers. */
+int pb2_debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float *out, void *stream);
+/* After a call: how many windows the last demultiplexer launch re-ran exactly, and whether a
+ * tensor-core kernel hit its barrier time-out (results invalid if non-zero).  Synchronises. */
+int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_timeouts);
+
 /* ---- measurement ----------------------------------------------------------
  * With profiling on, every kernel launch is bracketed by CUDA events on its own
  * stream.  pb2_profile_read synchronises the device, adds the elapsed times up per

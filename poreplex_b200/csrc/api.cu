@@ -76,7 +76,9 @@ void prof_end(pb2_context *ctx, cudaStream_t st)
 static const char *const kKernelNames[K_NUM] = {
     "k_pool", "k_scaler_prepare", "k_scaler_lstm", "k_segment", "k_viterbi_paths",
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
-    "k_unsplit_windows", "k_unsplit_decide", "k_event_means"};
+    "k_unsplit_windows", "k_unsplit_decide", "k_event_means", "k_lstm_tc_demux_l1",
+    "k_lstm_tc_demux_l2", "k_demux_head_tc", "k_lstm_tc_scaler_l1", "k_lstm_tc_scaler_l2",
+    "k_scaler_head_tc"};
 
 static void ws_free(Workspace &w)
 {
@@ -161,12 +163,14 @@ void pb2_destroy(pb2_context *ctx)
     free_lstm(ctx->demux.fwd); free_lstm(ctx->demux.bwd); free_lstm(ctx->demux.l2);
     cudaFree(ctx->demux.dense_kernel); cudaFree(ctx->demux.dense_bias);
     cudaFree(ctx->demux.pad_state); cudaFree(ctx->demux.pad_prefix);
+    cudaFree(ctx->demux.calibration_dev);
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
                         &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
-                        &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean};
+                        &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean,
+                        &ctx->ws_hlast, &ctx->ws_recheck, &ctx->ws_win2, &ctx->ws_read2};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -195,6 +199,48 @@ int pb2_set_exact_division(pb2_context *ctx, int on)
     if (!ctx) return PB2_EINVAL;
     ctx->exact_division = on != 0;
     ctx->no_pad_skip = on != 0;        // verification mode also steps every padded position
+    return PB2_OK;
+}
+
+int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta, double demux_probe_gain)
+{
+    if (!ctx) return PB2_EINVAL;
+    ctx->fast_lstm = on != 0;
+    if (demux_margin_delta > 0) ctx->demux_margin_delta = demux_margin_delta;
+    if (demux_probe_gain > 0) ctx->demux_probe_gain = demux_probe_gain;
+    return PB2_OK;
+}
+
+int pb2_demux_predict_tc(pb2_context *ctx, const float *windows, int64_t n, float *class_probs,
+                         float *logits, int32_t *barcode, int32_t *guess, int32_t *score,
+                         int32_t *unsafe, float *sensitivity, void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
+    DeviceGuard g(ctx->device);
+    return launch_demux_tc(ctx, windows, nullptr, n, nullptr, nullptr, class_probs, barcode, guess,
+                           score, logits, unsafe, sensitivity, /*recheck=*/false, (cudaStream_t)stream);
+}
+
+int pb2_debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float *out, void *stream)
+{
+    if (!ctx || !windows || !out) return PB2_EINVAL;
+    if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
+    DeviceGuard g(ctx->device);
+    return debug_demux_l1(ctx, windows, n, out, (cudaStream_t)stream);
+}
+
+int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_timeouts)
+{
+    if (!ctx) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    int32_t v[4] = {0, 0, 0, 0};
+    if (ctx->ws_recheck.ptr) {
+        PB_CUDA(ctx, cudaDeviceSynchronize());
+        PB_CUDA(ctx, cudaMemcpy(v, ctx->ws_recheck.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+    }
+    if (tc_timeouts) *tc_timeouts = v[0];
+    if (demux_rechecked) *demux_rechecked = v[1];
     return PB2_OK;
 }
 
@@ -290,6 +336,9 @@ int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p)
     for (int i = 0; i < PB2_MAX_CALIB; i++)
         D.calibration[i] = i < p->n_calibration ? p->calibration[i] : INFINITY;
     D.score_threshold = p->score_threshold;
+    if (!D.calibration_dev) PB_CUDA(ctx, cudaMalloc(&D.calibration_dev, sizeof(double) * PB2_MAX_CALIB));
+    PB_CUDA(ctx, cudaMemcpy(D.calibration_dev, D.calibration, sizeof(double) * PB2_MAX_CALIB,
+                            cudaMemcpyHostToDevice));
     if ((rc = build_pad_tables(ctx))) return rc;
     D.set = true;
     return PB2_OK;

@@ -17,6 +17,7 @@
 // memory with ONE block barrier per time step.
 #include "pb_internal.h"
 #include "pb_math.cuh"
+#include "demux_head.cuh"
 
 namespace pb {
 
@@ -718,61 +719,25 @@ k_demux_l2(const DemuxArgs A)
         // results go to the read that owns the row
         const int64_t r = (row < n_eff && A.slot_read) ? (int64_t)A.slot_read[A.row0 + row] : row;
         if (row < n_eff && (A.pushed == nullptr || A.pushed[r])) {
-            const float *hf = hs + cur * H2 * TB;
-            const int nc = A.n_classes;
-            float logit[PB2_MAX_CLASSES], e[PB2_MAX_CLASSES];
-#pragma unroll
-            for (int j = 0; j < PB2_MAX_CLASSES; j++) logit[j] = 0.f;
-            for (int k = 0; k < H2; k++) {
-                const float hk = hf[k * TB + tid];
+            DemuxCall call;
+            demux_head<H2>(hs + cur * H2 * TB + tid, TB, A.Wd, A.bd, A.n_classes, A.n_decoy,
+                           A.score_threshold, c_calibration, A.n_calibration, call);
+            if (A.class_probs) {
 #pragma unroll
                 for (int j = 0; j < PB2_MAX_CLASSES; j++)
-                    if (j < nc) logit[j] = pb::ffma(hk, A.Wd[k * nc + j], logit[j]);
+                    A.class_probs[r * PB2_MAX_CLASSES + j] = call.probs[j];
             }
-            float m = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < PB2_MAX_CLASSES; j++)
-                if (j < nc) { logit[j] = pb::fadd(logit[j], A.bd[j]); m = fmaxf(m, logit[j]); }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < PB2_MAX_CLASSES; j++)
-                if (j < nc) { e[j] = pb::exp_eigen(pb::fsub(logit[j], m)); sum = pb::fadd(sum, e[j]); }
-            const float rs = pb::fdiv(1.0f, sum);
-            int arg = 0;
-            float best = -1.f;
-#pragma unroll
-            for (int j = 0; j < PB2_MAX_CLASSES; j++) {
-                float p = 0.f;
-                if (j < nc) {
-                    p = pb::fmul(e[j], rs);
-                    if (p > best) { best = p; arg = j; }
-                }
-                if (A.class_probs) A.class_probs[r * PB2_MAX_CLASSES + j] = p;
-            }
-            // barcoding.py:108-118
-            const int bcid = arg - A.n_decoy;
-            const double sc = (double)best;
-            if (A.barcode) A.barcode[r] = (bcid >= 0 && sc >= A.score_threshold) ? bcid : -1;
-            if (A.guess) A.guess[r] = bcid;
-            if (A.score) {
-                int lo = 0;
-                if (sc > 0.0) {                 // bisect_right(calibration, score)
-                    int hi = A.n_calibration;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sc < c_calibration[mid]) hi = mid; else lo = mid + 1;
-                    }
-                }
-                A.score[r] = lo;
-            }
+            if (A.barcode) A.barcode[r] = call.barcode;
+            if (A.guess) A.guess[r] = call.guess;
+            if (A.score) A.score[r] = call.score;
         }
     }
 }
 
-int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
-                 const int *slot_count, const int32_t *slot_read,
-                 float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
-                 cudaStream_t st)
+int launch_demux_exact(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                       const int *slot_count, const int32_t *slot_read,
+                       float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                       cudaStream_t st)
 {
     if (n <= 0) return PB2_OK;
     const DemuxDev &D = ctx->demux;
@@ -895,4 +860,58 @@ int build_pad_tables(pb2_context *ctx)
     return PB2_OK;
 }
 
+}  // namespace pb
+
+namespace pb {
+// G[tile][t][K][TB] -> out[row][t][K]
+__global__ void k_debug_untile(const float *__restrict__ G, int64_t n, int T, int K, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * T * K) return;
+    const int k = (int)(i % K);
+    const int t = (int)((i / K) % T);
+    const int64_t row = i / ((int64_t)K * T);
+    out[i] = G[(((row / TB) * T + t) * K + k) * TB + row % TB];
+}
+
+// Verification: layer-1 outputs of the exact kernels for the first n <= 4096 windows,
+// out[n][T][2*H1] (forward | backward), every position stepped (no pad skipping).
+int debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float *out, cudaStream_t st)
+{
+    const DemuxDev &D = ctx->demux;
+    constexpr int H1 = 48;
+    if (D.fwd.units != H1 || n <= 0 || n > 4096) return fail(ctx, PB2_EINVAL, "debug_demux_l1: bad size");
+    const int T = D.trim_length;
+    const int64_t tiles = (n + TB - 1) / TB;
+    const size_t per_tile = sizeof(float) * (size_t)T * 2 * H1 * TB;
+    float *G = (float *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles);
+    if (!G) return PB2_ENOMEM;
+    const size_t smem1 = sizeof(float) * (H1 * 4 * H1 + 2 * H1 * TB);
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_demux_l1<H1, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    DemuxArgs A = {};
+    A.windows = windows; A.n = n; A.T = T;
+    A.Wf = D.fwd.kernel; A.Uf = D.fwd.recurrent; A.bf = D.fwd.bias;
+    A.Wb = D.bwd.kernel; A.Ub = D.bwd.recurrent; A.bb = D.bwd.bias;
+    A.G = G; A.pad_value = D.pad_value;
+    k_demux_l1<H1, true><<<dim3((unsigned)tiles, 2), (H1 / 2) * NRG, smem1, st>>>(A);
+    PB_LAUNCH_CHECK(ctx, "k_demux_l1<debug>");
+    k_debug_untile<<<(unsigned)((n * T * 2 * H1 + 255) / 256), 256, 0, st>>>(G, n, T, 2 * H1, out);
+    PB_LAUNCH_CHECK(ctx, "k_debug_untile");
+    return PB2_OK;
+}
+
+// The demultiplexer as the rest of the library calls it: tensor-core path with exact
+// re-check unless a verification mode asks for the exact kernels only.
+int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                 const int *slot_count, const int32_t *slot_read,
+                 float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                 cudaStream_t st)
+{
+    if (ctx->fast_lstm && !ctx->exact_division)
+        return launch_demux_tc(ctx, windows, pushed, n, slot_count, slot_read, class_probs, barcode,
+                               guess, score, nullptr, nullptr, nullptr, /*recheck=*/true, st);
+    return launch_demux_exact(ctx, windows, pushed, n, slot_count, slot_read, class_probs, barcode,
+                              guess, score, st);
+}
 }  // namespace pb

@@ -1,0 +1,542 @@
+// kernels_lstm_tc.cu -- tensor-core (tcgen05 / TMEM) LSTM layers for the barcode
+// demultiplexer (A7, barcoding.py:103-118) and the scaler network (A3,
+// signal_loader.py:89-109), plus the margin tests that keep the integer outputs
+// bit-identical to the exact path.
+//
+// Why a second LSTM implementation: the exact kernels (kernels_lstm.cu) evaluate every
+// pre-activation as the oracle's f32 fma chain and are bound by the FP32 FMA pipe.  Here
+// the recurrent products run on the 5th-generation tensor cores as split-fp16 GEMMs
+// (tc_core.cuh: a*b = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM), which
+// agrees with the f32 chain to about 1e-6 per pre-activation -- the same size as the
+// rounding noise of the chain itself -- but not bit for bit.  Every decision taken from
+// these approximate outputs is therefore guarded by a margin test (demux_call_is_safe):
+// a read whose decision could change under a perturbation of the size of the
+// approximation error is re-run through the exact kernels.  The exact path stays the
+// definition of the result; this path only decides which reads need it.
+//
+// One CTA = one tile of 128 reads = the 128 TMEM lanes.  Per time step
+//   warp 8, one thread : waits for h(t-1) [and x(t)] in TMEM, issues the MMAs
+//                        D[128][4H] = x(t) W + h(t-1) U, commits to an mbarrier;
+//   warps 0-7          : thread = (read, half of the units); tcgen05.ld its pre-activations,
+//                        adds bias / scalar input term, gates, cell update, writes h(t) back to
+//                        TMEM as packed fp16 hi/lo (the next step's A operand) and, for a
+//                        sequence-returning layer, to the scratch the next layer reads.
+// Layers with a scalar input (K = H only) need 4H + H <= 256 TMEM columns, so two CTAs share
+// an SM and one computes gates while the other's MMAs run.
+#include "pb_internal.h"
+#include "pb_math.cuh"
+#include "tc_core.cuh"
+#include "demux_head.cuh"
+
+namespace pb {
+
+using namespace pb::tc;
+
+constexpr int TCM = 128;                 // reads per tile (TMEM lanes)
+constexpr int TC_THREADS = 288;          // 8 gate warps + 1 MMA warp
+
+struct TcDir {                           // one direction of a layer
+    const float *U;                      // recurrent kernel [H][4H]
+    const float *W;                      // input kernel [KX][4H] (vector input) or [1][4H] (scalar)
+    const float *b;                      // bias [4H]
+    int reverse;                         // 1: walk the window from its last position
+    int skip_mode;                       // 0 none; 1 leading pad values (demux fwd); 2 zero head (scaler)
+    int g_hi, g_lo;                      // SEQ_OUT: word offsets of this direction's hi / lo halves
+    int coarse;                          // 1: leading fp16 product only (sensitivity probe)
+    float *h_last;                       // !SEQ_OUT: [rows][H] final hidden state
+};
+
+struct TcArgs {
+    TcDir dir[2];                        // blockIdx.y selects
+    // scalar input (KX == 0): x(t) of row r = t >= pad_r ? xsrc[base_r + t - pad_r] : padval
+    const float *xsrc;
+    const int64_t *xoff;                 // [n] element offset of the first real sample, or nullptr:
+    const int32_t *nreal;                //     rows are dense [n][T] and pad_r = 0
+    float padval;
+    int T;
+    int64_t n;                           // rows of this pass
+    const int *slot_count;               // device count of valid rows (or nullptr)
+    int64_t row0;
+    // state after s leading pad steps (read-independent): tab[s * tab_stride + tab_h/tab_c + u]
+    const float *tab;
+    int tab_stride, tab_h, tab_c;
+    int *tile_tstart;                    // producer (skip_mode != 0) writes, consumer (KX > 0) reads
+    int tstart_in;                       // KX > 0: 1 = start at tile_tstart[tile] from `tab`
+    // sequences: packed fp16 words, [tile][t][g_words][128 reads]
+    uint32_t *Gout;
+    const uint32_t *Gin;
+    int g_words;                         // words per (read, step) of Gout
+    int fill_skipped;                    // SEQ_OUT: also write the tabulated h of skipped steps
+    int *err;                            // set to 1 if a barrier wait timed out
+};
+
+// ---- gate non-linearities of the approximate path ----------------------------------
+// MUFU-based: absolute error about 1e-7, far below the split-GEMM / f32-chain noise floor.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {          // 1 / (1 + e^-x)
+    return rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, -1.4426950408889634f))));
+}
+__device__ __forceinline__ float tanh_fast(float x) {             // 1 - 2 / (1 + e^2x)
+    const float r = rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, 2.8853900817779268f))));
+    return __fmaf_rn(-2.0f, r, 1.0f);
+}
+
+template <int H, int KX>
+__host__ __device__ constexpr int tc_tmem_cols() { return (4 * H + H + KX <= 256) ? 256 : 512; }
+
+template <int H, int KX>
+constexpr size_t tc_smem_bytes() {
+    // B matrices (fp16 hi + lo) for U and, with a vector input, W; bias and scalar kernel
+    return (size_t)(H + KX) * 4 * H * 2 * 2 + (size_t)2 * 4 * H * sizeof(float) + 128;
+}
+
+template <int H, int KX, bool SEQ_OUT>
+__global__ void __launch_bounds__(TC_THREADS, (KX == 0 ? 2 : 1))
+k_lstm_tc(const TcArgs A)
+{
+    constexpr int N = 4 * H;
+    constexpr int HH = H / 2;            // units per gate thread
+    constexpr int NCH = HH / 8;          // chunks of 8 units (32 accumulator columns)
+    constexpr int TCOLS = tc_tmem_cols<H, KX>();
+    static_assert(HH % 8 == 0, "units per thread must be a multiple of 8");
+    static_assert(H % 16 == 0 && KX % 16 == 0, "K must be a multiple of 16");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half *bU_hi = reinterpret_cast<__half *>(smem_raw);
+    __half *bU_lo = bU_hi + H * N;
+    __half *bW_hi = bU_lo + H * N;
+    __half *bW_lo = bW_hi + KX * N;
+    float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);       // [N], n = 4u + gate
+    float *s_win = s_bias + N;                                        // [N] scalar input kernel
+    __shared__ __align__(8) uint64_t bar_d, bar_h;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_dead, s_tstart;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TcDir &dir = A.dir[blockIdx.y];
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TCM;
+    int64_t n_eff = A.n;
+    if (A.slot_count) {
+        n_eff = (int64_t)*A.slot_count - A.row0;
+        if (n_eff > A.n) n_eff = A.n;
+    }
+    if (tile0 >= n_eff) return;
+    const int T = A.T;
+
+    // ---- one-time setup ----------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&bar_d, 1);
+        mbar_init(&bar_h, 8);
+        mbar_fence_init();
+        s_dead = 0;
+        s_tstart = (dir.skip_mode != 0) ? T : 0;
+    }
+    if (warp == 8) tmem_alloc(&s_tmem, TCOLS);
+    load_b_split<H, H>(dir.U, bU_hi, bU_lo, tid, TC_THREADS);
+    if (KX > 0) load_b_split<(KX > 0 ? KX : 16), H>(dir.W, bW_hi, bW_lo, tid, TC_THREADS);
+    for (int i = tid; i < N; i += TC_THREADS) {
+        const int gate = i / H, u = i % H;
+        s_bias[4 * u + gate] = dir.b[i];
+        s_win[4 * u + gate] = (KX == 0) ? dir.W[i] : 0.f;
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    const uint32_t tbase = s_tmem;
+    const uint32_t col_d = 0, col_h = N, col_x = N + H;     // h: hi [H/2] then lo [H/2]; x alike
+
+    // ---- per-row input addressing and the common start step -------------------------
+    const int q = warp & 3, wg = (warp >> 2) & 1;
+    const int m = q * 32 + lane;
+    int64_t row = tile0 + m;
+    if (row >= n_eff) row = n_eff - 1;                     // duplicate the last row (no output)
+    const float *xbase = nullptr;
+    int pad = 0;
+    if (KX == 0 && warp < 8) {
+        if (A.xoff) {
+            const int nr = A.nreal[A.row0 + row];
+            pad = T - nr;
+            xbase = A.xsrc + (nr > 0 ? A.xoff[A.row0 + row] : 0) - pad;
+            if (nr <= 0) pad = T;                          // inactive row: all padding
+        } else {
+            xbase = A.xsrc + (A.row0 + row) * (int64_t)T;
+        }
+        if (wg == 0) {
+            if (dir.skip_mode == 1) {
+                int np = 0;
+                while (np < T && xbase[np] == A.padval) np++;
+                atomicMin(&s_tstart, np);
+            } else if (dir.skip_mode == 2) {
+                atomicMin(&s_tstart, pad);
+            }
+        }
+    }
+    __syncthreads();
+    int t_start = 0;
+    if (KX == 0) {
+        t_start = s_tstart;
+        if (t_start >= T) t_start = T - 1;                 // keep at least the last step live
+        if (!A.tab) t_start = 0;
+        if (dir.skip_mode != 0 && A.tile_tstart && tid == 0) A.tile_tstart[tile] = t_start;
+    } else if (A.tstart_in && A.tile_tstart) {
+        t_start = A.tile_tstart[tile];
+    }
+
+    if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t ph = 0;
+            for (int s = t_start; s < T; s++) {
+                mbar_wait(&bar_h, ph, &s_dead);
+                ph ^= 1;
+                fence_after_sync();
+                bool first = true;
+                if (KX > 0)
+                    issue_split_gemm<(KX > 0 ? KX : 16), N>(tbase + col_d, tbase + col_x,
+                                                            tbase + col_x + KX / 2,
+                                                            smem_u32(bW_hi), smem_u32(bW_lo), first,
+                                                            !dir.coarse);
+                issue_split_gemm<H, N>(tbase + col_d, tbase + col_h, tbase + col_h + H / 2,
+                                       smem_u32(bU_hi), smem_u32(bU_lo), first, !dir.coarse);
+                mma_commit(&bar_d);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== gate warps =====
+        const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+        const int u0 = wg * HH;                            // first unit of this thread
+        float c[HH];
+        // initial state: zeros, or the tabulated state after t_start pad steps
+        {
+            const float *tb = (t_start > 0 && A.tab) ? A.tab + (size_t)t_start * A.tab_stride : nullptr;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int u = u0 + ch * 8 + 2 * j;
+                    const float ha = tb ? tb[A.tab_h + u] : 0.f, hb = tb ? tb[A.tab_h + u + 1] : 0.f;
+                    c[ch * 8 + 2 * j] = tb ? tb[A.tab_c + u] : 0.f;
+                    c[ch * 8 + 2 * j + 1] = tb ? tb[A.tab_c + u + 1] : 0.f;
+                    hi[j] = split2(ha, hb, lo[j]);
+                }
+                tmem_st4(lane_addr + col_h + (u0 + ch * 8) / 2, hi[0], hi[1], hi[2], hi[3]);
+                tmem_st4(lane_addr + col_h + H / 2 + (u0 + ch * 8) / 2, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        // sequence scratch of this tile: words [t][w][128]
+        uint32_t *gout = SEQ_OUT ? A.Gout + (size_t)tile * T * A.g_words * TCM : nullptr;
+        const uint32_t *gin = (KX > 0) ? A.Gin + (size_t)tile * T * KX * TCM : nullptr;
+        if (SEQ_OUT && A.fill_skipped && A.tab) {
+            // h after pad step t is tab[t + 1]; the same for every read of the tile
+            for (int t = 0; t < t_start; t++) {
+                const float *tt = A.tab + (size_t)(t + 1) * A.tab_stride + A.tab_h;
+                uint32_t *gt = gout + (size_t)t * A.g_words * TCM + m;
+#pragma unroll
+                for (int j = 0; j < HH / 2; j++) {
+                    uint32_t lo;
+                    const uint32_t hi = split2(tt[u0 + 2 * j], tt[u0 + 2 * j + 1], lo);
+                    gt[(size_t)(dir.g_hi + u0 / 2 + j) * TCM] = hi;
+                    gt[(size_t)(dir.g_lo + u0 / 2 + j) * TCM] = lo;
+                }
+            }
+        }
+        // vector input of the first step -> TMEM
+        constexpr int XW = (KX > 0) ? KX / 2 : 1;          // x words per thread
+        uint32_t xw[XW];
+        if (KX > 0) {
+            const int t = dir.reverse ? (T - 1 - t_start) : t_start;
+            const uint32_t *gp = gin + (size_t)t * KX * TCM + (size_t)(wg * XW) * TCM + m;
+#pragma unroll
+            for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+#pragma unroll
+            for (int j = 0; j < XW; j += 4)
+                tmem_st4(lane_addr + col_x + wg * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_h);
+
+        uint32_t ph = 0;
+        for (int s = t_start; s < T; s++) {
+            const int t = dir.reverse ? (T - 1 - s) : s;
+            float xv = 0.f;
+            if (KX == 0) xv = (t >= pad) ? __ldg(xbase + t) : A.padval;
+            if (KX > 0 && s + 1 < T) {                     // prefetch the next step's input
+                const int tn = dir.reverse ? (T - 2 - s) : (s + 1);
+                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(wg * XW) * TCM + m;
+#pragma unroll
+                for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+            }
+            mbar_wait(&bar_d, ph, &s_dead);
+            ph ^= 1;
+            __syncwarp();
+            fence_after_sync();
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + col_d + (u0 + ch * 8) * 4, v);
+                tmem_ld_wait();
+                float hn[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int u = u0 + ch * 8 + j;
+                    const float4 bb = *reinterpret_cast<const float4 *>(s_bias + 4 * u);
+                    float zi = __fadd_rn(__uint_as_float(v[4 * j + 0]), bb.x);
+                    float zf = __fadd_rn(__uint_as_float(v[4 * j + 1]), bb.y);
+                    float zc = __fadd_rn(__uint_as_float(v[4 * j + 2]), bb.z);
+                    float zo = __fadd_rn(__uint_as_float(v[4 * j + 3]), bb.w);
+                    if (KX == 0) {
+                        const float4 ww = *reinterpret_cast<const float4 *>(s_win + 4 * u);
+                        zi = __fmaf_rn(xv, ww.x, zi);
+                        zf = __fmaf_rn(xv, ww.y, zf);
+                        zc = __fmaf_rn(xv, ww.z, zc);
+                        zo = __fmaf_rn(xv, ww.w, zo);
+                    }
+                    const float ig = sigmoid_fast(zi), fg = sigmoid_fast(zf);
+                    const float cg = tanh_fast(zc), og = sigmoid_fast(zo);
+                    const float cn = __fmaf_rn(fg, c[ch * 8 + j], __fmul_rn(ig, cg));
+                    c[ch * 8 + j] = cn;
+                    hn[j] = __fmul_rn(og, tanh_fast(cn));
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) hi[j] = split2(hn[2 * j], hn[2 * j + 1], lo[j]);
+                tmem_st4(lane_addr + col_h + (u0 + ch * 8) / 2, hi[0], hi[1], hi[2], hi[3]);
+                tmem_st4(lane_addr + col_h + H / 2 + (u0 + ch * 8) / 2, lo[0], lo[1], lo[2], lo[3]);
+                if (SEQ_OUT) {
+                    uint32_t *gt = gout + (size_t)t * A.g_words * TCM + m;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        gt[(size_t)(dir.g_hi + (u0 + ch * 8) / 2 + j) * TCM] = hi[j];
+                        gt[(size_t)(dir.g_lo + (u0 + ch * 8) / 2 + j) * TCM] = lo[j];
+                    }
+                }
+                if (!SEQ_OUT && s == T - 1 && tile0 + m < n_eff) {
+                    float *hl = dir.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) hl[j] = hn[j];
+                }
+            }
+            if (KX > 0 && s + 1 < T) {
+#pragma unroll
+                for (int j = 0; j < XW; j += 4)
+                    tmem_st4(lane_addr + col_x + wg * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+            }
+            tmem_st_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_h);
+        }
+    }
+
+    // ---- teardown ------------------------------------------------------------------
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        fence_after_sync();
+        tmem_dealloc(tbase, TCOLS);
+    }
+    if (tid == 0 && s_dead && A.err) *A.err = 1;
+}
+
+// ---- demultiplexer head on the approximate layer-2 state -----------------------------
+// One thread per window row: Dense + softmax + decision exactly as the exact kernel does it
+// (same code, demux_head.cuh), then the margin test.  Unsafe rows are appended to the
+// re-check list; their tentative outputs are overwritten by the exact kernels afterwards.
+struct TcHeadArgs {
+    const float *h_last;           // [rows][H2]
+    const float *h_probe;          // [rows][H2] the coarse (perturbed) evaluation
+    double delta0, probe_gain;     // per-window error bound = delta0 + probe_gain * |logit shift|
+    float *sens_out;               // optional [rows]: the measured logit shift
+    int64_t n;
+    const int *slot_count;
+    const int32_t *slot_read;      // row -> read (or nullptr: row == read)
+    const int32_t *pushed;         // optional mask (dense mode)
+    const float *Wd, *bd;
+    int n_classes, n_decoy, n_calibration;
+    double score_threshold;
+    const double *calibration;     // device copy
+    float *class_probs; int32_t *barcode, *guess, *score;
+    int *recheck_count; int32_t *recheck_rows;
+    float *logits_out;             // optional [rows][PB2_MAX_CLASSES] (verification)
+    int32_t *unsafe_out;           // optional [rows] (verification)
+};
+
+template <int H2>
+__global__ void k_demux_head_tc(const TcHeadArgs A)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n_eff = A.n;
+    if (A.slot_count && (int64_t)*A.slot_count < n_eff) n_eff = *A.slot_count;
+    if (row >= n_eff) return;
+    const int64_t r = A.slot_read ? (int64_t)A.slot_read[row] : row;
+    if (A.pushed && !A.pushed[r]) return;
+    DemuxCall call;
+    demux_head<H2>(A.h_last + (size_t)row * H2, 1, A.Wd, A.bd, A.n_classes, A.n_decoy,
+                   A.score_threshold, A.calibration, A.n_calibration, call);
+    // sensitivity of this window: how far the class logits (relative to the called class) move
+    // when every product is perturbed by about 2^-11 (the coarse evaluation)
+    DemuxCall probe;
+    demux_head<H2>(A.h_probe + (size_t)row * H2, 1, A.Wd, A.bd, A.n_classes, A.n_decoy,
+                   A.score_threshold, A.calibration, A.n_calibration, probe);
+    float shift = 0.f;
+#pragma unroll
+    for (int j = 0; j < PB2_MAX_CLASSES; j++)
+        if (j < A.n_classes)
+            shift = fmaxf(shift, fabsf((call.logit[j] - call.logit[call.arg]) -
+                                       (probe.logit[j] - probe.logit[call.arg])));
+    if (!(shift == shift)) shift = INFINITY;
+    const double delta = A.delta0 + A.probe_gain * (double)shift;
+    const bool safe = demux_call_is_safe(call, A.n_classes, delta, A.score_threshold,
+                                         A.calibration, A.n_calibration);
+    if (A.sens_out) A.sens_out[row] = shift;
+    if (A.class_probs) {
+#pragma unroll
+        for (int j = 0; j < PB2_MAX_CLASSES; j++) A.class_probs[r * PB2_MAX_CLASSES + j] = call.probs[j];
+    }
+    if (A.barcode) A.barcode[r] = call.barcode;
+    if (A.guess) A.guess[r] = call.guess;
+    if (A.score) A.score[r] = call.score;
+    if (A.logits_out) {
+#pragma unroll
+        for (int j = 0; j < PB2_MAX_CLASSES; j++) A.logits_out[row * PB2_MAX_CLASSES + j] = call.logit[j];
+    }
+    if (A.unsafe_out) A.unsafe_out[row] = safe ? 0 : 1;
+    if (!safe && A.recheck_rows) {
+        const int k = atomicAdd(A.recheck_count, 1);
+        A.recheck_rows[k] = (int32_t)row;
+    }
+}
+
+// copy the windows of the rows on the re-check list into a compact buffer
+__global__ void k_gather_recheck(const float *__restrict__ windows, int T,
+                                 const int *__restrict__ count, const int32_t *__restrict__ rows,
+                                 const int32_t *__restrict__ slot_read,
+                                 float *__restrict__ out, int32_t *__restrict__ out_read)
+{
+    const int k = blockIdx.x;
+    if (k >= *count) return;
+    const int32_t row = rows[k];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) out[(size_t)k * T + t] = windows[(size_t)row * T + t];
+    if (threadIdx.x == 0) out_read[k] = slot_read ? slot_read[row] : row;
+}
+
+template <int H, int KX, bool SEQ_OUT>
+static int tc_set_attr(pb2_context *ctx)
+{
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<H, KX, SEQ_OUT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc_smem_bytes<H, KX>()));
+    return PB2_OK;
+}
+
+// Approximate demultiplexer over `n` window rows + margin test.  With `recheck` the unsafe
+// rows are re-run through the exact kernels so that barcode / guess / score (and the class
+// probabilities of those rows) are the exact path's.
+int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                    const int *slot_count, const int32_t *slot_read,
+                    float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                    float *logits_out, int32_t *unsafe_out, float *sens_out, bool recheck,
+                    cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    DemuxDev &D = ctx->demux;
+    if (D.fwd.units != 48 || D.bwd.units != 48 || D.l2.units != 64 || D.fwd.in_dim != 1 ||
+        D.l2.in_dim != 96)
+        return fail(ctx, PB2_EUNSUPPORTED, "demux network shape not built "
+                    "(Bidirectional(LSTMCell 48) -> LSTMCell 64 expected)");
+    constexpr int H1 = 48, H2 = 64, KX = 2 * H1;
+    const int T = D.trim_length;
+    if (!ctx->attr_demux_tc) {
+        int rc;
+        if ((rc = tc_set_attr<H1, 0, true>(ctx))) return rc;
+        if ((rc = tc_set_attr<H2, KX, false>(ctx))) return rc;
+        ctx->attr_demux_tc = true;
+    }
+    const int64_t tiles = (n + TCM - 1) / TCM;
+    const size_t per_tile = sizeof(uint32_t) * (size_t)T * KX * TCM;
+    int64_t tiles_per_pass = (int64_t)(ctx->tc_scratch_bytes / per_tile);
+    if (tiles_per_pass < 1) tiles_per_pass = 1;
+    if (tiles_per_pass > tiles) tiles_per_pass = tiles;
+    uint32_t *G = (uint32_t *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
+    float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H2 * 2);
+    float *h_probe = h_last ? h_last + (size_t)n * H2 : nullptr;
+    int *tstart = (int *)ws_get(ctx, ctx->ws_tstart, sizeof(int) * (size_t)tiles_per_pass);
+    // [0] timeout flag, [1] re-check count, then the re-check rows
+    int32_t *rlist = (int32_t *)ws_get(ctx, ctx->ws_recheck, sizeof(int32_t) * ((size_t)n + 4));
+    if (!G || !h_last || !tstart || !rlist) return PB2_ENOMEM;
+    int *err = (int *)rlist, *rcount = (int *)rlist + 1;
+    int32_t *rrows = rlist + 4;
+    PB_CUDA(ctx, cudaMemsetAsync(rlist, 0, sizeof(int32_t) * 4, st));
+    const bool use_pad = D.pad_state && !ctx->no_pad_skip;
+
+    for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
+        const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
+        const int64_t r0 = t0 * TCM;
+        TcArgs A = {};
+        A.dir[0] = {D.fwd.recurrent, D.fwd.kernel, D.fwd.bias, 0, use_pad ? 1 : 0, 0, KX / 2, 0, nullptr};
+        A.dir[1] = {D.bwd.recurrent, D.bwd.kernel, D.bwd.bias, 1, 0, H1 / 2, KX / 2 + H1 / 2, 0, nullptr};
+        A.xsrc = windows; A.xoff = nullptr; A.nreal = nullptr; A.padval = D.pad_value;
+        A.T = T;
+        A.n = (n - r0 < nt * TCM) ? n - r0 : nt * TCM;
+        A.slot_count = slot_count; A.row0 = r0;
+        A.tab = use_pad ? D.pad_state : nullptr;
+        A.tab_stride = 2 * H1; A.tab_h = 0; A.tab_c = H1;
+        A.tile_tstart = tstart;
+        A.Gout = G; A.g_words = KX; A.fill_skipped = 1;
+        A.err = err;
+        PB_LAUNCH(ctx, K_DEMUX_TC_L1, "k_lstm_tc<demux l1>", st,
+            k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H1, 0>(), st>>>(A));
+        TcArgs B = {};
+        // blockIdx.y = 0: the result; 1: the coarse evaluation that measures each window's
+        // sensitivity (layer 2 amplifies perturbations by orders of magnitude for some windows)
+        B.dir[0] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 0, h_last};
+        B.dir[1] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 1, h_probe};
+        B.T = T; B.n = A.n; B.slot_count = slot_count; B.row0 = r0;
+        B.Gin = G; B.err = err;
+        PB_LAUNCH(ctx, K_DEMUX_TC_L2, "k_lstm_tc<demux l2>", st,
+            k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H2, KX>(), st>>>(B));
+    }
+    TcHeadArgs Hd = {};
+    Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.n = n;
+    Hd.delta0 = ctx->demux_margin_delta; Hd.probe_gain = ctx->demux_probe_gain;
+    Hd.sens_out = sens_out; Hd.slot_count = slot_count; Hd.slot_read = slot_read;
+    Hd.pushed = slot_read ? nullptr : pushed;
+    Hd.Wd = D.dense_kernel; Hd.bd = D.dense_bias;
+    Hd.n_classes = D.n_classes; Hd.n_decoy = D.n_decoy; Hd.n_calibration = D.n_calibration;
+    Hd.score_threshold = D.score_threshold;
+    Hd.calibration = D.calibration_dev;
+    Hd.class_probs = class_probs; Hd.barcode = barcode; Hd.guess = guess; Hd.score = score;
+    Hd.recheck_count = rcount; Hd.recheck_rows = recheck ? rrows : nullptr;
+    Hd.logits_out = logits_out; Hd.unsafe_out = unsafe_out;
+    PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc", st,
+        k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
+    if (!recheck) return PB2_OK;
+
+    // exact re-run of the unsafe rows (grids are sized for the worst case; CTAs beyond the
+    // device-side count leave at once)
+    float *win2 = (float *)ws_get(ctx, ctx->ws_win2, sizeof(float) * (size_t)n * T);
+    int32_t *read2 = (int32_t *)ws_get(ctx, ctx->ws_read2, sizeof(int32_t) * (size_t)n);
+    if (!win2 || !read2) return PB2_ENOMEM;
+    PB_LAUNCH(ctx, K_MISC, "k_gather_recheck", st,
+        k_gather_recheck<<<(unsigned)n, 64, 0, st>>>(windows, T, rcount, rrows, slot_read, win2, read2));
+    return launch_demux_exact(ctx, win2, nullptr, n, rcount, read2, class_probs, barcode, guess,
+                              score, st);
+}
+
+}  // namespace pb

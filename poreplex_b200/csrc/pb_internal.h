@@ -56,6 +56,7 @@ struct DemuxDev {
     // left-pad skipping tables (see kernels_lstm.cu DemuxArgs)
     float *pad_state = nullptr;       // [T+1][2][H1]
     float *pad_prefix = nullptr;      // [T][H2/2][4][2]
+    double *calibration_dev = nullptr;   // device copy of `calibration` (tensor-core path)
 };
 
 struct Workspace {                    // grow-only device scratch
@@ -68,7 +69,8 @@ struct Workspace {                    // grow-only device scratch
 namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
-                K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_NUM };
+                K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_DEMUX_TC_L1, K_DEMUX_TC_L2, K_DEMUX_TC_HEAD,
+                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 
@@ -76,6 +78,14 @@ struct pb2_context {
     int device = 0;
     bool profiling = false;
     bool attr_scaler = false, attr_demux = false;   // max-dynamic-smem attributes set
+    bool attr_demux_tc = false, attr_scaler_tc = false;
+    // tensor-core LSTM path (kernels_lstm_tc.cu): approximate outputs + margin test + exact
+    // re-run of the reads whose decisions are not safe.  Off = exact kernels only.
+    bool fast_lstm = true;
+    // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
+    double demux_margin_delta = 2e-3;
+    double demux_probe_gain = 0.25;
+    size_t tc_scratch_bytes = (size_t)12 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
     std::vector<pb::ProfEvent> prof_events;
@@ -99,7 +109,8 @@ struct pb2_context {
     // scratch
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
-        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean;
+        ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean,
+        ws_hlast, ws_recheck, ws_win2, ws_read2;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
@@ -166,6 +177,17 @@ int launch_demux(pb2_context *ctx, const float *windows, const int32_t *pushed, 
                  const int *slot_count, const int32_t *slot_read,
                  float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                  cudaStream_t st);
+// exact f32 kernels (kernels_lstm.cu) / tensor-core path with margin test (kernels_lstm_tc.cu)
+int launch_demux_exact(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                       const int *slot_count, const int32_t *slot_read,
+                       float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                       cudaStream_t st);
+int debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float *out, cudaStream_t st);
+int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
+                    const int *slot_count, const int32_t *slot_read,
+                    float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
+                    float *logits_out, int32_t *unsafe_out, float *sens_out, bool recheck,
+                    cudaStream_t st);
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);

@@ -221,6 +221,18 @@ class SignalEngine:
         """Verification mode: IEEE division in the LSTM kernels (same outputs, slower)."""
         self._check(self.lib.pb2_set_exact_division(self.handle, 1 if on else 0))
 
+    def set_fast_lstm(self, on=True, demux_margin_delta=0.0, demux_probe_gain=0.0):
+        """Tensor-core LSTM path with margin test + exact re-run (default on); off = exact
+        f32 kernels only."""
+        self._check(self.lib.pb2_set_fast_lstm(self.handle, 1 if on else 0,
+                                               float(demux_margin_delta), float(demux_probe_gain)))
+
+    def recheck_stats(self):
+        """(windows re-run exactly by the last demultiplexer launch, tensor-core time-outs)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.pb2_recheck_stats(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def profile_enable(self, on=True):
         self._check(self.lib.pb2_profile_enable(self.handle, 1 if on else 0))
 
@@ -526,6 +538,34 @@ class SignalEngine:
             n, probs.data_ptr(), bc.data_ptr(), guess.data_ptr(), score.data_ptr(),
             self._stream(stream)))
         return probs, bc, guess, score
+
+    def demux_predict_tc(self, windows, stream=None):
+        """Verification: tensor-core demultiplexer without the exact re-run ->
+        (probs, logits, barcode, guess, score, unsafe, sensitivity)."""
+        import torch
+        n = windows.shape[0]
+        dev = windows.device
+        probs = torch.zeros((n, N.MAX_CLASSES), dtype=torch.float32, device=dev)
+        logits = torch.zeros((n, N.MAX_CLASSES), dtype=torch.float32, device=dev)
+        bc = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        guess = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        score = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        unsafe = torch.zeros((n,), dtype=torch.int32, device=dev)
+        sens = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self._check(self.lib.pb2_demux_predict_tc(
+            self.handle, windows.data_ptr(), n, probs.data_ptr(), logits.data_ptr(),
+            bc.data_ptr(), guess.data_ptr(), score.data_ptr(), unsafe.data_ptr(),
+            sens.data_ptr(), self._stream(stream)))
+        return probs, logits, bc, guess, score, unsafe, sens
+
+    def debug_demux_l1(self, windows, stream=None):
+        """Verification: exact layer-1 outputs [n][T][2*units] (forward | backward)."""
+        import torch
+        n = windows.shape[0]
+        out = torch.zeros((n, self.trim_length, 96), dtype=torch.float32, device=windows.device)
+        self._check(self.lib.pb2_debug_demux_l1(self.handle, windows.data_ptr(), n, out.data_ptr(),
+                                                self._stream(stream)))
+        return out
 
     def scaler_predict(self, heads, stream=None):
         import torch

@@ -9,6 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-5
+PROB_ATOL = 2e-3     # approximate (tensor-core) class probabilities vs the exact f32 chain
 
 
 def _reads(preset, n, L, seed, **kw):
@@ -42,9 +43,14 @@ def _compare(out, ref, n_states=6, check_probs=True):
     assert np.array_equal(out['barcode_score'][pushed], ref['phred'][pushed])
     assert np.all(out['barcode'][~pushed] == -1)
     assert np.all(out['barcode_score'][~pushed] == -1)
-    if check_probs:
+    if check_probs == 'exact':
         assert np.array_equal(out['class_probs'][pushed][:, :5].view(np.uint32),
                               ref['probs'][pushed][:, :5].view(np.uint32)), 'softmax not bit-exact'
+    elif check_probs:
+        # default path: class probabilities of reads whose call passed the margin test come
+        # from the tensor-core kernels (diagnostic output, not part of the result dict)
+        assert np.allclose(out['class_probs'][pushed][:, :5], ref['probs'][pushed][:, :5],
+                           rtol=0, atol=PROB_ATOL), 'softmax outside tolerance'
 
 
 def test_whole_path_short_reads(eng_short, orc_short, preset_short):
@@ -155,8 +161,12 @@ def test_stage_windows_and_demux(eng_stock, orc_stock):
     for i in range(n):
         win[i, :npad[i]] = -1000.0
     win[0] = 0.0
-    probs, bc, guess, score = eng_stock.demux_predict(torch.from_numpy(win).to(dev))
-    torch.cuda.synchronize()
+    eng_stock.set_fast_lstm(False)
+    try:
+        probs, bc, guess, score = eng_stock.demux_predict(torch.from_numpy(win).to(dev))
+        torch.cuda.synchronize()
+    finally:
+        eng_stock.set_fast_lstm(True)
     pref = orc_stock.demux_predict(win)
     assert np.array_equal(probs.cpu().numpy()[:, :5].view(np.uint32), pref.view(np.uint32))
     for i in range(n):
@@ -187,12 +197,14 @@ def test_fast_division_equals_ieee_division(eng_short, preset_short):
     rd = _reads(preset_short, 160, 4000, seed=21)
     raw, off, ln = _dense_batch(rd)
     args = (raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
-    fast = eng_short.analyze_host(*args)
-    eng_short.set_exact_division(True)
+    eng_short.set_fast_lstm(False)
     try:
+        fast = eng_short.analyze_host(*args)
+        eng_short.set_exact_division(True)
         exact = eng_short.analyze_host(*args)
     finally:
         eng_short.set_exact_division(False)
+        eng_short.set_fast_lstm(True)
     for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts'):
         assert np.array_equal(fast[k], exact[k]), k
     assert np.array_equal(fast['scale_shift'].view(np.uint32), exact['scale_shift'].view(np.uint32))
@@ -307,6 +319,10 @@ def test_pipelined_host_path_equals_single_pass(eng_short, orc_short, preset_sho
             for i in np.nonzero(a['found'])[0]:
                 m = min(int(a['n_spikes'][i]), 48)
                 assert np.array_equal(a['spikes'][i, :m], b['spikes'][i, :m], equal_nan=True)
+        elif k == 'class_probs':
+            # tensor-core probabilities depend (within the approximation error) on which
+            # reads share a 128-read tile, i.e. on the chunking; the calls do not
+            assert np.allclose(a, b, rtol=0, atol=PROB_ATOL), k
         elif a.dtype.kind == 'f':
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
         else:

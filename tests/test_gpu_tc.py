@@ -1,0 +1,119 @@
+"""Tensor-core LSTM path (csrc/kernels_lstm_tc.cu) against the exact f32 kernels, which the
+other GPU tests tie to the CPU oracle bit for bit.
+
+The tensor-core kernels are approximate by construction (split-fp16 products, fp32
+accumulation in TMEM, MUFU gate functions).  What must hold:
+  * their class logits stay within the per-window error bound the margin test assumes
+    (delta0 + gain * shift under the coarse probe evaluation);
+  * every window the margin test calls safe gets exactly the exact path's
+    (barcode, guess, score);
+  * the default path (tensor-core + exact re-run of the unsafe windows) returns the exact
+    path's integer outputs for every window.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DELTA0, GAIN = 2e-3, 0.25     # pb2_context::demux_margin_delta / demux_probe_gain defaults
+
+
+def _windows(n, seed, T=300, min_len=60):
+    """Normalised adapter-like windows: piecewise-constant levels + noise, median/MAD
+    normalised, left-padded with -1000 to T (barcoding.py:77-98)."""
+    rng = np.random.default_rng(seed)
+    win = np.full((n, T), -1000.0, np.float32)
+    for i in range(n):
+        L = int(rng.integers(min_len, T + 1))
+        dwell = int(rng.integers(3, 12))
+        lv = np.repeat(rng.normal(0, 1.2, size=L // dwell + 1), dwell)[:L] + rng.normal(0, 0.4, size=L)
+        med = np.median(lv)
+        mad = np.median(np.abs(lv - med))
+        win[i, T - L:] = ((lv - med) / max(0.01, 1.4826 * mad)).astype(np.float32)
+    return win
+
+
+def _exact(eng, win_dev):
+    import torch
+    eng.set_fast_lstm(False)
+    try:
+        out = eng.demux_predict(win_dev)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_fast_lstm(True)
+    return [o.cpu().numpy() for o in out]
+
+
+def test_tc_demux_close_to_exact_and_safe_calls_identical(eng_stock):
+    import torch
+    dev = torch.device('cuda', 0)
+    win = _windows(6000, seed=3)
+    win[0, :] = 0.0                       # flat window (MAD = 0 upstream)
+    win[1, :] = -1000.0                   # all padding
+    wd = torch.from_numpy(win).to(dev)
+    p_ex, bc_ex, g_ex, s_ex = _exact(eng_stock, wd)
+    p_tc, lg_tc, bc_tc, g_tc, s_tc, unsafe, sens = [o.cpu().numpy() for o in eng_stock.demux_predict_tc(wd)]
+    torch.cuda.synchronize()
+    assert eng_stock.recheck_stats()[1] == 0, 'tensor-core kernel barrier time-out'
+    # class logits relative to the called class, recovered from the probabilities
+    pe, pt = p_ex[:, :5].astype(np.float64), p_tc[:, :5].astype(np.float64)
+    am = pe.argmax(1)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        le, lt = np.log(pe), np.log(pt)
+    d = np.abs((le - le[np.arange(len(am)), am][:, None]) - (lt - lt[np.arange(len(am)), am][:, None]))
+    d[~(pe > 1e-30)] = 0
+    err = d.max(1)
+    bound = DELTA0 + GAIN * sens.astype(np.float64)
+    dp = np.abs(pe - pt).max()
+    print('tc vs exact: logit error median %.2e max %.2e; max err/bound %.3f; max |dp| %.3e; '
+          'unsafe %.2f%%' % (np.median(err), err.max(), (err / bound).max(), dp, 100.0 * unsafe.mean()))
+    assert np.median(err) < 1e-4
+    assert (err <= bound).all(), 'approximation error exceeds the bound the margin test assumes'
+    assert dp < 2e-3
+    safe = unsafe == 0
+    assert safe.mean() > 0.7
+    assert np.array_equal(bc_tc[safe], bc_ex[safe])
+    assert np.array_equal(g_tc[safe], g_ex[safe])
+    assert np.array_equal(s_tc[safe], s_ex[safe])
+
+
+def test_tc_demux_with_recheck_equals_exact(eng_stock):
+    import torch
+    dev = torch.device('cuda', 0)
+    win = _windows(5000, seed=5, min_len=100)
+    wd = torch.from_numpy(win).to(dev)
+    p_ex, bc_ex, g_ex, s_ex = _exact(eng_stock, wd)
+    p, bc, g, s = [o.cpu().numpy() for o in eng_stock.demux_predict(wd)]
+    torch.cuda.synchronize()
+    rechecked, timeouts = eng_stock.recheck_stats()
+    assert timeouts == 0
+    assert 0 < rechecked < 0.3 * len(win)
+    assert np.array_equal(bc, bc_ex)
+    assert np.array_equal(g, g_ex)
+    assert np.array_equal(s, s_ex)
+    assert np.abs(p - p_ex).max() < 2e-3
+    # a tile boundary case: 1, 127, 128, 129 rows
+    for n in (1, 127, 128, 129):
+        sub = wd[:n].contiguous()
+        _, b1, g1, s1 = [o.cpu().numpy() for o in eng_stock.demux_predict(sub)]
+        assert np.array_equal(b1, bc_ex[:n]) and np.array_equal(g1, g_ex[:n]) and np.array_equal(s1, s_ex[:n])
+
+
+def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short):
+    """Default path vs exact-only path through pb2_analyze_host on calibrated synthetic reads."""
+    from poreplex_b200 import synth
+    rd = synth.to_numpy(synth.generate_reads(1500, synth.SynthSpec.for_length(4000), preset_short, seed=31))
+    n, L = rd['raw'].shape
+    args = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64),
+            rd['range'], rd['digitisation'], rd['offset'])
+    fast = eng_short.analyze_host(*args)
+    assert eng_short.recheck_stats()[1] == 0
+    eng_short.set_fast_lstm(False)
+    try:
+        exact = eng_short.analyze_host(*args)
+    finally:
+        eng_short.set_fast_lstm(True)
+    for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
+        assert np.array_equal(fast[k], exact[k]), k
+    assert np.array_equal(fast['scale_shift'].view(np.uint32), exact['scale_shift'].view(np.uint32))
+    assert (fast['barcode_score'] >= 0).sum() > 1000
