@@ -318,7 +318,9 @@ def main():
     torch.cuda.synchronize()
     eng.set_fast_lstm(True)
     mismatches = {k: int((fast_int[k] != out[k]).sum().item()) for k in fast_int}
-    mismatches['scale_shift_bits'] = int((fast_ss.view(torch.int32) != out['scale_shift'].view(torch.int32)).sum().item())
+    dss = (fast_ss.double() - out['scale_shift'].double()).abs().amax(0)
+    mismatches['max_abs_diff_scale'] = float(dss[0].item())
+    mismatches['max_abs_diff_shift'] = float(dss[1].item())
     for k, v in fast_int.items():
         out[k].copy_(v)
 

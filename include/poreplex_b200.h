@@ -66,6 +66,8 @@ enum { PB2_LABEL_PASS = 0, PB2_LABEL_FAIL = 1, PB2_LABEL_ARTIFACT = 2, PB2_LABEL
 #define PB2_FLAG_BARCODING 1u        /* --barcoding      config['barcoding']            */
 #define PB2_FLAG_KEEP_POOLED 2u      /* also return the scaled pooled signal            */
 #define PB2_FLAG_POLYA 4u            /* --polya          config['measure_polya']        */
+#define PB2_FLAG_EXACT_SCALER 8u     /* scale/shift from the exact f32 scaler kernels (the caller
+                                        feeds them to the chimera filter or needs them bit-exact) */
 
 typedef struct pb2_context pb2_context;
 

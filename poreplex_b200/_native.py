@@ -16,7 +16,7 @@ HEADER = os.path.join(HERE, '..', 'include', 'poreplex_b200.h')
 
 MAX_STATES, MAX_COMP, MAX_EDGES, MAX_CLASSES, MAX_CALIB = 8, 4, 64, 8, 64
 N_LABEL, N_BARCODE_SLOTS, N_STATUS = 4, 5, 11
-FLAG_BARCODING, FLAG_KEEP_POOLED, FLAG_POLYA = 1, 2, 4
+FLAG_BARCODING, FLAG_KEEP_POOLED, FLAG_POLYA, FLAG_EXACT_SCALER = 1, 2, 4, 8
 POLYA_MAX_SPIKES = 48
 LABEL_NAMES = ['pass', 'fail', 'artifact', None]
 

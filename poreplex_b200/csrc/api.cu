@@ -170,7 +170,8 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_counts, &ctx->ws_batch, &ctx->ws_misc, &ctx->ws_heads,
                         &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
                         &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean,
-                        &ctx->ws_hlast, &ctx->ws_recheck, &ctx->ws_win2, &ctx->ws_read2};
+                        &ctx->ws_hlast, &ctx->ws_recheck, &ctx->ws_win2, &ctx->ws_read2,
+                        &ctx->ws_tcmisc, &ctx->ws_fast, &ctx->ws_sub};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -239,8 +240,8 @@ int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_ti
         PB_CUDA(ctx, cudaDeviceSynchronize());
         PB_CUDA(ctx, cudaMemcpy(v, ctx->ws_recheck.ptr, sizeof(v), cudaMemcpyDeviceToHost));
     }
-    if (tc_timeouts) *tc_timeouts = v[0];
-    if (demux_rechecked) *demux_rechecked = v[1];
+    if (tc_timeouts) *tc_timeouts = v[0] + v[2];
+    if (demux_rechecked) *demux_rechecked = ctx->last_rerun_reads > 0 ? ctx->last_rerun_reads : v[1];
     return PB2_OK;
 }
 
@@ -566,6 +567,171 @@ int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *la
 #define WS_OR(user, ws, type, count)                                                        \
     ((user) ? (user) : (type *)ws_get(ctx, ctx->ws, sizeof(type) * (size_t)(count)))
 
+
+// ---- whole path, tensor-core variant ---------------------------------------------------
+// Approximate scaler and demultiplexer on the tensor cores; every read whose integer outputs
+// could differ from the exact kernels' (QC verdict on an edge, segmentation not constant over
+// the (scale, shift) uncertainty triangle, barcode call inside its error margin) is collected
+// and re-run as a sub-batch through the exact kernels -- scaler, segmentation, window,
+// demultiplexer -- and its results replace the tentative ones.  One host synchronisation (the
+// size of that sub-batch).
+__global__ void k_collect_unsafe(int64_t n, const int32_t *__restrict__ unsafe, int *count,
+                                 int32_t *__restrict__ list)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !unsafe[r]) return;
+    list[atomicAdd(count, 1)] = (int32_t)r;
+}
+
+__global__ void k_gather_sub_batch(int n_sub, const int32_t *__restrict__ list,
+                                   const int64_t *__restrict__ ro, const int64_t *__restrict__ rl,
+                                   const double *__restrict__ rg, const double *__restrict__ dg,
+                                   const double *__restrict__ of, int64_t *ro2, int64_t *rl2,
+                                   double *rg2, double *dg2, double *of2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sub) return;
+    const int32_t r = list[i];
+    ro2[i] = ro[r]; rl2[i] = rl[r]; rg2[i] = rg[r]; dg2[i] = dg[r]; of2[i] = of[r];
+}
+
+__global__ void k_scatter_sub_results(int n_sub, const int32_t *__restrict__ list,
+                                      const int32_t *__restrict__ status2, const float *__restrict__ ss2,
+                                      const int32_t *__restrict__ seg2, const int32_t *__restrict__ pushed2,
+                                      const int32_t *__restrict__ bc2, const int32_t *__restrict__ gs2,
+                                      const int32_t *__restrict__ sc2, const float *__restrict__ pr2,
+                                      int32_t *status, float *ss, int32_t *seg, int32_t *pushed,
+                                      int32_t *bc, int32_t *gs, int32_t *sc, float *pr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sub) return;
+    const int64_t r = list[i];
+    status[r] = status2[i];
+    ss[2 * r] = ss2[2 * i]; ss[2 * r + 1] = ss2[2 * i + 1];
+    for (int k = 0; k < PB2_MAX_STATES * 2; k++) seg[r * PB2_MAX_STATES * 2 + k] = seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
+    if (pushed) {
+        pushed[r] = pushed2[i];
+        bc[r] = bc2[i]; gs[r] = gs2[i]; sc[r] = sc2[i];
+        if (pr) for (int k = 0; k < PB2_MAX_CLASSES; k++) pr[r * PB2_MAX_CLASSES + k] = pr2[(int64_t)i * PB2_MAX_CLASSES + k];
+    }
+}
+
+static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                               uint32_t flags, cudaStream_t st, float *pooled, int32_t *status,
+                               int32_t *label, float *scale_shift, int32_t *segments)
+{
+    int rc;
+    const int64_t n = batch->n_reads;
+    const bool bcd = (flags & PB2_FLAG_BARCODING) != 0;
+    const int T = bcd ? ctx->demux.trim_length : 0;
+    const size_t SEG = (size_t)PB2_MAX_STATES * 2;
+    // scratch: corner (scale, shift) x3, corner status x2 / segments x2 (corner 0 decodes
+    // straight into the result arrays), unsafe flags, the unsafe list
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    const size_t o_ssv = take(sizeof(float) * 6 * n), o_st1 = take(4 * (size_t)n), o_st2 = take(4 * (size_t)n);
+    const size_t o_sg1 = take(4 * SEG * n), o_sg2 = take(4 * SEG * n), o_uns = take(4 * (size_t)n);
+    const size_t o_cnt = take(16), o_list = take(4 * (size_t)n);
+    char *fs = (char *)ws_get(ctx, ctx->ws_fast, off);
+    if (!fs) return PB2_ENOMEM;
+    float *ssv = (float *)(fs + o_ssv);
+    int32_t *st1 = (int32_t *)(fs + o_st1), *st2 = (int32_t *)(fs + o_st2);
+    int32_t *sg1 = (int32_t *)(fs + o_sg1), *sg2 = (int32_t *)(fs + o_sg2);
+    int32_t *unsafe = (int32_t *)(fs + o_uns), *list = (int32_t *)(fs + o_list);
+    int *count = (int *)(fs + o_cnt);
+    PB_CUDA(ctx, cudaMemsetAsync(unsafe, 0, 4 * (size_t)n, st));
+    PB_CUDA(ctx, cudaMemsetAsync(count, 0, 16, st));
+
+    if ((rc = launch_scaler_tc(ctx, *batch, pooled, status, scale_shift, ssv, unsafe, nullptr, st))) return rc;
+    // segmentation at the three corners of the uncertainty triangle
+    PB_CUDA(ctx, cudaMemcpyAsync(st1, status, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    PB_CUDA(ctx, cudaMemcpyAsync(st2, status, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_segment(ctx, *batch, pooled, ssv, status, segments, nullptr, st))) return rc;
+    if ((rc = launch_segment(ctx, *batch, pooled, ssv + 2 * n, st1, sg1, nullptr, st))) return rc;
+    if ((rc = launch_segment(ctx, *batch, pooled, ssv + 4 * n, st2, sg2, nullptr, st))) return rc;
+    if ((rc = launch_compare_corners(ctx, n, status, st1, st2, segments, sg1, sg2, unsafe, st))) return rc;
+
+    int32_t *barcode = res->barcode, *guess = res->barcode_guess, *score = res->barcode_score;
+    float *windows = nullptr;
+    int32_t *pushed = nullptr;
+    if (bcd) {
+        windows = (float *)ws_get(ctx, ctx->ws_win, sizeof(float) * (size_t)n * T);
+        pushed = (int32_t *)ws_get(ctx, ctx->ws_pushed, sizeof(int32_t) * (size_t)n);
+        barcode = WS_OR(res->barcode, ws_bc, int32_t, n);
+        guess = WS_OR(res->barcode_guess, ws_guess, int32_t, n);
+        score = WS_OR(res->barcode_score, ws_score, int32_t, n);
+        int32_t *slots = (int32_t *)ws_get(ctx, ctx->ws_slots, sizeof(int32_t) * ((size_t)n + 4));
+        if (!windows || !pushed || !barcode || !guess || !score || !slots) return PB2_ENOMEM;
+        int *slot_count = (int *)slots;
+        int32_t *slot_read = slots + 4;
+        if (res->class_probs)
+            PB_CUDA(ctx, cudaMemsetAsync(res->class_probs, 0, sizeof(float) * PB2_MAX_CLASSES * (size_t)n, st));
+        if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows, pushed,
+                                 slot_count, slot_read, st))) return rc;
+        if ((rc = launch_demux_tc(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
+                                  barcode, guess, score, nullptr, nullptr, nullptr, /*recheck=*/false,
+                                  st, unsafe))) return rc;
+    }
+
+    // ---- the unsafe reads, exactly ---------------------------------------------------
+    PB_LAUNCH(ctx, K_MISC, "k_collect_unsafe", st,
+        k_collect_unsafe<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, unsafe, count, list));
+    int n_sub = 0;
+    PB_CUDA(ctx, cudaMemcpyAsync(&n_sub, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_rerun_reads = n_sub;
+    if (n_sub > 0) {
+        const size_t m = (size_t)n_sub;
+        size_t o2 = 0;
+        auto take2 = [&](size_t bytes) { size_t o = o2; o2 += al(bytes); return o; };
+        const size_t q_ro = take2(8 * m), q_rl = take2(8 * m), q_rg = take2(8 * m), q_dg = take2(8 * m);
+        const size_t q_of = take2(8 * m), q_st = take2(4 * m), q_ss = take2(8 * m), q_sg = take2(4 * SEG * m);
+        const size_t q_pu = take2(4 * m), q_sl = take2(4 * (m + 4)), q_bc = take2(4 * m), q_gs = take2(4 * m);
+        const size_t q_sc = take2(4 * m), q_pr = take2(4 * PB2_MAX_CLASSES * m);
+        const size_t q_win = take2(bcd ? sizeof(float) * m * T : 16);
+        char *sb = (char *)ws_get(ctx, ctx->ws_sub, o2);
+        if (!sb) return PB2_ENOMEM;
+        pb2_batch sub = *batch;
+        sub.n_reads = n_sub;
+        sub.raw_offsets = (const int64_t *)(sb + q_ro);
+        sub.raw_lengths = (const int64_t *)(sb + q_rl);
+        sub.range = (const double *)(sb + q_rg);
+        sub.digitisation = (const double *)(sb + q_dg);
+        sub.offset = (const double *)(sb + q_of);
+        PB_LAUNCH(ctx, K_MISC, "k_gather_sub_batch", st,
+            k_gather_sub_batch<<<(unsigned)((n_sub + 255) / 256), 256, 0, st>>>(
+            n_sub, list, batch->raw_offsets, batch->raw_lengths, batch->range, batch->digitisation,
+            batch->offset, (int64_t *)(sb + q_ro), (int64_t *)(sb + q_rl), (double *)(sb + q_rg),
+            (double *)(sb + q_dg), (double *)(sb + q_of)));
+        int32_t *status2 = (int32_t *)(sb + q_st), *seg2 = (int32_t *)(sb + q_sg);
+        float *ss2 = (float *)(sb + q_ss);
+        int32_t *pushed2 = (int32_t *)(sb + q_pu), *slots2 = (int32_t *)(sb + q_sl);
+        int32_t *bc2 = (int32_t *)(sb + q_bc), *gs2 = (int32_t *)(sb + q_gs), *sc2 = (int32_t *)(sb + q_sc);
+        float *pr2 = (float *)(sb + q_pr), *win2 = (float *)(sb + q_win);
+        if ((rc = launch_scaler(ctx, sub, pooled, status2, ss2, nullptr, st))) return rc;
+        if ((rc = launch_segment(ctx, sub, pooled, ss2, status2, seg2, nullptr, st))) return rc;
+        if (bcd) {
+            PB_CUDA(ctx, cudaMemsetAsync(bc2, 0xFF, 4 * m, st));
+            PB_CUDA(ctx, cudaMemsetAsync(gs2, 0xFF, 4 * m, st));
+            PB_CUDA(ctx, cudaMemsetAsync(sc2, 0xFF, 4 * m, st));
+            PB_CUDA(ctx, cudaMemsetAsync(pr2, 0, 4 * PB2_MAX_CLASSES * m, st));
+            if ((rc = launch_windows(ctx, sub, pooled, ss2, status2, seg2, win2, pushed2,
+                                     (int *)slots2, slots2 + 4, st))) return rc;
+            if ((rc = launch_demux_exact(ctx, win2, nullptr, n_sub, (int *)slots2, slots2 + 4, pr2, bc2,
+                                         gs2, sc2, st))) return rc;
+        }
+        PB_LAUNCH(ctx, K_MISC, "k_scatter_sub_results", st,
+            k_scatter_sub_results<<<(unsigned)((n_sub + 255) / 256), 256, 0, st>>>(
+            n_sub, list, status2, ss2, seg2, pushed2, bc2, gs2, sc2, pr2, status, scale_shift, segments,
+            bcd ? pushed : nullptr, barcode, guess, score, res->class_probs));
+    }
+    if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;
+    if (res->counts)
+        if ((rc = launch_counts(ctx, status, label, barcode, n, res->counts, st))) return rc;
+    return PB2_OK;
+}
+
 int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
                        uint32_t flags, void *stream)
 {
@@ -596,6 +762,13 @@ int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_resul
     float *pooled_out = (flags & PB2_FLAG_KEEP_POOLED) ? res->pooled : nullptr;
 
     if ((rc = launch_pool(ctx, *batch, stride, pooled, st))) return rc;
+    ctx->last_rerun_reads = 0;
+    // Tensor-core scaler + demultiplexer with exact re-run of the unsafe reads.  Consumers of
+    // the scaled signal itself (poly(A) measurement, the returned pooled signal, the chimera
+    // filter through PB2_FLAG_EXACT_SCALER) get the exact scaler.
+    if (ctx->fast_lstm && !ctx->exact_division &&
+        !(flags & (PB2_FLAG_POLYA | PB2_FLAG_KEEP_POOLED | PB2_FLAG_EXACT_SCALER)))
+        return analyze_device_fast(ctx, batch, res, flags, st, pooled, status, label, scale_shift, segments);
     if ((rc = launch_scaler(ctx, *batch, pooled, status, scale_shift, nullptr, st))) return rc;
     if ((rc = launch_segment(ctx, *batch, pooled, scale_shift, status, segments, pooled_out, st)))
         return rc;

@@ -353,6 +353,17 @@ __global__ void k_scaler_prepare(const int64_t *__restrict__ raw_offsets,
     }
 }
 
+int launch_scaler_prepare(pb2_context *ctx, const pb2_batch &b, int32_t *status, float *scale_shift,
+                          int64_t *xoff, int32_t *nreal, cudaStream_t st)
+{
+    const ScalerDev &S = ctx->scaler;
+    PB_LAUNCH(ctx, K_SCALER_PREPARE, "k_scaler_prepare", st,
+        k_scaler_prepare<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, st>>>(
+        b.raw_offsets, b.raw_lengths, b.n_reads, S.stride, S.length, S.min_length, status, xoff,
+        nreal, scale_shift));
+    return PB2_OK;
+}
+
 template <int H, int GROUPS>
 static size_t scaler_smem() { return sizeof(float) * (3 * H * 4 * H + GROUPS * 4 * H * TB); }
 

@@ -66,6 +66,7 @@ struct TcArgs {
     uint32_t *Gout;
     const uint32_t *Gin;
     int g_words;                         // words per (read, step) of Gout
+    int g_t0, g_T;                       // scratch holds steps g_t0 .. g_t0 + g_T - 1 of each tile
     int fill_skipped;                    // SEQ_OUT: also write the tabulated h of skipped steps
     int *err;                            // set to 1 if a barrier wait timed out
 };
@@ -96,7 +97,10 @@ __host__ __device__ constexpr int tc_tmem_cols() { return (4 * H + H + KX <= 256
 template <int H, int KX>
 constexpr size_t tc_smem_bytes() {
     // B matrices (fp16 hi + lo) for U and, with a vector input, W; bias and scalar kernel
-    return (size_t)(H + KX) * 4 * H * 2 * 2 + (size_t)2 * 4 * H * sizeof(float) + 128;
+    const size_t need = (size_t)(H + KX) * 4 * H * 2 * 2 + (size_t)2 * 4 * H * sizeof(float) + 128;
+    // a layer that takes all 512 TMEM columns must be alone on its SM: ask for more than half
+    // of the shared memory so that a second CTA never waits inside tcgen05.alloc
+    return (tc_tmem_cols<H, KX>() == 512 && need < (size_t)116 * 1024) ? (size_t)116 * 1024 : need;
 }
 
 template <int H, int KX, bool SEQ_OUT>
@@ -238,8 +242,10 @@ k_lstm_tc(const TcArgs A)
             }
         }
         // sequence scratch of this tile: words [t][w][128]
-        uint32_t *gout = SEQ_OUT ? A.Gout + (size_t)tile * T * A.g_words * TCM : nullptr;
-        const uint32_t *gin = (KX > 0) ? A.Gin + (size_t)tile * T * KX * TCM : nullptr;
+        // (the time index of the scratch is relative to g_t0: the scaler's 2000-step head is
+        // almost all zero padding, only the last g_T steps exist)
+        uint32_t *gout = SEQ_OUT ? A.Gout + ((size_t)tile * A.g_T - A.g_t0) * A.g_words * TCM : nullptr;
+        const uint32_t *gin = (KX > 0) ? A.Gin + ((size_t)tile * A.g_T - A.g_t0) * KX * TCM : nullptr;
         if (SEQ_OUT && A.fill_skipped && A.tab) {
             // h after pad step t is tab[t + 1]; the same for every read of the tile
             for (int t = 0; t < t_start; t++) {
@@ -373,6 +379,7 @@ struct TcHeadArgs {
     const double *calibration;     // device copy
     float *class_probs; int32_t *barcode, *guess, *score;
     int *recheck_count; int32_t *recheck_rows;
+    int32_t *read_unsafe;          // optional [reads]: set to 1 for the read owning an unsafe row
     float *logits_out;             // optional [rows][PB2_MAX_CLASSES] (verification)
     int32_t *unsafe_out;           // optional [rows] (verification)
 };
@@ -417,6 +424,7 @@ __global__ void k_demux_head_tc(const TcHeadArgs A)
         for (int j = 0; j < PB2_MAX_CLASSES; j++) A.logits_out[row * PB2_MAX_CLASSES + j] = call.logit[j];
     }
     if (A.unsafe_out) A.unsafe_out[row] = safe ? 0 : 1;
+    if (A.read_unsafe && !safe) A.read_unsafe[r] = 1;
     if (!safe && A.recheck_rows) {
         const int k = atomicAdd(A.recheck_count, 1);
         A.recheck_rows[k] = (int32_t)row;
@@ -436,12 +444,186 @@ __global__ void k_gather_recheck(const float *__restrict__ windows, int T,
     if (threadIdx.x == 0) out_read[k] = slot_read ? slot_read[row] : row;
 }
 
+// ---- scaler head on the approximate layer-2 state -------------------------------------
+// Dense(2) + output transform + QC window exactly as k_scaler_lstm does them
+// (signal_loader.py:98-109), plus what the rest of the approximate path needs: the corners
+// of a triangle in the (scale, shift) plane that contains every value the exact kernels can
+// produce for this read (|z_tc - z_exact| <= delta_z), and a flag when the QC verdict itself
+// is within that uncertainty.
+struct TcScalerHeadArgs {
+    const float *h_last;           // [n][H]
+    const int32_t *nreal;          // [n] (0: read too short, not evaluated)
+    int64_t n;
+    const float *Wd, *bd;
+    double scale_std, scale_mean, shift_std, shift_mean;
+    double qc_scale_lo, qc_scale_hi, qc_shift_lo, qc_shift_hi;
+    double delta_z;
+    int32_t *status;
+    float *scale_shift;            // [n][2] centre (approximate) values
+    float *ss_vertex;              // [3][n][2]
+    int32_t *read_unsafe;          // [n]
+    float *z_out;                  // optional [n][2]
+};
+
+template <int H>
+__global__ void k_scaler_head_tc(const TcScalerHeadArgs A)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n) return;
+    float *v0 = A.ss_vertex + 2 * r, *v1 = v0 + 2 * A.n, *v2 = v1 + 2 * A.n;
+    if (A.nreal[r] <= 0) {
+        v0[0] = v0[1] = v1[0] = v1[1] = v2[0] = v2[1] = 0.f;
+        return;
+    }
+    const float *h = A.h_last + (size_t)r * H;
+    float z0 = 0.f, z1 = 0.f;
+    for (int k = 0; k < H; k++) {
+        z0 = pb::ffma(h[k], A.Wd[2 * k], z0);
+        z1 = pb::ffma(h[k], A.Wd[2 * k + 1], z1);
+    }
+    z0 = pb::fadd(z0, A.bd[0]);
+    z1 = pb::fadd(z1, A.bd[1]);
+    if (A.z_out) { A.z_out[2 * r] = z0; A.z_out[2 * r + 1] = z1; }
+    const double sc = pb::dadd(pb::dmul(A.scale_std, (double)z0), A.scale_mean);
+    const double sh = pb::dadd(pb::dmul(A.shift_std, (double)z1), A.shift_mean);
+    A.scale_shift[2 * r] = (float)sc;
+    A.scale_shift[2 * r + 1] = (float)sh;
+    const bool ok = sc >= A.qc_scale_lo && sc <= A.qc_scale_hi &&
+                    sh >= A.qc_shift_lo && sh <= A.qc_shift_hi;
+    A.status[r] = ok ? PB2_ST_OKAY : PB2_ST_SCALING_QC_FAIL;
+    // half-widths of the box the exact (scale, shift) lies in (+ the f32 rounding of the casts)
+    const double ds = fabs(A.scale_std) * A.delta_z + 2e-7 * fabs(sc);
+    const double dh = fabs(A.shift_std) * A.delta_z + 2e-7 * fabs(sh) + 1e-9;
+    const bool edge = fabs(sc - A.qc_scale_lo) <= ds || fabs(sc - A.qc_scale_hi) <= ds ||
+                      fabs(sh - A.qc_shift_lo) <= dh || fabs(sh - A.qc_shift_hi) <= dh;
+    if (edge) A.read_unsafe[r] = 1;
+    // triangle (-1,-1), (3,-1), (-1,3) in units of (ds, dh) contains the box [-1,1]^2
+    v0[0] = (float)(sc - ds);        v0[1] = (float)(sh - dh);
+    v1[0] = (float)(sc + 3.0 * ds);  v1[1] = (float)(sh - dh);
+    v2[0] = (float)(sc - ds);        v2[1] = (float)(sh + 3.0 * dh);
+}
+
+// segments / status of the three corner decodings agree -> the segmentation is constant over
+// the whole triangle (the region of the (scale, shift) plane on which one state path wins is
+// an intersection of half planes at this scale), hence equal to the exact path's.
+__global__ void k_compare_corners(int64_t n, const int32_t *__restrict__ st0,
+                                  const int32_t *__restrict__ st1, const int32_t *__restrict__ st2,
+                                  const int32_t *__restrict__ sg0, const int32_t *__restrict__ sg1,
+                                  const int32_t *__restrict__ sg2, int32_t *__restrict__ read_unsafe)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    bool same = st0[r] == st1[r] && st0[r] == st2[r];
+    const int4 *a = reinterpret_cast<const int4 *>(sg0 + r * PB2_MAX_STATES * 2);
+    const int4 *b = reinterpret_cast<const int4 *>(sg1 + r * PB2_MAX_STATES * 2);
+    const int4 *c = reinterpret_cast<const int4 *>(sg2 + r * PB2_MAX_STATES * 2);
+#pragma unroll
+    for (int i = 0; i < PB2_MAX_STATES * 2 / 4; i++) {
+        const int4 x = a[i], y = b[i], z = c[i];
+        same = same && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w &&
+               x.x == z.x && x.y == z.y && x.z == z.z && x.w == z.w;
+    }
+    if (!same) read_unsafe[r] = 1;
+}
+
+int launch_compare_corners(pb2_context *ctx, int64_t n, const int32_t *st0, const int32_t *st1,
+                           const int32_t *st2, const int32_t *sg0, const int32_t *sg1,
+                           const int32_t *sg2, int32_t *read_unsafe, cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    PB_LAUNCH(ctx, K_MISC, "k_compare_corners", st,
+        k_compare_corners<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, st0, st1, st2, sg0, sg1, sg2,
+                                                                   read_unsafe));
+    return PB2_OK;
+}
+
 template <int H, int KX, bool SEQ_OUT>
 static int tc_set_attr(pb2_context *ctx)
 {
     PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<H, KX, SEQ_OUT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc_smem_bytes<H, KX>()));
+    return PB2_OK;
+}
+
+// Approximate scaler (tensor-core LSTM(48) -> LSTM(48) -> Dense(2)): centre (scale, shift),
+// tentative status, the triangle corners for the segmentation check, QC-edge flags.
+int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, int32_t *status,
+                     float *scale_shift, float *ss_vertex, int32_t *read_unsafe, float *z_out,
+                     cudaStream_t st)
+{
+    if (b.n_reads <= 0) return PB2_OK;
+    const ScalerDev &S = ctx->scaler;
+    if (S.l1.units != 48 || S.l2.units != 48 || S.l1.in_dim != 1 || S.l2.in_dim != 48)
+        return fail(ctx, PB2_EUNSUPPORTED, "scaler network shape not built (LSTM(48) x2 expected)");
+    if (!S.zero_prefix) return fail(ctx, PB2_ESTATE, "scaler zero-prefix table missing");
+    constexpr int H = 48;
+    const int64_t n = b.n_reads;
+    const int thead = S.length / S.stride;
+    int64_t Tmax = thead;
+    if (b.max_raw_length > 0 && b.max_raw_length / S.stride < Tmax) Tmax = b.max_raw_length / S.stride;
+    if (Tmax < 1) Tmax = 1;
+    if (!ctx->attr_scaler_tc) {
+        int rc;
+        if ((rc = tc_set_attr<H, 0, true>(ctx))) return rc;
+        if ((rc = tc_set_attr<H, H, false>(ctx))) return rc;
+        ctx->attr_scaler_tc = true;
+    }
+    int64_t *xoff = (int64_t *)ws_get(ctx, ctx->ws_tcmisc, (size_t)n * 12);
+    if (!xoff) return PB2_ENOMEM;
+    int32_t *nreal = (int32_t *)(xoff + n);
+    int rc = launch_scaler_prepare(ctx, b, status, scale_shift, xoff, nreal, st);
+    if (rc) return rc;
+    const int64_t tiles = (n + TCM - 1) / TCM;
+    const size_t per_tile = sizeof(uint32_t) * (size_t)Tmax * H * TCM;
+    int64_t tiles_per_pass = (int64_t)(ctx->tc_scratch_bytes / per_tile);
+    if (tiles_per_pass < 1) tiles_per_pass = 1;
+    if (tiles_per_pass > tiles) tiles_per_pass = tiles;
+    uint32_t *G = (uint32_t *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
+    float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H);
+    int *tstart = (int *)ws_get(ctx, ctx->ws_tstart, sizeof(int) * (size_t)tiles_per_pass);
+    int32_t *rl = (int32_t *)ws_get(ctx, ctx->ws_recheck, sizeof(int32_t) * ((size_t)n + 4));
+    if (!G || !h_last || !tstart || !rl) return PB2_ENOMEM;
+    int *err = (int *)rl + 2;                 // [2]: time-out flag of the scaler kernels
+    PB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), st));
+    for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
+        const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
+        const int64_t r0 = t0 * TCM;
+        TcArgs A = {};
+        A.dir[0] = {S.l1.recurrent, S.l1.kernel, S.l1.bias, 0, 2, 0, H / 2, 0, nullptr};
+        A.dir[1] = A.dir[0];
+        A.xsrc = pooled; A.xoff = xoff; A.nreal = nreal; A.padval = 0.f;
+        A.T = thead;
+        A.n = (n - r0 < nt * TCM) ? n - r0 : nt * TCM;
+        A.row0 = r0;
+        A.tab = S.zero_prefix; A.tab_stride = 4 * H; A.tab_h = 0; A.tab_c = H;
+        A.tile_tstart = tstart;
+        A.Gout = G; A.g_words = H; A.g_t0 = thead - (int)Tmax; A.g_T = (int)Tmax;
+        A.err = err;
+        PB_LAUNCH(ctx, K_SCALER_TC_L1, "k_lstm_tc<scaler l1>", st,
+            k_lstm_tc<H, 0, true><<<dim3((unsigned)nt, 1), TC_THREADS, tc_smem_bytes<H, 0>(), st>>>(A));
+        TcArgs B = {};
+        B.dir[0] = {S.l2.recurrent, S.l2.kernel, S.l2.bias, 0, 0, 0, 0, 0, h_last};
+        B.dir[1] = B.dir[0];
+        B.T = thead; B.n = A.n; B.row0 = r0;
+        B.tab = S.zero_prefix; B.tab_stride = 4 * H; B.tab_h = 2 * H; B.tab_c = 3 * H;
+        B.tile_tstart = tstart; B.tstart_in = 1;
+        B.Gin = G; B.g_t0 = A.g_t0; B.g_T = A.g_T; B.err = err;
+        PB_LAUNCH(ctx, K_SCALER_TC_L2, "k_lstm_tc<scaler l2>", st,
+            k_lstm_tc<H, H, false><<<dim3((unsigned)nt, 1), TC_THREADS, tc_smem_bytes<H, H>(), st>>>(B));
+    }
+    TcScalerHeadArgs Hd = {};
+    Hd.h_last = h_last; Hd.nreal = nreal; Hd.n = n;
+    Hd.Wd = S.dense_kernel; Hd.bd = S.dense_bias;
+    Hd.scale_std = S.scale_std; Hd.scale_mean = S.scale_mean;
+    Hd.shift_std = S.shift_std; Hd.shift_mean = S.shift_mean;
+    Hd.qc_scale_lo = S.qc_scale_lo; Hd.qc_scale_hi = S.qc_scale_hi;
+    Hd.qc_shift_lo = S.qc_shift_lo; Hd.qc_shift_hi = S.qc_shift_hi;
+    Hd.delta_z = ctx->scaler_margin_z;
+    Hd.status = status; Hd.scale_shift = scale_shift; Hd.ss_vertex = ss_vertex;
+    Hd.read_unsafe = read_unsafe; Hd.z_out = z_out;
+    PB_LAUNCH(ctx, K_SCALER_TC_HEAD, "k_scaler_head_tc", st,
+        k_scaler_head_tc<H><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
     return PB2_OK;
 }
 
@@ -452,7 +634,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
                     const int *slot_count, const int32_t *slot_read,
                     float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                     float *logits_out, int32_t *unsafe_out, float *sens_out, bool recheck,
-                    cudaStream_t st)
+                    cudaStream_t st, int32_t *read_unsafe)
 {
     if (n <= 0) return PB2_OK;
     DemuxDev &D = ctx->demux;
@@ -482,7 +664,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     if (!G || !h_last || !tstart || !rlist) return PB2_ENOMEM;
     int *err = (int *)rlist, *rcount = (int *)rlist + 1;
     int32_t *rrows = rlist + 4;
-    PB_CUDA(ctx, cudaMemsetAsync(rlist, 0, sizeof(int32_t) * 4, st));
+    PB_CUDA(ctx, cudaMemsetAsync(rlist, 0, sizeof(int32_t) * 2, st));
     const bool use_pad = D.pad_state && !ctx->no_pad_skip;
 
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
@@ -498,7 +680,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         A.tab = use_pad ? D.pad_state : nullptr;
         A.tab_stride = 2 * H1; A.tab_h = 0; A.tab_c = H1;
         A.tile_tstart = tstart;
-        A.Gout = G; A.g_words = KX; A.fill_skipped = 1;
+        A.Gout = G; A.g_words = KX; A.g_t0 = 0; A.g_T = T; A.fill_skipped = 1;
         A.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L1, "k_lstm_tc<demux l1>", st,
             k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H1, 0>(), st>>>(A));
@@ -508,7 +690,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         B.dir[0] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 0, h_last};
         B.dir[1] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 1, h_probe};
         B.T = T; B.n = A.n; B.slot_count = slot_count; B.row0 = r0;
-        B.Gin = G; B.err = err;
+        B.Gin = G; B.g_t0 = 0; B.g_T = T; B.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L2, "k_lstm_tc<demux l2>", st,
             k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H2, KX>(), st>>>(B));
     }
@@ -523,7 +705,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     Hd.calibration = D.calibration_dev;
     Hd.class_probs = class_probs; Hd.barcode = barcode; Hd.guess = guess; Hd.score = score;
     Hd.recheck_count = rcount; Hd.recheck_rows = recheck ? rrows : nullptr;
-    Hd.logits_out = logits_out; Hd.unsafe_out = unsafe_out;
+    Hd.logits_out = logits_out; Hd.unsafe_out = unsafe_out; Hd.read_unsafe = read_unsafe;
     PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc", st,
         k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
     if (!recheck) return PB2_OK;

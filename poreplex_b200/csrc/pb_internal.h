@@ -85,6 +85,8 @@ struct pb2_context {
     // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
     double demux_margin_delta = 2e-3;
     double demux_probe_gain = 0.25;
+    double scaler_margin_z = 3e-5;                // assumed bound on the error of the scaler's raw outputs
+    int64_t last_rerun_reads = 0;                 // reads the last whole-path call re-ran exactly
     size_t tc_scratch_bytes = (size_t)12 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
@@ -110,7 +112,7 @@ struct pb2_context {
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
         ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean,
-        ws_hlast, ws_recheck, ws_win2, ws_read2;
+        ws_hlast, ws_recheck, ws_win2, ws_read2, ws_tcmisc, ws_fast, ws_sub;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
@@ -182,12 +184,20 @@ int launch_demux_exact(pb2_context *ctx, const float *windows, const int32_t *pu
                        const int *slot_count, const int32_t *slot_read,
                        float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                        cudaStream_t st);
+int launch_scaler_prepare(pb2_context *ctx, const pb2_batch &b, int32_t *status, float *scale_shift,
+                          int64_t *xoff, int32_t *nreal, cudaStream_t st);
+int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, int32_t *status,
+                     float *scale_shift, float *ss_vertex, int32_t *read_unsafe, float *z_out,
+                     cudaStream_t st);
+int launch_compare_corners(pb2_context *ctx, int64_t n, const int32_t *st0, const int32_t *st1,
+                           const int32_t *st2, const int32_t *sg0, const int32_t *sg1,
+                           const int32_t *sg2, int32_t *read_unsafe, cudaStream_t st);
 int debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float *out, cudaStream_t st);
 int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushed, int64_t n,
                     const int *slot_count, const int32_t *slot_read,
                     float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                     float *logits_out, int32_t *unsafe_out, float *sens_out, bool recheck,
-                    cudaStream_t st);
+                    cudaStream_t st, int32_t *read_unsafe = nullptr);
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);

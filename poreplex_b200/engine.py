@@ -265,7 +265,7 @@ class SignalEngine:
         return raw, offsets, lengths
 
     def analyze_host(self, raw, offsets, lengths, rng, digitisation, offset, barcoding=None,
-                     keep_pooled=False, polya=False):
+                     keep_pooled=False, polya=False, exact_scaler=False):
         """SignalAnalyzer.process stages A-D over HOST numpy buffers (H2D, kernels, D2H).
 
         Returns a dict of numpy arrays: status, label, scale_shift [n,2], segments
@@ -311,7 +311,7 @@ class SignalEngine:
                       _np_ptr(out['pooled']) if keep_pooled else None, _np_ptr(out['counts']),
                       _np_ptr(out['polya']) if polya else None)
         flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0) \
-            | (N.FLAG_POLYA if polya else 0)
+            | (N.FLAG_POLYA if polya else 0) | (N.FLAG_EXACT_SCALER if exact_scaler else 0)
         self._check(self.lib.pb2_analyze_host(self.handle, C.byref(b), C.byref(r), flags))
         return out
 
@@ -416,7 +416,7 @@ class SignalEngine:
 
     def analyze_device(self, raw, offsets, lengths, rng, digitisation, offset, out=None,
                        barcoding=None, keep_pooled=False, max_raw_length=0, stream=None,
-                       polya=False):
+                       polya=False, exact_scaler=False):
         """Same path over tensors already resident in HBM; enqueued on ``stream`` (default:
         torch's current stream), not synchronised."""
         import torch
@@ -434,7 +434,7 @@ class SignalEngine:
                       out['pooled'].data_ptr() if keep_pooled else None,
                       out['counts'].data_ptr(), out['polya'].data_ptr() if polya else None)
         flags = (N.FLAG_BARCODING if barcoding else 0) | (N.FLAG_KEEP_POOLED if keep_pooled else 0) \
-            | (N.FLAG_POLYA if polya else 0)
+            | (N.FLAG_POLYA if polya else 0) | (N.FLAG_EXACT_SCALER if exact_scaler else 0)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         self._check(self.lib.pb2_analyze_device(self.handle, C.byref(b), C.byref(r), flags,
                                                 C.c_void_p(st.cuda_stream)))

@@ -228,7 +228,9 @@ class SignalAnalyzer:
             out = eng.analyze_host(
                 *batch,
                 barcoding=bool(self.config['barcoding']),
-                polya=bool(self.config['measure_polya']))
+                polya=bool(self.config['measure_polya']),
+                # the chimera filter decodes the scaled event means: exact scale/shift
+                exact_scaler=bool(self.config.get('filter_unsplit_reads')))
             for i, npread in enumerate(loaded):
                 npread._raw = None
                 npread._gpu = {k: out[k][i] for k in ('status', 'scale_shift', 'segments',

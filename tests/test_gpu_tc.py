@@ -99,7 +99,7 @@ def test_tc_demux_with_recheck_equals_exact(eng_stock):
         assert np.array_equal(b1, bc_ex[:n]) and np.array_equal(g1, g_ex[:n]) and np.array_equal(s1, s_ex[:n])
 
 
-def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short):
+def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monkeypatch):
     """Default path vs exact-only path through pb2_analyze_host on calibrated synthetic reads."""
     from poreplex_b200 import synth
     rd = synth.to_numpy(synth.generate_reads(1500, synth.SynthSpec.for_length(4000), preset_short, seed=31))
@@ -107,7 +107,8 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short):
     args = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64),
             rd['range'], rd['digitisation'], rd['offset'])
     fast = eng_short.analyze_host(*args)
-    assert eng_short.recheck_stats()[1] == 0
+    rerun, timeouts = eng_short.recheck_stats()
+    assert timeouts == 0
     eng_short.set_fast_lstm(False)
     try:
         exact = eng_short.analyze_host(*args)
@@ -115,5 +116,16 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short):
         eng_short.set_fast_lstm(True)
     for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
         assert np.array_equal(fast[k], exact[k]), k
-    assert np.array_equal(fast['scale_shift'].view(np.uint32), exact['scale_shift'].view(np.uint32))
+    d = np.abs(fast['scale_shift'].astype(np.float64) - exact['scale_shift'])
+    print('scale/shift: max |d| %.2e / %.2e; exactly re-run reads %d of %d'
+          % (d[:, 0].max(), d[:, 1].max(), rerun, n))
+    assert d[:, 0].max() <= 4.2e-6 and d[:, 1].max() <= 3.2e-4      # inside the assumed box
+    assert (d.max(1) == 0).sum() >= rerun                            # re-run reads are exact
+    assert 0 < rerun < 0.35 * n
     assert (fast['barcode_score'] >= 0).sum() > 1000
+    # chunked host path: same integer outputs whatever the tiling of reads
+    monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(1_000_000))
+    piped = eng_short.analyze_host(*args)
+    monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
+    for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
+        assert np.array_equal(piped[k], exact[k]), k
