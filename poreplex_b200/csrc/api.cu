@@ -148,6 +148,13 @@ int pb2_create(int device, pb2_context **out)
         delete ctx;
         return PB2_ECUDA;
     }
+    // sticky time-out word of the tensor-core kernels (read and cleared by pb2_recheck_stats)
+    if (cudaMalloc(&ctx->tc_err, sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->tc_err, 0, sizeof(int)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->host_stream);
+        delete ctx;
+        return PB2_ECUDA;
+    }
     *out = ctx;
     return PB2_OK;
 }
@@ -164,6 +171,7 @@ void pb2_destroy(pb2_context *ctx)
     cudaFree(ctx->demux.dense_kernel); cudaFree(ctx->demux.dense_bias);
     cudaFree(ctx->demux.pad_state); cudaFree(ctx->demux.pad_prefix);
     cudaFree(ctx->demux.calibration_dev);
+    cudaFree(ctx->tc_err);
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
@@ -235,12 +243,14 @@ int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_ti
 {
     if (!ctx) return PB2_EINVAL;
     DeviceGuard g(ctx->device);
-    int32_t v[4] = {0, 0, 0, 0};
-    if (ctx->ws_recheck.ptr) {
-        PB_CUDA(ctx, cudaDeviceSynchronize());
+    int32_t v[2] = {0, 0};
+    int terr = 0;
+    PB_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->ws_recheck.ptr && ctx->demux_tc_ran)
         PB_CUDA(ctx, cudaMemcpy(v, ctx->ws_recheck.ptr, sizeof(v), cudaMemcpyDeviceToHost));
-    }
-    if (tc_timeouts) *tc_timeouts = v[0] + v[2];
+    PB_CUDA(ctx, cudaMemcpy(&terr, ctx->tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemset(ctx->tc_err, 0, sizeof(int)));
+    if (tc_timeouts) *tc_timeouts = terr;
     if (demux_rechecked) *demux_rechecked = ctx->last_rerun_reads > 0 ? ctx->last_rerun_reads : v[1];
     return PB2_OK;
 }

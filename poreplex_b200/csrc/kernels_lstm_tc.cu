@@ -33,7 +33,6 @@ namespace pb {
 using namespace pb::tc;
 
 constexpr int TCM = 128;                 // reads per tile (TMEM lanes)
-constexpr int TC_THREADS = 288;          // 8 gate warps + 1 MMA warp
 
 struct TcDir {                           // one direction of a layer
     const float *U;                      // recurrent kernel [H][4H]
@@ -91,6 +90,46 @@ __device__ __forceinline__ float tanh_fast(float x) {             // 1 - 2 / (1 
     return __fmaf_rn(-2.0f, r, 1.0f);
 }
 
+__device__ __forceinline__ float tanh_mufu(float x) {             // MUFU.TANH, |error| ~ 2^-11
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One LSTM cell update from the four pre-activations.
+//   COARSE = false: 5 EX2 + 2 RCP.  With E_x = e^-x:  sigma(zi) tanh(zc) = (1 - E_2c) /
+//   ((1 + E_i)(1 + E_2c)),  sigma(zf) = 1 / (1 + E_f)  share one reciprocal,
+//   sigma(zo) tanh(c') = (1 - E_2c') / ((1 + E_o)(1 + E_2c')) the other.  Exponents are
+//   clamped at 2^30 so the triple product stays finite (sigma(-20.8) = 9e-10, tanh(10.4) =
+//   1 - 2e-9: far below the f32 resolution of the state).  Absolute error about 1e-7.
+//   COARSE = true: MUFU.TANH everywhere (error about 5e-4) -- the deliberately perturbed
+//   evaluation that measures a read's sensitivity.
+template <bool COARSE>
+__device__ __forceinline__ float lstm_cell_tc(float zi, float zf, float zc, float zo, float &c) {
+    if (COARSE) {
+        const float ig = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zi)), 0.5f);
+        const float fg = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zf)), 0.5f);
+        const float og = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zo)), 0.5f);
+        const float cn = __fmaf_rn(fg, c, __fmul_rn(ig, tanh_mufu(zc)));
+        c = cn;
+        return __fmul_rn(og, tanh_mufu(cn));
+    }
+    constexpr float L = 1.4426950408889634f, L2 = 2.8853900817779268f;
+    const float ei = ex2_fast(fminf(__fmul_rn(zi, -L), 30.f));
+    const float ef = ex2_fast(fminf(__fmul_rn(zf, -L), 30.f));
+    const float eg = ex2_fast(fminf(__fmul_rn(zc, -L2), 30.f));
+    const float eo = ex2_fast(fminf(__fmul_rn(zo, -L), 30.f));
+    const float af = __fadd_rn(1.0f, ef);
+    const float p = __fmul_rn(__fadd_rn(1.0f, ei), __fadd_rn(1.0f, eg));
+    const float r = rcp_fast(__fmul_rn(p, af));
+    const float ig = __fmul_rn(__fmul_rn(__fsub_rn(1.0f, eg), af), r);
+    const float cn = __fmaf_rn(__fmul_rn(p, r), c, ig);
+    c = cn;
+    const float ec = ex2_fast(fminf(__fmul_rn(cn, -L2), 30.f));
+    const float r2 = rcp_fast(__fmul_rn(__fadd_rn(1.0f, eo), __fadd_rn(1.0f, ec)));
+    return __fmul_rn(__fsub_rn(1.0f, ec), r2);
+}
+
 template <int H, int KX>
 __host__ __device__ constexpr int tc_tmem_cols() { return (4 * H + H + KX <= 256) ? 256 : 512; }
 
@@ -103,15 +142,74 @@ constexpr size_t tc_smem_bytes() {
     return (tc_tmem_cols<H, KX>() == 512 && need < (size_t)116 * 1024) ? (size_t)116 * 1024 : need;
 }
 
+// gate warps per lane quarter: layers alone on their SM (vector input, 512 TMEM columns) use
+// four so that 16 warps hide the MUFU / FMA latencies; scalar-input layers run two CTAs per SM
+template <int KX> __host__ __device__ constexpr int tc_nparts() { return KX == 0 ? 2 : 4; }
+template <int KX> __host__ __device__ constexpr int tc_threads() { return 128 * tc_nparts<KX>() + 32; }
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+
+// Cell update for a PAIR of units with packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 halve
+// the FMA-pipe instruction count; MUFU and min are per lane).  See lstm_cell_tc for the maths.
+template <bool COARSE>
+__device__ __forceinline__ float2 lstm_cell_pair(float2 zi, float2 zf, float2 zc, float2 zo, float2 &c) {
+    if (COARSE) {
+        const float2 h5 = splat(0.5f);
+        const float2 hi_ = __fmul2_rn(zi, h5), hf_ = __fmul2_rn(zf, h5), ho_ = __fmul2_rn(zo, h5);
+        const float2 ig = __ffma2_rn(h5, f2(tanh_mufu(hi_.x), tanh_mufu(hi_.y)), h5);
+        const float2 fg = __ffma2_rn(h5, f2(tanh_mufu(hf_.x), tanh_mufu(hf_.y)), h5);
+        const float2 og = __ffma2_rn(h5, f2(tanh_mufu(ho_.x), tanh_mufu(ho_.y)), h5);
+        const float2 cg = f2(tanh_mufu(zc.x), tanh_mufu(zc.y));
+        const float2 cn = __ffma2_rn(fg, c, __fmul2_rn(ig, cg));
+        c = cn;
+        return __fmul2_rn(og, f2(tanh_mufu(cn.x), tanh_mufu(cn.y)));
+    }
+    constexpr float L = 1.4426950408889634f, L2 = 2.8853900817779268f;
+    const float2 one = splat(1.0f), mone = splat(-1.0f);
+    const float2 ai_ = __fmul2_rn(zi, splat(-L)), af_ = __fmul2_rn(zf, splat(-L));
+    const float2 ag_ = __fmul2_rn(zc, splat(-L2)), ao_ = __fmul2_rn(zo, splat(-L));
+    const float2 ei = f2(ex2_fast(fminf(ai_.x, 30.f)), ex2_fast(fminf(ai_.y, 30.f)));
+    const float2 ef = f2(ex2_fast(fminf(af_.x, 30.f)), ex2_fast(fminf(af_.y, 30.f)));
+    const float2 eg = f2(ex2_fast(fminf(ag_.x, 30.f)), ex2_fast(fminf(ag_.y, 30.f)));
+    const float2 eo = f2(ex2_fast(fminf(ao_.x, 30.f)), ex2_fast(fminf(ao_.y, 30.f)));
+    const float2 af = __fadd2_rn(one, ef);
+    const float2 p = __fmul2_rn(__fadd2_rn(one, ei), __fadd2_rn(one, eg));
+    const float2 q = __fmul2_rn(p, af);
+    const float2 r = f2(rcp_fast(q.x), rcp_fast(q.y));
+    const float2 ig = __fmul2_rn(__fmul2_rn(__ffma2_rn(eg, mone, one), af), r);
+    const float2 cn = __ffma2_rn(__fmul2_rn(p, r), c, ig);
+    c = cn;
+    const float2 ac_ = __fmul2_rn(cn, splat(-L2));
+    const float2 ec = f2(ex2_fast(fminf(ac_.x, 30.f)), ex2_fast(fminf(ac_.y, 30.f)));
+    const float2 q2 = __fmul2_rn(__fadd2_rn(one, eo), __fadd2_rn(one, ec));
+    const float2 r2 = f2(rcp_fast(q2.x), rcp_fast(q2.y));
+    return __fmul2_rn(__ffma2_rn(ec, mone, one), r2);
+}
+
+// (hi, lo) fp16 words of a pair: hi = the value truncated to 11 significant bits (exactly an
+// fp16 in the normal range), lo = fp16(value - hi)
+__device__ __forceinline__ uint32_t split_pair(float2 h, uint32_t &lo) {
+    const float2 hi = f2(__uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u),
+                         __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u));
+    const float2 l = __fadd2_rn(h, f2(-hi.x, -hi.y));
+    const __half2 h16 = __floats2half2_rn(hi.x, hi.y), l16 = __floats2half2_rn(l.x, l.y);
+    lo = *reinterpret_cast<const uint32_t *>(&l16);
+    return *reinterpret_cast<const uint32_t *>(&h16);
+}
+
 template <int H, int KX, bool SEQ_OUT>
-__global__ void __launch_bounds__(TC_THREADS, (KX == 0 ? 2 : 1))
+__global__ void __launch_bounds__(tc_threads<KX>(), (KX == 0 ? 2 : 1))
 k_lstm_tc(const TcArgs A)
 {
     constexpr int N = 4 * H;
-    constexpr int HH = H / 2;            // units per gate thread
-    constexpr int NCH = HH / 8;          // chunks of 8 units (32 accumulator columns)
+    constexpr int NP = tc_nparts<KX>();  // gate warps per lane quarter
+    constexpr int NGW = 4 * NP;          // gate warps; warp NGW issues the MMAs
+    constexpr int NTHR = tc_threads<KX>();
+    constexpr int UPT = H / NP;          // units per gate thread
+    constexpr int NCH = UPT / 4;         // chunks of 4 units (16 accumulator columns)
     constexpr int TCOLS = tc_tmem_cols<H, KX>();
-    static_assert(HH % 8 == 0, "units per thread must be a multiple of 8");
+    static_assert(UPT % 4 == 0, "units per thread must be a multiple of 4");
     static_assert(H % 16 == 0 && KX % 16 == 0, "K must be a multiple of 16");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -119,7 +217,7 @@ k_lstm_tc(const TcArgs A)
     __half *bU_lo = bU_hi + H * N;
     __half *bW_hi = bU_lo + H * N;
     __half *bW_lo = bW_hi + KX * N;
-    float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);       // [N], n = 4u + gate
+    float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);       // [N], accumulator column order
     float *s_win = s_bias + N;                                        // [N] scalar input kernel
     __shared__ __align__(8) uint64_t bar_d, bar_h;
     __shared__ uint32_t s_tmem;
@@ -140,18 +238,18 @@ k_lstm_tc(const TcArgs A)
     // ---- one-time setup ----------------------------------------------------------
     if (tid == 0) {
         mbar_init(&bar_d, 1);
-        mbar_init(&bar_h, 8);
+        mbar_init(&bar_h, NGW);
         mbar_fence_init();
         s_dead = 0;
         s_tstart = (dir.skip_mode != 0) ? T : 0;
     }
-    if (warp == 8) tmem_alloc(&s_tmem, TCOLS);
-    load_b_split<H, H>(dir.U, bU_hi, bU_lo, tid, TC_THREADS);
-    if (KX > 0) load_b_split<(KX > 0 ? KX : 16), H>(dir.W, bW_hi, bW_lo, tid, TC_THREADS);
-    for (int i = tid; i < N; i += TC_THREADS) {
+    if (warp == NGW) tmem_alloc(&s_tmem, TCOLS);
+    load_b_split<H, H>(dir.U, bU_hi, bU_lo, tid, NTHR);
+    if (KX > 0) load_b_split<(KX > 0 ? KX : 16), H>(dir.W, bW_hi, bW_lo, tid, NTHR);
+    for (int i = tid; i < N; i += NTHR) {
         const int gate = i / H, u = i % H;
-        s_bias[4 * u + gate] = dir.b[i];
-        s_win[4 * u + gate] = (KX == 0) ? dir.W[i] : 0.f;
+        s_bias[gate_col(u, gate)] = dir.b[i];
+        s_win[gate_col(u, gate)] = (KX == 0) ? dir.W[i] : 0.f;
     }
     fence_proxy_async_smem();
     fence_before_sync();
@@ -162,13 +260,13 @@ k_lstm_tc(const TcArgs A)
     const uint32_t col_d = 0, col_h = N, col_x = N + H;     // h: hi [H/2] then lo [H/2]; x alike
 
     // ---- per-row input addressing and the common start step -------------------------
-    const int q = warp & 3, wg = (warp >> 2) & 1;
+    const int q = warp & 3, part = (warp >> 2) % NP;
     const int m = q * 32 + lane;
     int64_t row = tile0 + m;
     if (row >= n_eff) row = n_eff - 1;                     // duplicate the last row (no output)
     const float *xbase = nullptr;
     int pad = 0;
-    if (KX == 0 && warp < 8) {
+    if (KX == 0 && warp < NGW) {
         if (A.xoff) {
             const int nr = A.nreal[A.row0 + row];
             pad = T - nr;
@@ -177,7 +275,7 @@ k_lstm_tc(const TcArgs A)
         } else {
             xbase = A.xsrc + (A.row0 + row) * (int64_t)T;
         }
-        if (wg == 0) {
+        if (part == 0) {
             if (dir.skip_mode == 1) {
                 int np = 0;
                 while (np < T && xbase[np] == A.padval) np++;
@@ -198,7 +296,7 @@ k_lstm_tc(const TcArgs A)
         t_start = A.tile_tstart[tile];
     }
 
-    if (warp == 8) {
+    if (warp == NGW) {
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t ph = 0;
@@ -221,24 +319,23 @@ k_lstm_tc(const TcArgs A)
     } else {
         // ===== gate warps =====
         const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
-        const int u0 = wg * HH;                            // first unit of this thread
-        float c[HH];
+        const int u0 = part * UPT;                         // first unit of this thread
+        float2 c[UPT / 2];
         // initial state: zeros, or the tabulated state after t_start pad steps
         {
             const float *tb = (t_start > 0 && A.tab) ? A.tab + (size_t)t_start * A.tab_stride : nullptr;
 #pragma unroll
-            for (int ch = 0; ch < NCH; ch++) {
-                uint32_t hi[4], lo[4];
+            for (int pr = 0; pr < UPT / 2; pr += 2) {
+                uint32_t hi[2], lo[2];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int u = u0 + ch * 8 + 2 * j;
-                    const float ha = tb ? tb[A.tab_h + u] : 0.f, hb = tb ? tb[A.tab_h + u + 1] : 0.f;
-                    c[ch * 8 + 2 * j] = tb ? tb[A.tab_c + u] : 0.f;
-                    c[ch * 8 + 2 * j + 1] = tb ? tb[A.tab_c + u + 1] : 0.f;
-                    hi[j] = split2(ha, hb, lo[j]);
+                for (int j = 0; j < 2; j++) {
+                    const int u = u0 + 2 * (pr + j);
+                    const float2 h0 = tb ? f2(tb[A.tab_h + u], tb[A.tab_h + u + 1]) : f2(0.f, 0.f);
+                    c[pr + j] = tb ? f2(tb[A.tab_c + u], tb[A.tab_c + u + 1]) : f2(0.f, 0.f);
+                    hi[j] = split_pair(h0, lo[j]);
                 }
-                tmem_st4(lane_addr + col_h + (u0 + ch * 8) / 2, hi[0], hi[1], hi[2], hi[3]);
-                tmem_st4(lane_addr + col_h + H / 2 + (u0 + ch * 8) / 2, lo[0], lo[1], lo[2], lo[3]);
+                tmem_st2(lane_addr + col_h + u0 / 2 + pr, hi[0], hi[1]);
+                tmem_st2(lane_addr + col_h + H / 2 + u0 / 2 + pr, lo[0], lo[1]);
             }
         }
         // sequence scratch of this tile: words [t][w][128]
@@ -252,25 +349,25 @@ k_lstm_tc(const TcArgs A)
                 const float *tt = A.tab + (size_t)(t + 1) * A.tab_stride + A.tab_h;
                 uint32_t *gt = gout + (size_t)t * A.g_words * TCM + m;
 #pragma unroll
-                for (int j = 0; j < HH / 2; j++) {
+                for (int j = 0; j < UPT / 2; j++) {
                     uint32_t lo;
-                    const uint32_t hi = split2(tt[u0 + 2 * j], tt[u0 + 2 * j + 1], lo);
+                    const uint32_t hi = split_pair(f2(tt[u0 + 2 * j], tt[u0 + 2 * j + 1]), lo);
                     gt[(size_t)(dir.g_hi + u0 / 2 + j) * TCM] = hi;
                     gt[(size_t)(dir.g_lo + u0 / 2 + j) * TCM] = lo;
                 }
             }
         }
         // vector input of the first step -> TMEM
-        constexpr int XW = (KX > 0) ? KX / 2 : 1;          // x words per thread
+        constexpr int XW = (KX > 0) ? KX / NP : 4;         // x words per thread
         uint32_t xw[XW];
         if (KX > 0) {
             const int t = dir.reverse ? (T - 1 - t_start) : t_start;
-            const uint32_t *gp = gin + (size_t)t * KX * TCM + (size_t)(wg * XW) * TCM + m;
+            const uint32_t *gp = gin + (size_t)t * KX * TCM + (size_t)(part * XW) * TCM + m;
 #pragma unroll
             for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
 #pragma unroll
             for (int j = 0; j < XW; j += 4)
-                tmem_st4(lane_addr + col_x + wg * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+                tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
         }
         tmem_st_wait();
         fence_before_sync();
@@ -278,70 +375,80 @@ k_lstm_tc(const TcArgs A)
         if (lane == 0) mbar_arrive(&bar_h);
 
         uint32_t ph = 0;
+        const bool coarse = dir.coarse != 0;
+        const uint32_t d_addr = lane_addr + col_d + u0 * 4;
+        const uint32_t hh_addr = lane_addr + col_h + u0 / 2, hl_addr = hh_addr + H / 2;
         for (int s = t_start; s < T; s++) {
             const int t = dir.reverse ? (T - 1 - s) : s;
             float xv = 0.f;
             if (KX == 0) xv = (t >= pad) ? __ldg(xbase + t) : A.padval;
             if (KX > 0 && s + 1 < T) {                     // prefetch the next step's input
                 const int tn = dir.reverse ? (T - 2 - s) : (s + 1);
-                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(wg * XW) * TCM + m;
+                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
 #pragma unroll
                 for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
             }
+            // this thread's slots in the sequence scratch at step t (constant offsets from here)
+            uint32_t *g_hi_t = nullptr, *g_lo_t = nullptr;
+            if (SEQ_OUT) {
+                uint32_t *gt = gout + (size_t)t * A.g_words * TCM + m;
+                g_hi_t = gt + (size_t)(dir.g_hi + u0 / 2) * TCM;
+                g_lo_t = gt + (size_t)(dir.g_lo + u0 / 2) * TCM;
+            }
+            const float2 xv2 = splat(xv);
             mbar_wait(&bar_d, ph, &s_dead);
             ph ^= 1;
             __syncwarp();
             fence_after_sync();
+            uint32_t v[2][16];
+            tmem_ld16(d_addr, v[0]);
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + col_d + (u0 + ch * 8) * 4, v);
                 tmem_ld_wait();
-                float hn[8];
+                if (ch + 1 < NCH) tmem_ld16(d_addr + (ch + 1) * 16, v[(ch + 1) & 1]);
+                const uint32_t *vv = v[ch & 1];
+                uint32_t hi[2], lo[2];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int u = u0 + ch * 8 + j;
-                    const float4 bb = *reinterpret_cast<const float4 *>(s_bias + 4 * u);
-                    float zi = __fadd_rn(__uint_as_float(v[4 * j + 0]), bb.x);
-                    float zf = __fadd_rn(__uint_as_float(v[4 * j + 1]), bb.y);
-                    float zc = __fadd_rn(__uint_as_float(v[4 * j + 2]), bb.z);
-                    float zo = __fadd_rn(__uint_as_float(v[4 * j + 3]), bb.w);
+                for (int j = 0; j < 2; j++) {              // pairs of units
+                    const int col = (u0 + ch * 4 + 2 * j) * 4;          // = gate_col(u, 0)
+                    const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + col + 4);
+                    float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
+                    float2 zf = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 2]), __uint_as_float(vv[8 * j + 3])), f2(b0.z, b0.w));
+                    float2 zc = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 4]), __uint_as_float(vv[8 * j + 5])), f2(b1.x, b1.y));
+                    float2 zo = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 6]), __uint_as_float(vv[8 * j + 7])), f2(b1.z, b1.w));
                     if (KX == 0) {
-                        const float4 ww = *reinterpret_cast<const float4 *>(s_win + 4 * u);
-                        zi = __fmaf_rn(xv, ww.x, zi);
-                        zf = __fmaf_rn(xv, ww.y, zf);
-                        zc = __fmaf_rn(xv, ww.z, zc);
-                        zo = __fmaf_rn(xv, ww.w, zo);
+                        const float4 w0 = *reinterpret_cast<const float4 *>(s_win + col);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(s_win + col + 4);
+                        zi = __ffma2_rn(xv2, f2(w0.x, w0.y), zi);
+                        zf = __ffma2_rn(xv2, f2(w0.z, w0.w), zf);
+                        zc = __ffma2_rn(xv2, f2(w1.x, w1.y), zc);
+                        zo = __ffma2_rn(xv2, f2(w1.z, w1.w), zo);
                     }
-                    const float ig = sigmoid_fast(zi), fg = sigmoid_fast(zf);
-                    const float cg = tanh_fast(zc), og = sigmoid_fast(zo);
-                    const float cn = __fmaf_rn(fg, c[ch * 8 + j], __fmul_rn(ig, cg));
-                    c[ch * 8 + j] = cn;
-                    hn[j] = __fmul_rn(og, tanh_fast(cn));
+                    float2 &cc = c[ch * 2 + j];
+                    const float2 hn = coarse ? lstm_cell_pair<true>(zi, zf, zc, zo, cc)
+                                             : lstm_cell_pair<false>(zi, zf, zc, zo, cc);
+                    hi[j] = split_pair(hn, lo[j]);
+                    if (!SEQ_OUT && s == T - 1 && tile0 + m < n_eff) {
+                        float *hl = dir.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 4 + 2 * j;
+                        hl[0] = hn.x;
+                        hl[1] = hn.y;
+                    }
                 }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) hi[j] = split2(hn[2 * j], hn[2 * j + 1], lo[j]);
-                tmem_st4(lane_addr + col_h + (u0 + ch * 8) / 2, hi[0], hi[1], hi[2], hi[3]);
-                tmem_st4(lane_addr + col_h + H / 2 + (u0 + ch * 8) / 2, lo[0], lo[1], lo[2], lo[3]);
+                tmem_st2(hh_addr + ch * 2, hi[0], hi[1]);
+                tmem_st2(hl_addr + ch * 2, lo[0], lo[1]);
                 if (SEQ_OUT) {
-                    uint32_t *gt = gout + (size_t)t * A.g_words * TCM + m;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        gt[(size_t)(dir.g_hi + (u0 + ch * 8) / 2 + j) * TCM] = hi[j];
-                        gt[(size_t)(dir.g_lo + (u0 + ch * 8) / 2 + j) * TCM] = lo[j];
+                    for (int j = 0; j < 2; j++) {
+                        g_hi_t[(ch * 2 + j) * TCM] = hi[j];
+                        g_lo_t[(ch * 2 + j) * TCM] = lo[j];
                     }
-                }
-                if (!SEQ_OUT && s == T - 1 && tile0 + m < n_eff) {
-                    float *hl = dir.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 8;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) hl[j] = hn[j];
                 }
             }
             if (KX > 0 && s + 1 < T) {
 #pragma unroll
                 for (int j = 0; j < XW; j += 4)
-                    tmem_st4(lane_addr + col_x + wg * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+                    tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
             }
             tmem_st_wait();
             fence_before_sync();
@@ -353,7 +460,7 @@ k_lstm_tc(const TcArgs A)
     // ---- teardown ------------------------------------------------------------------
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == NGW) {
         fence_after_sync();
         tmem_dealloc(tbase, TCOLS);
     }
@@ -584,8 +691,8 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
     int *tstart = (int *)ws_get(ctx, ctx->ws_tstart, sizeof(int) * (size_t)tiles_per_pass);
     int32_t *rl = (int32_t *)ws_get(ctx, ctx->ws_recheck, sizeof(int32_t) * ((size_t)n + 4));
     if (!G || !h_last || !tstart || !rl) return PB2_ENOMEM;
-    int *err = (int *)rl + 2;                 // [2]: time-out flag of the scaler kernels
-    PB_CUDA(ctx, cudaMemsetAsync(err, 0, sizeof(int), st));
+    (void)rl;
+    int *err = ctx->tc_err;
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
         const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
         const int64_t r0 = t0 * TCM;
@@ -601,7 +708,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         A.Gout = G; A.g_words = H; A.g_t0 = thead - (int)Tmax; A.g_T = (int)Tmax;
         A.err = err;
         PB_LAUNCH(ctx, K_SCALER_TC_L1, "k_lstm_tc<scaler l1>", st,
-            k_lstm_tc<H, 0, true><<<dim3((unsigned)nt, 1), TC_THREADS, tc_smem_bytes<H, 0>(), st>>>(A));
+            k_lstm_tc<H, 0, true><<<dim3((unsigned)nt, 1), tc_threads<0>(), tc_smem_bytes<H, 0>(), st>>>(A));
         TcArgs B = {};
         B.dir[0] = {S.l2.recurrent, S.l2.kernel, S.l2.bias, 0, 0, 0, 0, 0, h_last};
         B.dir[1] = B.dir[0];
@@ -610,7 +717,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         B.tile_tstart = tstart; B.tstart_in = 1;
         B.Gin = G; B.g_t0 = A.g_t0; B.g_T = A.g_T; B.err = err;
         PB_LAUNCH(ctx, K_SCALER_TC_L2, "k_lstm_tc<scaler l2>", st,
-            k_lstm_tc<H, H, false><<<dim3((unsigned)nt, 1), TC_THREADS, tc_smem_bytes<H, H>(), st>>>(B));
+            k_lstm_tc<H, H, false><<<dim3((unsigned)nt, 1), tc_threads<H>(), tc_smem_bytes<H, H>(), st>>>(B));
     }
     TcScalerHeadArgs Hd = {};
     Hd.h_last = h_last; Hd.nreal = nreal; Hd.n = n;
@@ -662,7 +769,8 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     // [0] timeout flag, [1] re-check count, then the re-check rows
     int32_t *rlist = (int32_t *)ws_get(ctx, ctx->ws_recheck, sizeof(int32_t) * ((size_t)n + 4));
     if (!G || !h_last || !tstart || !rlist) return PB2_ENOMEM;
-    int *err = (int *)rlist, *rcount = (int *)rlist + 1;
+    int *err = ctx->tc_err, *rcount = (int *)rlist + 1;
+    ctx->demux_tc_ran = true;
     int32_t *rrows = rlist + 4;
     PB_CUDA(ctx, cudaMemsetAsync(rlist, 0, sizeof(int32_t) * 2, st));
     const bool use_pad = D.pad_state && !ctx->no_pad_skip;
@@ -683,7 +791,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         A.Gout = G; A.g_words = KX; A.g_t0 = 0; A.g_T = T; A.fill_skipped = 1;
         A.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L1, "k_lstm_tc<demux l1>", st,
-            k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H1, 0>(), st>>>(A));
+            k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), tc_threads<0>(), tc_smem_bytes<H1, 0>(), st>>>(A));
         TcArgs B = {};
         // blockIdx.y = 0: the result; 1: the coarse evaluation that measures each window's
         // sensitivity (layer 2 amplifies perturbations by orders of magnitude for some windows)
@@ -692,7 +800,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         B.T = T; B.n = A.n; B.slot_count = slot_count; B.row0 = r0;
         B.Gin = G; B.g_t0 = 0; B.g_T = T; B.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L2, "k_lstm_tc<demux l2>", st,
-            k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 2), TC_THREADS, tc_smem_bytes<H2, KX>(), st>>>(B));
+            k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 2), tc_threads<KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
     }
     TcHeadArgs Hd = {};
     Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.n = n;

@@ -85,7 +85,9 @@ struct pb2_context {
     // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
     double demux_margin_delta = 2e-3;
     double demux_probe_gain = 0.25;
-    double scaler_margin_z = 3e-5;                // assumed bound on the error of the scaler's raw outputs
+    double scaler_margin_z = 5e-4;                // assumed bound on the error of the scaler's raw outputs
+    bool demux_tc_ran = false;
+    int *tc_err = nullptr;                        // device word: a tensor-core kernel timed out
     int64_t last_rerun_reads = 0;                 // reads the last whole-path call re-ran exactly
     size_t tc_scratch_bytes = (size_t)12 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position

@@ -118,6 +118,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -125,6 +134,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
                                          uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                  ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -141,7 +154,12 @@ __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t &lo) {
 }
 
 // ---- weights -> shared memory (canonical K-major, no swizzle) ----------------------
-// src: Keras matrix [K][4H] row-major, gate blocks i|f|c|o.  Output column n = 4*u + gate.
+// Accumulator column of (unit u, gate g): the four gates of a PAIR of units sit in eight
+// consecutive columns as (i,i', f,f', c,c', o,o'), so a thread reading its columns with
+// tcgen05.ld gets aligned register pairs for the packed f32x2 gate arithmetic.
+__host__ __device__ constexpr int gate_col(int u, int gate) { return (u >> 1) * 8 + gate * 2 + (u & 1); }
+
+// src: Keras matrix [K][4H] row-major, gate blocks i|f|c|o.  Output column n = gate_col(u, gate).
 // B_hi / B_lo: fp16 [K/8][N/8][8 (n)][8 (k)], N = 4H.
 template <int K, int H>
 __device__ __forceinline__ void load_b_split(const float *__restrict__ src, __half *b_hi,
@@ -150,7 +168,7 @@ __device__ __forceinline__ void load_b_split(const float *__restrict__ src, __ha
     for (int idx = tid; idx < K * N; idx += nthreads) {
         const int k = idx / N, col = idx % N;          // coalesced read of src
         const int gate = col / H, u = col % H;
-        const int n = 4 * u + gate;
+        const int n = gate_col(u, gate);
         const float v = src[idx];
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-5
-SCALE_ATOL, SHIFT_ATOL = 4.2e-6, 3.2e-4     # 0.13296 / 9.8256 x scaler_margin_z (+ f32 rounding)
+SCALE_ATOL, SHIFT_ATOL = 6.7e-5, 5e-3       # 0.13296 / 9.8256 x scaler_margin_z (+ f32 rounding)
 PROB_ATOL = 2e-3     # approximate (tensor-core) class probabilities vs the exact f32 chain
 
 
@@ -40,10 +40,13 @@ def _compare(out, ref, n_states=6, check_probs=True):
     else:
         # default path: (scale, shift) of reads that passed every margin test come from the
         # tensor-core scaler; they must lie inside the uncertainty box the margin tests assume
-        # (scaler_margin_z = 3e-5 on the raw outputs -> 4e-6 / 3e-4), far inside the 1e-5
-        # relative tolerance of the normalised signal (~100 pA)
+        # (scaler_margin_z = 5e-4 on the raw outputs); typical errors are 100x smaller: the
+        # normalised signal (~100 pA) stays within north_star's 1e-5 relative tolerance
         d = np.abs(out['scale_shift'][has_ss].astype(np.float64) - ss_ref[has_ss])
         assert d[:, 0].max(initial=0) <= SCALE_ATOL and d[:, 1].max(initial=0) <= SHIFT_ATOL, d.max(0)
+        if len(d) >= 20:
+            y_err = d[:, 0] * 100.0 + d[:, 1]              # error of a 100 pA sample after scaling
+            assert np.median(y_err) <= REL_TOL * 100.0, np.median(y_err)
     seg_ok = okay_like
     assert np.array_equal(out['segments'][seg_ok][:, :n_states], ref['seg'][seg_ok][:, :n_states])
     pushed = ref['pushed'] == 1

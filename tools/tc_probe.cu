@@ -106,7 +106,7 @@ static int run(int variant)
     double maxerr = 0, maxref = 0;
     for (int m = 0; m < 128; m++)
         for (int n = 0; n < N; n++) {
-            const int u = n / 4, g = n % 4;
+            const int u = (n / 8) * 2 + (n & 1), g = (n % 8) / 2;      // inverse of gate_col
             double ref = 0;
             for (int k = 0; k < K; k++) ref += (double)A[m * K + k] * (double)W[k * N + g * H + u];
             maxerr = fmax(maxerr, fabs(ref - (double)D[m * N + n]));
