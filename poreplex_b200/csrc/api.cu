@@ -992,19 +992,25 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             PB_CUDA(ctx, cudaEventRecord(ev_d2h[a], co));
             return PB2_OK;
         };
-        for (int c = 0; c < nchunks; c++) {
+        // inputs of chunk c go up on the first stream.  Issued one chunk EARLY (before the
+        // kernels of chunk c - 1 are queued): pb2_analyze_device may block the host while it
+        // waits for the size of its exact re-run, and the next upload must already be in flight.
+        // The arena's input region is free once the kernels of chunk c - 2 are done.
+        std::vector<int64_t> spans((size_t)nchunks), max_lens((size_t)nchunks);
+        auto upload = [&](int c) -> int {
             const int a = c & 1;
             char *A = base + (size_t)a * arena_bytes;
             const int64_t c0 = bounds[c], c1 = bounds[c + 1], nc = c1 - c0;
             const int64_t roff0 = hb->raw_offsets[c0];
             const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - roff0;
-            if (c >= 2) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_d2h[a], 0));
+            if (c >= 2) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[a], 0));
             rebased[a].resize((size_t)nc);
             int64_t max_len = 0;
             for (int64_t i = 0; i < nc; i++) {
                 rebased[a][i] = hb->raw_offsets[c0 + i] - roff0;
                 if (hb->raw_lengths[c0 + i] > max_len) max_len = hb->raw_lengths[c0 + i];
             }
+            spans[c] = span; max_lens[c] = max_len;
             cudaStream_t ci = ctx->copy_in;
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_raw, hb->raw + roff0, sizeof(int16_t) * (size_t)span, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_off, rebased[a].data(), 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
@@ -1013,6 +1019,15 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_dig, hb->digitisation + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_ofs, hb->offset + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaEventRecord(ev_h2d[a], ci));
+            return PB2_OK;
+        };
+        { int r0 = upload(0); if (r0) return r0; }
+        for (int c = 0; c < nchunks; c++) {
+            const int a = c & 1;
+            char *A = base + (size_t)a * arena_bytes;
+            const int64_t nc = bounds[c + 1] - bounds[c];
+            if (c + 1 < nchunks) { int r1 = upload(c + 1); if (r1) return r1; }
+            const int64_t span = spans[c], max_len = max_lens[c];
 
             pb2_batch db = {};
             db.n_reads = nc; db.n_raw_total = span; db.max_raw_length = max_len;
@@ -1029,6 +1044,8 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             dr.barcode_score = (int32_t *)(A + o_sc); dr.class_probs = (float *)(A + o_pr);
             dr.counts = (int64_t *)(A + o_cnt);
             dr.polya = want_polya ? (pb2_polya_result *)(A + o_polya) : nullptr;
+            // the arena's result region is free once the results of chunk c - 2 have left
+            if (c >= 2) PB_CUDA(ctx, cudaStreamWaitEvent(compute, ev_d2h[a], 0));
             PB_CUDA(ctx, cudaStreamWaitEvent(compute, ev_h2d[a], 0));
             if (!(flags & PB2_FLAG_BARCODING)) {
                 PB_CUDA(ctx, cudaMemsetAsync(dr.barcode, 0xFF, 4 * (size_t)nc, compute));
