@@ -50,6 +50,7 @@ def algorithmic(L, stride=15, trim=300, scaler_len=30000):
         # evaluation of layer 2 and the exact re-runs are overhead, not algorithmic work)
         'k_lstm_tc_demux_l1': ('tensor', 2 * 2 * (192 + 48 * 192) * trim),
         'k_lstm_tc_demux_l2': ('tensor', 2 * (96 * 256 + 64 * 256) * trim),
+        'k_lstm_tc_demux_l2_probe': ('tensor', 2 * (96 * 256 + 64 * 256) * trim),
         'k_lstm_tc_scaler_l1': ('tensor', 2 * (192 + 48 * 192) * H),
         'k_lstm_tc_scaler_l2': ('tensor', 2 * (2 * 48 * 192) * H),
     }
@@ -310,6 +311,7 @@ def main():
     # ---- default path (tensor cores + margin test + exact re-run) vs exact-only kernels:
     # every integer output of every read must be identical (outside the timed region)
     rechecked, tc_timeouts = eng.recheck_stats()
+    rerun_causes = eng.rerun_causes()
     fast_int = {k: out[k].clone() for k in ('status', 'segments', 'barcode', 'barcode_guess',
                                             'barcode_score', 'label', 'counts')}
     fast_ss = out['scale_shift'].clone()
@@ -397,7 +399,8 @@ def main():
                    'reads_per_gpu': n, 'read_length': args.length, 'preset': args.preset,
                    'l2_policy': 'inputs (%.1f GB per GPU) larger than L2' % (n * args.length * 2 / 1e9),
                    'status_mix': mix, 'classified_reads': classified,
-                   'exact_reruns_per_step': rechecked, 'tc_barrier_timeouts': tc_timeouts,
+                   'exact_reruns_per_step': rechecked, 'exact_rerun_causes': rerun_causes,
+                   'tc_barrier_timeouts': tc_timeouts,
                    'mismatches_vs_exact_only_kernels': mismatches,
                    'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)'},
         'clocks': clocks, 'gpu_launches': launches,

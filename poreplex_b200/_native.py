@@ -11,7 +11,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB_PATH = os.path.join(HERE, 'libporeplex_b200.so')
+# POREPLEX_B200_LIB: load another build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get('POREPLEX_B200_LIB') or os.path.join(HERE, 'libporeplex_b200.so')
 HEADER = os.path.join(HERE, '..', 'include', 'poreplex_b200.h')
 
 MAX_STATES, MAX_COMP, MAX_EDGES, MAX_CLASSES, MAX_CALIB = 8, 4, 64, 8, 64
@@ -123,7 +124,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
            'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
-           'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1']
+           'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes']
 
 
 def sources():
@@ -189,6 +190,7 @@ def load():
     L.pb2_demux_predict_tc.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pb2_recheck_stats.argtypes = [vp, _i64p, _i64p]
     L.pb2_debug_demux_l1.argtypes = [vp, vp, C.c_int64, vp, vp]
+    L.pb2_rerun_causes.argtypes = [vp, _i64p, _i64p, _i64p]
     L.pb2_set_polya.argtypes = [vp, C.POINTER(PolyaParams), C.c_int32]
     L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
     L.pb2_set_unsplit.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(UnsplitParams), C.c_int32,

@@ -78,7 +78,7 @@ static const char *const kKernelNames[K_NUM] = {
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
     "k_unsplit_windows", "k_unsplit_decide", "k_event_means", "k_lstm_tc_demux_l1",
     "k_lstm_tc_demux_l2", "k_demux_head_tc", "k_lstm_tc_scaler_l1", "k_lstm_tc_scaler_l2",
-    "k_scaler_head_tc"};
+    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe"};
 
 static void ws_free(Workspace &w)
 {
@@ -237,6 +237,15 @@ int pb2_debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float 
     if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
     DeviceGuard g(ctx->device);
     return debug_demux_l1(ctx, windows, n, out, (cudaStream_t)stream);
+}
+
+int pb2_rerun_causes(pb2_context *ctx, int64_t *qc, int64_t *segmentation, int64_t *barcode)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (qc) *qc = ctx->last_rerun_cause[0];
+    if (segmentation) *segmentation = ctx->last_rerun_cause[1];
+    if (barcode) *barcode = ctx->last_rerun_cause[2];
+    return PB2_OK;
 }
 
 int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_timeouts)
@@ -591,6 +600,9 @@ __global__ void k_collect_unsafe(int64_t n, const int32_t *__restrict__ unsafe, 
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n || !unsafe[r]) return;
     list[atomicAdd(count, 1)] = (int32_t)r;
+    if (unsafe[r] & 1) atomicAdd(count + 1, 1);       // per-cause tallies (diagnostics)
+    if (unsafe[r] & 2) atomicAdd(count + 2, 1);
+    if (unsafe[r] & 4) atomicAdd(count + 3, 1);
 }
 
 __global__ void k_gather_sub_batch(int n_sub, const int32_t *__restrict__ list,
@@ -687,10 +699,12 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
     // ---- the unsafe reads, exactly ---------------------------------------------------
     PB_LAUNCH(ctx, K_MISC, "k_collect_unsafe", st,
         k_collect_unsafe<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, unsafe, count, list));
-    int n_sub = 0;
-    PB_CUDA(ctx, cudaMemcpyAsync(&n_sub, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int tally[4] = {0, 0, 0, 0};
+    PB_CUDA(ctx, cudaMemcpyAsync(tally, count, sizeof(tally), cudaMemcpyDeviceToHost, st));
     PB_CUDA(ctx, cudaStreamSynchronize(st));
+    const int n_sub = tally[0];
     ctx->last_rerun_reads = n_sub;
+    for (int i = 0; i < 3; i++) ctx->last_rerun_cause[i] = tally[i + 1];
     if (n_sub > 0) {
         const size_t m = (size_t)n_sub;
         size_t o2 = 0;

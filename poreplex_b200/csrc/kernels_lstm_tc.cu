@@ -144,11 +144,39 @@ constexpr size_t tc_smem_bytes() {
 
 // gate warps per lane quarter: layers alone on their SM (vector input, 512 TMEM columns) use
 // four so that 16 warps hide the MUFU / FMA latencies; scalar-input layers run two CTAs per SM
-template <int KX> __host__ __device__ constexpr int tc_nparts() { return KX == 0 ? 2 : 4; }
-template <int KX> __host__ __device__ constexpr int tc_threads() { return 128 * tc_nparts<KX>() + 32; }
+// (units per thread must be a multiple of 8: H = 48 with a vector input uses three)
+template <int H, int KX> __host__ __device__ constexpr int tc_nparts() { return KX == 0 ? 2 : (H % 32 == 0 ? 4 : 3); }
+template <int H, int KX> __host__ __device__ constexpr int tc_threads() { return 128 * tc_nparts<H, KX>() + 32; }
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+
+// 2^y for a pair, y in [-125, 30], on the FMA pipe: y = n + f with n = round(y) taken from the
+// mantissa of y + 1.5 * 2^23, 2^f by a degree-5 polynomial (relative error 2.9e-7, the same
+// as MUFU.EX2), the exponent added to the bit pattern.  The MUFU unit is the busiest pipe of
+// the gate phase; moving some of the exponentials here balances it against the FMA pipe.
+__device__ __forceinline__ float2 exp2_poly_pair(float2 y) {
+    const float2 t = __fadd2_rn(y, splat(12582912.0f));
+    const float2 n = __fadd2_rn(t, splat(-12582912.0f));
+    const float2 f = __ffma2_rn(n, splat(-1.0f), y);
+    float2 q = splat(0.0013390866806730628f);
+    q = __ffma2_rn(q, f, splat(0.009666373953223228f));
+    q = __ffma2_rn(q, f, splat(0.055503569543361664f));
+    q = __ffma2_rn(q, f, splat(0.2402234822511673f));
+    q = __ffma2_rn(q, f, splat(0.6931471824645996f));
+    q = __ffma2_rn(q, f, splat(1.0f));
+    return f2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+              __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+__device__ __forceinline__ float2 clamp_exp_arg(float2 a) {
+    return f2(fmaxf(fminf(a.x, 30.f), -125.f), fmaxf(fminf(a.y, 30.f), -125.f));
+}
+
+#ifndef PB_TC_NPOLY
+#define PB_TC_NPOLY 0          // exponentials per cell evaluated by exp2_poly_pair (0..3);
+                              // measured on B200: 0 is fastest (the gate phase is issue- and
+                              // latency-bound, not MUFU-bound), kept as a tuning knob
+#endif
 
 // Cell update for a PAIR of units with packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 halve
 // the FMA-pipe instruction count; MUFU and min are per lane).  See lstm_cell_tc for the maths.
@@ -169,10 +197,13 @@ __device__ __forceinline__ float2 lstm_cell_pair(float2 zi, float2 zf, float2 zc
     const float2 one = splat(1.0f), mone = splat(-1.0f);
     const float2 ai_ = __fmul2_rn(zi, splat(-L)), af_ = __fmul2_rn(zf, splat(-L));
     const float2 ag_ = __fmul2_rn(zc, splat(-L2)), ao_ = __fmul2_rn(zo, splat(-L));
-    const float2 ei = f2(ex2_fast(fminf(ai_.x, 30.f)), ex2_fast(fminf(ai_.y, 30.f)));
-    const float2 ef = f2(ex2_fast(fminf(af_.x, 30.f)), ex2_fast(fminf(af_.y, 30.f)));
+    const float2 ei = PB_TC_NPOLY >= 1 ? exp2_poly_pair(clamp_exp_arg(ai_))
+                                       : f2(ex2_fast(fminf(ai_.x, 30.f)), ex2_fast(fminf(ai_.y, 30.f)));
+    const float2 ef = PB_TC_NPOLY >= 2 ? exp2_poly_pair(clamp_exp_arg(af_))
+                                       : f2(ex2_fast(fminf(af_.x, 30.f)), ex2_fast(fminf(af_.y, 30.f)));
     const float2 eg = f2(ex2_fast(fminf(ag_.x, 30.f)), ex2_fast(fminf(ag_.y, 30.f)));
-    const float2 eo = f2(ex2_fast(fminf(ao_.x, 30.f)), ex2_fast(fminf(ao_.y, 30.f)));
+    const float2 eo = PB_TC_NPOLY >= 3 ? exp2_poly_pair(clamp_exp_arg(ao_))
+                                       : f2(ex2_fast(fminf(ao_.x, 30.f)), ex2_fast(fminf(ao_.y, 30.f)));
     const float2 af = __fadd2_rn(one, ef);
     const float2 p = __fmul2_rn(__fadd2_rn(one, ei), __fadd2_rn(one, eg));
     const float2 q = __fmul2_rn(p, af);
@@ -198,18 +229,21 @@ __device__ __forceinline__ uint32_t split_pair(float2 h, uint32_t &lo) {
     return *reinterpret_cast<const uint32_t *>(&h16);
 }
 
-template <int H, int KX, bool SEQ_OUT>
-__global__ void __launch_bounds__(tc_threads<KX>(), (KX == 0 ? 2 : 1))
+// COARSE: the deliberately perturbed evaluation (leading fp16 product only, MUFU.TANH gates);
+// a template parameter so that the unrolled gate loop is one basic block the compiler can
+// interleave across unit pairs.
+template <int H, int KX, bool SEQ_OUT, bool COARSE = false>
+__global__ void __launch_bounds__(tc_threads<H, KX>(), (KX == 0 ? 2 : 1))
 k_lstm_tc(const TcArgs A)
 {
     constexpr int N = 4 * H;
-    constexpr int NP = tc_nparts<KX>();  // gate warps per lane quarter
+    constexpr int NP = tc_nparts<H, KX>();   // gate warps per lane quarter
     constexpr int NGW = 4 * NP;          // gate warps; warp NGW issues the MMAs
-    constexpr int NTHR = tc_threads<KX>();
+    constexpr int NTHR = tc_threads<H, KX>();
     constexpr int UPT = H / NP;          // units per gate thread
-    constexpr int NCH = UPT / 4;         // chunks of 4 units (16 accumulator columns)
+    constexpr int NCH = UPT / 8;         // chunks of 8 units (32 accumulator columns, 4 pairs)
     constexpr int TCOLS = tc_tmem_cols<H, KX>();
-    static_assert(UPT % 4 == 0, "units per thread must be a multiple of 4");
+    static_assert(UPT % 8 == 0 && H % NP == 0, "units per thread must be a multiple of 8");
     static_assert(H % 16 == 0 && KX % 16 == 0, "K must be a multiple of 16");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -309,9 +343,9 @@ k_lstm_tc(const TcArgs A)
                     issue_split_gemm<(KX > 0 ? KX : 16), N>(tbase + col_d, tbase + col_x,
                                                             tbase + col_x + KX / 2,
                                                             smem_u32(bW_hi), smem_u32(bW_lo), first,
-                                                            !dir.coarse);
+                                                            !COARSE);
                 issue_split_gemm<H, N>(tbase + col_d, tbase + col_h, tbase + col_h + H / 2,
-                                       smem_u32(bU_hi), smem_u32(bU_lo), first, !dir.coarse);
+                                       smem_u32(bU_hi), smem_u32(bU_lo), first, !COARSE);
                 mma_commit(&bar_d);
             }
         }
@@ -375,7 +409,6 @@ k_lstm_tc(const TcArgs A)
         if (lane == 0) mbar_arrive(&bar_h);
 
         uint32_t ph = 0;
-        const bool coarse = dir.coarse != 0;
         const uint32_t d_addr = lane_addr + col_d + u0 * 4;
         const uint32_t hh_addr = lane_addr + col_h + u0 / 2, hl_addr = hh_addr + H / 2;
         for (int s = t_start; s < T; s++) {
@@ -400,17 +433,16 @@ k_lstm_tc(const TcArgs A)
             ph ^= 1;
             __syncwarp();
             fence_after_sync();
-            uint32_t v[2][16];
-            tmem_ld16(d_addr, v[0]);
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
+                uint32_t vv[32];
+                tmem_ld32(d_addr + ch * 32, vv);
                 tmem_ld_wait();
-                if (ch + 1 < NCH) tmem_ld16(d_addr + (ch + 1) * 16, v[(ch + 1) & 1]);
-                const uint32_t *vv = v[ch & 1];
-                uint32_t hi[2], lo[2];
+                uint32_t hi[4], lo[4];
+                float2 hn[4];
 #pragma unroll
-                for (int j = 0; j < 2; j++) {              // pairs of units
-                    const int col = (u0 + ch * 4 + 2 * j) * 4;          // = gate_col(u, 0)
+                for (int j = 0; j < 4; j++) {              // four independent pairs of units
+                    const int col = (u0 + ch * 8 + 2 * j) * 4;          // = gate_col(u, 0)
                     const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col);
                     const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + col + 4);
                     float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
@@ -425,24 +457,22 @@ k_lstm_tc(const TcArgs A)
                         zc = __ffma2_rn(xv2, f2(w1.x, w1.y), zc);
                         zo = __ffma2_rn(xv2, f2(w1.z, w1.w), zo);
                     }
-                    float2 &cc = c[ch * 2 + j];
-                    const float2 hn = coarse ? lstm_cell_pair<true>(zi, zf, zc, zo, cc)
-                                             : lstm_cell_pair<false>(zi, zf, zc, zo, cc);
-                    hi[j] = split_pair(hn, lo[j]);
-                    if (!SEQ_OUT && s == T - 1 && tile0 + m < n_eff) {
-                        float *hl = dir.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 4 + 2 * j;
-                        hl[0] = hn.x;
-                        hl[1] = hn.y;
-                    }
+                    hn[j] = lstm_cell_pair<COARSE>(zi, zf, zc, zo, c[ch * 4 + j]);
+                    hi[j] = split_pair(hn[j], lo[j]);
                 }
-                tmem_st2(hh_addr + ch * 2, hi[0], hi[1]);
-                tmem_st2(hl_addr + ch * 2, lo[0], lo[1]);
+                tmem_st4(hh_addr + ch * 4, hi[0], hi[1], hi[2], hi[3]);
+                tmem_st4(hl_addr + ch * 4, lo[0], lo[1], lo[2], lo[3]);
                 if (SEQ_OUT) {
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        g_hi_t[(ch * 2 + j) * TCM] = hi[j];
-                        g_lo_t[(ch * 2 + j) * TCM] = lo[j];
+                    for (int j = 0; j < 4; j++) {
+                        g_hi_t[(ch * 4 + j) * TCM] = hi[j];
+                        g_lo_t[(ch * 4 + j) * TCM] = lo[j];
                     }
+                }
+                if (!SEQ_OUT && s == T - 1 && tile0 + m < n_eff) {
+                    float *hl = dir.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
                 }
             }
             if (KX > 0 && s + 1 < T) {
@@ -531,7 +561,7 @@ __global__ void k_demux_head_tc(const TcHeadArgs A)
         for (int j = 0; j < PB2_MAX_CLASSES; j++) A.logits_out[row * PB2_MAX_CLASSES + j] = call.logit[j];
     }
     if (A.unsafe_out) A.unsafe_out[row] = safe ? 0 : 1;
-    if (A.read_unsafe && !safe) A.read_unsafe[r] = 1;
+    if (A.read_unsafe && !safe) atomicOr(&A.read_unsafe[r], 4);       // cause bit 4: barcode call
     if (!safe && A.recheck_rows) {
         const int k = atomicAdd(A.recheck_count, 1);
         A.recheck_rows[k] = (int32_t)row;
@@ -603,7 +633,7 @@ __global__ void k_scaler_head_tc(const TcScalerHeadArgs A)
     const double dh = fabs(A.shift_std) * A.delta_z + 2e-7 * fabs(sh) + 1e-9;
     const bool edge = fabs(sc - A.qc_scale_lo) <= ds || fabs(sc - A.qc_scale_hi) <= ds ||
                       fabs(sh - A.qc_shift_lo) <= dh || fabs(sh - A.qc_shift_hi) <= dh;
-    if (edge) A.read_unsafe[r] = 1;
+    if (edge) atomicOr(&A.read_unsafe[r], 1);                         // cause bit 1: QC verdict
     // triangle (-1,-1), (3,-1), (-1,3) in units of (ds, dh) contains the box [-1,1]^2
     v0[0] = (float)(sc - ds);        v0[1] = (float)(sh - dh);
     v1[0] = (float)(sc + 3.0 * ds);  v1[1] = (float)(sh - dh);
@@ -630,7 +660,7 @@ __global__ void k_compare_corners(int64_t n, const int32_t *__restrict__ st0,
         same = same && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w &&
                x.x == z.x && x.y == z.y && x.z == z.z && x.w == z.w;
     }
-    if (!same) read_unsafe[r] = 1;
+    if (!same) atomicOr(&read_unsafe[r], 2);                          // cause bit 2: segmentation
 }
 
 int launch_compare_corners(pb2_context *ctx, int64_t n, const int32_t *st0, const int32_t *st1,
@@ -644,10 +674,10 @@ int launch_compare_corners(pb2_context *ctx, int64_t n, const int32_t *st0, cons
     return PB2_OK;
 }
 
-template <int H, int KX, bool SEQ_OUT>
+template <int H, int KX, bool SEQ_OUT, bool COARSE = false>
 static int tc_set_attr(pb2_context *ctx)
 {
-    PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<H, KX, SEQ_OUT>,
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<H, KX, SEQ_OUT, COARSE>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc_smem_bytes<H, KX>()));
     return PB2_OK;
@@ -708,7 +738,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         A.Gout = G; A.g_words = H; A.g_t0 = thead - (int)Tmax; A.g_T = (int)Tmax;
         A.err = err;
         PB_LAUNCH(ctx, K_SCALER_TC_L1, "k_lstm_tc<scaler l1>", st,
-            k_lstm_tc<H, 0, true><<<dim3((unsigned)nt, 1), tc_threads<0>(), tc_smem_bytes<H, 0>(), st>>>(A));
+            k_lstm_tc<H, 0, true><<<dim3((unsigned)nt, 1), tc_threads<48, 0>(), tc_smem_bytes<H, 0>(), st>>>(A));
         TcArgs B = {};
         B.dir[0] = {S.l2.recurrent, S.l2.kernel, S.l2.bias, 0, 0, 0, 0, 0, h_last};
         B.dir[1] = B.dir[0];
@@ -717,7 +747,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         B.tile_tstart = tstart; B.tstart_in = 1;
         B.Gin = G; B.g_t0 = A.g_t0; B.g_T = A.g_T; B.err = err;
         PB_LAUNCH(ctx, K_SCALER_TC_L2, "k_lstm_tc<scaler l2>", st,
-            k_lstm_tc<H, H, false><<<dim3((unsigned)nt, 1), tc_threads<H>(), tc_smem_bytes<H, H>(), st>>>(B));
+            k_lstm_tc<H, H, false><<<dim3((unsigned)nt, 1), tc_threads<H, H>(), tc_smem_bytes<H, H>(), st>>>(B));
     }
     TcScalerHeadArgs Hd = {};
     Hd.h_last = h_last; Hd.nreal = nreal; Hd.n = n;
@@ -755,6 +785,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         int rc;
         if ((rc = tc_set_attr<H1, 0, true>(ctx))) return rc;
         if ((rc = tc_set_attr<H2, KX, false>(ctx))) return rc;
+        if ((rc = tc_set_attr<H2, KX, false, true>(ctx))) return rc;
         ctx->attr_demux_tc = true;
     }
     const int64_t tiles = (n + TCM - 1) / TCM;
@@ -791,16 +822,20 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         A.Gout = G; A.g_words = KX; A.g_t0 = 0; A.g_T = T; A.fill_skipped = 1;
         A.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L1, "k_lstm_tc<demux l1>", st,
-            k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), tc_threads<0>(), tc_smem_bytes<H1, 0>(), st>>>(A));
+            k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), tc_threads<48, 0>(), tc_smem_bytes<H1, 0>(), st>>>(A));
         TcArgs B = {};
-        // blockIdx.y = 0: the result; 1: the coarse evaluation that measures each window's
-        // sensitivity (layer 2 amplifies perturbations by orders of magnitude for some windows)
+        // the result, then the coarse evaluation that measures each window's sensitivity
+        // (layer 2 amplifies perturbations by orders of magnitude for some windows)
         B.dir[0] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 0, h_last};
-        B.dir[1] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 1, h_probe};
+        B.dir[1] = B.dir[0];
         B.T = T; B.n = A.n; B.slot_count = slot_count; B.row0 = r0;
         B.Gin = G; B.g_t0 = 0; B.g_T = T; B.err = err;
         PB_LAUNCH(ctx, K_DEMUX_TC_L2, "k_lstm_tc<demux l2>", st,
-            k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 2), tc_threads<KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+            k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+        B.dir[0].coarse = 1; B.dir[0].h_last = h_probe;
+        B.dir[1] = B.dir[0];
+        PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe>", st,
+            k_lstm_tc<H2, KX, false, true><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
     }
     TcHeadArgs Hd = {};
     Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.n = n;

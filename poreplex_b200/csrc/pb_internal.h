@@ -70,7 +70,7 @@ namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
                 K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_DEMUX_TC_L1, K_DEMUX_TC_L2, K_DEMUX_TC_HEAD,
-                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_NUM };
+                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 
@@ -88,6 +88,7 @@ struct pb2_context {
     double scaler_margin_z = 5e-4;                // assumed bound on the error of the scaler's raw outputs
     bool demux_tc_ran = false;
     int *tc_err = nullptr;                        // device word: a tensor-core kernel timed out
+    int64_t last_rerun_cause[3] = {0, 0, 0};      // ... because of QC edge / segmentation / barcode call
     int64_t last_rerun_reads = 0;                 // reads the last whole-path call re-ran exactly
     size_t tc_scratch_bytes = (size_t)12 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position

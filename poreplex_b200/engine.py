@@ -233,6 +233,12 @@ class SignalEngine:
         self._check(self.lib.pb2_recheck_stats(self.handle, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def rerun_causes(self):
+        """{cause: reads} behind the exact re-runs of the last whole-path call."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.pb2_rerun_causes(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {'qc_edge': int(a.value), 'segmentation': int(b.value), 'barcode_call': int(c.value)}
+
     def profile_enable(self, on=True):
         self._check(self.lib.pb2_profile_enable(self.handle, 1 if on else 0))
 
