@@ -321,6 +321,8 @@ def main():
         eng.analyze_device(work['raw'], work['offsets'], work['lengths'], work['range'],
                            work['digitisation'], work['offset'], out=out, barcoding=True,
                            max_raw_length=args.length)
+        if world > 1:
+            dist.all_reduce(out['counts'])
         torch.cuda.synchronize()
         eng.set_fast_lstm(True)
         mismatches = {k: int((fast_int[k] != out[k]).sum().item()) for k in fast_int}

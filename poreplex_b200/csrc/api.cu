@@ -617,11 +617,33 @@ __global__ void k_gather_sub_batch(int n_sub, const int32_t *__restrict__ list,
     ro2[i] = ro[r]; rl2[i] = rl[r]; rg2[i] = rg[r]; dg2[i] = dg[r]; of2[i] = of[r];
 }
 
+// A read that was re-run only because of its QC verdict or its segmentation keeps its
+// tensor-core barcode call when the exact status and segments equal the tentative ones: the
+// window then differs from the one that call was made on by the rounding of (scale, shift)
+// only (~1e-7), far inside the margin the call passed.  status_win: status as the window
+// kernel should see it (not OKAY = no window).
+__global__ void k_sub_needs_demux(int n_sub, const int32_t *__restrict__ list,
+                                  const int32_t *__restrict__ unsafe, const int32_t *__restrict__ status,
+                                  const int32_t *__restrict__ seg, const int32_t *__restrict__ status2,
+                                  const int32_t *__restrict__ seg2, int32_t *__restrict__ status_win,
+                                  int32_t *__restrict__ need)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sub) return;
+    const int64_t r = list[i];
+    bool nd = (unsafe[r] & 4) != 0 || status[r] != status2[i];
+    for (int k = 0; k < PB2_MAX_STATES * 2; k++)
+        nd = nd || seg[r * PB2_MAX_STATES * 2 + k] != seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
+    need[i] = nd ? 1 : 0;
+    status_win[i] = nd ? status2[i] : PB2_ST_UNKNOWN_ERROR;
+}
+
 __global__ void k_scatter_sub_results(int n_sub, const int32_t *__restrict__ list,
                                       const int32_t *__restrict__ status2, const float *__restrict__ ss2,
                                       const int32_t *__restrict__ seg2, const int32_t *__restrict__ pushed2,
                                       const int32_t *__restrict__ bc2, const int32_t *__restrict__ gs2,
                                       const int32_t *__restrict__ sc2, const float *__restrict__ pr2,
+                                      const int32_t *__restrict__ need,
                                       int32_t *status, float *ss, int32_t *seg, int32_t *pushed,
                                       int32_t *bc, int32_t *gs, int32_t *sc, float *pr)
 {
@@ -631,7 +653,7 @@ __global__ void k_scatter_sub_results(int n_sub, const int32_t *__restrict__ lis
     status[r] = status2[i];
     ss[2 * r] = ss2[2 * i]; ss[2 * r + 1] = ss2[2 * i + 1];
     for (int k = 0; k < PB2_MAX_STATES * 2; k++) seg[r * PB2_MAX_STATES * 2 + k] = seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
-    if (pushed) {
+    if (pushed && need[i]) {
         pushed[r] = pushed2[i];
         bc[r] = bc2[i]; gs[r] = gs2[i]; sc[r] = sc2[i];
         if (pr) for (int k = 0; k < PB2_MAX_CLASSES; k++) pr[r * PB2_MAX_CLASSES + k] = pr2[(int64_t)i * PB2_MAX_CLASSES + k];
@@ -714,6 +736,7 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
         const size_t q_pu = take2(4 * m), q_sl = take2(4 * (m + 4)), q_bc = take2(4 * m), q_gs = take2(4 * m);
         const size_t q_sc = take2(4 * m), q_pr = take2(4 * PB2_MAX_CLASSES * m);
         const size_t q_win = take2(bcd ? sizeof(float) * m * T : 16);
+        const size_t q_nd = take2(4 * m), q_sw = take2(4 * m);
         char *sb = (char *)ws_get(ctx, ctx->ws_sub, o2);
         if (!sb) return PB2_ENOMEM;
         pb2_batch sub = *batch;
@@ -735,19 +758,23 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
         float *pr2 = (float *)(sb + q_pr), *win2 = (float *)(sb + q_win);
         if ((rc = launch_scaler(ctx, sub, pooled, status2, ss2, nullptr, st))) return rc;
         if ((rc = launch_segment(ctx, sub, pooled, ss2, status2, seg2, nullptr, st))) return rc;
+        int32_t *need = (int32_t *)(sb + q_nd), *status_win = (int32_t *)(sb + q_sw);
+        PB_LAUNCH(ctx, K_MISC, "k_sub_needs_demux", st,
+            k_sub_needs_demux<<<(unsigned)((n_sub + 255) / 256), 256, 0, st>>>(
+            n_sub, list, unsafe, status, segments, status2, seg2, status_win, need));
         if (bcd) {
             PB_CUDA(ctx, cudaMemsetAsync(bc2, 0xFF, 4 * m, st));
             PB_CUDA(ctx, cudaMemsetAsync(gs2, 0xFF, 4 * m, st));
             PB_CUDA(ctx, cudaMemsetAsync(sc2, 0xFF, 4 * m, st));
             PB_CUDA(ctx, cudaMemsetAsync(pr2, 0, 4 * PB2_MAX_CLASSES * m, st));
-            if ((rc = launch_windows(ctx, sub, pooled, ss2, status2, seg2, win2, pushed2,
+            if ((rc = launch_windows(ctx, sub, pooled, ss2, status_win, seg2, win2, pushed2,
                                      (int *)slots2, slots2 + 4, st))) return rc;
             if ((rc = launch_demux_exact(ctx, win2, nullptr, n_sub, (int *)slots2, slots2 + 4, pr2, bc2,
                                          gs2, sc2, st))) return rc;
         }
         PB_LAUNCH(ctx, K_MISC, "k_scatter_sub_results", st,
             k_scatter_sub_results<<<(unsigned)((n_sub + 255) / 256), 256, 0, st>>>(
-            n_sub, list, status2, ss2, seg2, pushed2, bc2, gs2, sc2, pr2, status, scale_shift, segments,
+            n_sub, list, status2, ss2, seg2, pushed2, bc2, gs2, sc2, pr2, need, status, scale_shift, segments,
             bcd ? pushed : nullptr, barcode, guess, score, res->class_probs));
     }
     if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;
@@ -1103,19 +1130,26 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     int64_t min_elems = (int64_t)256 << 20;      // below this the copies are not worth hiding
     int64_t min_reads = 65536;
     int64_t nchunks = 4;
+    bool uniform = false;
     if (const char *env = getenv("POREPLEX_B200_HOST_CHUNK_ELEMS")) {     // tests / tuning
         const long long v = atoll(env);
-        if (v > 0) { min_elems = v; min_reads = 2048; nchunks = (hb->n_raw_total + v - 1) / v; }
+        if (v > 0) { min_elems = v; min_reads = 2048; nchunks = (hb->n_raw_total + v - 1) / v; uniform = true; }
     }
     while (hb->n_raw_total / nchunks > ((int64_t)4 << 30)) nchunks *= 2;
     const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
     if (n < min_reads || keep || hb->n_raw_total < min_elems || nchunks < 2)
         return analyze_host_single(ctx, hb, hr, flags);
     std::vector<int64_t> bounds;
-    for (int64_t c = 0; c <= nchunks; c++) {
-        int64_t b = (n * c) / nchunks;
-        if (c < nchunks) b -= b % 64;            // keep chunk starts tile aligned
+    // The first upload and the last download are not hidden behind kernels: make the first and
+    // the last chunk half as large as the others (weights 1 2 2 ... 2 1).
+    const int64_t parts = uniform ? nchunks : nchunks + 1;
+    const int64_t wsum = uniform ? nchunks : 2 * nchunks;
+    int64_t acc = 0;
+    for (int64_t c = 0; c <= parts; c++) {
+        int64_t b = (n * acc) / wsum;
+        if (c < parts) b -= b % 128;             // keep chunk starts tile aligned
         if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
+        acc += uniform ? 1 : ((c == 0 || c == parts - 1) ? 1 : 2);
     }
     if (bounds.back() != n) bounds.push_back(n);
     if (bounds.size() < 3) return analyze_host_single(ctx, hb, hr, flags);
