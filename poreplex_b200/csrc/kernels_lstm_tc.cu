@@ -131,7 +131,7 @@ __device__ __forceinline__ float lstm_cell_tc(float zi, float zf, float zc, floa
 }
 
 template <int H, int KX>
-__host__ __device__ constexpr int tc_tmem_cols() { return (4 * H + H + KX <= 256) ? 256 : 512; }
+__host__ __device__ constexpr int tc_tmem_cols() { return (4 * H + (KX > 0 ? 2 : 1) * H + KX <= 256) ? 256 : 512; }
 
 template <int H, int KX>
 constexpr size_t tc_smem_bytes() {
@@ -253,7 +253,19 @@ k_lstm_tc(const TcArgs A)
     __half *bW_lo = bW_hi + KX * N;
     float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);       // [N], accumulator column order
     float *s_win = s_bias + N;                                        // [N] scalar input kernel
-    __shared__ __align__(8) uint64_t bar_d, bar_h;
+    // Column groups = the accumulator columns of one gate-warp part.  The MMAs of a step are
+    // issued group by group, each with its own commit barrier, so the gate warps of group 0
+    // start while the tensor pipe still works on the later groups (vector-input layers, which
+    // are alone on their SM; scalar-input layers have one group and a second CTA instead).
+    // Two groups measured best on B200 (N = 128 + 128 for H = 64, 128 + 64 for H = 48): with one
+    // group per part the N = 64 MMAs are issued too slowly to keep the tensor pipe fed.
+    constexpr int NGRP = (KX > 0) ? 2 : 1;
+    constexpr int HB = (KX > 0) ? 2 : 1;      // h operand buffers (group 1's MMAs still read
+                                              // h(t-1) while group 0's gate warps write h(t))
+    constexpr int G0_PARTS = (NGRP == 2) ? 2 : NP;           // parts in group 0
+    constexpr int N0 = G0_PARTS * UPT * 4, N1 = N - N0;      // accumulator columns of the groups
+    static_assert(N0 % 16 == 0 && N1 % 16 == 0, "bad column grouping");
+    __shared__ __align__(8) uint64_t bar_d[2], bar_h;
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead, s_tstart;
 
@@ -271,7 +283,8 @@ k_lstm_tc(const TcArgs A)
 
     // ---- one-time setup ----------------------------------------------------------
     if (tid == 0) {
-        mbar_init(&bar_d, 1);
+        mbar_init(&bar_d[0], 1);
+        mbar_init(&bar_d[1], 1);
         mbar_init(&bar_h, NGW);
         mbar_fence_init();
         s_dead = 0;
@@ -291,7 +304,8 @@ k_lstm_tc(const TcArgs A)
     fence_after_sync();
 
     const uint32_t tbase = s_tmem;
-    const uint32_t col_d = 0, col_h = N, col_x = N + H;     // h: hi [H/2] then lo [H/2]; x alike
+    // h: HB buffers of (hi [H/2] | lo [H/2]); x: hi [KX/2] | lo [KX/2]
+    const uint32_t col_d = 0, col_h = N, col_x = N + HB * H;
 
     // ---- per-row input addressing and the common start step -------------------------
     const int q = warp & 3, part = (warp >> 2) % NP;
@@ -338,15 +352,29 @@ k_lstm_tc(const TcArgs A)
                 mbar_wait(&bar_h, ph, &s_dead);
                 ph ^= 1;
                 fence_after_sync();
+                // h(t-1) sits in buffer (s - t_start) & 1 (the initial state is written to buffer 0)
+                const uint32_t hcol = tbase + col_h + (HB == 2 ? ((s - t_start) & 1) * H : 0);
                 bool first = true;
                 if (KX > 0)
-                    issue_split_gemm<(KX > 0 ? KX : 16), N>(tbase + col_d, tbase + col_x,
-                                                            tbase + col_x + KX / 2,
-                                                            smem_u32(bW_hi), smem_u32(bW_lo), first,
-                                                            !COARSE);
-                issue_split_gemm<H, N>(tbase + col_d, tbase + col_h, tbase + col_h + H / 2,
-                                       smem_u32(bU_hi), smem_u32(bU_lo), first, !COARSE);
-                mma_commit(&bar_d);
+                    issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
+                                                                tbase + col_x + KX / 2,
+                                                                smem_u32(bW_hi), smem_u32(bW_lo), first,
+                                                                !COARSE);
+                issue_split_gemm<H, N, N0>(tbase + col_d, hcol, hcol + H / 2,
+                                           smem_u32(bU_hi), smem_u32(bU_lo), first, !COARSE);
+                mma_commit(&bar_d[0]);
+                if (NGRP == 2) {
+                    constexpr uint32_t BOFS = (N0 / 8) * 128;          // bytes into each k-chunk
+                    first = true;
+                    if (KX > 0)
+                        issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
+                            tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
+                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first, !COARSE);
+                    issue_split_gemm<H, N, (N1 > 0 ? N1 : 16)>(tbase + col_d + N0, hcol, hcol + H / 2,
+                                                               smem_u32(bU_hi) + BOFS, smem_u32(bU_lo) + BOFS,
+                                                               first, !COARSE);
+                    mma_commit(&bar_d[1]);
+                }
             }
         }
         __syncwarp();
@@ -409,8 +437,8 @@ k_lstm_tc(const TcArgs A)
         if (lane == 0) mbar_arrive(&bar_h);
 
         uint32_t ph = 0;
+        const int grp = (NGRP == 2 && part >= G0_PARTS) ? 1 : 0;
         const uint32_t d_addr = lane_addr + col_d + u0 * 4;
-        const uint32_t hh_addr = lane_addr + col_h + u0 / 2, hl_addr = hh_addr + H / 2;
         for (int s = t_start; s < T; s++) {
             const int t = dir.reverse ? (T - 1 - s) : s;
             float xv = 0.f;
@@ -429,8 +457,10 @@ k_lstm_tc(const TcArgs A)
                 g_lo_t = gt + (size_t)(dir.g_lo + u0 / 2) * TCM;
             }
             const float2 xv2 = splat(xv);
-            mbar_wait(&bar_d, ph, &s_dead);
-            ph ^= 1;
+            // h(t) goes to the buffer the MMAs of this step do not read
+            const uint32_t hh_addr = lane_addr + col_h + (HB == 2 ? ((s - t_start + 1) & 1) * H : 0) + u0 / 2;
+            const uint32_t hl_addr = hh_addr + H / 2;
+            mbar_wait(&bar_d[grp], ph, &s_dead);
             __syncwarp();
             fence_after_sync();
 #pragma unroll
@@ -476,10 +506,17 @@ k_lstm_tc(const TcArgs A)
                 }
             }
             if (KX > 0 && s + 1 < T) {
+                // the x operand may be replaced only when every MMA of this step is done
+                if (NGRP > 1 && grp != NGRP - 1) {
+                    mbar_wait(&bar_d[NGRP - 1], ph, &s_dead);
+                    __syncwarp();
+                    fence_after_sync();
+                }
 #pragma unroll
                 for (int j = 0; j < XW; j += 4)
                     tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
             }
+            ph ^= 1;
             tmem_st_wait();
             fence_before_sync();
             __syncwarp();

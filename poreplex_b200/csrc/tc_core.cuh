@@ -184,12 +184,15 @@ __device__ __forceinline__ void load_b_split(const float *__restrict__ src, __ha
 // addresses of the canonical B matrices with N output columns.
 // full = false issues only the leading product A_hi B_hi (relative error about 2^-11): the
 // deliberately perturbed evaluation used to measure how sensitive a read's result is.
-template <int K, int N>
+// N = columns of the whole B matrix in shared memory (sets the stride between its k-chunks),
+// NSUB = columns this call produces: d_tmem / b_hi / b_lo already point at the first of them
+// (a column block of B starts (n0 / 8) * 128 bytes into each k-chunk).
+template <int K, int N, int NSUB = N>
 __device__ __forceinline__ void issue_split_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo,
                                                  uint32_t b_hi, uint32_t b_lo, bool &first,
                                                  bool full = true) {
     constexpr uint32_t LBO = N * 16, SBO = 128;
-    constexpr uint32_t idesc = idesc_f16(128, N);
+    constexpr uint32_t idesc = idesc_f16(128, NSUB);
 #pragma unroll
     for (int j = 0; j < K / 16; j++) {
         const uint64_t dh = smem_desc(b_hi + j * 2 * LBO, LBO, SBO);

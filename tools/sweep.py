@@ -66,6 +66,23 @@ def main():
                        'classified': int((res['barcode_score'] >= 0).sum().item()),
                        'status_mix': mix,
                        'kernels_ms': {k: v[0] / args.steps for k, v in prof.items()}}
+                if not polya:
+                    # default path = tensor-core LSTMs + exact re-runs; compare with the exact-only
+                    # kernels: time and every integer output
+                    ent['exact_reruns'] = eng.recheck_stats()[0]
+                    fast = {k: res[k].clone() for k in ('status', 'segments', 'barcode',
+                                                        'barcode_guess', 'barcode_score', 'label')}
+                    eng.set_fast_lstm(False)
+                    eng.analyze_device(*work, out=res, max_raw_length=L)
+                    torch.cuda.synchronize()
+                    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    x0.record()
+                    eng.analyze_device(*work, out=res, max_raw_length=L)
+                    x1.record()
+                    torch.cuda.synchronize()
+                    eng.set_fast_lstm(True)
+                    ent['exact_only_ms_per_step'] = x0.elapsed_time(x1)
+                    ent['mismatches_vs_exact_only'] = {k: int((fast[k] != res[k]).sum().item()) for k in fast}
                 if polya:
                     pol = res['polya'].cpu().numpy().view(np.dtype([('found', 'i4'), ('rest', 'V804')]))
                     ent['polya_found'] = int(pol['found'].sum())
