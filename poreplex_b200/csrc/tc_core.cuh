@@ -127,6 +127,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
