@@ -56,6 +56,20 @@ def algorithmic(L, stride=15, trim=300, scaler_len=30000):
     }
 
 
+# MUFU (XU pipe) operations per read of the tensor-core kernels: 5 EX2 + 2 RCP per unit and step
+# (5 MUFU.TANH for the coarse probe), full step counts.  The gate phase is bound by this pipe
+# (16 lanes/clk/SM), see DESIGN.md section 5.
+def mufu_per_read(L, stride=15, trim=300, scaler_len=30000):
+    H = min(L, scaler_len) // stride
+    return {
+        'k_lstm_tc_demux_l1': 7 * 48 * 2 * trim,
+        'k_lstm_tc_demux_l2': 7 * 64 * trim,
+        'k_lstm_tc_demux_l2_probe': 5 * 64 * trim,
+        'k_lstm_tc_scaler_l1': 7 * 48 * H,
+        'k_lstm_tc_scaler_l2': 7 * 48 * H,
+    }
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -362,9 +376,16 @@ def main():
                 fp32_peak = 148 * 128 * 2 * (clocks.get('sm_mhz') or 1965.0) * 1e6 / 1e12
                 ent.update({'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_tflops'],
                             'unit': 'TFLOP/s', 'frac': ach / peaks['tensor_tflops'],
-                            'algorithmic_flops_per_read': per_read,
-                            'fp32_simt_peak_tflops_at_clock': fp32_peak,
-                            'frac_of_fp32_simt': ach / fp32_peak})
+                            'algorithmic_flops_per_read': per_read})
+                if name.startswith('k_lstm_tc'):
+                    mp = mufu_per_read(args.length).get(name)
+                    if mp:
+                        xu_peak = 148 * 16 * (clocks.get('sm_mhz') or 1965.0) * 1e6
+                        ent.update({'mufu_ops_per_read': mp, 'xu_peak_ops_per_s_at_clock': xu_peak,
+                                    'frac_of_mufu_peak': mp * units / (per_step_ms / 1e3) / xu_peak})
+                else:
+                    ent.update({'fp32_simt_peak_tflops_at_clock': fp32_peak,
+                                'frac_of_fp32_simt': ach / fp32_peak})
         kernels.append(ent)
     dom = kernels[0] if kernels else {}
     roofline = {k: dom.get(k) for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
@@ -383,11 +404,13 @@ def main():
                      'share_of_step': dom.get('share'),
                      'note': 'k_lstm_tc_*: tcgen05 split-fp16 (3 MMAs per product, fp32 accumulate in '
                              'TMEM) LSTM layers, algorithmic FLOPs = the f32 products of the '
-                             'reference network; k_scaler_lstm / k_demux_l1 / k_demux_l2: exact-f32 '
+                             'reference network (frac_of_mufu_peak: the pipe that actually bounds '
+                             'their gate phase); k_scaler_lstm / k_demux_l1 / k_demux_l2: exact-f32 '
                              'SIMT kernels (packed FFMA2, see frac_of_fp32_simt), which also re-run '
                              'the reads the margin test flags'})
-    if 'frac_of_fp32_simt' in dom:
-        roofline['frac_of_fp32_simt'] = dom['frac_of_fp32_simt']
+    for k in ('frac_of_fp32_simt', 'frac_of_mufu_peak'):
+        if k in dom:
+            roofline[k] = dom[k]
 
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,

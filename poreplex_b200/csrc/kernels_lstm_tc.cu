@@ -15,14 +15,19 @@
 // definition of the result; this path only decides which reads need it.
 //
 // One CTA = one tile of 128 reads = the 128 TMEM lanes.  Per time step
-//   warp 8, one thread : waits for h(t-1) [and x(t)] in TMEM, issues the MMAs
-//                        D[128][4H] = x(t) W + h(t-1) U, commits to an mbarrier;
-//   warps 0-7          : thread = (read, half of the units); tcgen05.ld its pre-activations,
-//                        adds bias / scalar input term, gates, cell update, writes h(t) back to
-//                        TMEM as packed fp16 hi/lo (the next step's A operand) and, for a
+//   last warp, one thread : waits for h(t-1) [and x(t)] in TMEM, issues the MMAs
+//                        D[128][4H] = x(t) W + h(t-1) U and commits them to an mbarrier -- in two
+//                        column groups with a barrier each for the vector-input layers;
+//   4 * NP gate warps  : thread = (read, 1/NP of the units); tcgen05.ld its pre-activations in
+//                        chunks of 8 units, adds bias / scalar input term, packed-f32x2 gates and
+//                        cell update on four unit pairs at a time, writes h(t) back to TMEM as
+//                        packed fp16 hi/lo (the next step's A operand) and, for a
 //                        sequence-returning layer, to the scratch the next layer reads.
 // Layers with a scalar input (K = H only) need 4H + H <= 256 TMEM columns, so two CTAs share
-// an SM and one computes gates while the other's MMAs run.
+// an SM and one computes gates while the other's MMAs run.  Vector-input layers need all 512
+// columns (one CTA per SM): the gate warps of column group 0 start while the tensor pipe still
+// works on group 1, and the h operand is double buffered so that they may write h(t) meanwhile.
+// The gate phase is bound by the MUFU (XU) pipe: 7 MUFU per unit and step at 16 lanes/clk/SM.
 #include "pb_internal.h"
 #include "pb_math.cuh"
 #include "tc_core.cuh"
@@ -84,52 +89,10 @@ __device__ __forceinline__ float rcp_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) {          // 1 / (1 + e^-x)
-    return rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, -1.4426950408889634f))));
-}
-__device__ __forceinline__ float tanh_fast(float x) {             // 1 - 2 / (1 + e^2x)
-    const float r = rcp_fast(__fadd_rn(1.0f, ex2_fast(__fmul_rn(x, 2.8853900817779268f))));
-    return __fmaf_rn(-2.0f, r, 1.0f);
-}
-
 __device__ __forceinline__ float tanh_mufu(float x) {             // MUFU.TANH, |error| ~ 2^-11
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// One LSTM cell update from the four pre-activations.
-//   COARSE = false: 5 EX2 + 2 RCP.  With E_x = e^-x:  sigma(zi) tanh(zc) = (1 - E_2c) /
-//   ((1 + E_i)(1 + E_2c)),  sigma(zf) = 1 / (1 + E_f)  share one reciprocal,
-//   sigma(zo) tanh(c') = (1 - E_2c') / ((1 + E_o)(1 + E_2c')) the other.  Exponents are
-//   clamped at 2^30 so the triple product stays finite (sigma(-20.8) = 9e-10, tanh(10.4) =
-//   1 - 2e-9: far below the f32 resolution of the state).  Absolute error about 1e-7.
-//   COARSE = true: MUFU.TANH everywhere (error about 5e-4) -- the deliberately perturbed
-//   evaluation that measures a read's sensitivity.
-template <bool COARSE>
-__device__ __forceinline__ float lstm_cell_tc(float zi, float zf, float zc, float zo, float &c) {
-    if (COARSE) {
-        const float ig = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zi)), 0.5f);
-        const float fg = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zf)), 0.5f);
-        const float og = __fmaf_rn(0.5f, tanh_mufu(__fmul_rn(0.5f, zo)), 0.5f);
-        const float cn = __fmaf_rn(fg, c, __fmul_rn(ig, tanh_mufu(zc)));
-        c = cn;
-        return __fmul_rn(og, tanh_mufu(cn));
-    }
-    constexpr float L = 1.4426950408889634f, L2 = 2.8853900817779268f;
-    const float ei = ex2_fast(fminf(__fmul_rn(zi, -L), 30.f));
-    const float ef = ex2_fast(fminf(__fmul_rn(zf, -L), 30.f));
-    const float eg = ex2_fast(fminf(__fmul_rn(zc, -L2), 30.f));
-    const float eo = ex2_fast(fminf(__fmul_rn(zo, -L), 30.f));
-    const float af = __fadd_rn(1.0f, ef);
-    const float p = __fmul_rn(__fadd_rn(1.0f, ei), __fadd_rn(1.0f, eg));
-    const float r = rcp_fast(__fmul_rn(p, af));
-    const float ig = __fmul_rn(__fmul_rn(__fsub_rn(1.0f, eg), af), r);
-    const float cn = __fmaf_rn(__fmul_rn(p, r), c, ig);
-    c = cn;
-    const float ec = ex2_fast(fminf(__fmul_rn(cn, -L2), 30.f));
-    const float r2 = rcp_fast(__fmul_rn(__fadd_rn(1.0f, eo), __fadd_rn(1.0f, ec)));
-    return __fmul_rn(__fsub_rn(1.0f, ec), r2);
 }
 
 template <int H, int KX>
@@ -182,8 +145,16 @@ constexpr int TC_FREEZE = 32;
                               // latency-bound, not MUFU-bound), kept as a tuning knob
 #endif
 
-// Cell update for a PAIR of units with packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2 halve
-// the FMA-pipe instruction count; MUFU and min are per lane).  See lstm_cell_tc for the maths.
+// One LSTM cell update from the four pre-activations, for a PAIR of units with packed f32x2
+// arithmetic (FMUL2 / FADD2 / FFMA2 halve the FMA-pipe instruction count; MUFU and min are
+// per lane).
+//   COARSE = false: 5 EX2 + 2 RCP per unit.  With E_x = e^-x:  sigma(zi) tanh(zc) = (1 - E_2c) /
+//   ((1 + E_i)(1 + E_2c)) and sigma(zf) = 1 / (1 + E_f) share one reciprocal,
+//   sigma(zo) tanh(c') = (1 - E_2c') / ((1 + E_o)(1 + E_2c')) takes the other.  Exponents are
+//   clamped at 2^30 so the triple product stays finite (sigma(-20.8) = 9e-10, tanh(10.4) =
+//   1 - 2e-9: far below the f32 resolution of the state).  Absolute error about 1e-7.
+//   COARSE = true: MUFU.TANH everywhere (error about 5e-4) -- the deliberately perturbed
+//   evaluation that measures a read's sensitivity.
 template <bool COARSE>
 __device__ __forceinline__ float2 lstm_cell_pair(float2 zi, float2 zf, float2 zc, float2 zo, float2 &c) {
     if (COARSE) {
@@ -786,6 +757,9 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
     const size_t per_tile = sizeof(uint32_t) * (size_t)Tmax * H * TCM;
     int64_t tiles_per_pass = (int64_t)(ctx->tc_scratch_bytes / per_tile);
     if (tiles_per_pass < 1) tiles_per_pass = 1;
+    // whole waves: a vector-input layer runs one CTA per SM, so a pass of k * SMs tiles has no
+    // partly filled last wave
+    if (tiles_per_pass > ctx->sm_count) tiles_per_pass -= tiles_per_pass % ctx->sm_count;
     if (tiles_per_pass > tiles) tiles_per_pass = tiles;
     uint32_t *G = (uint32_t *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
     float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H);
@@ -863,6 +837,9 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     const size_t per_tile = sizeof(uint32_t) * (size_t)T * KX * TCM;
     int64_t tiles_per_pass = (int64_t)(ctx->tc_scratch_bytes / per_tile);
     if (tiles_per_pass < 1) tiles_per_pass = 1;
+    // whole waves: a vector-input layer runs one CTA per SM, so a pass of k * SMs tiles has no
+    // partly filled last wave
+    if (tiles_per_pass > ctx->sm_count) tiles_per_pass -= tiles_per_pass % ctx->sm_count;
     if (tiles_per_pass > tiles) tiles_per_pass = tiles;
     uint32_t *G = (uint32_t *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
     float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H2 * 2);

@@ -90,7 +90,7 @@ struct pb2_context {
     int *tc_err = nullptr;                        // device word: a tensor-core kernel timed out
     int64_t last_rerun_cause[3] = {0, 0, 0};      // ... because of QC edge / segmentation / barcode call
     int64_t last_rerun_reads = 0;                 // reads the last whole-path call re-ran exactly
-    size_t tc_scratch_bytes = (size_t)12 << 30;   // layer-1 sequence scratch per pass
+    size_t tc_scratch_bytes = (size_t)14 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
     std::vector<pb::ProfEvent> prof_events;
