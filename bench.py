@@ -343,6 +343,14 @@ def main():
         dss = (fast_ss.double() - out['scale_shift'].double()).abs().amax(0)
         mismatches['max_abs_diff_scale'] = float(dss[0].item())
         mismatches['max_abs_diff_shift'] = float(dss[1].item())
+        okay = out['status'] == 0
+        if bool(okay.any()):
+            dok = (fast_ss.double() - out['scale_shift'].double()).abs()[okay]
+            # error of the scaler's raw outputs implied by the (scale, shift) differences of the
+            # reads that went on to segmentation, against the margin the guards assume
+            mismatches['max_scaler_z_error_okay_reads'] = float(torch.maximum(
+                dok[:, 0] / 0.13295630234669656, dok[:, 1] / 9.82564593783874).max().item())
+            mismatches['scaler_margin_z'] = 5e-4
     for k, v in fast_int.items():
         out[k].copy_(v)
 

@@ -130,3 +130,41 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monk
     monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
     for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
         assert np.array_equal(piped[k], exact[k]), k
+
+
+def test_tc_demux_extreme_windows_equal_exact(eng_stock):
+    """Saturating and degenerate windows through the default path: huge normalised values
+    (|x| up to 100: MAD clamp at 0.01), constant windows, alternating signs, windows that are
+    all padding or have a single real sample -- every call must equal the exact kernels'."""
+    import torch
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(11)
+    n, T = 1024, 300
+    win = _windows(n, seed=13)
+    win[0:64] = rng.normal(0, 30, (64, T)).astype(np.float32)                 # wild amplitudes
+    win[64:96] = np.where(rng.random((32, T)) < 0.5, 100.0, -100.0)           # clamp-level values
+    win[96:128] = 0.0
+    win[128:160] = -1000.0                                                    # all padding
+    win[160:192] = -1000.0
+    win[160:192, -1] = rng.normal(0, 1, 32).astype(np.float32)                # one real sample
+    win[192:224] = np.tile(np.where(np.arange(T) % 2 == 0, 1.0, -1.0), (32, 1))
+    wd = torch.from_numpy(np.ascontiguousarray(win, np.float32)).to(dev)
+    p_ex, bc_ex, g_ex, s_ex = _exact(eng_stock, wd)
+    p, bc, g, s = [o.cpu().numpy() for o in eng_stock.demux_predict(wd)]
+    torch.cuda.synchronize()
+    assert eng_stock.recheck_stats()[1] == 0
+    assert np.isfinite(p).all()
+    assert np.array_equal(bc, bc_ex) and np.array_equal(g, g_ex) and np.array_equal(s, s_ex)
+
+
+def test_rerun_causes_are_reported(eng_short, preset_short):
+    from poreplex_b200 import synth
+    rd = synth.to_numpy(synth.generate_reads(2000, synth.SynthSpec.for_length(4000), preset_short, seed=5))
+    n, L = rd['raw'].shape
+    eng_short.analyze_host(rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L,
+                           np.full(n, L, np.int64), rd['range'], rd['digitisation'], rd['offset'])
+    rerun, timeouts = eng_short.recheck_stats()
+    causes = eng_short.rerun_causes()
+    assert timeouts == 0 and rerun > 0
+    assert set(causes) == {'qc_edge', 'segmentation', 'barcode_call'}
+    assert max(causes.values()) <= rerun <= sum(causes.values())
