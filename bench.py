@@ -348,9 +348,9 @@ def main():
             dok = (fast_ss.double() - out['scale_shift'].double()).abs()[okay]
             # error of the scaler's raw outputs implied by the (scale, shift) differences of the
             # reads that went on to segmentation, against the margin the guards assume
-            mismatches['max_scaler_z_error_okay_reads'] = float(torch.maximum(
-                dok[:, 0] / 0.13295630234669656, dok[:, 1] / 9.82564593783874).max().item())
-            mismatches['scaler_margin_z'] = 5e-4
+            mismatches['max_scaler_z0_error_okay_reads'] = float((dok[:, 0] / 0.13295630234669656).max().item())
+            mismatches['max_scaler_z1_error_okay_reads'] = float((dok[:, 1] / 9.82564593783874).max().item())
+            mismatches['scaler_margin_z0_z1'] = [2.5e-4, 1.5e-3]
     for k, v in fast_int.items():
         out[k].copy_(v)
 

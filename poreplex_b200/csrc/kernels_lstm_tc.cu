@@ -463,6 +463,8 @@ k_lstm_tc(const TcArgs A)
                     float2 zc = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 4]), __uint_as_float(vv[8 * j + 5])), f2(b1.x, b1.y));
                     float2 zo = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 6]), __uint_as_float(vv[8 * j + 7])), f2(b1.z, b1.w));
                     if (KX == 0) {
+                        // (evaluating the input term in the exact kernels' own order -- (x w + b) + h U
+                        // or (x w + h U) + b -- was measured: same error distribution, 1 % slower)
                         const float4 w0 = *reinterpret_cast<const float4 *>(s_win + col);
                         const float4 w1 = *reinterpret_cast<const float4 *>(s_win + col + 4);
                         zi = __ffma2_rn(xv2, f2(w0.x, w0.y), zi);
@@ -627,7 +629,7 @@ __global__ void k_gather_recheck(const float *__restrict__ windows, int T,
 // Dense(2) + output transform + QC window exactly as k_scaler_lstm does them
 // (signal_loader.py:98-109), plus what the rest of the approximate path needs: the corners
 // of a triangle in the (scale, shift) plane that contains every value the exact kernels can
-// produce for this read (|z_tc - z_exact| <= delta_z), and a flag when the QC verdict itself
+// produce for this read (|z_tc - z_exact| <= delta_z0 / delta_z1), and a flag when the QC verdict itself
 // is within that uncertainty.
 struct TcScalerHeadArgs {
     const float *h_last;           // [n][H]
@@ -636,7 +638,7 @@ struct TcScalerHeadArgs {
     const float *Wd, *bd;
     double scale_std, scale_mean, shift_std, shift_mean;
     double qc_scale_lo, qc_scale_hi, qc_shift_lo, qc_shift_hi;
-    double delta_z;
+    double delta_z0, delta_z1;
     int32_t *status;
     float *scale_shift;            // [n][2] centre (approximate) values
     float *ss_vertex;              // [3][n][2]
@@ -671,8 +673,8 @@ __global__ void k_scaler_head_tc(const TcScalerHeadArgs A)
                     sh >= A.qc_shift_lo && sh <= A.qc_shift_hi;
     A.status[r] = ok ? PB2_ST_OKAY : PB2_ST_SCALING_QC_FAIL;
     // half-widths of the box the exact (scale, shift) lies in (+ the f32 rounding of the casts)
-    const double ds = fabs(A.scale_std) * A.delta_z + 2e-7 * fabs(sc);
-    const double dh = fabs(A.shift_std) * A.delta_z + 2e-7 * fabs(sh) + 1e-9;
+    const double ds = fabs(A.scale_std) * A.delta_z0 + 2e-7 * fabs(sc);
+    const double dh = fabs(A.shift_std) * A.delta_z1 + 2e-7 * fabs(sh) + 1e-9;
     const bool edge = fabs(sc - A.qc_scale_lo) <= ds || fabs(sc - A.qc_scale_hi) <= ds ||
                       fabs(sh - A.qc_shift_lo) <= dh || fabs(sh - A.qc_shift_hi) <= dh;
     if (edge) atomicOr(&A.read_unsafe[r], 1);                         // cause bit 1: QC verdict
@@ -733,8 +735,9 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
 {
     if (b.n_reads <= 0) return PB2_OK;
     const ScalerDev &S = ctx->scaler;
-    if (S.l1.units != 48 || S.l2.units != 48 || S.l1.in_dim != 1 || S.l2.in_dim != 48)
-        return fail(ctx, PB2_EUNSUPPORTED, "scaler network shape not built (LSTM(48) x2 expected)");
+    if (S.l1.units != 48 || S.l2.units != 48 || S.l1.in_dim != 1 || S.l2.in_dim != 48 ||
+        S.l1.impl != 1 || S.l2.impl != 1)
+        return fail(ctx, PB2_EUNSUPPORTED, "scaler network shape not built (LSTM(48, impl 1) x2 expected)");
     if (!S.zero_prefix) return fail(ctx, PB2_ESTATE, "scaler zero-prefix table missing");
     constexpr int H = 48;
     const int64_t n = b.n_reads;
@@ -801,7 +804,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
     Hd.shift_std = S.shift_std; Hd.shift_mean = S.shift_mean;
     Hd.qc_scale_lo = S.qc_scale_lo; Hd.qc_scale_hi = S.qc_scale_hi;
     Hd.qc_shift_lo = S.qc_shift_lo; Hd.qc_shift_hi = S.qc_shift_hi;
-    Hd.delta_z = ctx->scaler_margin_z;
+    Hd.delta_z0 = ctx->scaler_margin_z0; Hd.delta_z1 = ctx->scaler_margin_z1;
     Hd.status = status; Hd.scale_shift = scale_shift; Hd.ss_vertex = ss_vertex;
     Hd.read_unsafe = read_unsafe; Hd.z_out = z_out;
     PB_LAUNCH(ctx, K_SCALER_TC_HEAD, "k_scaler_head_tc", st,
@@ -821,9 +824,9 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     if (n <= 0) return PB2_OK;
     DemuxDev &D = ctx->demux;
     if (D.fwd.units != 48 || D.bwd.units != 48 || D.l2.units != 64 || D.fwd.in_dim != 1 ||
-        D.l2.in_dim != 96)
+        D.l2.in_dim != 96 || D.fwd.impl != 2 || D.bwd.impl != 2 || D.l2.impl != 2)
         return fail(ctx, PB2_EUNSUPPORTED, "demux network shape not built "
-                    "(Bidirectional(LSTMCell 48) -> LSTMCell 64 expected)");
+                    "(Bidirectional(LSTMCell 48) -> LSTMCell 64, impl 2 expected)");
     constexpr int H1 = 48, H2 = 64, KX = 2 * H1;
     const int T = D.trim_length;
     if (!ctx->attr_demux_tc) {

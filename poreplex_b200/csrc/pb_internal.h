@@ -85,7 +85,9 @@ struct pb2_context {
     // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
     double demux_margin_delta = 2e-3;
     double demux_probe_gain = 0.25;
-    double scaler_margin_z = 5e-4;                // assumed bound on the error of the scaler's raw outputs
+    // assumed bounds on the error of the scaler's two raw outputs (z0 -> scale, z1 -> shift); the
+    // shift output has the heavier tail (largest seen on 1 M reads: 4.4e-5 / 2.9e-4)
+    double scaler_margin_z0 = 2.5e-4, scaler_margin_z1 = 1.5e-3;
     bool demux_tc_ran = false;
     int *tc_err = nullptr;                        // device word: a tensor-core kernel timed out
     int64_t last_rerun_cause[3] = {0, 0, 0};      // ... because of QC edge / segmentation / barcode call

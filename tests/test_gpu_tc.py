@@ -119,7 +119,7 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monk
     d = np.abs(fast['scale_shift'].astype(np.float64) - exact['scale_shift'])
     print('scale/shift: max |d| %.2e / %.2e; exactly re-run reads %d of %d'
           % (d[:, 0].max(), d[:, 1].max(), rerun, n))
-    assert d[:, 0].max() <= 6.7e-5 and d[:, 1].max() <= 5e-3        # inside the assumed box
+    assert d[:, 0].max() <= 3.4e-5 and d[:, 1].max() <= 1.5e-2      # inside the assumed box
     assert np.median(d[:, 0]) < 1e-6 and np.median(d[:, 1]) < 5e-5
     assert (d.max(1) == 0).sum() >= rerun                            # re-run reads are exact
     assert 0 < rerun < 0.35 * n
