@@ -208,6 +208,7 @@ int pb2_set_exact_division(pb2_context *ctx, int on)
     if (!ctx) return PB2_EINVAL;
     ctx->exact_division = on != 0;
     ctx->no_pad_skip = on != 0;        // verification mode also steps every padded position
+    ctx->generic_viterbi = on != 0;    // ... and decodes with the generic (any-topology) Viterbi step
     return PB2_OK;
 }
 

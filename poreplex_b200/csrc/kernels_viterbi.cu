@@ -24,6 +24,15 @@ constexpr int VT_THREADS = 128;
 // k_segment: scale (signal_loader.py:262, unfused) + Viterbi + run-length segments
 // (signal_analyzer.py:355-362: a later run of a state overwrites an earlier one).
 // ---------------------------------------------------------------------------
+// Topology of the stock segmentation model (rna-r941.cfg:61-101 in pomegranate's baked, i.e.
+// alphabetical, state order: adapter, leader-high, leader-low, polya-tail, pre-leader,
+// transcript): in-edges 0<-{0,1} 1<-{1,2} 2<-{2,4} 3<-{0,3} 4<-{4} 5<-{0,3,5}.  k_segment is
+// compiled once for it (EDGES != 0) and once generically; launch_segment picks by comparing masks.
+constexpr uint32_t SEG_STOCK_NCOMP = 0x211112;      // mixture components: adapter 2, transcript 2, others 1
+constexpr uint64_t SEG_STOCK_EDGES =
+    (0x03ull << 0) | (0x06ull << 8) | (0x14ull << 16) | (0x09ull << 24) | (0x10ull << 32) | (0x29ull << 40);
+
+template <uint64_t EDGES, int NS>
 __global__ void __launch_bounds__(VT_THREADS)
 k_segment(const HmmDev M, const HmmMask K, const int64_t *__restrict__ raw_offsets,
           const int64_t *__restrict__ raw_lengths, const float *__restrict__ pooled,
@@ -49,14 +58,17 @@ k_segment(const HmmDev M, const HmmMask K, const int64_t *__restrict__ raw_offse
     {
         const float y = pb::fadd(pb::fmul(scale, x[0]), shift);
         if (pooled_scaled_out) pooled_scaled_out[po] = y;
-        hmm_emissions(M, (double)y, e);
+        if (EDGES != 0) hmm_emissions_topo<SEG_STOCK_NCOMP, NS>(M, (double)y, e);
+        else hmm_emissions(M, (double)y, e);
         viterbi_init(M, v, e);
     }
     for (int t = 1; t < T; t++) {
         const float y = pb::fadd(pb::fmul(scale, x[t]), shift);
         if (pooled_scaled_out) pooled_scaled_out[po + t] = y;
-        hmm_emissions(M, (double)y, e);
-        bp[(int64_t)t * n_chunk + i] = viterbi_step(M, K, v, e);
+        if (EDGES != 0) hmm_emissions_topo<SEG_STOCK_NCOMP, NS>(M, (double)y, e);
+        else hmm_emissions(M, (double)y, e);
+        bp[(int64_t)t * n_chunk + i] = (EDGES != 0) ? viterbi_step_topo<EDGES, NS>(K, v, e)
+                                                    : viterbi_step(M, K, v, e);
     }
     double best;
     int cur = viterbi_end(M, v, best);
@@ -88,6 +100,8 @@ int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
     if (b.n_reads <= 0) return PB2_OK;
     HmmMask K;
     make_mask(ctx->seg_hmm, K);
+    const bool stock_topology = ctx->seg_hmm.n_states == 6 && pack_edges(K) == SEG_STOCK_EDGES &&
+                                pack_ncomp(ctx->seg_hmm) == SEG_STOCK_NCOMP && !ctx->generic_viterbi;
     int64_t Tmax = ctx->scan_limit_pooled;
     if (b.max_raw_length > 0 && b.max_raw_length / ctx->scaler.stride < Tmax)
         Tmax = b.max_raw_length / ctx->scaler.stride;
@@ -101,11 +115,20 @@ int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
     if (!bp) return PB2_ENOMEM;
     for (int64_t r0 = 0; r0 < b.n_reads; r0 += chunk) {
         const int64_t nc = (b.n_reads - r0 < chunk) ? b.n_reads - r0 : chunk;
-        PB_LAUNCH(ctx, K_SEGMENT, "k_segment", st,
-            k_segment<<<(unsigned)((nc + VT_THREADS - 1) / VT_THREADS), VT_THREADS, 0, st>>>(
-            ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
-            ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
-            pooled_scaled_out));
+        const unsigned grid = (unsigned)((nc + VT_THREADS - 1) / VT_THREADS);
+        if (stock_topology) {
+            PB_LAUNCH(ctx, K_SEGMENT, "k_segment<stock>", st,
+                k_segment<SEG_STOCK_EDGES, 6><<<grid, VT_THREADS, 0, st>>>(
+                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
+                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
+                pooled_scaled_out));
+        } else {
+            PB_LAUNCH(ctx, K_SEGMENT, "k_segment", st,
+                k_segment<0, 0><<<grid, VT_THREADS, 0, st>>>(
+                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
+                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
+                pooled_scaled_out));
+        }
     }
     return PB2_OK;
 }

@@ -95,6 +95,7 @@ struct pb2_context {
     size_t tc_scratch_bytes = (size_t)14 << 30;   // layer-1 sequence scratch per pass
     bool no_pad_skip = false;      // verification mode: step every padded position
     bool exact_division = false;   // verification mode: IEEE __fdiv_rn in the LSTM kernels
+    bool generic_viterbi = false;  // verification mode: never use the topology-specialised k_segment
     std::vector<pb::ProfEvent> prof_events;
     std::vector<cudaEvent_t> prof_pool;
     std::string error;
