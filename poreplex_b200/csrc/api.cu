@@ -172,6 +172,7 @@ void pb2_destroy(pb2_context *ctx)
     cudaFree(ctx->demux.pad_state); cudaFree(ctx->demux.pad_prefix);
     cudaFree(ctx->demux.calibration_dev);
     cudaFree(ctx->tc_err);
+    if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
@@ -989,8 +990,15 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
     const size_t arena_bytes = off;
     char *base = (char *)ws_get(ctx, ctx->ws_batch, 2 * arena_bytes);
     if (!base) return PB2_ENOMEM;
-    int64_t *counts_host = nullptr;
-    PB_CUDA(ctx, cudaMallocHost(&counts_host, sizeof(int64_t) * n_bins * nchunks));
+    // pinned landing area for the per-chunk counts, kept across calls
+    const size_t counts_bytes = sizeof(int64_t) * n_bins * (size_t)nchunks;
+    if (ctx->counts_host_bytes < counts_bytes) {
+        if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
+        ctx->counts_host = nullptr; ctx->counts_host_bytes = 0;
+        PB_CUDA(ctx, cudaMallocHost(&ctx->counts_host, counts_bytes));
+        ctx->counts_host_bytes = counts_bytes;
+    }
+    int64_t *counts_host = ctx->counts_host;
     cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming);
@@ -1116,7 +1124,6 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
     }
     if (rc != PB2_OK) cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_d2h[i]); }
-    cudaFreeHost(counts_host);
     return rc;
 }
 

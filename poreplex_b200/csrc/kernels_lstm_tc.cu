@@ -678,10 +678,13 @@ __global__ void k_scaler_head_tc(const TcScalerHeadArgs A)
     const bool edge = fabs(sc - A.qc_scale_lo) <= ds || fabs(sc - A.qc_scale_hi) <= ds ||
                       fabs(sh - A.qc_shift_lo) <= dh || fabs(sh - A.qc_shift_hi) <= dh;
     if (edge) atomicOr(&A.read_unsafe[r], 1);                         // cause bit 1: QC verdict
-    // triangle (-1,-1), (3,-1), (-1,3) in units of (ds, dh) contains the box [-1,1]^2
-    v0[0] = (float)(sc - ds);        v0[1] = (float)(sh - dh);
-    v1[0] = (float)(sc + 3.0 * ds);  v1[1] = (float)(sh - dh);
-    v2[0] = (float)(sc - ds);        v2[1] = (float)(sh + 3.0 * dh);
+    // triangle (-3.1, -1.05), (3.1, -1.05), (0, 2.15) in units of (ds, dh) contains the box
+    // [-1,1]^2 (its slanted edges pass x = +-1 at y = 1.118).  Wide along the scale axis, whose
+    // uncertainty moves the signal five times less than the shift's: this shape minimises the
+    // spread of the three decoded signals, i.e. the number of reads flagged.
+    v0[0] = (float)(sc - 3.1 * ds);  v0[1] = (float)(sh - 1.05 * dh);
+    v1[0] = (float)(sc + 3.1 * ds);  v1[1] = (float)(sh - 1.05 * dh);
+    v2[0] = (float)sc;               v2[1] = (float)(sh + 2.15 * dh);
 }
 
 // segments / status of the three corner decodings agree -> the segmentation is constant over

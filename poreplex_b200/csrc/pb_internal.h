@@ -122,6 +122,8 @@ struct pb2_context {
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
+    int64_t *counts_host = nullptr;                       // pinned, per-chunk counts
+    size_t counts_host_bytes = 0;
 };
 
 namespace pb {

@@ -270,8 +270,24 @@ class SignalEngine:
             raw[o:o + n] = s
         return raw, offsets, lengths
 
+    def alloc_host_results(self, n, pinned=True):
+        """Result buffers for ``analyze_host(..., out=...)``: reusable across calls and, when
+        pinned, written by direct DMA instead of through the driver's staging buffer."""
+        import torch
+        def mk(shape, dtype):
+            return torch.zeros(shape, dtype=dtype, pin_memory=pinned).numpy()
+        return {
+            'status': mk(n, torch.int32), 'label': mk(n, torch.int32),
+            'scale_shift': mk((n, 2), torch.float32),
+            'segments': mk((n, N.MAX_STATES, 2), torch.int32),
+            'barcode': mk(n, torch.int32), 'barcode_guess': mk(n, torch.int32),
+            'barcode_score': mk(n, torch.int32),
+            'class_probs': mk((n, N.MAX_CLASSES), torch.float32),
+            'counts': mk((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), torch.int64),
+        }
+
     def analyze_host(self, raw, offsets, lengths, rng, digitisation, offset, barcoding=None,
-                     keep_pooled=False, polya=False, exact_scaler=False):
+                     keep_pooled=False, polya=False, exact_scaler=False, out=None):
         """SignalAnalyzer.process stages A-D over HOST numpy buffers (H2D, kernels, D2H).
 
         Returns a dict of numpy arrays: status, label, scale_shift [n,2], segments
@@ -293,15 +309,21 @@ class SignalEngine:
             raise ValueError('raw_offsets must be multiples of 8 samples (see pack_reads)')
         if n and int((offsets + lengths).max()) > raw.size:
             raise ValueError('read extends past the raw buffer')
-        out = {
-            'status': np.empty(n, np.int32), 'label': np.empty(n, np.int32),
-            'scale_shift': np.zeros((n, 2), np.float32),
-            'segments': np.empty((n, N.MAX_STATES, 2), np.int32),
-            'barcode': np.empty(n, np.int32), 'barcode_guess': np.empty(n, np.int32),
-            'barcode_score': np.empty(n, np.int32),
-            'class_probs': np.zeros((n, N.MAX_CLASSES), np.float32),
-            'counts': np.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), np.int64),
-        }
+        if out is not None:
+            # caller-owned buffers (alloc_host_results): same keys, shapes and dtypes
+            if out['status'].shape != (n,) or out['segments'].shape != (n, N.MAX_STATES, 2):
+                raise ValueError('out buffers do not match the batch size')
+            out = dict(out)
+        else:
+            out = {
+                'status': np.empty(n, np.int32), 'label': np.empty(n, np.int32),
+                'scale_shift': np.zeros((n, 2), np.float32),
+                'segments': np.empty((n, N.MAX_STATES, 2), np.int32),
+                'barcode': np.empty(n, np.int32), 'barcode_guess': np.empty(n, np.int32),
+                'barcode_score': np.empty(n, np.int32),
+                'class_probs': np.zeros((n, N.MAX_CLASSES), np.float32),
+                'counts': np.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), np.int64),
+            }
         if keep_pooled:
             out['pooled'] = np.zeros(raw.size // self.stride + 2, np.float32)
         if polya:
