@@ -133,6 +133,23 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs NVML
+    reports as local to this GPU, so the H2D copies of the host path do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def make_workload(args, device, seed):
     """Synthetic reads generated straight into HBM (torch RNG on the device)."""
     import torch
@@ -260,6 +277,7 @@ def main():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
 
@@ -435,7 +453,8 @@ def main():
                    'exact_reruns_per_step': rechecked, 'exact_rerun_causes': rerun_causes,
                    'tc_barrier_timeouts': tc_timeouts,
                    'mismatches_vs_exact_only_kernels': mismatches,
-                   'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)'},
+                   'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)',
+                   'cpus_bound_per_rank': numa},
         'clocks': clocks, 'gpu_launches': launches,
         'roofline': roofline, 'kernels': kernels,
     }

@@ -325,6 +325,12 @@ int pb2_debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float 
 /* After a call: how many windows the last demultiplexer launch re-ran exactly, and whether a
  * tensor-core kernel hit its barrier time-out (results invalid if non-zero).  Synchronises. */
 int pb2_recheck_stats(pb2_context *ctx, int64_t *demux_rechecked, int64_t *tc_timeouts);
+/* Audit of the tensor-core path in production: additionally re-run a pseudo-random `fraction`
+ * (0..1) of the reads that PASSED every guard through the exact kernels and count those whose
+ * status / segments / barcode / guess / score differ from the tensor-core values (the exact
+ * values are returned either way).  pb2_audit_stats reads and clears the two counters. */
+int pb2_set_audit_fraction(pb2_context *ctx, double fraction);
+int pb2_audit_stats(pb2_context *ctx, int64_t *audited, int64_t *mismatched);
 /* Of the reads the last pb2_analyze_device call re-ran exactly: how many because the QC verdict,
  * the segmentation, the barcode call was inside its error margin (a read can count twice). */
 int pb2_rerun_causes(pb2_context *ctx, int64_t *qc, int64_t *segmentation, int64_t *barcode);

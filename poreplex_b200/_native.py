@@ -124,7 +124,8 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
            'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
-           'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes']
+           'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
+           'pb2_audit_stats']
 
 
 def sources():
@@ -191,6 +192,8 @@ def load():
     L.pb2_recheck_stats.argtypes = [vp, _i64p, _i64p]
     L.pb2_debug_demux_l1.argtypes = [vp, vp, C.c_int64, vp, vp]
     L.pb2_rerun_causes.argtypes = [vp, _i64p, _i64p, _i64p]
+    L.pb2_set_audit_fraction.argtypes = [vp, C.c_double]
+    L.pb2_audit_stats.argtypes = [vp, _i64p, _i64p]
     L.pb2_set_polya.argtypes = [vp, C.POINTER(PolyaParams), C.c_int32]
     L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
     L.pb2_set_unsplit.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(UnsplitParams), C.c_int32,

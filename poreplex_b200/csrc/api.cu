@@ -149,8 +149,9 @@ int pb2_create(int device, pb2_context **out)
         return PB2_ECUDA;
     }
     // sticky time-out word of the tensor-core kernels (read and cleared by pb2_recheck_stats)
-    if (cudaMalloc(&ctx->tc_err, sizeof(int)) != cudaSuccess ||
-        cudaMemset(ctx->tc_err, 0, sizeof(int)) != cudaSuccess) {
+    // (+ [2], [3]: reads audited / audited reads whose exact results differed, pb2_audit_stats)
+    if (cudaMalloc(&ctx->tc_err, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->tc_err, 0, 4 * sizeof(int)) != cudaSuccess) {
         cudaStreamDestroy(ctx->host_stream);
         delete ctx;
         return PB2_ECUDA;
@@ -239,6 +240,26 @@ int pb2_debug_demux_l1(pb2_context *ctx, const float *windows, int64_t n, float 
     if (!ctx->demux.set) return fail(ctx, PB2_ESTATE, "demux not set");
     DeviceGuard g(ctx->device);
     return debug_demux_l1(ctx, windows, n, out, (cudaStream_t)stream);
+}
+
+int pb2_set_audit_fraction(pb2_context *ctx, double fraction)
+{
+    if (!ctx || !(fraction >= 0.0) || fraction > 1.0) return PB2_EINVAL;
+    ctx->audit_threshold = fraction >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(fraction * 4294967296.0);
+    return PB2_OK;
+}
+
+int pb2_audit_stats(pb2_context *ctx, int64_t *audited, int64_t *mismatched)
+{
+    if (!ctx) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    int v[2] = {0, 0};
+    PB_CUDA(ctx, cudaDeviceSynchronize());
+    PB_CUDA(ctx, cudaMemcpy(v, ctx->tc_err + 2, sizeof(v), cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemset(ctx->tc_err + 2, 0, sizeof(v)));
+    if (audited) *audited = v[0];
+    if (mismatched) *mismatched = v[1];
+    return PB2_OK;
 }
 
 int pb2_rerun_causes(pb2_context *ctx, int64_t *qc, int64_t *segmentation, int64_t *barcode)
@@ -596,11 +617,19 @@ int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *la
 // and re-run as a sub-batch through the exact kernels -- scaler, segmentation, window,
 // demultiplexer -- and its results replace the tentative ones.  One host synchronisation (the
 // size of that sub-batch).
-__global__ void k_collect_unsafe(int64_t n, const int32_t *__restrict__ unsafe, int *count,
-                                 int32_t *__restrict__ list)
+// audit_threshold: a pseudo-random fraction audit_threshold / 2^32 of the reads that passed every
+// guard is re-run as well (cause bit 8), purely to compare: see k_scatter_sub_results.
+__global__ void k_collect_unsafe(int64_t n, int32_t *__restrict__ unsafe, int *count,
+                                 int32_t *__restrict__ list, uint32_t audit_threshold, uint32_t seed)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n || !unsafe[r]) return;
+    if (r >= n) return;
+    if (!unsafe[r] && audit_threshold) {
+        uint32_t h = (uint32_t)r * 2654435761u + seed;          // integer hash of the read index
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        if (h < audit_threshold) unsafe[r] = 8;
+    }
+    if (!unsafe[r]) return;
     list[atomicAdd(count, 1)] = (int32_t)r;
     if (unsafe[r] & 1) atomicAdd(count + 1, 1);       // per-cause tallies (diagnostics)
     if (unsafe[r] & 2) atomicAdd(count + 2, 1);
@@ -633,7 +662,7 @@ __global__ void k_sub_needs_demux(int n_sub, const int32_t *__restrict__ list,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sub) return;
     const int64_t r = list[i];
-    bool nd = (unsafe[r] & 4) != 0 || status[r] != status2[i];
+    bool nd = (unsafe[r] & (4 | 8)) != 0 || status[r] != status2[i];
     for (int k = 0; k < PB2_MAX_STATES * 2; k++)
         nd = nd || seg[r * PB2_MAX_STATES * 2 + k] != seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
     need[i] = nd ? 1 : 0;
@@ -646,12 +675,24 @@ __global__ void k_scatter_sub_results(int n_sub, const int32_t *__restrict__ lis
                                       const int32_t *__restrict__ bc2, const int32_t *__restrict__ gs2,
                                       const int32_t *__restrict__ sc2, const float *__restrict__ pr2,
                                       const int32_t *__restrict__ need,
+                                      const int32_t *__restrict__ unsafe, int *audit,
                                       int32_t *status, float *ss, int32_t *seg, int32_t *pushed,
                                       int32_t *bc, int32_t *gs, int32_t *sc, float *pr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sub) return;
     const int64_t r = list[i];
+    if (unsafe[r] == 8) {
+        // audited read: it passed every guard, so the exact results must equal the tentative ones
+        bool same = status[r] == status2[i];
+        for (int k = 0; k < PB2_MAX_STATES * 2; k++)
+            same = same && seg[r * PB2_MAX_STATES * 2 + k] == seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
+        if (pushed)
+            same = same && pushed[r] == pushed2[i] &&
+                   (!pushed2[i] || (bc[r] == bc2[i] && gs[r] == gs2[i] && sc[r] == sc2[i]));
+        atomicAdd(audit, 1);
+        if (!same) atomicAdd(audit + 1, 1);
+    }
     status[r] = status2[i];
     ss[2 * r] = ss2[2 * i]; ss[2 * r + 1] = ss2[2 * i + 1];
     for (int k = 0; k < PB2_MAX_STATES * 2; k++) seg[r * PB2_MAX_STATES * 2 + k] = seg2[(int64_t)i * PB2_MAX_STATES * 2 + k];
@@ -722,7 +763,8 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
 
     // ---- the unsafe reads, exactly ---------------------------------------------------
     PB_LAUNCH(ctx, K_MISC, "k_collect_unsafe", st,
-        k_collect_unsafe<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, unsafe, count, list));
+        k_collect_unsafe<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        n, unsafe, count, list, ctx->audit_threshold, (uint32_t)ctx->launches));
     int tally[4] = {0, 0, 0, 0};
     PB_CUDA(ctx, cudaMemcpyAsync(tally, count, sizeof(tally), cudaMemcpyDeviceToHost, st));
     PB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -776,7 +818,8 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
         }
         PB_LAUNCH(ctx, K_MISC, "k_scatter_sub_results", st,
             k_scatter_sub_results<<<(unsigned)((n_sub + 255) / 256), 256, 0, st>>>(
-            n_sub, list, status2, ss2, seg2, pushed2, bc2, gs2, sc2, pr2, need, status, scale_shift, segments,
+            n_sub, list, status2, ss2, seg2, pushed2, bc2, gs2, sc2, pr2, need, unsafe, ctx->tc_err + 2,
+            status, scale_shift, segments,
             bcd ? pushed : nullptr, barcode, guess, score, res->class_probs));
     }
     if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;

@@ -89,6 +89,7 @@ struct pb2_context {
     // shift output has the heavier tail (largest seen on 1 M reads: 4.4e-5 / 2.9e-4)
     double scaler_margin_z0 = 2.5e-4, scaler_margin_z1 = 1.5e-3;
     bool demux_tc_ran = false;
+    uint32_t audit_threshold = 0;                 // fraction of guard-passing reads re-run to compare, x 2^32
     int *tc_err = nullptr;                        // device word: a tensor-core kernel timed out
     int64_t last_rerun_cause[3] = {0, 0, 0};      // ... because of QC edge / segmentation / barcode call
     int64_t last_rerun_reads = 0;                 // reads the last whole-path call re-ran exactly

@@ -233,6 +233,16 @@ class SignalEngine:
         self._check(self.lib.pb2_recheck_stats(self.handle, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def set_audit_fraction(self, fraction):
+        """Also re-run this fraction of the guard-passing reads exactly and count disagreements."""
+        self._check(self.lib.pb2_set_audit_fraction(self.handle, float(fraction)))
+
+    def audit_stats(self):
+        """(reads audited, audited reads whose exact integer outputs differed) since the last call."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.pb2_audit_stats(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def rerun_causes(self):
         """{cause: reads} behind the exact re-runs of the last whole-path call."""
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

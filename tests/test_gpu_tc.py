@@ -168,3 +168,28 @@ def test_rerun_causes_are_reported(eng_short, preset_short):
     assert timeouts == 0 and rerun > 0
     assert set(causes) == {'qc_edge', 'segmentation', 'barcode_call'}
     assert max(causes.values()) <= rerun <= sum(causes.values())
+
+
+def test_audit_mode_counts_and_finds_no_disagreement(eng_short, preset_short):
+    """pb2_set_audit_fraction: a sample of the reads that passed every guard is re-run through
+    the exact kernels as well; none of them may disagree, and the outputs stay the exact ones."""
+    from poreplex_b200 import synth
+    rd = synth.to_numpy(synth.generate_reads(3000, synth.SynthSpec.for_length(4000), preset_short, seed=9))
+    n, L = rd['raw'].shape
+    args = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64),
+            rd['range'], rd['digitisation'], rd['offset'])
+    plain = eng_short.analyze_host(*args)
+    rerun_plain = eng_short.recheck_stats()[0]
+    eng_short.audit_stats()
+    eng_short.set_audit_fraction(0.25)
+    try:
+        audited_run = eng_short.analyze_host(*args)
+        rerun_audit = eng_short.recheck_stats()[0]
+        audited, mismatched = eng_short.audit_stats()
+    finally:
+        eng_short.set_audit_fraction(0.0)
+    assert 0.15 * n < audited < 0.35 * n
+    assert mismatched == 0
+    assert rerun_audit == rerun_plain + audited
+    for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'label', 'counts'):
+        assert np.array_equal(plain[k], audited_run[k]), k
