@@ -148,6 +148,10 @@ int pb2_create(int device, pb2_context **out)
         delete ctx;
         return PB2_ECUDA;
     }
+    if (const char *env = getenv("POREPLEX_B200_DEMUX_PROBES")) {      // tuning / measurements
+        const int v = atoi(env);
+        if (v == 1 || v == 2) ctx->demux_probes = v;
+    }
     // sticky time-out word of the tensor-core kernels (read and cleared by pb2_recheck_stats)
     // (+ [2], [3]: reads audited / audited reads whose exact results differed, pb2_audit_stats)
     if (cudaMalloc(&ctx->tc_err, 4 * sizeof(int)) != cudaSuccess ||
@@ -220,6 +224,7 @@ int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta, doubl
     ctx->fast_lstm = on != 0;
     if (demux_margin_delta > 0) ctx->demux_margin_delta = demux_margin_delta;
     if (demux_probe_gain > 0) ctx->demux_probe_gain = demux_probe_gain;
+
     return PB2_OK;
 }
 

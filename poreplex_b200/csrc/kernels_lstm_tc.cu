@@ -204,10 +204,13 @@ __device__ __forceinline__ uint32_t split_pair(float2 h, uint32_t &lo) {
     return *reinterpret_cast<const uint32_t *>(&h16);
 }
 
-// COARSE: the deliberately perturbed evaluation (leading fp16 product only, MUFU.TANH gates);
+// COARSE != 0: a deliberately perturbed evaluation (leading fp16 product only, MUFU.TANH gates);
 // a template parameter so that the unrolled gate loop is one basic block the compiler can
-// interleave across unit pairs.
-template <int H, int KX, bool SEQ_OUT, bool COARSE = false>
+// interleave across unit pairs.  COARSE == 2 additionally rounds h stochastically to its 11
+// leading bits (pseudo-random per read, unit and step) instead of truncating it: its perturbation
+// has a component that is independent of probe 1's, so that the two probes do not both
+// under-estimate a window's sensitivity by an unlucky projection.
+template <int H, int KX, bool SEQ_OUT, int COARSE = 0>
 __global__ void __launch_bounds__(tc_threads<H, KX>(), (KX == 0 ? 2 : 1))
 k_lstm_tc(const TcArgs A)
 {
@@ -342,9 +345,9 @@ k_lstm_tc(const TcArgs A)
                     issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
                                                                 tbase + col_x + KX / 2,
                                                                 smem_u32(bW_hi), smem_u32(bW_lo), first,
-                                                                !COARSE);
+                                                                COARSE == 0);
                 issue_split_gemm<H, N, N0>(tbase + col_d, hcol, hcol + H / 2,
-                                           smem_u32(bU_hi), smem_u32(bU_lo), first, !COARSE);
+                                           smem_u32(bU_hi), smem_u32(bU_lo), first, COARSE == 0);
                 mma_commit(&bar_d[0]);
                 if (NGRP == 2) {
                     constexpr uint32_t BOFS = (N0 / 8) * 128;          // bytes into each k-chunk
@@ -352,10 +355,10 @@ k_lstm_tc(const TcArgs A)
                     if (KX > 0)
                         issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
                             tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
-                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first, !COARSE);
+                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first, COARSE == 0);
                     issue_split_gemm<H, N, (N1 > 0 ? N1 : 16)>(tbase + col_d + N0, hcol, hcol + H / 2,
                                                                smem_u32(bU_hi) + BOFS, smem_u32(bU_lo) + BOFS,
-                                                               first, !COARSE);
+                                                               first, COARSE == 0);
                     mma_commit(&bar_d[1]);
                 }
             }
@@ -420,6 +423,7 @@ k_lstm_tc(const TcArgs A)
         if (lane == 0) mbar_arrive(&bar_h);
 
         uint32_t ph = 0;
+        uint32_t rng = ((uint32_t)(A.row0 + tile0 + m) * 2654435761u) ^ ((uint32_t)part * 0x9E3779B9u) ^ 0x85EBCA6Bu;
         const int grp = (NGRP == 2 && part >= G0_PARTS) ? 1 : 0;
         const uint32_t d_addr = lane_addr + col_d + u0 * 4;
         for (int s = t_start; s < s_end; s++) {
@@ -472,8 +476,16 @@ k_lstm_tc(const TcArgs A)
                         zc = __ffma2_rn(xv2, f2(w1.x, w1.y), zc);
                         zo = __ffma2_rn(xv2, f2(w1.z, w1.w), zo);
                     }
-                    hn[j] = lstm_cell_pair<COARSE>(zi, zf, zc, zo, c[ch * 4 + j]);
-                    hi[j] = split_pair(hn[j], lo[j]);
+                    hn[j] = lstm_cell_pair<(COARSE != 0)>(zi, zf, zc, zo, c[ch * 4 + j]);
+                    if (COARSE == 2) {
+                        // stochastic rounding: random 13 bits below the kept 11 before truncation
+                        rng = rng * 1664525u + 1013904223u;
+                        float2 hd = f2(__uint_as_float(__float_as_uint(hn[j].x) + (rng >> 19)),
+                                       __uint_as_float(__float_as_uint(hn[j].y) + ((rng >> 6) & 0x1FFFu)));
+                        hi[j] = split_pair(hd, lo[j]);
+                    } else {
+                        hi[j] = split_pair(hn[j], lo[j]);
+                    }
                 }
                 tmem_st4(hh_addr + ch * 4, hi[0], hi[1], hi[2], hi[3]);
                 tmem_st4(hl_addr + ch * 4, lo[0], lo[1], lo[2], lo[3]);
@@ -548,6 +560,7 @@ k_lstm_tc(const TcArgs A)
 struct TcHeadArgs {
     const float *h_last;           // [rows][H2]
     const float *h_probe;          // [rows][H2] the coarse (perturbed) evaluation
+    const float *h_probe2;         // second, independently perturbed probe (or nullptr)
     double delta0, probe_gain;     // per-window error bound = delta0 + probe_gain * |logit shift|
     float *sens_out;               // optional [rows]: the measured logit shift
     int64_t n;
@@ -588,6 +601,15 @@ __global__ void k_demux_head_tc(const TcHeadArgs A)
         if (j < A.n_classes)
             shift = fmaxf(shift, fabsf((call.logit[j] - call.logit[call.arg]) -
                                        (probe.logit[j] - probe.logit[call.arg])));
+    if (A.h_probe2) {
+        demux_head<H2>(A.h_probe2 + (size_t)row * H2, 1, A.Wd, A.bd, A.n_classes, A.n_decoy,
+                       A.score_threshold, A.calibration, A.n_calibration, probe);
+#pragma unroll
+        for (int j = 0; j < PB2_MAX_CLASSES; j++)
+            if (j < A.n_classes)
+                shift = fmaxf(shift, fabsf((call.logit[j] - call.logit[call.arg]) -
+                                           (probe.logit[j] - probe.logit[call.arg])));
+    }
     if (!(shift == shift)) shift = INFINITY;
     const double delta = A.delta0 + A.probe_gain * (double)shift;
     const bool safe = demux_call_is_safe(call, A.n_classes, delta, A.score_threshold,
@@ -721,7 +743,7 @@ int launch_compare_corners(pb2_context *ctx, int64_t n, const int32_t *st0, cons
     return PB2_OK;
 }
 
-template <int H, int KX, bool SEQ_OUT, bool COARSE = false>
+template <int H, int KX, bool SEQ_OUT, int COARSE = 0>
 static int tc_set_attr(pb2_context *ctx)
 {
     PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<H, KX, SEQ_OUT, COARSE>,
@@ -836,7 +858,8 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         int rc;
         if ((rc = tc_set_attr<H1, 0, true>(ctx))) return rc;
         if ((rc = tc_set_attr<H2, KX, false>(ctx))) return rc;
-        if ((rc = tc_set_attr<H2, KX, false, true>(ctx))) return rc;
+        if ((rc = tc_set_attr<H2, KX, false, 1>(ctx))) return rc;
+        if ((rc = tc_set_attr<H2, KX, false, 2>(ctx))) return rc;
         ctx->attr_demux_tc = true;
     }
     const int64_t tiles = (n + TCM - 1) / TCM;
@@ -848,8 +871,9 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     if (tiles_per_pass > ctx->sm_count) tiles_per_pass -= tiles_per_pass % ctx->sm_count;
     if (tiles_per_pass > tiles) tiles_per_pass = tiles;
     uint32_t *G = (uint32_t *)ws_get(ctx, ctx->ws_h1, per_tile * (size_t)tiles_per_pass);
-    float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H2 * 2);
+    float *h_last = (float *)ws_get(ctx, ctx->ws_hlast, sizeof(float) * (size_t)n * H2 * 3);
     float *h_probe = h_last ? h_last + (size_t)n * H2 : nullptr;
+    float *h_probe2 = h_last ? h_last + (size_t)n * H2 * 2 : nullptr;
     int *tstart = (int *)ws_get(ctx, ctx->ws_tstart, sizeof(int) * (size_t)tiles_per_pass);
     // [0] timeout flag, [1] re-check count, then the re-check rows
     int32_t *rlist = (int32_t *)ws_get(ctx, ctx->ws_recheck, sizeof(int32_t) * ((size_t)n + 4));
@@ -889,10 +913,16 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         B.dir[0].coarse = 1; B.dir[0].h_last = h_probe;
         B.dir[1] = B.dir[0];
         PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe>", st,
-            k_lstm_tc<H2, KX, false, true><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+            k_lstm_tc<H2, KX, false, 1><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+        if (ctx->demux_probes >= 2) {
+            B.dir[0].h_last = h_probe2;
+            B.dir[1] = B.dir[0];
+            PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe 2>", st,
+                k_lstm_tc<H2, KX, false, 2><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+        }
     }
     TcHeadArgs Hd = {};
-    Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.n = n;
+    Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.h_probe2 = ctx->demux_probes >= 2 ? h_probe2 : nullptr; Hd.n = n;
     Hd.delta0 = ctx->demux_margin_delta; Hd.probe_gain = ctx->demux_probe_gain;
     Hd.sens_out = sens_out; Hd.slot_count = slot_count; Hd.slot_read = slot_read;
     Hd.pushed = slot_read ? nullptr : pushed;

@@ -83,8 +83,9 @@ struct pb2_context {
     // re-run of the reads whose decisions are not safe.  Off = exact kernels only.
     bool fast_lstm = true;
     // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
-    double demux_margin_delta = 2e-3;
-    double demux_probe_gain = 0.25;
+    double demux_margin_delta = 1e-3;
+    double demux_probe_gain = 0.1;
+    int demux_probes = 2;                         // coarse probe evaluations of layer 2 (1 or 2)
     // assumed bounds on the error of the scaler's two raw outputs (z0 -> scale, z1 -> shift); the
     // shift output has the heavier tail (largest seen on 1 M reads: 4.4e-5 / 2.9e-4)
     double scaler_margin_z0 = 2.5e-4, scaler_margin_z1 = 1.5e-3;

@@ -55,12 +55,12 @@ def main():
     ratio = rowmax / np.maximum(sens, 1e-12)
     print('err / shift quantiles (50,90,99,99.9,max):', np.quantile(ratio, [0.5, 0.9, 0.99, 0.999, 1.0]))
     for d0 in (5e-4, 1e-3, 2e-3):
-        for gain in (0.05, 0.1, 0.25):
+        for gain in (0.03, 0.05, 0.08, 0.1, 0.25):
             bound = d0 + gain * sens
             viol = rowmax > bound
             print('  delta0 %.0e gain %.2f: max err/bound %.3f, windows with err > bound: %d, > bound/4: %d'
                   % (d0, gain, (rowmax / bound).max(), viol.sum(), (rowmax > bound / 4).sum()))
-    i = int(np.argmax(rowmax / (1e-3 + 0.1 * sens)))
+    i = int(np.argmax(rowmax / (2e-3 + 0.08 * sens)))
     print('  worst window for (1e-3, 0.1): row %d err %.3e shift %.3e pad %d' % (i, rowmax[i], sens[i], npad[i]))
     # error vs smallest prob involved
     for thr in (1e-2, 1e-4, 1e-6, 1e-10):
