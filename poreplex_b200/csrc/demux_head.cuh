@@ -69,9 +69,11 @@ __device__ __forceinline__ void demux_head(const float *h, int hstride, const fl
     out.score = lo;
 }
 
-// Can a perturbation of every logit by at most `delta` change (arg, barcode, score)?
-// |p_best' - p_best| <= 2 delta p (1 - p) for such a perturbation; `slack` covers the f32
-// rounding of the softmax itself.  Returns true when the call is safe.
+// Can (arg, barcode, score) change if every class logit RELATIVE TO THE CALLED CLASS,
+// d_j = l_j - l_arg, moves by at most `delta`?  p_best = 1 / (1 + sum_j exp(d_j)) then moves by
+// at most delta p (1 - p); 1e-6 covers the f32 rounding of the softmax itself.  Returns true
+// when the call is safe.  (`delta` is calibrated on exactly this quantity, the largest
+// |d_j(tensor core) - d_j(exact)| of a window, see tools/tc_diag.py.)
 __device__ __forceinline__ bool demux_call_is_safe(const DemuxCall &c, int nc, double delta,
                                                    double score_threshold,
                                                    const double *calibration, int n_calibration)
@@ -80,9 +82,9 @@ __device__ __forceinline__ bool demux_call_is_safe(const DemuxCall &c, int nc, d
 #pragma unroll
     for (int j = 0; j < PB2_MAX_CLASSES; j++)
         if (j < nc && j != c.arg) second = fmaxf(second, c.logit[j]);
-    if ((double)c.logit[c.arg] - (double)second <= 2.0 * delta) return false;
+    if ((double)c.logit[c.arg] - (double)second <= delta) return false;
     const double s = (double)c.best;
-    const double tol = 2.0 * delta * s * (1.0 - s) + 1e-6;
+    const double tol = delta * s * (1.0 - s) + 1e-6;
     if (fabs(s - score_threshold) <= tol) return false;
     for (int i = 0; i < n_calibration; i++)
         if (fabs(s - calibration[i]) <= tol) return false;
