@@ -98,3 +98,51 @@ def test_tracker_fed_by_device_histogram_and_batch_writer(tmp_path):
     w2 = summary.SequencingSummaryWriter(config, str(d2), labels, barcodes)
     w2.write_batch(meta, out, polya_dwell=dwell); w2.close()
     assert (d1 / 'sequencing_summary.txt').read_text() == (d2 / 'sequencing_summary.txt').read_text()
+
+
+def _hist(results):
+    lab = {'pass': 0, 'fail': 1, 'artifact': 2}
+    counts = np.zeros((4, 5, 11), np.int64)
+    for e in results:
+        counts[lab.get(e.get('label'), 3), e.get('barcode', -1) + 1, STATUS_CODES[e['status']]] += 1
+    return counts
+
+
+def _gloo_table_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from poreplex_b200.sharding import shard_range, reduce_counts
+    results, config, labels, barcodes = _case('barcoding_polya')
+    lo, hi = shard_range(len(results), rank, world)
+    total = reduce_counts(torch.from_numpy(_hist(results[lo:hi]))).numpy()
+    t = summary.FinalSummaryTracker(labels, barcodes)
+    t.feed_counts(total)
+    buf = io.StringIO()
+    t.print_results(buf)
+    q.put((rank, buf.getvalue()))
+    dist.destroy_process_group()
+
+
+def test_final_table_from_all_reduced_histogram_gloo():
+    """Multi-GPU aggregation as the product does it, on CPU: every rank counts
+    its shard, ONE all-reduce of int64[4][5][11], and each rank can print the reference's
+    final table from the reduced tensor -- equal to the table of the whole run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_table_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    results, config, labels, barcodes = _case('barcoding_polya')
+    t = summary.FinalSummaryTracker(labels, barcodes)
+    t.feed_counts(_hist(results))
+    buf = io.StringIO()
+    t.print_results(buf)
+    assert got[0] == got[1] == buf.getvalue()
+    assert 'Successfully processed' in got[0] and 'BC4' in got[0]
