@@ -14,6 +14,12 @@ all-reduce of the per-(label, barcode, status) counts per step when N > 1.
 Prints ONE JSON line (rank 0).  `value` is measured with the batch resident in HBM
 (CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
 pb2_analyze_host with pinned HOST buffers, copies inside the timed region.
+
+The timed path is the library's default: both LSTM networks on the tensor cores (tcgen05 /
+TMEM), guards, and the exact re-run of the reads the guards flag.  After the
+timed region one more step runs with the exact-only kernels and every integer output of
+every read is compared (`config.mismatches_vs_exact_only_kernels`; `--no-verify` skips it
+for profiling runs); `cpu_baseline` compares a sample with the CPU oracle.
 """
 import argparse
 import json
