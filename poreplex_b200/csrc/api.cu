@@ -185,7 +185,8 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_flags, &ctx->ws_slots, &ctx->ws_polya,
                         &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean,
                         &ctx->ws_hlast, &ctx->ws_recheck, &ctx->ws_win2, &ctx->ws_read2,
-                        &ctx->ws_tcmisc, &ctx->ws_fast, &ctx->ws_sub};
+                        &ctx->ws_tcmisc, &ctx->ws_fast, &ctx->ws_sub,
+                        &ctx->ws_slotof};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);

@@ -125,13 +125,91 @@ __device__ __forceinline__ float warp_median(const float *v, int n, int lane,
     return pb::fdiv(pb::fadd(lo, hi), 2.0f);        // np.mean of the two middle values
 }
 
+// Slot assignment for the compacted window list: an exclusive prefix sum of the accept test of
+// BarcodeDemultiplexer.push (barcoding.py:77-84), so that slots follow read order.
+// k_window_accept: the test + the prefix inside each block of ACCEPT_BLOCK reads + block totals;
+// k_window_slot_bases: exclusive scan of the block totals (one block) and the grand total.
+constexpr int ACCEPT_BLOCK = 1024;
+
+__device__ __forceinline__ bool window_accepted(const int32_t *__restrict__ status,
+                                                const int32_t *__restrict__ segments, int64_t r,
+                                                int adapter_state, int min_len, int max_len)
+{
+    if (status[r] != PB2_ST_OKAY) return false;
+    const int a0 = segments[(r * PB2_MAX_STATES + adapter_state) * 2 + 0];
+    const int a1 = segments[(r * PB2_MAX_STATES + adapter_state) * 2 + 1];
+    const int len = a1 - a0 + 1;
+    return (a0 >= 0) && (len > 0) && (min_len <= len) && (len <= max_len);
+}
+
+// exclusive prefix of `v` over the ACCEPT_BLOCK threads of the block; total in *block_total
+__device__ __forceinline__ int block_exclusive_sum(int v, int *wsum /* [32] shared */, int *block_total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    __syncthreads();                       // wsum may still be read from a previous call
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        wsum[lane] = wi - w;
+        if (lane == 31) *block_total = wi;
+    }
+    __syncthreads();
+    return wsum[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(ACCEPT_BLOCK)
+k_window_accept(const int32_t *__restrict__ status, const int32_t *__restrict__ segments,
+                int64_t n_reads, int adapter_state, int min_len, int max_len,
+                int32_t *__restrict__ slot_of, int32_t *__restrict__ block_sums)
+{
+    __shared__ int wsum[32];
+    __shared__ int total;
+    const int64_t r = (int64_t)blockIdx.x * ACCEPT_BLOCK + threadIdx.x;
+    const int ok = (r < n_reads &&
+                    window_accepted(status, segments, r, adapter_state, min_len, max_len)) ? 1 : 0;
+    const int ex = block_exclusive_sum(ok, wsum, &total);
+    if (r < n_reads) slot_of[r] = ex;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(ACCEPT_BLOCK)
+k_window_slot_bases(int32_t *__restrict__ block_sums, int n_blocks, int *__restrict__ slot_count)
+{
+    __shared__ int wsum[32];
+    __shared__ int total;
+    int carry = 0;
+    for (int base = 0; base < n_blocks; base += ACCEPT_BLOCK) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_sums[i] : 0;
+        const int ex = block_exclusive_sum(v, wsum, &total);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += total;
+        __syncthreads();                   // everyone has read `total` before it is rewritten
+    }
+    if (threadIdx.x == 0) *slot_count = carry;
+}
+
 __global__ void __launch_bounds__(WIN_WARPS * 32)
 k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ pooled,
           const float *__restrict__ scale_shift, const int32_t *__restrict__ status,
           const int32_t *__restrict__ segments, int64_t n_reads, int stride,
           int adapter_state, int min_len, int max_len, int trim_len, float pad_value,
           float *__restrict__ windows, int32_t *__restrict__ pushed,
-          int *__restrict__ slot_count, int32_t *__restrict__ slot_read)
+          const int32_t *__restrict__ slot_of, const int32_t *__restrict__ slot_base,
+          int32_t *__restrict__ slot_read)
 {
     __shared__ float sx[WIN_WARPS][PB2_WINDOW_MAX];
     __shared__ float sd[WIN_WARPS][PB2_WINDOW_MAX];
@@ -139,7 +217,7 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * WIN_WARPS + warp;
     if (r >= n_reads) return;
-    const bool compact = slot_count != nullptr;
+    const bool compact = slot_of != nullptr;
     float *out = windows + r * trim_len;
     int ok = 0;
     int a0 = -1, a1 = -1;
@@ -156,14 +234,12 @@ k_windows(const int64_t *__restrict__ raw_offsets, const float *__restrict__ poo
         return;
     }
     if (compact) {
-        // accepted windows are packed densely (order is irrelevant: every read is
-        // classified independently and results are scattered back through slot_read)
-        int slot = 0;
-        if (lane == 0) {
-            slot = atomicAdd(slot_count, 1);
-            slot_read[slot] = (int32_t)r;
-        }
-        slot = __shfl_sync(0xffffffffu, slot, 0);
+        // accepted windows are packed densely IN READ ORDER (slot = number of accepted reads
+        // before r, from k_window_accept + k_window_slot_bases): which windows share a 128-slot
+        // tile of the tensor-core classifier, and with it every float it produces, is then a
+        // function of the batch alone, not of the order in which warps happened to run
+        const int slot = slot_base[r / ACCEPT_BLOCK] + slot_of[r];
+        if (lane == 0) slot_read[slot] = (int32_t)r;
         out = windows + (int64_t)slot * trim_len;
     }
     const int len = a1 - a0 + 1;
@@ -196,14 +272,29 @@ int launch_windows(pb2_context *ctx, const pb2_batch &b, const float *pooled,
     if (d.trim_length > PB2_WINDOW_MAX)
         return fail(ctx, PB2_EUNSUPPORTED, "signal_trim_length %d > %d", d.trim_length,
                     PB2_WINDOW_MAX);
-    if (slot_count) PB_CUDA(ctx, cudaMemsetAsync(slot_count, 0, sizeof(int), st));
+    const int32_t *slot_of = nullptr, *slot_base = nullptr;
+    if (slot_count) {
+        const int n_blocks = (int)((b.n_reads + ACCEPT_BLOCK - 1) / ACCEPT_BLOCK);
+        int32_t *so = (int32_t *)ws_get(ctx, ctx->ws_slotof,
+                                        sizeof(int32_t) * ((size_t)b.n_reads + n_blocks));
+        if (!so) return PB2_ENOMEM;
+        int32_t *sums = so + b.n_reads;
+        PB_LAUNCH(ctx, K_MISC, "k_window_accept", st,
+            k_window_accept<<<n_blocks, ACCEPT_BLOCK, 0, st>>>(status, segments, b.n_reads,
+                                                           ctx->adapter_state, d.min_length,
+                                                           d.max_length, so, sums));
+        PB_LAUNCH(ctx, K_MISC, "k_window_slot_bases", st,
+            k_window_slot_bases<<<1, ACCEPT_BLOCK, 0, st>>>(sums, n_blocks, slot_count));
+        slot_of = so;
+        slot_base = sums;
+    }
     const unsigned grid = (unsigned)((b.n_reads + WIN_WARPS - 1) / WIN_WARPS);
     PB_LAUNCH(ctx, K_WINDOWS, "k_windows", st,
         k_windows<<<grid, WIN_WARPS * 32, 0, st>>>(b.raw_offsets, pooled, scale_shift, status,
                                                segments, b.n_reads, ctx->scaler.stride,
                                                ctx->adapter_state, d.min_length, d.max_length,
                                                d.trim_length, d.pad_value, windows, pushed,
-                                               slot_count, slot_read));
+                                               slot_of, slot_base, slot_read));
     return PB2_OK;
 }
 

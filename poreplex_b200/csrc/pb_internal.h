@@ -120,7 +120,7 @@ struct pb2_context {
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
         ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean,
-        ws_hlast, ws_recheck, ws_win2, ws_read2, ws_tcmisc, ws_fast, ws_sub;
+        ws_hlast, ws_recheck, ws_win2, ws_read2, ws_tcmisc, ws_fast, ws_sub, ws_slotof;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
