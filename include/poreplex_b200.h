@@ -276,6 +276,24 @@ int pb2_scaler_predict(pb2_context *ctx, const float *heads, int64_t n, float *z
 int pb2_measure_polya(pb2_context *ctx, const pb2_batch *batch, const float *scale_shift,
                       const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                       void *stream);
+/* csupport.detect_events (src/csupport.c:70-124; scrappie event_detection.c:273-324), the
+ * reference's own native entry point, for a batch of float32 signals: signal i is
+ * signal[offsets[i] .. offsets[i] + lengths[i]).  All pointers are DEVICE pointers.  Two calls:
+ *   records == NULL: event_counts[i] = number of events of signal i (0 for an empty signal,
+ *                    where csupport raises);
+ *   records != NULL: the events of signal i are written as packed 28-byte records
+ *                    {u8 start, f4 length, f4 mean, f4 stdv, i4 pos = -1, i4 state = -1}
+ *                    (the numpy dtype of csupport.c:156-159) starting at record
+ *                    event_offsets[i] (the exclusive prefix sum of the counts).
+ * Window lengths up to 255 samples. */
+typedef struct pb2_detector_params {
+    int64_t window_length1, window_length2;    /* csupport defaults 30, 120 */
+    float threshold1, threshold2, peak_height; /* 3.0, 9.0, 8.0 */
+} pb2_detector_params;
+int pb2_detect_events(pb2_context *ctx, const float *signal, const int64_t *offsets,
+                      const int64_t *lengths, int64_t n_signals, const pb2_detector_params *p,
+                      int64_t *event_counts, const int64_t *event_offsets, void *records,
+                      void *stream);
 /* SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443) for reads whose status is
  * okay and that have an event table.  `batch` (the reads' raw signal, same read order) is only
  * needed when events->mean is NULL and may be NULL otherwise.  flag[i]: 1 unsplit, 0 not, <0 internal overflow/no path.

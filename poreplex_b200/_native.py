@@ -35,6 +35,11 @@ class LstmWeights(C.Structure):
                 ('kernel', _fp), ('recurrent', _fp), ('bias', _fp)]
 
 
+class DetectorParams(C.Structure):
+    _fields_ = [('window_length1', C.c_int64), ('window_length2', C.c_int64),
+                ('threshold1', C.c_float), ('threshold2', C.c_float), ('peak_height', C.c_float)]
+
+
 class ScalerParams(C.Structure):
     _fields_ = [('l1', LstmWeights), ('l2', LstmWeights), ('dense_kernel', _fp),
                 ('dense_bias', _fp), ('stride', C.c_int32), ('length', C.c_int32),
@@ -125,7 +130,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
            'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
-           'pb2_audit_stats']
+           'pb2_audit_stats', 'pb2_detect_events']
 
 
 def sources():
@@ -195,6 +200,8 @@ def load():
     L.pb2_set_audit_fraction.argtypes = [vp, C.c_double]
     L.pb2_audit_stats.argtypes = [vp, _i64p, _i64p]
     L.pb2_set_polya.argtypes = [vp, C.POINTER(PolyaParams), C.c_int32]
+    L.pb2_detect_events.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(DetectorParams), vp, vp,
+                                    vp, vp]
     L.pb2_measure_polya.argtypes = [vp, C.POINTER(Batch), vp, vp, vp, vp, vp]
     L.pb2_set_unsplit.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(UnsplitParams), C.c_int32,
                                   C.c_int32, C.c_int32]

@@ -603,6 +603,19 @@ int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_batch *hb, const pb2_eve
     return PB2_OK;
 }
 
+int pb2_detect_events(pb2_context *ctx, const float *signal, const int64_t *offsets,
+                      const int64_t *lengths, int64_t n_signals, const pb2_detector_params *p,
+                      int64_t *event_counts, const int64_t *event_offsets, void *records,
+                      void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (n_signals < 0 || !p || (n_signals > 0 && (!signal || !offsets || !lengths)))
+        return fail(ctx, PB2_EINVAL, "detect_events: bad arguments");
+    DeviceGuard g(ctx->device);
+    return launch_detect_events(ctx, signal, offsets, lengths, n_signals, *p, event_counts,
+                                event_offsets, records, (cudaStream_t)stream);
+}
+
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream)
 {

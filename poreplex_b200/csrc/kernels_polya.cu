@@ -67,4 +67,85 @@ int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
     return PB2_OK;
 }
 
+// ---------------------------------------------------------------------------
+// k_detect_events: csupport.detect_events (src/csupport.c:70-124 ->
+// src/contrib/scrappie/event_detection.c:273-324) for a batch of float32 signals, the
+// reference's one native entry point as a stand-alone call.  One thread per signal runs the
+// same streaming detector k_polya uses (EventStreamT over the plain signal).  The number of
+// events is not known up front: a first pass (FILL = false) counts, the caller turns counts
+// into offsets, a second pass writes the 28-byte records of csupport.c:156-159
+// (start u8, length f4, mean f4, stdv f4, pos i4 = -1, state i4 = -1).
+// ---------------------------------------------------------------------------
+constexpr int DETECT_THREADS = 64;
+
+template <int RING, bool FILL>
+__global__ void __launch_bounds__(DETECT_THREADS)
+k_detect_events(const PolyaParams P, const float *__restrict__ signal,
+                const int64_t *__restrict__ offsets, const int64_t *__restrict__ lengths, int64_t n,
+                int64_t *__restrict__ counts, const int64_t *__restrict__ event_offsets,
+                uint32_t *__restrict__ records)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t len = lengths[r];
+    int64_t k = 0;
+    if (len > 0) {                                 // empty signal: no events (csupport raises)
+        PlainSource src;
+        src.x = signal + offsets[r]; src.n = len; src.next = 0;
+        PlainEventStream<RING> es;
+        es.begin(src, P);
+        Event ev[2];
+        const int64_t base = FILL ? event_offsets[r] : 0;
+        while (!es.finished()) {
+            const int m = es.step(ev);
+            for (int q = 0; q < m; q++) {
+                if (FILL) {
+                    uint32_t *w = records + (base + k) * 7;
+                    w[0] = (uint32_t)ev[q].start;
+                    w[1] = (uint32_t)(ev[q].start >> 32);
+                    w[2] = __float_as_uint(ev[q].length);
+                    w[3] = __float_as_uint(ev[q].mean);
+                    w[4] = __float_as_uint(ev[q].stdv);
+                    w[5] = 0xFFFFFFFFu;
+                    w[6] = 0xFFFFFFFFu;
+                }
+                k++;
+            }
+        }
+    }
+    if (!FILL) counts[r] = k;
+}
+
+int launch_detect_events(pb2_context *ctx, const float *signal, const int64_t *offsets,
+                         const int64_t *lengths, int64_t n, const pb2_detector_params &dp,
+                         int64_t *counts, const int64_t *event_offsets, void *records,
+                         cudaStream_t st)
+{
+    if (n <= 0) return PB2_OK;
+    if (dp.window_length1 < 1 || dp.window_length2 < 1)
+        return fail(ctx, PB2_EINVAL, "detect_events: window lengths must be >= 1");
+    const int64_t wmax = dp.window_length1 > dp.window_length2 ? dp.window_length1 : dp.window_length2;
+    if (2 * wmax + 2 > 512)
+        return fail(ctx, PB2_EUNSUPPORTED, "detect_events: window length %lld > 255", (long long)wmax);
+    PolyaParams P = {};
+    P.w1 = (int32_t)dp.window_length1; P.w2 = (int32_t)dp.window_length2;
+    P.thr1 = dp.threshold1; P.thr2 = dp.threshold2; P.peak_height = dp.peak_height;
+    const unsigned grid = (unsigned)((n + DETECT_THREADS - 1) / DETECT_THREADS);
+    const bool small = 2 * wmax + 2 <= 64;
+    uint32_t *rec = (uint32_t *)records;
+#define PB_DETECT(RING, FILL)                                                                  \
+    PB_LAUNCH(ctx, K_MISC, "k_detect_events", st,                                              \
+        k_detect_events<RING, FILL><<<grid, DETECT_THREADS, 0, st>>>(P, signal, offsets, lengths, n,  \
+                                                                    counts, event_offsets, rec))
+    if (records) {
+        if (!event_offsets) return fail(ctx, PB2_EINVAL, "detect_events: records without event_offsets");
+        if (small) PB_DETECT(64, true); else PB_DETECT(512, true);
+    } else {
+        if (!counts) return fail(ctx, PB2_EINVAL, "detect_events: neither counts nor records");
+        if (small) PB_DETECT(64, false); else PB_DETECT(512, false);
+    }
+#undef PB_DETECT
+    return PB2_OK;
+}
+
 }  // namespace pb

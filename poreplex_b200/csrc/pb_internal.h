@@ -208,6 +208,10 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
                     float *class_probs, int32_t *barcode, int32_t *guess, int32_t *score,
                     float *logits_out, int32_t *unsafe_out, float *sens_out, bool recheck,
                     cudaStream_t st, int32_t *read_unsafe = nullptr);
+int launch_detect_events(pb2_context *ctx, const float *signal, const int64_t *offsets,
+                         const int64_t *lengths, int64_t n, const pb2_detector_params &dp,
+                         int64_t *counts, const int64_t *event_offsets, void *records,
+                         cudaStream_t st);
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);

@@ -173,6 +173,15 @@ struct WindowSource {
     }
 };
 
+// ---- a float32 signal as it is: the input csupport.detect_events itself takes ------
+struct PlainSource {
+    const float *x;
+    int64_t n;
+    int64_t next;
+    PB_HD void seek(int64_t i) { next = i; }
+    PB_HD float pop() { return x[next++]; }       // EventStream never pops past n
+};
+
 // ---- event_detection.c as an iterator --------------------------------------------
 struct Detector {
     float threshold;
@@ -182,22 +191,26 @@ struct Detector {
     double snapS, snapQ;          // prefix sums at peak_pos
 };
 
-struct EventStream {
-    WindowSource src;
+// RING: entries of the prefix-sum ring, a power of two >= 2 * max(window) + 2 (index i needs
+// S[i - w] .. S[i + w] and the fill runs one ahead).
+template <class Source, int RING = 64>
+struct EventStreamT {
+    static constexpr int64_t MASK = RING - 1;
+    Source src;
     int64_t n;
     int64_t head;                 // prefix sums S[0..head] are in the ring
-    double S[64], Q[64];
+    double S[RING], Q[RING];
     int64_t det_i;
     Detector d[2];
     float peak_height;
-    int64_t w[2];
+    int64_t w[2], wmax;
     // event emission
     uint64_t prev_pos; double prevS, prevQ;
     Event pend_ev[2]; int n_pend;          // only used by next()
     int64_t n_peaks;
     bool tail_emitted;
 
-    PB_HD void begin(const WindowSource &s, const PolyaParams &P) {
+    PB_HD void begin(const Source &s, const PolyaParams &P) {
         src = s;
         src.seek(0);
         n = s.n;
@@ -205,6 +218,7 @@ struct EventStream {
         S[0] = 0.0; Q[0] = 0.0;
         det_i = 0;
         w[0] = P.w1; w[1] = P.w2;
+        wmax = P.w1 > P.w2 ? P.w1 : P.w2;
         peak_height = P.peak_height;
         for (int k = 0; k < 2; k++) {
             d[k].threshold = k ? P.thr2 : P.thr1;
@@ -224,11 +238,11 @@ struct EventStream {
         if (idx > n) idx = n;
         while (head < idx) {
             const float m = src.pop();
-            const double s = pb::dadd(S[head & 63], (double)m);
-            const double q = pb::dadd(Q[head & 63], (double)pb::fmul(m, m));
+            const double s = pb::dadd(S[head & MASK], (double)m);
+            const double q = pb::dadd(Q[head & MASK], (double)pb::fmul(m, m));
             head++;
-            S[head & 63] = s;
-            Q[head & 63] = q;
+            S[head & MASK] = s;
+            Q[head & MASK] = q;
         }
     }
     // compute_tstat (event_detection.c:61-117) at index i for window wl
@@ -236,13 +250,13 @@ struct EventStream {
         if (n < 2 * wl || wl < 2) return 0.0f;
         if (i < wl || i > n - wl) return 0.0f;
         const float wf = (float)wl;
-        double sum1 = S[i & 63], sumsq1 = Q[i & 63];
+        double sum1 = S[i & MASK], sumsq1 = Q[i & MASK];
         if (i > wl) {
-            sum1 = pb::dsub(sum1, S[(i - wl) & 63]);
-            sumsq1 = pb::dsub(sumsq1, Q[(i - wl) & 63]);
+            sum1 = pb::dsub(sum1, S[(i - wl) & MASK]);
+            sumsq1 = pb::dsub(sumsq1, Q[(i - wl) & MASK]);
         }
-        const float sum2 = (float)pb::dsub(S[(i + wl) & 63], S[i & 63]);
-        const float sumsq2 = (float)pb::dsub(Q[(i + wl) & 63], Q[i & 63]);
+        const float sum2 = (float)pb::dsub(S[(i + wl) & MASK], S[i & MASK]);
+        const float sumsq2 = (float)pb::dsub(Q[(i + wl) & MASK], Q[i & MASK]);
         const float mean1 = (float)pb::ddiv(sum1, (double)wf);
         const float mean2 = pb::fdiv(sum2, wf);
         double cv = pb::dsub(pb::ddiv(sumsq1, (double)wf), (double)pb::fmul(mean1, mean1));
@@ -279,13 +293,13 @@ struct EventStream {
                 // create_events with no peak: create_event(0, peaks[0] = 0)
                 make_event(0, 0.0, 0.0, 0, 0.0, 0.0, out[0]);
             } else {
-                make_event(prev_pos, prevS, prevQ, (uint64_t)n, S[n & 63], Q[n & 63], out[0]);
+                make_event(prev_pos, prevS, prevQ, (uint64_t)n, S[n & MASK], Q[n & MASK], out[0]);
             }
             return 1;
         }
         // short_long_peak_detector, one index (event_detection.c:124-201)
         const int64_t i = det_i++;
-        fill_to(i + w[1] + 1);
+        fill_to(i + wmax + 1);
         int nout = 0;
         for (int k = 0; k < 2; k++) {
             Detector &D = d[k];
@@ -297,13 +311,13 @@ struct EventStream {
                 } else if (pb::fsub(cur, D.peak_value) > peak_height) {
                     D.peak_value = cur;
                     D.peak_pos = i;
-                    D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
+                    D.snapS = S[i & MASK]; D.snapQ = Q[i & MASK];
                 }
             } else {
                 if (cur > D.peak_value) {
                     D.peak_value = cur;
                     D.peak_pos = i;
-                    D.snapS = S[i & 63]; D.snapQ = Q[i & 63];
+                    D.snapS = S[i & MASK]; D.snapQ = Q[i & MASK];
                 }
                 if (k == 0 && D.peak_value > D.threshold) {
                     d[1].masked_to = D.peak_pos + D.window;
@@ -342,6 +356,9 @@ struct EventStream {
         }
     }
 };
+
+using EventStream = EventStreamT<WindowSource>;      // poly(A): raw -> pA -> scale -> medfilt(7)
+template <int RING> using PlainEventStream = EventStreamT<PlainSource, RING>;   // csupport.detect_events(signal)
 
 // ---- event iteration with a replay cache --------------------------------------------
 // The first complete walk over a window records its events (16 bytes each) in a per-read

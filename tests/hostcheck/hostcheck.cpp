@@ -5,6 +5,25 @@
 #include <cmath>
 #include "../../poreplex_b200/csrc/polya_core.cuh"
 
+// csupport.detect_events on a plain float32 signal (the stream k_detect_events runs);
+// ring: 64 or 512 prefix-sum entries
+template <int RING>
+static int64_t detect_plain(const float *x, int64_t n, const pb::PolyaParams *P, uint64_t *start,
+                            float *length, float *mean, float *stdv, int64_t cap)
+{
+    pb::PlainSource src;
+    src.x = x; src.n = n; src.next = 0;
+    pb::PlainEventStream<RING> es;
+    es.begin(src, *P);
+    pb::Event ev;
+    int64_t k = 0;
+    while (es.next(ev)) {
+        if (k < cap) { start[k] = ev.start; length[k] = ev.length; mean[k] = ev.mean; stdv[k] = ev.stdv; }
+        k++;
+    }
+    return k;
+}
+
 extern "C" {
 
 float hc_median7(const float *v) { return pb::median7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]); }
@@ -36,6 +55,13 @@ int64_t hc_detect_events(const int16_t *raw, int64_t n, double gain, double offs
         k++;
     }
     return k;
+}
+
+int64_t hc_detect_events_plain(const float *x, int64_t n, const pb::PolyaParams *P, int ring,
+                               uint64_t *start, float *length, float *mean, float *stdv, int64_t cap)
+{
+    return ring == 64 ? detect_plain<64>(x, n, P, start, length, mean, stdv, cap)
+                      : detect_plain<512>(x, n, P, start, length, mean, stdv, cap);
 }
 
 void hc_polya(const pb::PolyaParams *P, const int16_t *raw, int64_t full_length, double gain,

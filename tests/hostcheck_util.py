@@ -61,6 +61,7 @@ def load():
     L.hc_median5.restype = C.c_float
     L.hc_pairwise_sum.restype = C.c_float
     L.hc_detect_events.restype = C.c_int64
+    L.hc_detect_events_plain.restype = C.c_int64
     assert L.hc_sizeof_params() == C.sizeof(PolyaParamsC)
     assert L.hc_sizeof_result() == C.sizeof(PolyaResultC)
     return L

@@ -84,6 +84,41 @@ def test_event_stream_matches_reference_scrappie(hc, oracle_mod, preset):
         assert np.array_equal(sd[:k], want['stdv'], equal_nan=True)
 
 
+def test_plain_event_stream_matches_reference_scrappie(hc, oracle_mod):
+    """The stream behind pb2_detect_events (float32 signal in, no filtering) == the reference's
+    event_detection.c for the csupport default windows (30, 120: the 512-entry ring), the
+    preset's (7, 20: both rings) and a short-detector window larger than the long one."""
+    detect = oracle_mod.detect_events_ref if oracle_mod.have_ref_scrappie() \
+        else oracle_mod.detect_events_restated
+    rng = np.random.default_rng(5)
+    cases = [(dict(window_length1=30, window_length2=120, threshold1=3.0, threshold2=9.0, peak_height=8.0), (512,)),
+             (dict(window_length1=7, window_length2=20, threshold1=3.0, threshold2=8.0, peak_height=4.0), (64, 512)),
+             (dict(window_length1=25, window_length2=10, threshold1=2.0, threshold2=5.0, peak_height=1.0), (64, 512)),
+             (dict(window_length1=2, window_length2=255, threshold1=1.5, threshold2=4.0, peak_height=0.5), (512,))]
+    for kw, rings in cases:
+        P = H.PolyaParamsC()
+        P.w1, P.w2 = kw['window_length1'], kw['window_length2']
+        P.thr1, P.thr2, P.peak_height = kw['threshold1'], kw['threshold2'], kw['peak_height']
+        for n in (1, 2, 13, 59, 60, 61, 239, 240, 241, 1000, 20000):
+            step = int(rng.integers(5, 60))
+            sig = (np.repeat(rng.normal(100, 12, n // step + 1), step)[:n] +
+                   rng.normal(0, 2.0, n)).astype(np.float32)
+            want = detect(sig, **kw)
+            for ring in rings:
+                cap = n + 2
+                st = np.zeros(cap, np.uint64); ln = np.zeros(cap, np.float32)
+                mn = np.zeros(cap, np.float32); sd = np.zeros(cap, np.float32)
+                k = hc.hc_detect_events_plain(sig.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(P),
+                                              C.c_int(ring), st.ctypes.data_as(C.c_void_p),
+                                              ln.ctypes.data_as(C.c_void_p), mn.ctypes.data_as(C.c_void_p),
+                                              sd.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+                assert k == len(want), (kw, n, ring)
+                assert np.array_equal(st[:k], want['start']), (kw, n, ring)
+                assert np.array_equal(ln[:k], want['length']), (kw, n, ring)
+                assert np.array_equal(mn[:k], want['mean'], equal_nan=True), (kw, n, ring)
+                assert np.array_equal(sd[:k], want['stdv'], equal_nan=True), (kw, n, ring)
+
+
 def _make_case(rng, kind):
     na = int(rng.integers(3000, 6000)); npa = int(rng.integers(100, 6000)); nt = int(rng.integers(500, 8000))
     lvl, sd = 108.95, 1.8
