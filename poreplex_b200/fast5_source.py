@@ -5,20 +5,33 @@ signal path -- per-read metadata, the int16 ``Signal`` dataset *untouched* (the
 int16 -> pA conversion of ``get_raw_data`` runs on the GPU) and the basecall summary
 behind ``NanoporeRead.load_fast5_events`` (signal_loader.py:266-279).  Uses whatever
 ``h5py`` module is importable (the parity tests install an in-memory one); without
-h5py this module raises -- FAST5 ingest itself is outside the accelerated path
-(SURVEY.md section 8f rank 2).
+h5py it reads the files through ``poreplex_b200.hdf5_min`` (SURVEY.md section 8f rank 2;
+``poreplex_b200.fast5_loader`` is the native batch form for the raw signals).
 """
 import numpy as np
 
 __all__ = ['Fast5Source']
 
 
+class _MinimalH5py:
+    """``h5py.File`` stand-in over poreplex_b200.hdf5_min (read-only; the classic HDF5 format with
+    gzip / shuffle / VBZ chunked datasets that FAST5 files use)."""
+
+    @staticmethod
+    def File(path, mode='r'):
+        if mode != 'r':
+            raise ValueError('hdf5_min is read-only')
+        from .hdf5_min import Hdf5File
+        return Hdf5File(path)
+
+
 def _h5py():
+    """h5py when it is importable (the parity tests install an in-memory one), else the built-in
+    minimal reader: I/O only, the signal path itself has no CPU fallback."""
     try:
         import h5py
-    except ImportError as exc:                      # pragma: no cover - depends on image
-        raise ImportError('poreplex_b200.process_batch needs h5py to read FAST5 files; '
-                          'use SignalEngine.analyze_host() for in-memory signals') from exc
+    except ImportError:
+        return _MinimalH5py
     return h5py
 
 

@@ -7,13 +7,17 @@ understands exactly the subset of the HDF5 file format those two files use:
 * superblock version 0, 8-byte offsets/lengths
 * version-1 object headers (with continuation blocks)
 * "old style" groups: symbol-table message -> v1 B-tree -> SNOD nodes + local heap
-* contiguous (and compact) unfiltered datasets of fixed-point / IEEE-float / compound type
+* contiguous (and compact) unfiltered datasets of fixed-point / IEEE-float / string / compound type
+* chunked datasets (layout class 2, v1 chunk B-tree) with the deflate, shuffle, fletcher32 and
+  VBZ (32020, needs libzstd) filters -- the ``Signal`` / ``Move`` datasets of FAST5 files
 * version 1..3 attribute messages holding fixed- or variable-length strings and
   numeric scalars/arrays (vlen data lives in global heap collections)
 
 Anything else raises ``Hdf5FormatError`` instead of guessing.
 """
+import mmap
 import struct
+import zlib
 
 import numpy as np
 
@@ -116,6 +120,135 @@ def _parse_dataspace(buf, pos):
     return tuple(int(d) for d in dims), p - pos
 
 
+# ---- filters -------------------------------------------------------------------------------
+_zstd = None
+
+
+def _zstd_decompress(src, expected):
+    """One zstd frame -> bytes, through the system libzstd (no Python binding in this image)."""
+    global _zstd
+    import ctypes as C
+    if _zstd is None:
+        for name in ('libzstd.so.1', 'libzstd.so'):
+            try:
+                _zstd = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        else:
+            raise Hdf5FormatError('VBZ-compressed dataset: libzstd is not available')
+        _zstd.ZSTD_decompress.restype = C.c_size_t
+        _zstd.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        _zstd.ZSTD_isError.argtypes = [C.c_size_t]
+        _zstd.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+        _zstd.ZSTD_getFrameContentSize.argtypes = [C.c_void_p, C.c_size_t]
+    src = bytes(src)
+    size = _zstd.ZSTD_getFrameContentSize(src, len(src))
+    if size >= (1 << 62):                          # unknown / error: fall back on the bound
+        size = expected
+    dst = C.create_string_buffer(max(int(size), 1))
+    n = _zstd.ZSTD_decompress(dst, int(size), src, len(src))
+    if _zstd.ZSTD_isError(n):
+        raise Hdf5FormatError('zstd decompression failed')
+    return dst.raw[:n]
+
+
+def _svb_decode(buf, count, key_bits):
+    """streamvbyte: ``count`` little-endian codes; key_bits = 1 (svb16: 1 or 2 bytes per value,
+    one key bit each) or 2 (classic: 1..4 bytes, two key bits each).  Keys first, data after."""
+    per = 8 // key_bits
+    nkeys = (count + per - 1) // per
+    keys = np.frombuffer(buf, np.uint8, nkeys)
+    shifts = (np.arange(per, dtype=np.uint8) * key_bits)
+    codes = ((keys[:, None] >> shifts[None, :]) & ((1 << key_bits) - 1)).reshape(-1)[:count]
+    lens = codes.astype(np.int64) + 1
+    ends = np.cumsum(lens)
+    starts = ends - lens
+    data = np.frombuffer(buf, np.uint8, int(ends[-1]) if count else 0, nkeys)
+    out = np.zeros(count, np.uint32)
+    for b in range(1 << key_bits):
+        m = lens > b
+        out[m] |= data[starts[m] + b].astype(np.uint32) << np.uint32(8 * b)
+    return out
+
+
+def _vbz_decode(chunk, cd_values, expected):
+    """ONT VBZ filter (id 32020).  cd_values = (version, integer size, delta+zigzag, zstd level).
+    Layout as published in ONT's vbz_compression: uint32 uncompressed size, then an optional zstd
+    frame around the streamvbyte stream of the (delta, zigzag) coded samples; version 1 codes
+    2-byte integers with svb16 (1-bit keys), everything else with the classic 2-bit keys.
+    NOT checked against a file written by ONT's plugin (none available here)."""
+    version, isize, zigzag, level = (list(cd_values) + [0, 0, 0, 0])[:4]
+    if version > 1:
+        raise Hdf5FormatError('unsupported VBZ version %d' % version)
+    size = struct.unpack_from('<I', chunk, 0)[0]
+    body = bytes(chunk[4:])
+    if level != 0:
+        body = _zstd_decompress(body, max(expected, size) * 2 + 64)
+    if isize in (0, 1):
+        return body[:size]
+    count = size // isize
+    svb16 = version == 1 and isize == 2
+    vals = _svb_decode(body, count, 1 if svb16 else 2)
+    if zigzag:
+        if svb16:
+            v = vals.astype(np.uint16)
+            d = ((v >> np.uint16(1)) ^ (np.uint16(0) - (v & np.uint16(1)))).astype(np.uint16)
+            vals = np.cumsum(d, dtype=np.uint16)
+        else:
+            d = (vals >> np.uint32(1)) ^ (np.uint32(0) - (vals & np.uint32(1)))
+            vals = np.cumsum(d, dtype=np.uint32)
+    return vals.astype({1: np.uint8, 2: np.uint16, 4: np.uint32}[isize]).tobytes()
+
+
+def _unshuffle(raw, elsize):
+    a = np.frombuffer(raw, np.uint8)
+    n = len(a) // elsize
+    return a[:n * elsize].reshape(elsize, n).T.tobytes() + a[n * elsize:].tobytes()
+
+
+def _parse_pipeline(mbuf):
+    """Filter pipeline message -> [(filter id, client data values)] in application order."""
+    version, nfilters = mbuf[0], mbuf[1]
+    p = 8 if version == 1 else 2
+    filters = []
+    for _ in range(nfilters):
+        fid = struct.unpack_from('<H', mbuf, p)[0]
+        p += 2
+        if version == 1 or fid >= 256:
+            nlen = struct.unpack_from('<H', mbuf, p)[0]
+            p += 2
+        else:
+            nlen = 0
+        _flags, ncd = struct.unpack_from('<HH', mbuf, p)
+        p += 4
+        p += _pad8(nlen) if version == 1 else nlen
+        cd = struct.unpack_from('<%dI' % ncd, mbuf, p)
+        p += 4 * ncd
+        if version == 1 and ncd & 1:
+            p += 4
+        filters.append((fid, cd))
+    return filters
+
+
+def _defilter(raw, filters, mask, expected):
+    for i in reversed(range(len(filters))):
+        if mask & (1 << i):
+            continue
+        fid, cd = filters[i]
+        if fid == 1:
+            raw = zlib.decompress(raw)
+        elif fid == 2:
+            raw = _unshuffle(raw, cd[0])
+        elif fid == 3:
+            raw = raw[:-4]                          # fletcher32 checksum, not verified
+        elif fid == 32020:
+            raw = _vbz_decode(raw, cd, expected)
+        else:
+            raise Hdf5FormatError('unsupported filter %d' % fid)
+    return raw
+
+
 class _Attrs(dict):
     pass
 
@@ -137,6 +270,8 @@ class Hdf5Dataset(_Node):
     def __init__(self, h5, addr, name):
         super().__init__(h5, addr, name)
         self.shape = self._dtype = self._data_addr = self._compact = None
+        self._chunk_btree = self._chunk_shape = None
+        self._filters = []
         for mtype, mbuf in self._msgs:
             if mtype == 0x0001:
                 self.shape, _ = _parse_dataspace(mbuf, 0)
@@ -148,7 +283,7 @@ class Hdf5Dataset(_Node):
             elif mtype == 0x0008:
                 self._parse_layout(mbuf)
             elif mtype == 0x000B:
-                raise Hdf5FormatError('filtered datasets are not supported')
+                self._filters = _parse_pipeline(mbuf)
         if self.shape is None or self._dtype is None:
             raise Hdf5FormatError('not a dataset: ' + name)
 
@@ -170,19 +305,69 @@ class Hdf5Dataset(_Node):
             elif lclass == 0:
                 size = struct.unpack_from('<H', mbuf, 2)[0]
                 self._compact = bytes(mbuf[4:4 + size])
+            elif lclass == 2:
+                ndim = mbuf[2]                       # rank + 1 (the last one is the element size)
+                self._chunk_btree = struct.unpack_from('<Q', mbuf, 3)[0]
+                self._chunk_shape = struct.unpack_from('<%dI' % ndim, mbuf, 11)[:-1]
             else:
-                raise Hdf5FormatError('chunked layout is not supported')
+                raise Hdf5FormatError('unsupported layout class %d' % lclass)
         elif version in (1, 2):
             rank, lclass = mbuf[1], mbuf[2]
-            if lclass != 1:
-                raise Hdf5FormatError('only contiguous v1/v2 layouts are supported')
-            self._data_addr = struct.unpack_from('<Q', mbuf, 8)[0]
+            if lclass == 2:
+                self._chunk_btree = struct.unpack_from('<Q', mbuf, 8)[0]
+                self._chunk_shape = struct.unpack_from('<%dI' % rank, mbuf, 16)[:-1]
+            elif lclass == 1:
+                self._data_addr = struct.unpack_from('<Q', mbuf, 8)[0]
+            else:
+                raise Hdf5FormatError('unsupported v1/v2 layout class %d' % lclass)
         else:
             raise Hdf5FormatError('unsupported layout version %d' % version)
+
+    def chunks(self):
+        """Yield (element offsets, stored size, filter mask, file address) of every chunk."""
+        buf, rank = self._h5._buf, len(self.shape)
+        klen = 8 + 8 * (rank + 1)
+
+        def walk(node):
+            if buf[node:node + 4] != b'TREE' or buf[node + 4] != 1:
+                raise Hdf5FormatError('bad chunk B-tree node')
+            level = buf[node + 5]
+            used = struct.unpack_from('<H', buf, node + 6)[0]
+            p = node + 24
+            for _ in range(used):
+                size, mask = struct.unpack_from('<II', buf, p)
+                offs = struct.unpack_from('<%dQ' % rank, buf, p + 8)
+                child = struct.unpack_from('<Q', buf, p + klen)[0]
+                p += klen + 8
+                if level:
+                    yield from walk(child)
+                else:
+                    yield offs, size, mask, child
+
+        if self._chunk_btree is not None and self._chunk_btree != _UNDEF:
+            yield from walk(self._chunk_btree)
+
+    def _read_chunked(self):
+        out = np.zeros(self.shape, self._dtype)
+        cshape = tuple(self._chunk_shape)
+        cbytes = int(np.prod(cshape, dtype=np.int64)) * self._dtype.itemsize
+        for offs, size, mask, addr in self.chunks():
+            raw = self._h5._buf[addr:addr + size]
+            if self._filters:
+                raw = _defilter(raw, self._filters, mask, cbytes)
+            if len(raw) < cbytes:
+                raise Hdf5FormatError('short chunk in ' + self.name)
+            chunk = np.frombuffer(raw, self._dtype, count=cbytes // self._dtype.itemsize).reshape(cshape)
+            dst = tuple(slice(o, min(o + c, d)) for o, c, d in zip(offs, cshape, self.shape))
+            src = tuple(slice(0, s.stop - s.start) for s in dst)
+            out[dst] = chunk[src]
+        return out
 
     def read(self):
         n = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
         nbytes = n * self._dtype.itemsize
+        if self._chunk_shape is not None:
+            return self._read_chunked()
         if self._compact is not None:
             raw = self._compact[:nbytes]
         else:
@@ -255,10 +440,23 @@ class Hdf5Group(_Node):
 
 class Hdf5File(Hdf5Group):
     def __init__(self, path):
-        with open(path, 'rb') as f:
-            self._buf = f.read()
+        # mapped, not read: a multi-read FAST5 is hundreds of MB and one read is a few KB of it
+        self._fh = open(path, 'rb')
+        try:
+            self._buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:                          # empty file
+            self._fh.close()
+            raise Hdf5FormatError('not an HDF5 file: ' + path)
+        self._cache = {}
+        try:
+            self._open_root(path)
+        except Exception:
+            self.close()
+            raise
+
+    def _open_root(self, path):
         buf = self._buf
-        if buf[:8] != _SIGNATURE:
+        if len(buf) < 96 or buf[:8] != _SIGNATURE:
             raise Hdf5FormatError('not an HDF5 file: ' + path)
         if buf[8] != 0:
             raise Hdf5FormatError('unsupported superblock version %d' % buf[8])
@@ -270,11 +468,17 @@ class Hdf5File(Hdf5Group):
         # root symbol table entry follows the four addresses at byte 24
         root_entry = 24 + 4 * 8
         _name_off, ohdr = struct.unpack_from('<QQ', buf, root_entry)
-        self._cache = {}
         Hdf5Group.__init__(self, self, ohdr, '/')
 
     def close(self):
-        pass
+        if self._fh is not None:
+            self._cache = {}
+            try:
+                self._buf.close()
+            except BufferError:                     # a numpy view of the map is still alive
+                pass
+            self._fh.close()
+            self._fh = None
 
     def __enter__(self):
         return self
@@ -320,7 +524,7 @@ class Hdf5File(Hdf5Group):
 
         def heap_string(off):
             start = heap_data + off
-            return buf[start:buf.index(b'\0', start)].decode()
+            return buf[start:buf.find(b'\0', start)].decode()
 
         def walk(node):
             if buf[node:node + 4] == b'TREE':

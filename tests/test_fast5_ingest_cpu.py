@@ -1,0 +1,260 @@
+"""FAST5 ingest without h5py: the HDF5 writer, the Python reader
+(hdf5_min) and the native batch loader (libpb_fast5.so) against each other and against the
+in-memory trees the oracle runs on.  There is no libhdf5 in this image, so "real" files are the
+ones hdf5_write produces; the reader's group / attribute / contiguous-dataset code is also
+exercised on the reference's own h5py-written model files (tests/test_host_cpu.py)."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from fast5_files import write_fast5, to_single_read, vbz_encoder
+from poreplex_b200 import fast5_loader as FL
+from poreplex_b200 import hdf5_min as R
+from poreplex_b200 import hdf5_write as W
+
+
+@pytest.fixture(scope='module')
+def lib():
+    FL.build()
+    return FL.load()
+
+
+def _tree(n, seed=0, lengths=None, basecalls=True):
+    from oracle import fake_fast5, refshim
+    rng = np.random.default_rng(seed)
+    f5 = refshim.FakeFile()
+    sigs, ids = [], []
+    for i in range(n):
+        L = int(lengths[i]) if lengths is not None else int(rng.integers(900, 9000))
+        raw = np.clip(rng.normal(500, 80, L), -32768, 32767).astype(np.int16)
+        rid = '%08x-%04d-read' % (int(rng.integers(0, 2 ** 31)), i)
+        bc = fake_fast5.synth_basecall(L, rng) if basecalls else None
+        fake_fast5.add_read(f5, rid, raw, 8192.0, 1400.0 + i, 3.0 + (i % 7), 3012.0,
+                            channel=str(1 + i % 512), start_time=1000 * i, run_id='run%d' % (i % 3),
+                            sample_id='sample', basecall=bc)
+        sigs.append(raw)
+        ids.append(rid)
+    return f5, ids, sigs
+
+
+STORAGE = [None, dict(chunks=1000), dict(chunks=4096, gzip=1), dict(chunks=777, gzip=6, shuffle=True)]
+
+
+def test_header_symbols_all_exported(lib):
+    import re
+    hdr = open(FL.HEADER).read()
+    declared = sorted(set(re.findall(r'\b(pb2f_[a-z0-9_]+)\s*\(', hdr)))
+    assert declared and sorted(FL.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pb2f_abi_version() == 1
+
+
+@pytest.mark.parametrize('storage', STORAGE)
+def test_python_reader_round_trip(tmp_path, storage):
+    f5, ids, sigs = _tree(12, seed=1)
+    path = str(tmp_path / 'multi.fast5')
+    write_fast5(path, f5, signal_kw=storage, move_kw=dict(chunks=100, gzip=4) if storage else None)
+    with R.Hdf5File(path) as h:
+        assert 'UniqueGlobalKey' not in h
+        assert sorted(h.keys()) == sorted('read_' + r for r in ids)
+        for rid, sig in zip(ids, sigs):
+            g = h['read_' + rid]
+            node = g['Raw/Signal']
+            assert len(node) == len(sig) and np.array_equal(node[0:len(node)], sig)
+            assert g['Raw'].attrs['read_id'].decode() == rid
+            assert int(g['Raw'].attrs['duration']) == len(sig)
+            want = f5['read_' + rid]
+            for grp in ('channel_id', 'tracking_id'):
+                for k, v in want[grp].attrs.items():
+                    got = g[grp].attrs[k]
+                    assert (got.decode() == v.decode()) if isinstance(v, bytes) else (got == v), (grp, k)
+            t = 'Analyses/Basecall_1D_000/BaseCalled_template/'
+            assert g[t + 'Fastq'][()] == want[t + 'Fastq'][()]
+            assert np.array_equal(g[t + 'Move'][()], want[t + 'Move'][()])
+            assert g['Analyses/Basecall_1D_000'].name.rsplit('_', 1)[-1] == '000'
+
+
+def test_many_children_compound_and_empty(tmp_path):
+    """> 256 children (two B-tree levels), a compound table, an empty group, empty datasets."""
+    root = W.Group(attrs={'file_version': b'2.0', 'count': 700, 'ratio': 0.25,
+                          'vec': np.arange(4, dtype=np.int32)})
+    for i in range(700):
+        root.group('read_%05d' % i, attrs={'i': i})
+    ev = np.zeros(9, dtype=[('start', '<u8'), ('move', 'u1'), ('mean', '<f4'), ('kmer', 'S5')])
+    ev['start'] = np.arange(9) * 15
+    ev['mean'] = np.linspace(80, 120, 9)
+    ev['kmer'] = b'ACGUA'
+    root.group('tables').dataset('Events', ev)
+    root.group('empty')
+    root.dataset('nothing', np.zeros(0, np.int16))
+    root.dataset('nothing_chunked', np.zeros(0, np.int16), chunks=64, gzip=1)
+    path = str(tmp_path / 'wide.h5')
+    W.write_file(path, root)
+    with R.Hdf5File(path) as h:
+        keys = h.keys()
+        assert len(keys) == 704 and keys == sorted(keys)
+        assert h.attrs['count'] == 700 and h.attrs['ratio'] == 0.25
+        assert np.array_equal(h.attrs['vec'], np.arange(4))
+        assert all(h['read_%05d' % i].attrs['i'] == i for i in (0, 1, 255, 256, 257, 699))
+        got = h['tables/Events'][()]
+        assert got.dtype.names == ev.dtype.names and all(np.array_equal(got[n], ev[n]) for n in ev.dtype.names)
+        assert h['empty'].keys() == [] and len(h['nothing'][()]) == 0 and len(h['nothing_chunked'][()]) == 0
+
+
+@pytest.mark.parametrize('storage', STORAGE)
+def test_native_file_api(lib, tmp_path, storage):
+    f5, ids, sigs = _tree(40, seed=2)
+    path = str(tmp_path / 'multi.fast5')
+    write_fast5(path, f5, signal_kw=storage)
+    with FL.Fast5File(path) as f:
+        assert f.is_multiread
+        assert f.read_names() == sorted(ids)
+        for rid, sig in zip(ids, sigs):
+            m = f.meta(rid)
+            want = f5['read_' + rid]
+            assert m['signal_length'] == len(sig) == m['duration']
+            assert m['read_id'] == rid and m['run_id'] == want['tracking_id'].attrs['run_id'].decode()
+            assert m['channel_number'] == want['channel_id'].attrs['channel_number'].decode()
+            for k in ('digitisation', 'offset', 'range', 'sampling_rate'):
+                assert m[k] == want['channel_id'].attrs[k]
+            assert m['start_time'] == want['Raw'].attrs['start_time']
+            assert np.array_equal(f.signal(rid), sig)
+        with pytest.raises(FL.Fast5Error):
+            f.meta('no-such-read')
+    # single-read layout (fast5_file.py:76-82): read_id None = the first read
+    spath = str(tmp_path / 'single.fast5')
+    write_fast5(spath, to_single_read(f5, ids[3]), signal_kw=storage)
+    with FL.Fast5File(spath) as f:
+        assert not f.is_multiread and f.read_names() == ['Read_17']
+        assert f.meta()['read_id'] == ids[3]
+        assert np.array_equal(f.signal(), sigs[3])
+        assert np.array_equal(f.signal(ids[3]), sigs[3])
+        with pytest.raises(FL.Fast5Error):          # fast5_file.py:105-108
+            f.meta(ids[4])
+
+
+def test_native_batch_loader(lib, tmp_path):
+    """Several files, every storage form, missing / foreign / truncated files and unknown reads:
+    packed layout equals SignalEngine.pack_reads', statuses follow signal_analyzer.py:90-92 and
+    signal_loader.py:200-207."""
+    from poreplex_b200.engine import SignalEngine
+    reads, want = [], []
+    for k, storage in enumerate(STORAGE):
+        f5, ids, sigs = _tree(30, seed=10 + k)
+        path = str(tmp_path / ('f%d.fast5' % k))
+        write_fast5(path, f5, signal_kw=storage)
+        reads += [(path, r) for r in ids]
+        want += sigs
+    order = np.random.default_rng(0).permutation(len(reads))
+    reads = [reads[i] for i in order]
+    want = [want[i] for i in order]
+    garbage = str(tmp_path / 'garbage.fast5')
+    open(garbage, 'wb').write(b'this is not HDF5' * 100)
+    empty = str(tmp_path / 'empty.fast5')
+    open(empty, 'wb').close()
+    bad = [(str(tmp_path / 'gone.fast5'), 'x'), (garbage, 'x'), (empty, 'x'), (reads[0][0], 'unknown-read')]
+    allreads = reads[:50] + bad + reads[50:]
+    for threads in (1, 4):
+        out = FL.load_batch(allreads, threads=threads, full_meta=True)
+        st = out['status']
+        assert list(st[50:54]) == [FL.READ_DISAPPEARED, FL.READ_IRREGULAR, FL.READ_IRREGULAR, FL.READ_IRREGULAR]
+        ok = np.ones(len(allreads), bool)
+        ok[50:54] = False
+        assert (st[ok] == FL.READ_OK).all() and (out['lengths'][~ok] == 0).all()
+        assert (out['offsets'] % 8 == 0).all()
+        got = [out['raw'][o:o + n] for o, n in zip(out['offsets'][ok], out['lengths'][ok])]
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        # the same layout SignalEngine.pack_reads builds from in-memory arrays
+        praw, poff, plen = SignalEngine.pack_reads(want)
+        assert np.array_equal(poff, out['offsets'][ok])       # unreadable reads take no space
+        assert np.array_equal(plen, out['lengths'][ok])
+        assert [m['read_id'] for m, k in zip(out['meta'], ok) if k] == [r for _, r in reads]
+        assert (out['range'][ok] >= 1400.0).all() and (out['digitisation'][ok] == 8192.0).all()
+    assert FL.load_batch([])['raw'].size >= 0
+
+
+def test_truncated_files_never_crash(lib, tmp_path):
+    f5, ids, sigs = _tree(6, seed=3)
+    path = str(tmp_path / 'whole.fast5')
+    size = write_fast5(path, f5, signal_kw=dict(chunks=512, gzip=1))
+    blob = open(path, 'rb').read()
+    for cut in (8, 95, 96, 200, size // 4, size // 2, size - 9000, size - 100, size - 1):
+        tpath = str(tmp_path / ('cut_%d.fast5' % cut))
+        open(tpath, 'wb').write(blob[:cut])
+        out = FL.load_batch([(tpath, r) for r in ids], threads=2)
+        for i, (s, n) in enumerate(zip(out['status'], out['lengths'])):
+            if s == FL.READ_OK:                     # whatever still decodes must be right
+                assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + n], sigs[i])
+            else:
+                assert s == FL.READ_IRREGULAR and n == 0
+    # flipped bytes inside the compressed chunks: zlib notices, the read becomes irregular
+    dam = bytearray(blob)
+    for p in range(size // 2, size // 2 + 4000, 37):
+        dam[p] ^= 0x5A
+    dpath = str(tmp_path / 'damaged.fast5')
+    open(dpath, 'wb').write(bytes(dam))
+    out = FL.load_batch([(dpath, r) for r in ids])
+    assert set(out['status']) <= {FL.READ_OK, FL.READ_IRREGULAR}
+
+
+@pytest.mark.parametrize('version,zigzag,level', [(1, True, 1), (1, True, 0), (0, True, 3), (1, False, 1)])
+def test_vbz_self_consistency(lib, tmp_path, version, zigzag, level):
+    """VBZ (filter 32020) decoders of both readers against an encoder written from the same
+    description -- NOT against ONT's plugin, which does not exist in this image."""
+    f5, ids, sigs = _tree(8, seed=4)
+    path = str(tmp_path / 'vbz.fast5')
+    write_fast5(path, f5, signal_kw=dict(chunks=2000, encoder=vbz_encoder(np.int16, version, zigzag, level)))
+    with R.Hdf5File(path) as h:
+        for rid, sig in zip(ids, sigs):
+            assert np.array_equal(h['read_' + rid + '/Raw/Signal'][()], sig)
+    out = FL.load_batch([(path, r) for r in ids])
+    assert (out['status'] == FL.READ_OK).all()
+    for i, sig in enumerate(sigs):
+        assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + out['lengths'][i]], sig)
+
+
+def test_native_reader_walks_h5py_written_files(lib):
+    """The reference's model files were written by h5py / libhdf5: the native group walker must
+    get through their symbol tables (no reads in them, so the answer is an empty list)."""
+    root = '/root/reference/poreplex/presets/MIN106-RNA001'
+    if not os.path.isdir(root):
+        pytest.skip('reference tree not present')
+    for name in ('scaler-r3.hdf5', 'demux-tetra-r4.hdf5'):
+        with FL.Fast5File(os.path.join(root, name)) as f:
+            assert f.is_multiread and f.read_names() == []
+        with R.Hdf5File(os.path.join(root, name)) as h:
+            assert 'model_weights' in h
+
+
+def test_fast5_source_over_hdf5_min(tmp_path, monkeypatch):
+    """Fast5Source (the drop-in's FAST5 access) over real files through hdf5_min gives what it
+    gives over the in-memory h5py the golden runs use."""
+    import sys
+    from oracle import refshim
+    from poreplex_b200 import fast5_source as FS
+    f5, ids, sigs = _tree(5, seed=5)
+    path = str(tmp_path / 'reads.fast5')
+    write_fast5(path, f5, signal_kw=dict(chunks=1024, gzip=1, shuffle=True), move_kw=dict(chunks=64, gzip=1))
+    refshim.install_fake_h5py()
+    refshim.clear_fast5()
+    refshim.register_fast5(path, f5)
+    via_fake = [FS.Fast5Source(path, r) for r in ids]
+    monkeypatch.setitem(sys.modules, 'h5py', None)          # "import h5py" now fails
+    via_min = [FS.Fast5Source(path, r) for r in ids]
+    for a, b in zip(via_fake, via_min):
+        for k in ('duration', 'start_time', 'read_id', 'channel_number', 'digitization', 'offset',
+                  'range', 'sampling_rate', 'run_id', 'sample_id', 'is_multiread'):
+            assert getattr(a, k) == getattr(b, k), k
+        assert np.array_equal(a.raw_int16(), b.raw_int16())
+        sa, sb = a.get_basecall(want_events=True), b.get_basecall(want_events=True)
+        assert set(sa) == set(sb)
+        for k in sa:
+            if k == 'events':
+                assert set(sa[k]) == set(sb[k])
+                assert all(np.array_equal(sa[k][c], sb[k][c]) for c in sa[k])
+            else:
+                assert sa[k] == sb[k], k
+        b.close()
