@@ -410,15 +410,38 @@ void unshuffle(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, uint32_t es
     buf.swap(tmp);
 }
 
-void inflate_chunk(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, size_t expected)
+// per-thread working memory: two byte buffers and one zlib stream that is reset, not rebuilt,
+// between chunks (inflateInit allocates the 32 KB window every time)
+struct Scratch {
+    std::vector<uint8_t> a, b;
+    z_stream zs;
+    bool zs_ready = false;
+    Scratch() { memset(&zs, 0, sizeof zs); }
+    ~Scratch() { if (zs_ready) inflateEnd(&zs); }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
+void inflate_chunk(std::vector<uint8_t> &buf, Scratch &s, size_t expected)
 {
+    std::vector<uint8_t> &tmp = s.b;
     size_t cap = expected ? expected : buf.size() * 4 + 64;
     for (int attempt = 0; attempt < 8; attempt++) {
+        if (!s.zs_ready) {
+            if (inflateInit(&s.zs) != Z_OK) bad("zlib: cannot initialise");
+            s.zs_ready = true;
+        } else if (inflateReset(&s.zs) != Z_OK) {
+            bad("zlib: cannot reset");
+        }
         tmp.resize(cap);
-        uLongf out = (uLongf)cap;
-        const int rc = uncompress(tmp.data(), &out, buf.data(), (uLong)buf.size());
-        if (rc == Z_OK) { tmp.resize(out); buf.swap(tmp); return; }
-        if (rc != Z_BUF_ERROR) bad("zlib: corrupt chunk (%d)", rc);
+        s.zs.next_in = buf.data();
+        s.zs.avail_in = (uInt)buf.size();
+        s.zs.next_out = tmp.data();
+        s.zs.avail_out = (uInt)cap;
+        const int rc = inflate(&s.zs, Z_FINISH);
+        if (rc == Z_STREAM_END) { tmp.resize(cap - s.zs.avail_out); buf.swap(tmp); return; }
+        if (rc != Z_BUF_ERROR && rc != Z_OK) bad("zlib: corrupt chunk (%d)", rc);
+        if (s.zs.avail_out != 0) bad("zlib: truncated chunk");
         cap *= 2;
     }
     bad("zlib: chunk larger than expected");
@@ -508,8 +531,6 @@ void vbz_decode(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, const std:
     buf.swap(out);
 }
 
-struct Scratch { std::vector<uint8_t> a, b; };
-
 void defilter(std::vector<uint8_t> &buf, Scratch &s, const std::vector<Filter> &filters,
               uint32_t mask, size_t expected)
 {
@@ -517,7 +538,7 @@ void defilter(std::vector<uint8_t> &buf, Scratch &s, const std::vector<Filter> &
         if (mask & (1u << k)) continue;
         const Filter &f = filters[k];
         switch (f.id) {
-        case 1: inflate_chunk(buf, s.b, expected); break;
+        case 1: inflate_chunk(buf, s, expected); break;
         case 2: unshuffle(buf, s.b, f.cd.empty() ? 1 : f.cd[0]); break;
         case 3: if (buf.size() < 4) bad("fletcher32: short chunk"); buf.resize(buf.size() - 4); break;
         case 32020: vbz_decode(buf, s.b, f.cd); break;
