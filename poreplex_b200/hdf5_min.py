@@ -415,16 +415,22 @@ class Hdf5Group(_Node):
         except KeyError:
             return False
 
+    def _find(self, name):
+        """Object header address of child ``name`` (None if absent) by descending the B-tree
+        through its keys: O(log n), no listing of a 4000-read root group per lookup."""
+        if self._children is not None:
+            return self._children.get(name)
+        return self._h5._find_in_group(self._stab[0], self._stab[1], name.encode())
+
     def __getitem__(self, path):
         node = self
         for part in [p for p in path.split('/') if p]:
             if not isinstance(node, Hdf5Group):
                 raise KeyError(path)
-            children = node._load()
-            if part not in children:
+            addr = node._find(part)
+            if addr is None:
                 raise KeyError(path)
-            node = node._h5._open(children[part],
-                                  (node.name.rstrip('/') + '/' + part))
+            node = node._h5._open(addr, (node.name.rstrip('/') + '/' + part))
         return node
 
     def visit_datasets(self, prefix=''):
@@ -547,6 +553,39 @@ class Hdf5File(Hdf5Group):
                 raise Hdf5FormatError('bad group node signature')
 
         yield from walk(btree_addr)
+
+    def _find_in_group(self, node, heap_addr, name):
+        buf = self._buf
+        if buf[heap_addr:heap_addr + 4] != b'HEAP':
+            raise Hdf5FormatError('bad local heap signature')
+        heap_data = struct.unpack_from('<Q', buf, heap_addr + 24)[0]
+
+        def heap_bytes(off):
+            start = heap_data + off
+            return buf[start:buf.find(b'\0', start)]
+
+        for _depth in range(64):
+            sig = buf[node:node + 4]
+            if sig == b'TREE':
+                used = struct.unpack_from('<H', buf, node + 6)[0]
+                p = node + 24                       # key0, child0, key1, child1, ...
+                for i in range(used):
+                    hi = heap_bytes(struct.unpack_from('<Q', buf, p + 16 * i + 16)[0])
+                    if name <= hi:
+                        node = struct.unpack_from('<Q', buf, p + 16 * i + 8)[0]
+                        break
+                else:
+                    return None
+            elif sig == b'SNOD':
+                nsym = struct.unpack_from('<H', buf, node + 6)[0]
+                for i in range(nsym):
+                    name_off, ohdr = struct.unpack_from('<QQ', buf, node + 8 + 40 * i)
+                    if heap_bytes(name_off) == name:
+                        return ohdr
+                return None
+            else:
+                raise Hdf5FormatError('bad group node signature')
+        raise Hdf5FormatError('group B-tree too deep')
 
     def _global_heap_object(self, coll_addr, index):
         buf = self._buf

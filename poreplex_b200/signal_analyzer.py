@@ -189,6 +189,22 @@ class SignalAnalyzer:
     def close(self):
         pass
 
+    def prefetch_signals(self, reads):
+        """Raw signals of the whole batch through the native FAST5 loader (thread pool, one open
+        per file) when the files are read without h5py; {index in reads: int16 array}.  Reads it
+        cannot serve are simply absent and go through Fast5Source one by one."""
+        from . import fast5_source
+        if fast5_source._h5py() is not fast5_source._MinimalH5py or not reads:
+            return {}
+        try:
+            from . import fast5_loader
+            b = fast5_loader.load_batch(reads, inputdir=self.config['inputdir'],
+                                        threads=int(self.config.get('ingest_threads', 0)) or None)
+        except Exception:
+            return {}
+        return {i: b['raw'][b['offsets'][i]:b['offsets'][i] + b['lengths'][i]]
+                for i in range(len(reads)) if b['status'][i] == fast5_loader.READ_OK}
+
     def process(self, reads):
         inputdir = self.config['inputdir']
         eng = self.engine
@@ -196,7 +212,8 @@ class SignalAnalyzer:
 
         # STAGE A: open reads, early exits (signal_analyzer.py:84-104)
         nextprocs = []
-        for f5file, read_id in reads:
+        prefetched = self.prefetch_signals(reads)
+        for ridx, (f5file, read_id) in enumerate(reads):
             if not os.path.exists(os.path.join(inputdir, f5file)):
                 results.append({'filename': f5file, 'status': 'disappeared'})
                 continue
@@ -211,7 +228,9 @@ class SignalAnalyzer:
                 if npread.is_stopped():
                     results.append(npread.report())
                 else:
-                    npread._raw = npread.fast5.raw_int16()
+                    npread._raw = prefetched.get(ridx)
+                    if npread._raw is None:
+                        npread._raw = npread.fast5.raw_int16()
                     nextprocs.append(SignalAnalysis(npread, self))
                     loaded.append(npread)
             except Exception as exc:

@@ -64,6 +64,54 @@ def test_process_batch_matches_reference_dicts(name, preset, preset_short, eng_s
     pickle.loads(pickle.dumps(got))                 # crosses a process pool in pipeline.py
 
 
+@pytest.mark.parametrize('name', ['short4k', 'chimera40k'])
+def test_process_batch_over_real_fast5_files(name, preset, preset_short, eng_stock, eng_short,
+                                             monkeypatch, tmp_path):
+    """The same golden comparison with the reads in REAL FAST5 files on disk (gzip + shuffle
+    chunked Signal / Move datasets) and no h5py at all: raw signals come through the native batch
+    loader (libpb_fast5.so), metadata and basecall tables through poreplex_b200.hdf5_min."""
+    import sys
+    from oracle import fake_fast5, refshim
+    from fast5_files import write_fast5
+    from poreplex_b200 import fast5_loader, fast5_source, signal_analyzer as sa
+    z, doc = load_golden(name)
+    tree = refshim.FakeFile()
+    ids = [str(s) for s in z['read_ids']]
+    reads_np, basecalls = golden_reads(z), golden_basecalls(z)
+    for i, rid in enumerate(ids):
+        raw = reads_np['raw'][i]
+        if 'length' in reads_np:
+            raw = raw[:int(reads_np['length'][i])]
+        fake_fast5.add_read(tree, rid, raw, reads_np['digitisation'][i], reads_np['range'][i],
+                            reads_np['offset'][i], reads_np['sampling_rate'][i],
+                            channel=str(1 + i % 512), start_time=1000 * i,
+                            basecall=None if basecalls is None else basecalls[i])
+    write_fast5(str(tmp_path / 'reads.fast5'), tree, signal_kw=dict(chunks=4096, gzip=1, shuffle=True),
+                move_kw=dict(chunks=512, gzip=1))
+    fast5_loader.build()
+    monkeypatch.setitem(sys.modules, 'h5py', None)              # "import h5py" fails from here on
+    assert fast5_source._h5py() is fast5_source._MinimalH5py
+    p = preset_short if doc['preset'] == 'bench-short' else preset
+    reads = [tuple(r) for r in doc['reads']]
+    calls = []
+    real = fast5_loader.load_batch
+    monkeypatch.setattr(fast5_loader, 'load_batch', lambda *a, **k: calls.append(1) or real(*a, **k))
+    checked = 0
+    for key, sw in (('results_trim_barcoding', dict(trim_adapter=True, barcoding=True)),
+                    ('results_all_switches', dict(trim_adapter=True, barcoding=True,
+                                                  measure_polya=True, filter_unsplit_reads=True))):
+        if key not in doc:
+            continue
+        got = sa.process_batch(0, reads, _config(p, str(tmp_path), **sw))
+        assert not isinstance(got, tuple), got
+        want = doc[key]
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert normalise_result(g) == normalise_result(w)
+        checked += 1
+    assert checked and len(calls) == checked                    # the native loader did serve the batches
+
+
 def test_unbuilt_switches_fail_loudly(preset, eng_stock):
     from poreplex_b200 import signal_analyzer as sa
     z, doc, tmp = _serve('stock16k')
