@@ -31,6 +31,9 @@
 namespace {
 
 constexpr uint64_t UNDEF = ~0ull;
+// sanity limits: sizes read from a (possibly damaged) file never drive an allocation beyond these
+constexpr uint64_t MAX_SIGNAL = 1ull << 31;        // samples per read
+constexpr uint64_t MAX_CHUNK_BYTES = 1ull << 28;   // decoded bytes per chunk
 
 struct FormatError : std::runtime_error { using std::runtime_error::runtime_error; };
 struct NotFound : std::runtime_error { using std::runtime_error::runtime_error; };
@@ -433,6 +436,7 @@ void inflate_chunk(std::vector<uint8_t> &buf, Scratch &s, size_t expected)
         } else if (inflateReset(&s.zs) != Z_OK) {
             bad("zlib: cannot reset");
         }
+        if (cap > 2 * MAX_CHUNK_BYTES) bad("zlib: chunk larger than any plausible size");
         tmp.resize(cap);
         s.zs.next_in = buf.data();
         s.zs.avail_in = (uInt)buf.size();
@@ -469,7 +473,8 @@ void svb_decode(const uint8_t *src, size_t len, size_t count, int key_bits, std:
 // ONT VBZ (filter 32020): uint32 uncompressed size, optional zstd frame, streamvbyte of the
 // (delta, zigzag) coded integers; version 1 codes 2-byte integers with 1-bit keys.  Layout per
 // ONT's published vbz_compression; NOT checked against a file written by ONT's plugin.
-void vbz_decode(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, const std::vector<uint32_t> &cd)
+void vbz_decode(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, const std::vector<uint32_t> &cd,
+                size_t expected)
 {
     const uint32_t version = cd.size() > 0 ? cd[0] : 0, isize = cd.size() > 1 ? cd[1] : 0;
     const uint32_t zigzag = cd.size() > 2 ? cd[2] : 0, level = cd.size() > 3 ? cd[3] : 0;
@@ -477,6 +482,7 @@ void vbz_decode(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, const std:
     if (buf.size() < 4) bad("VBZ: short chunk");
     uint32_t size;
     memcpy(&size, buf.data(), 4);
+    if (size > (expected ? expected : MAX_CHUNK_BYTES)) bad("VBZ: chunk decodes to more than its size");
     const uint8_t *body = buf.data() + 4;
     size_t blen = buf.size() - 4;
     if (level != 0) {
@@ -484,6 +490,7 @@ void vbz_decode(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, const std:
         if (!z.ok()) bad("VBZ-compressed dataset: libzstd is not available");
         unsigned long long fs = z.frame_size(body, blen);
         if (fs >= (1ull << 62)) fs = (unsigned long long)size * 2 + 64;
+        if (fs > 5ull * size + 1024) bad("VBZ: implausible zstd frame size");
         tmp.resize((size_t)fs ? (size_t)fs : 1);
         const size_t got = z.decompress(tmp.data(), tmp.size(), body, blen);
         if (z.is_error(got)) bad("VBZ: zstd decompression failed");
@@ -541,7 +548,7 @@ void defilter(std::vector<uint8_t> &buf, Scratch &s, const std::vector<Filter> &
         case 1: inflate_chunk(buf, s, expected); break;
         case 2: unshuffle(buf, s.b, f.cd.empty() ? 1 : f.cd[0]); break;
         case 3: if (buf.size() < 4) bad("fletcher32: short chunk"); buf.resize(buf.size() - 4); break;
-        case 32020: vbz_decode(buf, s.b, f.cd); break;
+        case 32020: vbz_decode(buf, s.b, f.cd, expected); break;
         default: bad("unsupported filter %u", (unsigned)f.id);
         }
     }
@@ -561,6 +568,7 @@ void read_int16(const pb2f_file &f, const Dataset &d, int16_t *dst, Scratch &s)
     }
     if (d.chunk.size() != 1 || d.chunk[0] == 0) bad("unexpected chunk shape");
     const uint64_t clen = d.chunk[0];
+    if (clen * 2 > MAX_CHUNK_BYTES) bad("implausible chunk length %llu", (unsigned long long)clen);
     memset(dst, 0, n * 2);                         // chunks never written read as the fill value
     if (d.btree == UNDEF) return;
     struct Walk {
@@ -651,6 +659,12 @@ void load_meta(pb2f_file &f, const char *read_id, pb2f_read_meta &out, Dataset *
     if (sig == UNDEF) throw NotFound("read without a Signal dataset");
     const Dataset d = f.dataset(sig);
     if (d.dims.size() != 1) bad("Signal is not one-dimensional");
+    if (d.dims[0] > MAX_SIGNAL) bad("implausible Signal length %llu", (unsigned long long)d.dims[0]);
+    if ((d.layout == 0 || (d.layout == 1 && d.addr != UNDEF)))
+        f.m.at(d.addr, d.dims[0] * 2);             // contiguous data must lie inside the file
+    else if (d.dims[0] * 2 > f.m.n * 256)          // no filter here packs better than 256:1
+        bad("Signal length %llu is implausible for a %llu-byte file",
+            (unsigned long long)d.dims[0], (unsigned long long)f.m.n);
     out.signal_length = (int64_t)d.dims[0];
     if (sig_out) *sig_out = d;
 }

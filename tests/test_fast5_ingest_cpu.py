@@ -200,6 +200,40 @@ def test_truncated_files_never_crash(lib, tmp_path):
     assert set(out['status']) <= {FL.READ_OK, FL.READ_IRREGULAR}
 
 
+def test_mutated_files_never_crash(lib, tmp_path):
+    """Random byte damage anywhere in the file (headers, B-trees, heaps, chunk data): every read
+    comes back okay or irregular_fast5; sizes taken from the damaged file never drive a crash, an
+    endless walk or a giant allocation (bounds-checked map + sanity limits in fast5_loader.cpp)."""
+    f5, ids, sigs = _tree(5, seed=6)
+    path = str(tmp_path / 'whole.fast5')
+    rng = np.random.default_rng(123)
+    for storage in (dict(chunks=512, gzip=1, shuffle=True),
+                    dict(chunks=1000, encoder=vbz_encoder(np.int16, 1, True, 1)), None):
+        size = write_fast5(path, f5, signal_kw=storage)
+        blob = np.frombuffer(open(path, 'rb').read(), np.uint8)
+        mpath = str(tmp_path / 'mutant.fast5')
+        for trial in range(150):
+            m = blob.copy()
+            if trial % 3 == 0:                      # a burst in the metadata-heavy tail of the file
+                p0 = int(rng.integers(size // 2, size - 64))
+                m[p0:p0 + 64] = rng.integers(0, 256, 64)
+            else:                                   # scattered single bytes, biased to 0x00 / 0xFF
+                pos = rng.integers(8, size, int(rng.integers(1, 40)))
+                m[pos] = rng.choice([0, 255, 1, 128, int(rng.integers(0, 256))], len(pos))
+            m.tofile(mpath)
+            out = FL.load_batch([(mpath, r) for r in ids] + [(mpath, None)], threads=2)
+            assert set(out['status']) <= {FL.READ_OK, FL.READ_IRREGULAR}
+            assert (out['lengths'] >= 0).all() and out['lengths'].sum() < 1 << 24
+            try:
+                with R.Hdf5File(mpath) as h:        # the Python reader: exceptions only
+                    for rid in ids:
+                        node = h['read_' + rid + '/Raw/Signal']
+                        if node.shape and node.shape[0] < 1 << 20:
+                            node[0:len(node)]
+            except Exception:
+                pass
+
+
 @pytest.mark.parametrize('version,zigzag,level', [(1, True, 1), (1, True, 0), (0, True, 3), (1, False, 1)])
 def test_vbz_self_consistency(lib, tmp_path, version, zigzag, level):
     """VBZ (filter 32020) decoders of both readers against an encoder written from the same
