@@ -100,8 +100,6 @@ def _as_array(value):
     if isinstance(value, (bytes, np.bytes_)):
         b = bytes(value)
         return np.array(b, dtype='S%d' % max(len(b) + 1, 1)), ()
-    if isinstance(value, str):
-        return _as_array(value.encode())
     if isinstance(value, bool):
         return np.array(value, np.int8), ()
     if isinstance(value, int):
@@ -122,6 +120,17 @@ def _attribute(name, value):
     return body + np.ascontiguousarray(a).tobytes()
 
 
+_VLEN_STR = struct.pack('<BBBBI', 0x19, 0x01, 0x01, 0, 16) + struct.pack('<BBBBI', 0x13, 0x00, 0, 0, 1)
+
+
+def _attribute_raw(name, dt, ds, payload):
+    nm = name.encode() + b'\0'
+    body = struct.pack('<BBHHH', 1, 0, len(nm), len(dt), len(ds))
+    body += nm.ljust(_pad8(len(nm)), b'\0') + dt.ljust(_pad8(len(dt)), b'\0') + \
+        ds.ljust(_pad8(len(ds)), b'\0')
+    return body + payload
+
+
 def _shuffle(raw, elsize):
     a = np.frombuffer(raw, np.uint8)
     n = len(a) // elsize
@@ -138,6 +147,18 @@ class _Writer:
         addr = len(self.buf)
         self.buf += data
         return addr
+
+    def attribute(self, name, value):
+        """``str`` values become variable-length UTF-8 strings in a global heap collection (what
+        h5py writes for ``attrs[k] = 'text'``); everything else is stored inline."""
+        if not isinstance(value, str):
+            return _attribute(name, value)
+        data = value.encode()
+        obj = struct.pack('<HHIQ', 1, 1, 0, len(data)) + data.ljust(_pad8(len(data)), b'\0')
+        size = 16 + len(obj) + 16                       # header, the object, the free-space object
+        coll = self.alloc(b'GCOL' + struct.pack('<BBBBQ', 1, 0, 0, 0, size) + obj + bytes(16))
+        return _attribute_raw(name, _VLEN_STR, _dataspace(()),
+                              struct.pack('<IQI', len(data), coll, 1))
 
     # ---- B-trees --------------------------------------------------------------------
     def _btree(self, node_type, leaves, key_bytes, k):
@@ -200,7 +221,7 @@ class _Writer:
         heap_data = self.alloc(bytes(heap))
         hp = self.alloc(b'HEAP' + struct.pack('<BBBBQQQ', 0, 0, 0, 0, len(heap), 1, heap_data))
         msgs = [(0x0011, struct.pack('<QQ', bt, hp))]
-        msgs += [(0x000C, _attribute(k, v)) for k, v in g.attrs.items()]
+        msgs += [(0x000C, self.attribute(k, v)) for k, v in g.attrs.items()]
         return self._header(msgs), bt, hp
 
     def dataset(self, d):
@@ -251,7 +272,7 @@ class _Writer:
                     if len(cd) & 1:
                         body += b'\0' * 4
                 msgs.append((0x000B, body))
-        msgs += [(0x000C, _attribute(k, v)) for k, v in d.attrs.items()]
+        msgs += [(0x000C, self.attribute(k, v)) for k, v in d.attrs.items()]
         return self._header(msgs)
 
 

@@ -136,6 +136,34 @@ def test_native_file_api(lib, tmp_path, storage):
             f.meta(ids[4])
 
 
+def test_variable_length_string_attributes(lib, tmp_path):
+    """h5py stores ``attrs[k] = 'text'`` as variable-length UTF-8 strings in a global heap (what
+    ont_fast5_api-written files carry); MinKNOW-style fixed-length strings are the default case of
+    the other tests.  Both readers must serve both."""
+    from poreplex_b200 import fast5_source as FS
+    import sys
+    f5, ids, sigs = _tree(6, seed=7, basecalls=False)
+    for rid in ids:
+        g = f5['read_' + rid]
+        g['Raw'].attrs['read_id'] = rid                                  # str -> vlen
+        for k in ('run_id', 'sample_id'):
+            g['tracking_id'].attrs[k] = g['tracking_id'].attrs[k].decode() + '-\u00b5'
+        g['channel_id'].attrs['channel_number'] = g['channel_id'].attrs['channel_number'].decode()
+    path = str(tmp_path / 'vlen.fast5')
+    write_fast5(path, f5, signal_kw=dict(chunks=2048, gzip=1))
+    out = FL.load_batch([(path, r) for r in ids], full_meta=True)
+    assert (out['status'] == FL.READ_OK).all()
+    with R.Hdf5File(path) as h:
+        for i, rid in enumerate(ids):
+            want = f5['read_' + rid]
+            m = out['meta'][i]
+            assert m['read_id'] == rid and m['run_id'] == want['tracking_id'].attrs['run_id']
+            assert m['sample_id'] == 'sample-\u00b5' and m['channel_number'] == want['channel_id'].attrs['channel_number']
+            assert h['read_' + rid + '/tracking_id'].attrs['run_id'].decode() == want['tracking_id'].attrs['run_id']
+            assert h['read_' + rid + '/Raw'].attrs['read_id'].decode() == rid
+            assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + out['lengths'][i]], sigs[i])
+
+
 def test_native_batch_loader(lib, tmp_path):
     """Several files, every storage form, missing / foreign / truncated files and unknown reads:
     packed layout equals SignalEngine.pack_reads', statuses follow signal_analyzer.py:90-92 and
