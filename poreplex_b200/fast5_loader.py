@@ -145,6 +145,19 @@ class Fast5File:
         return out
 
 
+def get_read_ids(filename, basedir=None):
+    """``fast5_file.get_read_ids`` (fast5_file.py:37-58): the ``(filename, read_id)`` pairs of
+    one file -- what pipeline.py:324,363 queues for ``process_batch``."""
+    path = filename if basedir is None else os.path.join(basedir, filename)
+    with Fast5File(path) as f:
+        if f.is_multiread:
+            return [(filename, rid) for rid in f.read_names()]
+        try:
+            return [(filename, f.meta()['read_id'])]
+        except Fast5Error:                                   # the reference's KeyError branch
+            return []
+
+
 def _ptr(a, typ):
     return a.ctypes.data_as(C.POINTER(typ))
 

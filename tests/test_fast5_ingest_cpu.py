@@ -124,9 +124,11 @@ def test_native_file_api(lib, tmp_path, storage):
             assert np.array_equal(f.signal(rid), sig)
         with pytest.raises(FL.Fast5Error):
             f.meta('no-such-read')
+    assert FL.get_read_ids('multi.fast5', str(tmp_path)) == [('multi.fast5', r) for r in sorted(ids)]
     # single-read layout (fast5_file.py:76-82): read_id None = the first read
     spath = str(tmp_path / 'single.fast5')
     write_fast5(spath, to_single_read(f5, ids[3]), signal_kw=storage)
+    assert FL.get_read_ids(spath) == [(spath, ids[3])]
     with FL.Fast5File(spath) as f:
         assert not f.is_multiread and f.read_names() == ['Read_17']
         assert f.meta()['read_id'] == ids[3]
