@@ -11,8 +11,8 @@
  * (the step immediately before the accelerated path.)
  *
  * Supported HDF5 subset: superblock version 0 (8-byte offsets), version-1 object headers,
- * symbol-table groups, contiguous / compact / chunked (v1 B-tree) datasets, filters deflate (1),
- * shuffle (2), fletcher32 (3) and ONT VBZ (32020; needs libzstd.so.1 at run time).  Anything else
+ * symbol-table groups, contiguous / compact / chunked (v1 B-tree) datasets, filters deflate (1;
+ * own table-driven inflater, no zlib), shuffle (2), fletcher32 (3) and ONT VBZ (32020; needs libzstd.so.1 at run time).  Anything else
  * is reported as PB2F_EFORMAT, never guessed at.
  */
 #ifndef POREPLEX_B200_FAST5_H
@@ -88,6 +88,11 @@ int64_t pb2f_batch_plan(const pb2f_batch *b, int64_t *raw_offsets, int64_t *raw_
 int pb2f_batch_read(pb2f_batch *b, int16_t *raw, int64_t raw_capacity, const int64_t *raw_offsets,
                     int n_threads);
 void pb2f_batch_close(pb2f_batch *b);
+
+/* The inflater the deflate filter uses (csrc_host/inflate_fast.h), on its own: one complete zlib
+ * stream (RFC 1950) -> dst.  Returns the number of bytes written, PB2F_ENOSPC when dst is too
+ * small, PB2F_EFORMAT for truncated / corrupt input or an Adler-32 mismatch. */
+int64_t pb2f_inflate(const void *src, int64_t src_len, void *dst, int64_t dst_capacity);
 
 #ifdef __cplusplus
 }

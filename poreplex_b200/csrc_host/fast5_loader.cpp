@@ -26,7 +26,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
-#include <zlib.h>
+#include "inflate_fast.h"
 
 namespace {
 
@@ -413,16 +413,11 @@ void unshuffle(std::vector<uint8_t> &buf, std::vector<uint8_t> &tmp, uint32_t es
     buf.swap(tmp);
 }
 
-// per-thread working memory: two byte buffers and one zlib stream that is reset, not rebuilt,
-// between chunks (inflateInit allocates the 32 KB window every time)
+// per-thread working memory: two byte buffers and the Huffman tables of the inflater (35 KB)
 struct Scratch {
     std::vector<uint8_t> a, b;
-    z_stream zs;
-    bool zs_ready = false;
-    Scratch() { memset(&zs, 0, sizeof zs); }
-    ~Scratch() { if (zs_ready) inflateEnd(&zs); }
-    Scratch(const Scratch &) = delete;
-    Scratch &operator=(const Scratch &) = delete;
+    std::unique_ptr<pbinf::Tables> tables;
+    Scratch() : tables(new pbinf::Tables) {}
 };
 
 void inflate_chunk(std::vector<uint8_t> &buf, Scratch &s, size_t expected)
@@ -430,25 +425,14 @@ void inflate_chunk(std::vector<uint8_t> &buf, Scratch &s, size_t expected)
     std::vector<uint8_t> &tmp = s.b;
     size_t cap = expected ? expected : buf.size() * 4 + 64;
     for (int attempt = 0; attempt < 8; attempt++) {
-        if (!s.zs_ready) {
-            if (inflateInit(&s.zs) != Z_OK) bad("zlib: cannot initialise");
-            s.zs_ready = true;
-        } else if (inflateReset(&s.zs) != Z_OK) {
-            bad("zlib: cannot reset");
-        }
-        if (cap > 2 * MAX_CHUNK_BYTES) bad("zlib: chunk larger than any plausible size");
+        if (cap > 2 * MAX_CHUNK_BYTES) bad("deflate: chunk larger than any plausible size");
         tmp.resize(cap);
-        s.zs.next_in = buf.data();
-        s.zs.avail_in = (uInt)buf.size();
-        s.zs.next_out = tmp.data();
-        s.zs.avail_out = (uInt)cap;
-        const int rc = inflate(&s.zs, Z_FINISH);
-        if (rc == Z_STREAM_END) { tmp.resize(cap - s.zs.avail_out); buf.swap(tmp); return; }
-        if (rc != Z_BUF_ERROR && rc != Z_OK) bad("zlib: corrupt chunk (%d)", rc);
-        if (s.zs.avail_out != 0) bad("zlib: truncated chunk");
+        const int64_t got = pbinf::zlib_decompress(buf.data(), buf.size(), tmp.data(), cap, *s.tables);
+        if (got >= 0) { tmp.resize((size_t)got); buf.swap(tmp); return; }
+        if (got != pbinf::ERR_OVERFLOW) bad("deflate: corrupt chunk (%lld)", (long long)got);
         cap *= 2;
     }
-    bad("zlib: chunk larger than expected");
+    bad("deflate: chunk larger than expected");
 }
 
 // streamvbyte: `count` little-endian codes, keys first (key_bits = 1: svb16, 1..2 bytes;
@@ -927,5 +911,16 @@ int pb2f_batch_read(pb2f_batch *b, int16_t *raw, int64_t raw_capacity, const int
 }
 
 void pb2f_batch_close(pb2f_batch *b) { delete b; }
+
+int64_t pb2f_inflate(const void *src, int64_t src_len, void *dst, int64_t dst_capacity)
+{
+    if (!src || src_len < 0 || (!dst && dst_capacity > 0) || dst_capacity < 0) return PB2F_EINVAL;
+    static thread_local std::unique_ptr<pbinf::Tables> tables;
+    if (!tables) tables.reset(new pbinf::Tables);
+    const int64_t got = pbinf::zlib_decompress((const uint8_t *)src, (size_t)src_len, (uint8_t *)dst,
+                                               (size_t)dst_capacity, *tables);
+    if (got == pbinf::ERR_OVERFLOW) return PB2F_ENOSPC;
+    return got < 0 ? PB2F_EFORMAT : got;
+}
 
 }  // extern "C"

@@ -16,6 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc_host', 'fast5_loader.cpp')
+SRC_DEPS = [os.path.join(HERE, 'csrc_host', 'inflate_fast.h')]
 LIB_PATH = os.path.join(HERE, 'libpb_fast5.so')
 HEADER = os.path.join(HERE, '..', 'include', 'poreplex_b200_fast5.h')
 
@@ -25,7 +26,7 @@ STATUS_NAMES = {READ_OK: 'okay', READ_DISAPPEARED: 'disappeared', READ_IRREGULAR
 EXPORTS = ['pb2f_abi_version', 'pb2f_last_error', 'pb2f_open', 'pb2f_close', 'pb2f_is_multiread',
            'pb2f_num_reads', 'pb2f_read_name', 'pb2f_read_meta_get', 'pb2f_read_signal',
            'pb2f_batch_open', 'pb2f_batch_meta', 'pb2f_batch_meta_full', 'pb2f_batch_plan',
-           'pb2f_batch_read', 'pb2f_batch_close']
+           'pb2f_batch_read', 'pb2f_batch_close', 'pb2f_inflate']
 
 
 class Fast5Error(Exception):
@@ -50,14 +51,14 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in (SRC, HEADER))
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in [SRC, HEADER] + SRC_DEPS)
 
 
 def build(force=False):
-    """g++ -> poreplex_b200/libpb_fast5.so (host code only: zlib, pthreads, dlopen of libzstd)."""
+    """g++ -> poreplex_b200/libpb_fast5.so (host code only: pthreads, dlopen of libzstd)."""
     if force or needs_build():
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-Wall', '-fPIC', '-shared', '-pthread',
-                               '-o', LIB_PATH, SRC, '-lz', '-ldl'])
+                               '-o', LIB_PATH, SRC, '-ldl'])
     return LIB_PATH
 
 
@@ -92,6 +93,8 @@ def load():
         L.pb2f_batch_read.argtypes = [vp, vp, C.c_int64, i64p, C.c_int]
         L.pb2f_batch_close.argtypes = [vp]
         L.pb2f_batch_close.restype = None
+        L.pb2f_inflate.argtypes = [vp, C.c_int64, vp, C.c_int64]
+        L.pb2f_inflate.restype = C.c_int64
         if L.pb2f_abi_version() != 1:
             raise RuntimeError('libpb_fast5.so: ABI version mismatch')
         _lib = L

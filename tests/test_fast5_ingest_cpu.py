@@ -322,3 +322,74 @@ def test_fast5_source_over_hdf5_min(tmp_path, monkeypatch):
             else:
                 assert sa[k] == sb[k], k
         b.close()
+
+
+# ---- the inflater behind the deflate filter (csrc_host/inflate_fast.h) against zlib -----------
+def _inflate(lib, src, cap):
+    import ctypes as C
+    dst = C.create_string_buffer(max(cap, 1))
+    n = lib.pb2f_inflate(src, len(src), dst, cap)
+    return n, dst.raw[:max(n, 0)]
+
+
+def _inflate_cases(rng):
+    yield b''
+    yield b'a'
+    for n in (1, 2, 7, 8, 9, 15, 16, 17, 100, 255, 256, 257, 258, 259, 270, 271, 272, 273, 300, 511,
+              512, 600, 1000, 4096, 8192, 65535, 65536, 65537):
+        yield bytes(rng.integers(0, 256, n, dtype=np.uint8))                        # incompressible
+        yield bytes(rng.integers(0, 4, n, dtype=np.uint8))                          # short codes
+        yield (b'the quick brown fox jumps over the lazy dog. ' * (n // 40 + 1))[:n]  # long matches
+        yield bytes(n)                                                              # distance-1 runs
+        yield (np.repeat(rng.normal(500, 60, n // 40 + 1), 20)[:n // 2] +
+               rng.normal(0, 12, n // 2)).astype(np.int16).tobytes()                # signal-like
+        yield bytes(np.tile(np.arange(7, dtype=np.uint8), n // 7 + 1)[:n])          # overlapping copies
+        yield bytes(np.tile(np.arange(3, dtype=np.uint8), n // 3 + 1)[:n])
+
+
+def test_inflater_matches_zlib(lib):
+    """Every block type (stored, fixed, dynamic), compression level and strategy zlib offers,
+    multi-block streams, small windows, sizes around the fast-loop margins (16 input / 272 output
+    bytes); exact-size and oversized destinations; too-small destinations and truncated streams are
+    errors."""
+    import zlib
+    rng = np.random.default_rng(0)
+    n_variants = 0
+    for data in _inflate_cases(rng):
+        variants = [zlib.compress(data, lvl) for lvl in (0, 1, 6, 9)]
+        for strat in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, strat)
+            variants.append(co.compress(data) + co.flush())
+        co, parts, step = zlib.compressobj(1), b'', max(len(data) // 5, 1)
+        for i in range(0, len(data), step):
+            parts += co.compress(data[i:i + step]) + co.flush(zlib.Z_FULL_FLUSH)
+        variants.append(parts + co.flush())
+        co = zlib.compressobj(9, zlib.DEFLATED, 9, 1)                                # 512-byte window
+        variants.append(co.compress(data) + co.flush())
+        for v in variants:
+            for cap in (len(data), len(data) + 1000):
+                n, out = _inflate(lib, v, cap)
+                assert n == len(data) and out == data, (len(data), n)
+            if data:
+                assert _inflate(lib, v, len(data) - 1)[0] == -5                      # PB2F_ENOSPC
+            for cut in (1, len(v) // 2, len(v) - 5, len(v) - 1):
+                if 0 <= cut < len(v):
+                    assert _inflate(lib, v[:cut], len(data) + 10)[0] == -3, cut      # PB2F_EFORMAT
+            n_variants += 1
+    assert n_variants > 1500
+
+
+def test_inflater_survives_corruption(lib):
+    """Bit flips anywhere in a stream: an error or -- never observed -- the right bytes; no crash,
+    no write past the destination (the buffer is sized exactly + a guard)."""
+    import zlib
+    rng = np.random.default_rng(1)
+    data = bytes(rng.integers(0, 64, 5000, dtype=np.uint8)) + b'xyz' * 700
+    for lvl in (1, 6):
+        v = zlib.compress(data, lvl)
+        for _ in range(3000):
+            m = bytearray(v)
+            for _k in range(int(rng.integers(1, 4))):
+                m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            n, out = _inflate(lib, bytes(m), len(data) + 300)
+            assert n < 0 or out == data
