@@ -52,6 +52,8 @@ def test_struct_layouts_match_header_sizes(native):
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pb2_lstm_weights), sizeof(pb2_scaler_params),
          sizeof(pb2_hmm_params), sizeof(pb2_demux_params), sizeof(pb2_batch), sizeof(pb2_results));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(pb2_polya_params), sizeof(pb2_polya_result),
+         sizeof(pb2_unsplit_params), sizeof(pb2_event_tables), sizeof(pb2_detector_params));
   return 0; }
 '''
     import tempfile
@@ -62,7 +64,24 @@ int main(void) {
     sizes = [int(x) for x in subprocess.check_output([os.path.join(d, 't')]).split()]
     N = native
     assert sizes == [C.sizeof(N.LstmWeights), C.sizeof(N.ScalerParams), C.sizeof(N.HmmParams),
-                     C.sizeof(N.DemuxParams), C.sizeof(N.Batch), C.sizeof(N.Results)]
+                     C.sizeof(N.DemuxParams), C.sizeof(N.Batch), C.sizeof(N.Results),
+                     C.sizeof(N.PolyaParams), C.sizeof(N.PolyaResult), C.sizeof(N.UnsplitParams),
+                     C.sizeof(N.EventTables), C.sizeof(N.DetectorParams)]
+
+
+def test_fast5_struct_layout_matches_header():
+    from poreplex_b200 import fast5_loader as FL
+    src = r'''
+#include <stdio.h>
+#include "poreplex_b200_fast5.h"
+int main(void) { printf("%zu\n", sizeof(pb2f_read_meta)); return 0; }
+'''
+    import tempfile
+    d = tempfile.mkdtemp()
+    open(os.path.join(d, 't.c'), 'w').write(src)
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', os.path.join(d, 't'),
+                           os.path.join(d, 't.c')])
+    assert int(subprocess.check_output([os.path.join(d, 't')])) == C.sizeof(FL.ReadMeta)
 
 
 def test_no_gpu_means_loud_failure(native):
