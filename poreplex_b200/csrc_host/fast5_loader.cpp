@@ -263,6 +263,11 @@ struct pb2f_file {
         else if (t.cls == 9) {
             t.vlen_string = (bits & 0x0F) == 1;
             t.consumed = 8 + datatype(p + 8).consumed;
+        } else if (t.cls == 8) {                    // enumeration: read as its base integer
+            const Datatype base = datatype(p + 8);
+            if (base.cls != 0) bad("unsupported enumeration base type");
+            t.cls = 0; t.is_signed = base.is_signed; t.big_endian = base.big_endian;
+            t.consumed = 0;
         } else {
             t.consumed = 0;                         // compound etc.: usable only as "skip"
         }

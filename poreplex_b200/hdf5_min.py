@@ -95,6 +95,17 @@ def _parse_datatype(buf, pos):
         dt = np.dtype({'names': names, 'formats': formats, 'offsets': offsets,
                        'itemsize': size})
         return _Datatype(cls, size, dt, consumed=p - pos)
+    if cls == 8:      # enumeration (e.g. Raw/end_reason): values are read as the base integer
+        nmemb = bits & 0xFFFF
+        base = _parse_datatype(buf, p)
+        if base.dtype is None:
+            raise Hdf5FormatError('unsupported enumeration base type')
+        q = p + base.consumed
+        for _ in range(nmemb):
+            end = buf.index(b'\0', q)
+            q = q + _pad8(end - q + 1) if version < 3 else end + 1
+        q += nmemb * base.size
+        return _Datatype(cls, size, base.dtype, consumed=q - pos)
     if cls == 9:      # variable length
         is_string = (bits & 0x0F) == 1
         base = _parse_datatype(buf, p)
@@ -262,7 +273,10 @@ class _Node:
         self.attrs = _Attrs()
         for mtype, mbuf in self._msgs:
             if mtype == 0x000C:
-                k, v = h5._parse_attribute(mbuf)
+                try:
+                    k, v = h5._parse_attribute(mbuf)
+                except (Hdf5FormatError, struct.error, ValueError, IndexError):
+                    continue        # an attribute of a type outside the subset hides only itself
                 self.attrs[k] = v
 
 

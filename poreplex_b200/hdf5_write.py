@@ -17,7 +17,7 @@ import zlib
 
 import numpy as np
 
-__all__ = ['Group', 'Dataset', 'write_file', 'FILTER_DEFLATE', 'FILTER_SHUFFLE', 'FILTER_VBZ']
+__all__ = ['Group', 'Dataset', 'Enum', 'RawAttr', 'write_file', 'FILTER_DEFLATE', 'FILTER_SHUFFLE', 'FILTER_VBZ']
 
 _SIGNATURE = b'\x89HDF\r\n\x1a\n'
 _UNDEF = 0xFFFFFFFFFFFFFFFF
@@ -88,6 +88,31 @@ def _datatype(dt):
     raise ValueError('unsupported dtype %r' % dt)
 
 
+class Enum:
+    """Attribute value of an enumeration type: ``Enum({'unknown': 0, 'signal_positive': 2}, 2)``."""
+
+    def __init__(self, members, value, base=np.uint8):
+        self.members, self.value, self.base = dict(members), value, np.dtype(base)
+
+
+class RawAttr:
+    """Attribute given as ready-made datatype / dataspace messages and payload bytes (tests use it
+    to plant types the readers do not know)."""
+
+    def __init__(self, datatype, dataspace, payload):
+        self.datatype, self.dataspace, self.payload = datatype, dataspace, payload
+
+
+def _enum_datatype(e):
+    body = _datatype(e.base)
+    for name in e.members:
+        nm = name.encode() + b'\0'
+        body += nm.ljust(_pad8(len(nm)), b'\0')
+    body += np.array(list(e.members.values()), e.base).tobytes()
+    n = len(e.members)
+    return struct.pack('<BBBBI', 0x18, n & 0xFF, (n >> 8) & 0xFF, 0, e.base.itemsize) + body
+
+
 def _dataspace(shape):
     body = struct.pack('<BBBBI', 1, len(shape), 0, 0, 0)
     for d in shape:
@@ -151,6 +176,11 @@ class _Writer:
     def attribute(self, name, value):
         """``str`` values become variable-length UTF-8 strings in a global heap collection (what
         h5py writes for ``attrs[k] = 'text'``); everything else is stored inline."""
+        if isinstance(value, RawAttr):
+            return _attribute_raw(name, value.datatype, value.dataspace, value.payload)
+        if isinstance(value, Enum):
+            return _attribute_raw(name, _enum_datatype(value), _dataspace(()),
+                                  np.array(value.value, value.base).tobytes())
         if not isinstance(value, str):
             return _attribute(name, value)
         data = value.encode()

@@ -151,6 +151,14 @@ def test_variable_length_string_attributes(lib, tmp_path):
         for k in ('run_id', 'sample_id'):
             g['tracking_id'].attrs[k] = g['tracking_id'].attrs[k].decode() + '-\u00b5'
         g['channel_id'].attrs['channel_number'] = g['channel_id'].attrs['channel_number'].decode()
+        # newer MinKNOW files carry an enumeration attribute next to the ones the path reads, and
+        # there may be types outside the subset altogether:
+        # neither may hide the rest of the group
+        g['Raw'].attrs['end_reason'] = W.Enum({'unknown': 0, 'signal_positive': 2, 'signal_negative': 3}, 2)
+        import struct
+        opaque = struct.pack('<BBBBI', 0x15, 0, 0, 0, 4) + b'tag\0'.ljust(8, b'\0')   # class 5: opaque
+        g['Raw'].attrs['aaa_unknown_type'] = W.RawAttr(opaque, struct.pack('<BBBBI', 1, 0, 0, 0, 0), b'\1\2\3\4')
+        g['channel_id'].attrs['zzz_unknown_type'] = W.RawAttr(opaque, struct.pack('<BBBBI', 1, 0, 0, 0, 0), b'\1\2\3\4')
     path = str(tmp_path / 'vlen.fast5')
     write_fast5(path, f5, signal_kw=dict(chunks=2048, gzip=1))
     out = FL.load_batch([(path, r) for r in ids], full_meta=True)
@@ -163,6 +171,10 @@ def test_variable_length_string_attributes(lib, tmp_path):
             assert m['sample_id'] == 'sample-\u00b5' and m['channel_number'] == want['channel_id'].attrs['channel_number']
             assert h['read_' + rid + '/tracking_id'].attrs['run_id'].decode() == want['tracking_id'].attrs['run_id']
             assert h['read_' + rid + '/Raw'].attrs['read_id'].decode() == rid
+            assert h['read_' + rid + '/Raw'].attrs['end_reason'] == 2
+            assert 'aaa_unknown_type' not in h['read_' + rid + '/Raw'].attrs
+            assert h['read_' + rid + '/channel_id'].attrs['range'] == want['channel_id'].attrs['range']
+            assert int(h['read_' + rid + '/Raw'].attrs['duration']) == len(sigs[i])
             assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + out['lengths'][i]], sigs[i])
 
 
