@@ -286,14 +286,20 @@ class Hdf5Dataset(_Node):
         self.shape = self._dtype = self._data_addr = self._compact = None
         self._chunk_btree = self._chunk_shape = None
         self._filters = []
+        self._vlen = False
         for mtype, mbuf in self._msgs:
             if mtype == 0x0001:
                 self.shape, _ = _parse_dataspace(mbuf, 0)
             elif mtype == 0x0003:
                 dt = _parse_datatype(mbuf, 0)
-                if dt.dtype is None:
+                if dt.vlen_string:
+                    # elements are (length u4, global heap collection u8, object index u4)
+                    self._vlen = True
+                    self._dtype = np.dtype([('len', '<u4'), ('coll', '<u8'), ('idx', '<u4')])
+                elif dt.dtype is None:
                     raise Hdf5FormatError('unsupported dataset datatype')
-                self._dtype = dt.dtype
+                else:
+                    self._dtype = dt.dtype
             elif mtype == 0x0008:
                 self._parse_layout(mbuf)
             elif mtype == 0x000B:
@@ -378,6 +384,19 @@ class Hdf5Dataset(_Node):
         return out
 
     def read(self):
+        arr = self._read_fixed()
+        if not self._vlen:
+            return arr
+        # variable-length strings (what h5py writes for str data): bytes objects, like h5py 3
+        flat = [bytes(self._h5._global_heap_object(int(e['coll']), int(e['idx'])))[:int(e['len'])]
+                for e in arr.reshape(-1)]
+        if not self.shape:
+            return np.array(flat[0], dtype=object)
+        out = np.empty(len(flat), dtype=object)
+        out[:] = flat
+        return out.reshape(self.shape)
+
+    def _read_fixed(self):
         n = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
         nbytes = n * self._dtype.itemsize
         if self._chunk_shape is not None:

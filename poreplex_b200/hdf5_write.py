@@ -183,12 +183,7 @@ class _Writer:
                                   np.array(value.value, value.base).tobytes())
         if not isinstance(value, str):
             return _attribute(name, value)
-        data = value.encode()
-        obj = struct.pack('<HHIQ', 1, 1, 0, len(data)) + data.ljust(_pad8(len(data)), b'\0')
-        size = 16 + len(obj) + 16                       # header, the object, the free-space object
-        coll = self.alloc(b'GCOL' + struct.pack('<BBBBQ', 1, 0, 0, 0, size) + obj + bytes(16))
-        return _attribute_raw(name, _VLEN_STR, _dataspace(()),
-                              struct.pack('<IQI', len(data), coll, 1))
+        return _attribute_raw(name, _VLEN_STR, _dataspace(()), self._heap_string(value))
 
     # ---- B-trees --------------------------------------------------------------------
     def _btree(self, node_type, leaves, key_bytes, k):
@@ -254,7 +249,21 @@ class _Writer:
         msgs += [(0x000C, self.attribute(k, v)) for k, v in g.attrs.items()]
         return self._header(msgs), bt, hp
 
+    def _heap_string(self, text):
+        """One global heap collection holding ``text``; returns the 16-byte vlen element."""
+        data = text.encode()
+        obj = struct.pack('<HHIQ', 1, 1, 0, len(data)) + data.ljust(_pad8(len(data)), b'\0')
+        size = 16 + len(obj) + 16                       # header, the object, the free-space object
+        coll = self.alloc(b'GCOL' + struct.pack('<BBBBQ', 1, 0, 0, 0, size) + obj + bytes(16))
+        return struct.pack('<IQI', len(data), coll, 1)
+
     def dataset(self, d):
+        if isinstance(d.data, str):                     # scalar variable-length string (h5py: str data)
+            elem = self._heap_string(d.data)
+            msgs = [(0x0001, _dataspace(())), (0x0003, _VLEN_STR),
+                    (0x0008, struct.pack('<BBQQ', 3, 1, self.alloc(elem), len(elem)))]
+            msgs += [(0x000C, self.attribute(k, v)) for k, v in d.attrs.items()]
+            return self._header(msgs)
         a, shape = _as_array(d.data)
         a = np.ascontiguousarray(a)
         msgs = [(0x0001, _dataspace(shape)), (0x0003, _datatype(a.dtype))]

@@ -8,25 +8,30 @@ import numpy as np
 from poreplex_b200 import hdf5_write as W
 
 
-def tree_to_hdf5(node, signal_kw=None, move_kw=None):
+def tree_to_hdf5(node, signal_kw=None, move_kw=None, fastq_vlen=False):
     """oracle.refshim FakeGroup -> hdf5_write.Group.  ``signal_kw`` / ``move_kw``: storage of the
-    Signal / Move datasets (chunks, gzip, shuffle, encoder); others are contiguous."""
+    Signal / Move datasets (chunks, gzip, shuffle, encoder); others are contiguous.
+    ``fastq_vlen``: store Fastq as a variable-length string (h5py's form for str data) instead of
+    a fixed-length one."""
     g = W.Group(attrs=dict(node.attrs))
     for name, child in node._children.items():
         if hasattr(child, '_children'):
-            g.children[name] = tree_to_hdf5(child, signal_kw, move_kw)
+            g.children[name] = tree_to_hdf5(child, signal_kw, move_kw, fastq_vlen)
         else:
             kw = {}
             if name == 'Signal' and signal_kw:
                 kw = signal_kw
             elif name == 'Move' and move_kw:
                 kw = move_kw
-            g.children[name] = W.Dataset(child._data, attrs=dict(child.attrs), **kw)
+            data = child._data
+            if name == 'Fastq' and fastq_vlen:
+                data = bytes(data).decode()
+            g.children[name] = W.Dataset(data, attrs=dict(child.attrs), **kw)
     return g
 
 
-def write_fast5(path, tree, signal_kw=None, move_kw=None):
-    return W.write_file(path, tree_to_hdf5(tree, signal_kw, move_kw))
+def write_fast5(path, tree, signal_kw=None, move_kw=None, fastq_vlen=False):
+    return W.write_file(path, tree_to_hdf5(tree, signal_kw, move_kw, fastq_vlen))
 
 
 def to_single_read(multi_tree, read_id):

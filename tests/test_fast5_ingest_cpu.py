@@ -305,7 +305,8 @@ def test_native_reader_walks_h5py_written_files(lib):
             assert 'model_weights' in h
 
 
-def test_fast5_source_over_hdf5_min(tmp_path, monkeypatch):
+@pytest.mark.parametrize('fastq_vlen', [False, True])
+def test_fast5_source_over_hdf5_min(tmp_path, monkeypatch, fastq_vlen):
     """Fast5Source (the drop-in's FAST5 access) over real files through hdf5_min gives what it
     gives over the in-memory h5py the golden runs use."""
     import sys
@@ -313,7 +314,8 @@ def test_fast5_source_over_hdf5_min(tmp_path, monkeypatch):
     from poreplex_b200 import fast5_source as FS
     f5, ids, sigs = _tree(5, seed=5)
     path = str(tmp_path / 'reads.fast5')
-    write_fast5(path, f5, signal_kw=dict(chunks=1024, gzip=1, shuffle=True), move_kw=dict(chunks=64, gzip=1))
+    write_fast5(path, f5, signal_kw=dict(chunks=1024, gzip=1, shuffle=True), move_kw=dict(chunks=64, gzip=1),
+                fastq_vlen=fastq_vlen)
     refshim.install_fake_h5py()
     refshim.clear_fast5()
     refshim.register_fast5(path, f5)
