@@ -440,23 +440,43 @@ void inflate_chunk(std::vector<uint8_t> &buf, Scratch &s, size_t expected)
     bad("deflate: chunk larger than expected");
 }
 
-// streamvbyte: `count` little-endian codes, keys first (key_bits = 1: svb16, 1..2 bytes;
-// key_bits = 2: classic, 1..4 bytes), data after
-void svb_decode(const uint8_t *src, size_t len, size_t count, int key_bits, std::vector<uint32_t> &out)
+// streamvbyte: `count` little-endian codes, keys first (KEY_BITS = 1: svb16, 1..2 bytes per value;
+// KEY_BITS = 2: classic, 1..4 bytes), data after
+template <int KEY_BITS>
+void svb_decode_t(const uint8_t *src, size_t len, size_t count, uint32_t *out)
 {
-    const size_t per = 8 / key_bits, nkeys = (count + per - 1) / per;
+    constexpr unsigned PER = 8 / KEY_BITS, SHIFT = KEY_BITS == 1 ? 3 : 2, KMASK = (1u << KEY_BITS) - 1;
+    const size_t nkeys = (count + PER - 1) / PER;
     if (nkeys > len) bad("VBZ: truncated key block");
     const uint8_t *data = src + nkeys, *end = src + len;
-    out.resize(count);
-    for (size_t i = 0; i < count; i++) {
-        const unsigned code = (src[i / per] >> ((i % per) * key_bits)) & ((1u << key_bits) - 1);
-        const unsigned nb = code + 1;
+    size_t i = 0;
+    // whole key bytes while at least 4 * PER data bytes remain: no per-value bounds check
+    while (i + PER <= count && (size_t)(end - data) >= 4 * PER) {
+        unsigned key = src[i >> SHIFT];
+        for (unsigned k = 0; k < PER; k++, key >>= KEY_BITS) {
+            const unsigned nb = (key & KMASK) + 1;
+            uint32_t v;
+            memcpy(&v, data, 4);
+            out[i + k] = nb == 4 ? v : v & ((1u << (8 * nb)) - 1);
+            data += nb;
+        }
+        i += PER;
+    }
+    for (; i < count; i++) {
+        const unsigned nb = ((src[i >> SHIFT] >> ((i & (PER - 1)) * KEY_BITS)) & KMASK) + 1;
         if (data + nb > end) bad("VBZ: truncated data block");
         uint32_t v = 0;
-        for (unsigned b = 0; b < nb; b++) v |= (uint32_t)data[b] << (8 * b);
+        for (unsigned b2 = 0; b2 < nb; b2++) v |= (uint32_t)data[b2] << (8 * b2);
         data += nb;
         out[i] = v;
     }
+}
+
+void svb_decode(const uint8_t *src, size_t len, size_t count, int key_bits, std::vector<uint32_t> &out)
+{
+    out.resize(count);
+    if (key_bits == 1) svb_decode_t<1>(src, len, count, out.data());
+    else svb_decode_t<2>(src, len, count, out.data());
 }
 
 // ONT VBZ (filter 32020): uint32 uncompressed size, optional zstd frame, streamvbyte of the

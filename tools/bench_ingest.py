@@ -25,6 +25,14 @@ STORAGE = {'contiguous': {}, 'chunked': dict(chunks=4096), 'gzip1': dict(chunks=
            'gzip1-shuffle': dict(chunks=4096, gzip=1, shuffle=True)}
 
 
+def vbz_storage():
+    """VBZ (svb16 + zstd level 1), through the test suite's encoder: the decoders are checked only
+    against that encoder, not against ONT's plugin."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
+    from fast5_files import vbz_encoder
+    return dict(chunks=4096, encoder=vbz_encoder(np.int16, 1, True, 1))
+
+
 def make_files(tmp, n_files, per_file, length, storage, seed):
     rng = np.random.default_rng(seed)
     reads = []
@@ -51,13 +59,14 @@ def main():
     ap.add_argument('--reads', type=int, default=16000)
     ap.add_argument('--length', type=int, default=4000)
     ap.add_argument('--files', type=int, default=4)
-    ap.add_argument('--storage', default='gzip1', choices=sorted(STORAGE))
+    ap.add_argument('--storage', default='gzip1', choices=sorted(STORAGE) + ['vbz'])
     ap.add_argument('--threads', type=int, default=os.cpu_count() or 1)
     ap.add_argument('--python-reads', type=int, default=1000)
     args = ap.parse_args()
     FL.build()
     tmp = tempfile.mkdtemp(prefix='ingest_')
-    reads = make_files(tmp, args.files, args.reads // args.files, args.length, STORAGE[args.storage], 1)
+    storage = vbz_storage() if args.storage == 'vbz' else STORAGE[args.storage]
+    reads = make_files(tmp, args.files, args.reads // args.files, args.length, storage, 1)
     file_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
     FL.load_batch(reads[:64], threads=args.threads)                       # warm-up (page cache, zlib)
     best = {}
