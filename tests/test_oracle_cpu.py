@@ -230,6 +230,60 @@ def test_lstm_networks_against_float64(orc_stock):
     assert abs(pr.sum() - 1) < 1e-5
 
 
+def _torch_lstm(layer, xs, reverse=False):
+    """The same layer through torch.nn.LSTM (float64): a third-party implementation of the LSTM
+    equations with the Keras weights mapped onto it (Keras gate blocks i|f|c|o = torch i|f|g|o;
+    kernel [in, 4H] -> weight_ih [4H, in]; Keras has one bias, so bias_hh = 0)."""
+    import torch
+    H, I = layer.units, layer.kernel.shape[0]
+    m = torch.nn.LSTM(I, H, batch_first=True).double()
+    with torch.no_grad():
+        m.weight_ih_l0.copy_(torch.from_numpy(np.ascontiguousarray(layer.kernel.T, np.float64)))
+        m.weight_hh_l0.copy_(torch.from_numpy(np.ascontiguousarray(layer.recurrent.T, np.float64)))
+        m.bias_ih_l0.copy_(torch.from_numpy(np.asarray(layer.bias, np.float64)))
+        m.bias_hh_l0.zero_()
+        x = torch.from_numpy(np.ascontiguousarray(xs[::-1] if reverse else xs, np.float64))[None]
+        out, (h, _c) = m(x)
+    seq = out[0].numpy()
+    return (seq[::-1].copy() if reverse else seq), h[0, 0].numpy()
+
+
+def test_lstm_networks_against_torch_lstm(orc_stock):
+    """TensorFlow cannot be installed here, so the Keras LSTM restatement (gate order, bias
+    placement, sequence direction and where the backward layer's output lands, final-state
+    selection) is cross-checked against an implementation the build did not write: torch.nn.LSTM
+    in float64, on several heads / windows including padded ones."""
+    from poreplex_b200 import params
+    p = orc_stock.preset
+    sc = params.load_scaler_model(p['signal_processing']['scaler_model'])
+    dm = params.load_demux_model(p['demultiplexing']['demux_model'])
+    rng = np.random.default_rng(11)
+    heads = np.zeros((3, 2000), np.float32)
+    for k, n in enumerate((600, 1500, 2000)):
+        heads[k, 2000 - n:] = (90 + 12 * rng.standard_normal(n)).astype(np.float32)
+    z = orc_stock.scaler_predict(heads)
+    for k in range(len(heads)):
+        s1, _ = _torch_lstm(sc.l1, heads[k][:, None].astype(np.float64))
+        _, h2 = _torch_lstm(sc.l2, s1)
+        z64 = h2 @ sc.dense_kernel.astype(np.float64) + sc.dense_bias
+        assert np.abs(z[k] - z64).max() < 2e-3, k
+    wins = rng.normal(0, 1.2, (4, 300)).astype(np.float32)
+    wins[1, :40] = -1000.0
+    wins[2, :5] = -1000.0
+    wins[3] = np.sort(wins[3])                       # a strongly direction-dependent window
+    pr = orc_stock.demux_predict(wins)
+    for k in range(len(wins)):
+        x = wins[k][:, None].astype(np.float64)
+        f, _ = _torch_lstm(dm.fwd, x)
+        b, _ = _torch_lstm(dm.bwd, x, reverse=True)
+        _, hl = _torch_lstm(dm.l2, np.concatenate([f, b], axis=1))
+        logit = hl @ dm.dense_kernel.astype(np.float64) + dm.dense_bias
+        p64 = np.exp(logit - logit.max())
+        p64 /= p64.sum()
+        assert np.abs(pr[k] - p64).max() < 2e-3, k
+        assert int(np.argmax(pr[k])) == int(np.argmax(p64)), k
+
+
 @pytest.mark.parametrize('name', ['stock16k', 'short4k', 'chimera40k'])
 def test_oracle_pipeline_reproduces_reference_run(oracle_mod, name):
     """The standalone oracle pipeline (orc_process_batch) must reproduce what was captured
