@@ -189,6 +189,53 @@ def test_viterbi_against_independent_float64(orc_stock, preset):
             assert abs(lp - lp2) < 1e-8 * abs(lp2)
 
 
+def test_viterbi_against_exhaustive_search(orc_stock, preset):
+    """Not a second dynamic programme but NO dynamic programme: for short signals every one of
+    the S^T state paths is scored directly (start + emissions + transitions, float64) and the best
+    one must be the path the oracle's Viterbi returns, with the same log-probability."""
+    import itertools
+    rng = np.random.default_rng(8)
+    levels = np.array([71.5, 102.0, 112.0, 80.5, 109.0, 95.0])
+    for which, key in (('seg', 'segmentation_model'), ('unsplit', 'unsplit_read_detection_model')):
+        hmm_def = preset[key]
+        names = sorted(s['name'] for s in hmm_def)
+        idx = {n: i for i, n in enumerate(names)}
+        S = len(names)
+        logT = np.full((S, S), -np.inf)
+        start = np.full(S, -np.inf)
+        em = [None] * S
+        for st in hmm_def:
+            i = idx[st['name']]
+            em[i] = st['emission']
+            if st.get('start_prob', 0) > 0:
+                start[i] = math.log(st['start_prob'])
+            for nxt, pr in st['transition']:
+                logT[i, idx[nxt]] = math.log(pr)
+
+        def emis(i, v):
+            comps = em[i]
+            w = np.array([c[2] if len(c) > 2 else 1.0 for c in comps])
+            w = w / w.sum()
+            lps = [-math.log(c[1] * math.sqrt(2 * math.pi)) - (v - c[0]) ** 2 / (2 * c[1] ** 2) + math.log(wi)
+                   for c, wi in zip(comps, w)]
+            return lps[0] if len(lps) == 1 else float(np.logaddexp(lps[0], lps[1]))
+
+        for T in (1, 2, 3, 5, 6):
+            for trial in range(4):
+                x = (levels[np.sort(rng.integers(0, S, T))] + rng.normal(0, 5.0, T)).astype(np.float32)
+                E = np.array([[emis(i, float(v)) for i in range(S)] for v in x])       # [T][S]
+                best, best_path = -np.inf, None
+                for path in itertools.product(range(S), repeat=T):
+                    lp = start[path[0]] + E[0, path[0]]
+                    for t in range(1, T):
+                        lp += logT[path[t - 1], path[t]] + E[t, path[t]]
+                    if lp > best:
+                        best, best_path = lp, path
+                lp_o, path_o = orc_stock.viterbi(x, which)
+                assert tuple(int(v) for v in path_o) == best_path, (which, T, trial)
+                assert abs(lp_o - best) < 1e-9 * max(1.0, abs(best))
+
+
 def _lstm_f64(layer, xs, reverse=False):
     H = layer.units
     W, U, b = (a.astype(np.float64) for a in (layer.kernel, layer.recurrent, layer.bias))
