@@ -691,6 +691,8 @@ pb2f_file *open_file(const char *path)
     if (p == MAP_FAILED) throw std::runtime_error(std::string("cannot map ") + path);
     f->m.p = (const uint8_t *)p;
     f->m.n = (uint64_t)st.st_size;
+    close(f->fd);                                  // the mapping outlives the descriptor: a batch of
+    f->fd = -1;                                    // single-read files must not exhaust RLIMIT_NOFILE
     static const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
     if (memcmp(f->m.p, sig, 8) != 0) bad("not an HDF5 file: %s", path);
     if (f->m.u8(8) != 0) bad("unsupported superblock version %d", f->m.u8(8));

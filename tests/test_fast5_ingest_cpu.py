@@ -218,6 +218,27 @@ def test_native_batch_loader(lib, tmp_path):
     assert FL.load_batch([])['raw'].size >= 0
 
 
+def test_batch_of_single_read_files_under_a_low_descriptor_limit(lib, tmp_path):
+    """Older runs are one file per read: a batch then opens thousands of files.  The loader keeps
+    mappings, not descriptors, so RLIMIT_NOFILE does not bound the batch size."""
+    import resource
+    f5, ids, sigs = _tree(600, seed=9, lengths=np.full(600, 950), basecalls=False)
+    reads = []
+    for i, rid in enumerate(ids):
+        path = str(tmp_path / ('single_%04d.fast5' % i))
+        write_fast5(path, to_single_read(f5, rid), signal_kw=dict(chunks=1024, gzip=1))
+        reads.append((path, rid if i % 2 else None))
+    soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+    resource.setrlimit(resource.RLIMIT_NOFILE, (128, hard))
+    try:
+        out = FL.load_batch(reads, threads=4)
+    finally:
+        resource.setrlimit(resource.RLIMIT_NOFILE, (soft, hard))
+    assert (out['status'] == FL.READ_OK).all()
+    for i in (0, 1, 299, 599):
+        assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + out['lengths'][i]], sigs[i])
+
+
 def test_truncated_files_never_crash(lib, tmp_path):
     f5, ids, sigs = _tree(6, seed=3)
     path = str(tmp_path / 'whole.fast5')
