@@ -13,6 +13,58 @@ import numpy as np
 __all__ = ['Fast5Source']
 
 
+class _SharedFile:
+    """One open hdf5_min file shared by every Fast5Source of the same path: the drop-in keeps a
+    handle per loaded read until the batch ends (as the reference does), and a batch is 10^4-10^5
+    reads of a few multi-read files -- one mapping per file, not one per read."""
+
+    _open = {}                                    # abspath -> [Hdf5File, reference count]
+
+    def __init__(self, path):
+        import os
+        from .hdf5_min import Hdf5File
+        self._file = None
+        self._key = os.path.abspath(path)
+        slot = self._open.get(self._key)
+        if slot is None:
+            slot = self._open[self._key] = [Hdf5File(path), 0]
+        slot[1] += 1
+        self._file = slot[0]
+
+    def close(self):
+        if self._file is None:
+            return
+        slot = self._open.get(self._key)
+        self._file = None
+        if slot is not None:
+            slot[1] -= 1
+            if slot[1] <= 0:
+                del self._open[self._key]
+                slot[0].close()
+
+    def __del__(self):                            # sources dropped without close() (reads stopped
+        try:                                      # before the GPU stage) release their share too
+            self.close()
+        except Exception:
+            pass
+
+    def __getitem__(self, path):
+        return self._file[path]
+
+    def __contains__(self, path):
+        return path in self._file
+
+    def __iter__(self):
+        return iter(self._file)
+
+    def keys(self):
+        return self._file.keys()
+
+    @property
+    def attrs(self):
+        return self._file.attrs
+
+
 class _MinimalH5py:
     """``h5py.File`` stand-in over poreplex_b200.hdf5_min (read-only; the classic HDF5 format with
     gzip / shuffle / VBZ chunked datasets that FAST5 files use)."""
@@ -21,8 +73,7 @@ class _MinimalH5py:
     def File(path, mode='r'):
         if mode != 'r':
             raise ValueError('hdf5_min is read-only')
-        from .hdf5_min import Hdf5File
-        return Hdf5File(path)
+        return _SharedFile(path)
 
 
 def _h5py():
@@ -45,19 +96,23 @@ class Fast5Source:
         self.path = path
         self.read_id = read_id
         self.handle = _h5py().File(path, 'r')
-        self.is_multiread = 'UniqueGlobalKey' not in self.handle
-        if self.is_multiread:
-            self.read_node = 'read_{}/Raw'.format(read_id)
-            self.channel_node = 'read_{}/channel_id'.format(read_id)
-            self.tracking_node = 'read_{}/tracking_id'.format(read_id)
-            self.analyses_node = 'read_{}/Analyses'.format(read_id)
-        else:
-            first_read_name = next(iter(self.handle['Raw/Reads'].keys()))
-            self.read_node = 'Raw/Reads/' + first_read_name
-            self.channel_node = 'UniqueGlobalKey/channel_id'
-            self.tracking_node = 'UniqueGlobalKey/tracking_id'
-            self.analyses_node = 'Analyses'
-        self._load_metadata()
+        try:
+            self.is_multiread = 'UniqueGlobalKey' not in self.handle
+            if self.is_multiread:
+                self.read_node = 'read_{}/Raw'.format(read_id)
+                self.channel_node = 'read_{}/channel_id'.format(read_id)
+                self.tracking_node = 'read_{}/tracking_id'.format(read_id)
+                self.analyses_node = 'read_{}/Analyses'.format(read_id)
+            else:
+                first_read_name = next(iter(self.handle['Raw/Reads'].keys()))
+                self.read_node = 'Raw/Reads/' + first_read_name
+                self.channel_node = 'UniqueGlobalKey/channel_id'
+                self.tracking_node = 'UniqueGlobalKey/tracking_id'
+                self.analyses_node = 'Analyses'
+            self._load_metadata()
+        except BaseException:
+            self.close()                          # an unreadable read must not pin the file open
+            raise
 
     def close(self):
         if self.handle is not None:

@@ -16,6 +16,7 @@ understands exactly the subset of the HDF5 file format those two files use:
 Anything else raises ``Hdf5FormatError`` instead of guessing.
 """
 import mmap
+import os
 import struct
 import zlib
 
@@ -25,6 +26,7 @@ __all__ = ['Hdf5File', 'Hdf5FormatError']
 
 _SIGNATURE = b'\x89HDF\r\n\x1a\n'
 _UNDEF = 0xFFFFFFFFFFFFFFFF
+_READ_WHOLE_BELOW = 8 << 20
 
 
 class Hdf5FormatError(Exception):
@@ -479,13 +481,16 @@ class Hdf5Group(_Node):
 
 class Hdf5File(Hdf5Group):
     def __init__(self, path):
-        # mapped, not read: a multi-read FAST5 is hundreds of MB and one read is a few KB of it
+        # Large files are mapped, not read: a multi-read FAST5 is hundreds of MB and one read is a
+        # few KB of it.  Small ones (single-read FAST5, model files) are read whole, so that a
+        # batch of thousands of open single-read files holds no descriptors at all.
         self._fh = open(path, 'rb')
-        try:
-            self._buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
-        except ValueError:                          # empty file
+        if os.fstat(self._fh.fileno()).st_size <= _READ_WHOLE_BELOW:
+            self._buf = self._fh.read()
             self._fh.close()
-            raise Hdf5FormatError('not an HDF5 file: ' + path)
+            self._fh = None
+        else:
+            self._buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
         self._cache = {}
         try:
             self._open_root(path)
@@ -510,8 +515,8 @@ class Hdf5File(Hdf5Group):
         Hdf5Group.__init__(self, self, ohdr, '/')
 
     def close(self):
+        self._cache = {}
         if self._fh is not None:
-            self._cache = {}
             try:
                 self._buf.close()
             except BufferError:                     # a numpy view of the map is still alive
@@ -528,6 +533,8 @@ class Hdf5File(Hdf5Group):
     # -- low level ---------------------------------------------------------
     def _open(self, addr, name):
         if addr not in self._cache:
+            if len(self._cache) > 8192:             # a shared handle visits every read of the file
+                self._cache.clear()
             msgs = self._read_object_header(addr)
             types = {t for t, _ in msgs}
             cls = Hdf5Group if 0x0011 in types else Hdf5Dataset

@@ -239,6 +239,36 @@ def test_batch_of_single_read_files_under_a_low_descriptor_limit(lib, tmp_path):
         assert np.array_equal(out['raw'][out['offsets'][i]:out['offsets'][i] + out['lengths'][i]], sigs[i])
 
 
+def test_many_open_sources_under_a_low_descriptor_limit(tmp_path, monkeypatch):
+    """The drop-in keeps one Fast5Source per loaded read until the batch ends.  Without h5py the
+    sources of one multi-read file share a single mapping and single-read files are read whole, so
+    a large batch does not run into RLIMIT_NOFILE."""
+    import resource
+    import sys
+    from poreplex_b200 import fast5_source as FS
+    monkeypatch.setitem(sys.modules, 'h5py', None)
+    f5, ids, sigs = _tree(400, seed=12, lengths=np.full(400, 950), basecalls=False)
+    mpath = str(tmp_path / 'multi.fast5')
+    write_fast5(mpath, f5, signal_kw=dict(chunks=1024, gzip=1))
+    singles = []
+    for i, rid in enumerate(ids[:300]):
+        path = str(tmp_path / ('s%03d.fast5' % i))
+        write_fast5(path, to_single_read(f5, rid))
+        singles.append((path, rid))
+    soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+    resource.setrlimit(resource.RLIMIT_NOFILE, (64, hard))
+    try:
+        srcs = [FS.Fast5Source(mpath, r) for r in ids] + [FS.Fast5Source(p, r) for p, r in singles]
+        assert len(FS._SharedFile._open) == 1 + len(singles)
+        for k in (0, 399, 400, 699):
+            assert np.array_equal(srcs[k].raw_int16(), sigs[k if k < 400 else k - 400])
+        for s in srcs:
+            s.close()
+        assert not FS._SharedFile._open
+    finally:
+        resource.setrlimit(resource.RLIMIT_NOFILE, (soft, hard))
+
+
 def test_truncated_files_never_crash(lib, tmp_path):
     f5, ids, sigs = _tree(6, seed=3)
     path = str(tmp_path / 'whole.fast5')
