@@ -68,11 +68,14 @@ inline uint32_t dist_symbol(unsigned sym)
 }
 inline uint32_t pre_symbol(unsigned sym) { return entry(sym, K_LITERAL, 0, 0); }
 
-inline unsigned reverse_bits(unsigned code, int len)
+inline unsigned reverse_bits(unsigned code, int len)       // len <= 15
 {
-    unsigned r = 0;
-    for (int i = 0; i < len; i++) { r = (r << 1) | (code & 1); code >>= 1; }
-    return r;
+    unsigned v = code;
+    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+    v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu);
+    v = ((v & 0x00FFu) << 8) | ((v >> 8) & 0x00FFu);
+    return v >> (16 - len);
 }
 
 // Canonical Huffman decoding table from code lengths.  Returns false for an over-subscribed
@@ -168,8 +171,9 @@ struct Stream {
     uint64_t bitbuf = 0;
     unsigned bitcnt = 0;
 
-    // careful refill: byte by byte, never past in_end
+    // careful refill: never past in_end (one 8-byte load while that much input remains)
     void refill_safe() {
+        if (in_end - in >= 8) { refill_fast(); return; }
         while (bitcnt <= 56 && in < in_end) { bitbuf |= (uint64_t)*in++ << bitcnt; bitcnt += 8; }
     }
     // fast refill: needs in + 8 <= in_end; leaves 56..63 valid bits
