@@ -77,6 +77,21 @@ def test_python_reader_round_trip(tmp_path, storage):
             assert g['Analyses/Basecall_1D_000'].name.rsplit('_', 1)[-1] == '000'
 
 
+def test_python_reader_mapped_and_whole_file_paths_agree(tmp_path, monkeypatch):
+    """hdf5_min reads small files whole and maps large ones; both paths must serve the same data."""
+    f5, ids, sigs = _tree(8, seed=13)
+    path = str(tmp_path / 'multi.fast5')
+    write_fast5(path, f5, signal_kw=dict(chunks=1000, gzip=1, shuffle=True))
+    for limit in (0, 1 << 30):
+        monkeypatch.setattr(R, '_READ_WHOLE_BELOW', limit)
+        with R.Hdf5File(path) as h:
+            assert (h._fh is None) == (limit > 0)
+            for rid, sig in zip(ids, sigs):
+                assert np.array_equal(h['read_' + rid + '/Raw/Signal'][()], sig)
+                assert h['read_' + rid + '/Raw'].attrs['read_id'].decode() == rid
+            assert sorted(h.keys()) == sorted('read_' + r for r in ids)
+
+
 def test_many_children_compound_and_empty(tmp_path):
     """> 256 children (two B-tree levels), a compound table, an empty group, empty datasets."""
     root = W.Group(attrs={'file_version': b'2.0', 'count': 700, 'ratio': 0.25,
