@@ -15,11 +15,20 @@ Prints ONE JSON line (rank 0).  `value` is measured with the batch resident in H
 (CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
 pb2_analyze_host with pinned HOST buffers, copies inside the timed region.
 
-The timed path is the library's default: both LSTM networks on the tensor cores (tcgen05 /
-TMEM), guards, and the exact re-run of the reads the guards flag.  After the
-timed region one more step runs with the exact-only kernels and every integer output of
-every read is compared (`config.mismatches_vs_exact_only_kernels`; `--no-verify` skips it
-for profiling runs); `cpu_baseline` compares a sample with the CPU oracle.
+The timed path is the library's default (`--mode fast`): both LSTM networks on the tensor
+cores (tcgen05 / TMEM), guards, and the exact re-run of the reads the guards flag (DESIGN.md
+3a).  After the timed region the same batch is run and timed in the two other modes --
+`strict` (exact scaler / segmentation / windows for every read, tensor-core classifier) and
+`exact` (exact f32 kernels only) -- reported side by side under `modes`, and every integer
+output of every read of the timed mode is compared with the exact-only run
+(`config.mismatches_vs_exact_only_kernels`; `--no-verify` skips all of this for profiling
+runs); `cpu_baseline` compares a sample with the CPU oracle.
+
+`--config full` is BASELINE configs[3]: the same reads with synthetic guppy Move tables,
+`--trim-adapter --barcoding --filter-chimera` + poly(A): stages A-D with the poly(A) kernel,
+then the event-table derivation and the chimera filter (k_event_means / k_unsplit_*).
+`--reads 1250000 --gpus 8` is the literal 10 M-read configs[4] line; `--length` sweeps the
+read length (preset `stock` from 10500 samples up).
 """
 import argparse
 import json
@@ -59,6 +68,14 @@ def algorithmic(L, stride=15, trim=300, scaler_len=30000):
         'k_lstm_tc_demux_l2_probe': ('tensor', 2 * (96 * 256 + 64 * 256) * trim),
         'k_lstm_tc_scaler_l1': ('tensor', 2 * (192 + 48 * 192) * H),
         'k_lstm_tc_scaler_l2': ('tensor', 2 * (2 * 48 * 192) * H),
+        # config full: poly(A) walks the raw samples of its window once (window ~ poly(A) span
+        # + 2 * 200 refinement samples; here: 1/8 of the read as the per-read figure) and
+        # writes one record; the chimera filter reads 14 B per event (start is implicit for
+        # guppy tables: move u1 .. here i4, p f8) and derives means from the raw signal
+        'k_polya': ('hbm', 2 * (L // 8) + 8 + 48 + 24),
+        'k_event_means': ('hbm', 2 * L + 4 * T),
+        'k_unsplit_windows': ('hbm', (8 + 4 + 4 + 8) * T),
+        'k_unsplit_decide': ('hbm', (4 + 8) * T + 4),
     }
 
 
@@ -243,6 +260,30 @@ def run_reference(args, rank, world, emit):
     emit(line)
 
 
+def make_event_tables(args, work, device, seed):
+    """config full: synthetic guppy Move tables for every read, generated on the device --
+    one event per 15 samples from sample 0 (fast5_file.py:209-216), move ~ Bernoulli(0.3) with
+    move[0] = 1, p_model_state uniform in (0.2, 1)."""
+    import torch
+    n = int(work['lengths'].numel())
+    E = args.length // 15
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 977)
+    move = (torch.rand((n, E), generator=g, device=device) < 0.3).to(torch.int32)
+    move[:, 0] = 1
+    pstate = 0.2 + 0.8 * torch.rand((n, E), generator=g, device=device, dtype=torch.float64)
+    start = (torch.arange(E, device=device, dtype=torch.int64) * 15).repeat(n, 1)
+    return {
+        'ev_offsets': torch.arange(n + 1, device=device, dtype=torch.int64) * E,
+        'start': start.reshape(-1), 'move': move.reshape(-1), 'p_model_state': pstate.reshape(-1),
+        'sampling_rate': torch.full((n,), 3012.0, dtype=torch.float64, device=device),
+        'first_sample': torch.zeros(n, dtype=torch.int64, device=device),
+        'block_stride': 15,
+        # windows: range(payload_start, last_end, int(3 s * rate)) (signal_analyzer.py:384)
+        'max_windows': max(1, -(-args.length // int(3.0 * 3012.0))),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -251,15 +292,23 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--reads', type=int, default=1000000, help='reads per GPU per step')
     ap.add_argument('--length', type=int, default=4000, help='raw samples per read')
-    ap.add_argument('--preset', default='bench-short', choices=['bench-short', 'stock'])
+    ap.add_argument('--preset', default=None, choices=['bench-short', 'stock'],
+                    help='default: bench-short below 10500 samples, stock from there')
+    ap.add_argument('--config', default='demux', choices=['demux', 'full'],
+                    help='demux: BASELINE configs[1]+[2]; full: configs[3] (+ poly(A), event '
+                         'tables, chimera filter)')
+    ap.add_argument('--mode', default='fast', choices=['fast', 'strict', 'exact'],
+                    help='which LSTM mode is the timed one (the others are timed beside it)')
     ap.add_argument('--seed', type=int, default=20261017)
     ap.add_argument('--ref-reads', type=int, default=8192, help='reads per step of the CPU arm')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target CPU-baseline time')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-verify', action='store_true',
-                    help='skip the exact-only comparison step (profiling runs)')
+                    help='skip the other-mode runs and the exact-only comparison (profiling runs)')
     args = ap.parse_args()
+    if args.preset is None:
+        args.preset = 'bench-short' if args.length < 10500 else 'stock'
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -298,100 +347,160 @@ def main():
     cfg = dict(preset)
     cfg['barcoding'] = True
     eng = SignalEngine(cfg, device=local_rank)
+    eng.set_fast_lstm(args.mode)
     n = args.reads
-    out = eng.alloc_results(n)
+    full = args.config == 'full'
+    out = eng.alloc_results(n, polya=full)
+    ev = make_event_tables(args, work, device, args.seed + rank) if full else None
+    batch = (work['raw'], work['offsets'], work['lengths'], work['range'], work['digitisation'],
+             work['offset'])
     torch.cuda.synchronize()
+    chimera = {}
 
     def step():
-        eng.analyze_device(work['raw'], work['offsets'], work['lengths'], work['range'],
-                           work['digitisation'], work['offset'], out=out, barcoding=True,
-                           max_raw_length=args.length)
+        eng.analyze_device(*batch, out=out, barcoding=True, max_raw_length=args.length, polya=full)
+        if full:
+            # event-table derivation (block means of the medfilt(5) pA signal) + chimera filter
+            chimera['flag'] = eng.detect_unsplit_device(
+                batch, ev['ev_offsets'], ev['start'], ev['move'], ev['p_model_state'],
+                ev['sampling_rate'], ev['first_sample'], ev['block_stride'], out['scale_shift'],
+                out['status'], out['segments'], ev['max_windows'])
         if world > 1:
             dist.all_reduce(out['counts'])        # the one collective of the path
+
+    def timed(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / k
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     launches0 = eng.kernel_launches
     eng.profile_enable(True)
     eng.profile_read()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    ms_per_step = timed(args.steps)
     clocks = sampler.stop()
     prof = eng.profile_read()
     eng.profile_enable(False)
     launches = eng.kernel_launches - launches0
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
     value = world * n / (ms_per_step / 1e3)
 
-    # status mix of the workload (from the last step)
+    # status / barcode mix of the workload (from the last step)
     status = out['status'].cpu().numpy()
     from poreplex_b200.params import STATUS_NAMES
     mix = {STATUS_NAMES[s]: int(c) for s, c in zip(*np.unique(status, return_counts=True))}
-    classified = int((out['barcode_score'] >= 0).sum().item())
+    score_np = out['barcode_score'].cpu().numpy()
+    classified = int((score_np >= 0).sum())
+    bc_np = out['barcode'].cpu().numpy()
+    guess_np = out['barcode_guess'].cpu().numpy()
+    pushed = score_np >= 0
+    barcode_mix = {('BC%d' % (b + 1)) if b >= 0 else 'undetermined': int(c)
+                   for b, c in zip(*np.unique(bc_np[pushed], return_counts=True))}
+    guess_mix = {('BC%d' % (b + 1)) if b >= 0 else 'decoy': int(c)
+                 for b, c in zip(*np.unique(guess_np[pushed], return_counts=True))}
+    phred_hist = np.bincount(score_np[pushed], minlength=30).tolist()
+    counts_np = out['counts'].cpu().numpy()
+    # steps the pad-skipping layer-1 walks execute (tiles of 128 windows in read order)
+    seg_np = out['segments'].cpu().numpy()
+    ia = eng.adapter_state
+    wl = np.minimum(seg_np[pushed, ia, 1] - seg_np[pushed, ia, 0] + 1, 300).astype(np.int64)
+    if len(wl):
+        padt = np.pad(wl, (0, (-len(wl)) % 128), constant_values=300).reshape(-1, 128).max(axis=1)
+        steps_fwd = float(padt.mean())
+        steps_bwd = float(np.minimum(padt + 32, 300).mean())
+    else:
+        steps_fwd = steps_bwd = 300.0
 
-    # ---- default path (tensor cores + margin test + exact re-run) vs exact-only kernels:
+    # ---- the other modes, timed beside the timed one; the exact-only run is also the checker:
     # every integer output of every read must be identical (outside the timed region)
     rechecked, tc_timeouts = eng.recheck_stats()
     rerun_causes = eng.rerun_causes()
-    fast_int = {k: out[k].clone() for k in ('status', 'segments', 'barcode', 'barcode_guess',
-                                            'barcode_score', 'label', 'counts')}
+    int_keys = ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'label', 'counts')
+    fast_int = {k: out[k].clone() for k in int_keys}
     fast_ss = out['scale_shift'].clone()
     mismatches = None
+    modes = {args.mode: {'value': value, 'ms_per_step': ms_per_step, 'timed': True}}
     if not args.no_verify:
-        eng.set_fast_lstm(False)
-        eng.analyze_device(work['raw'], work['offsets'], work['lengths'], work['range'],
-                           work['digitisation'], work['offset'], out=out, barcoding=True,
-                           max_raw_length=args.length)
-        if world > 1:
-            dist.all_reduce(out['counts'])
-        torch.cuda.synchronize()
-        eng.set_fast_lstm(True)
-        mismatches = {k: int((fast_int[k] != out[k]).sum().item()) for k in fast_int}
-        dss = (fast_ss.double() - out['scale_shift'].double()).abs().amax(0)
-        mismatches['max_abs_diff_scale'] = float(dss[0].item())
-        mismatches['max_abs_diff_shift'] = float(dss[1].item())
-        okay = out['status'] == 0
-        if bool(okay.any()):
-            dok = (fast_ss.double() - out['scale_shift'].double()).abs()[okay]
-            # error of the scaler's raw outputs implied by the (scale, shift) differences of the
-            # reads that went on to segmentation, against the margin the guards assume
-            mismatches['max_scaler_z0_error_okay_reads'] = float((dok[:, 0] / 0.13295630234669656).max().item())
-            mismatches['max_scaler_z1_error_okay_reads'] = float((dok[:, 1] / 9.82564593783874).max().item())
-            mismatches['scaler_margin_z0_z1'] = [2.5e-4, 1.5e-3]
-    for k, v in fast_int.items():
-        out[k].copy_(v)
+        for mode in ('fast', 'strict', 'exact'):
+            if mode == args.mode:
+                continue
+            eng.set_fast_lstm(mode)
+            step()
+            ms = timed(2)
+            modes[mode] = {'value': world * n / (ms / 1e3), 'ms_per_step': ms, 'timed': False}
+            modes[mode]['mismatches_vs_timed_mode'] = \
+                {k: int((fast_int[k] != out[k]).sum().item()) for k in int_keys}
+            if mode == 'exact':
+                mismatches = dict(modes[mode]['mismatches_vs_timed_mode'])
+                d = (fast_ss.double() - out['scale_shift'].double()).abs()
+                dss = d.amax(0)
+                mismatches['max_abs_diff_scale'] = float(dss[0].item())
+                mismatches['max_abs_diff_shift'] = float(dss[1].item())
+                okay = out['status'] == 0
+                if bool(okay.any()):
+                    # relative error of the normalised signal y = scale * x + shift this implies
+                    # at x = 100 pA (north_star: 1e-5)
+                    ex = out['scale_shift'].double()[okay]
+                    rel = (d[okay][:, 0] * 100.0 + d[okay][:, 1]) / (ex[:, 0] * 100.0 + ex[:, 1]).abs()
+                    mismatches['max_rel_error_normalised_signal_at_100pA'] = float(rel.max().item())
+                    mismatches['reads_over_1e-5_rel'] = int((rel > 1e-5).sum().item())
+        eng.set_fast_lstm(args.mode)
+        for k, v in fast_int.items():
+            out[k].copy_(v)
+    for m_ in modes.values():
+        m_['unit'] = UNIT
+    modes['note'] = ('fast: tensor-core scaler + classifier, guards, exact re-run (integer outputs '
+                     'bit-identical, floats approximate); strict: exact scaler / segmentation / '
+                     'windows for every read (scale, shift and the normalised signal bit-exact), '
+                     'tensor-core classifier with guard + exact re-run; exact: f32 SIMT kernels only '
+                     '(every output bit-exact)')
 
-    # ---- roofline of every kernel, dominant one on top ------------------------
+    # ---- roofline of every kernel ---------------------------------------------------
     peaks = load_peaks()
     alg = algorithmic(args.length)
     kernels = []
     total_kernel_ms = sum(ms for ms, _ in prof.values()) or 1.0
     n_classified = max(classified, 1)
+    sm_mhz = clocks.get('sm_mhz') or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    xu_peak = 148 * 16 * sm_mhz * 1e6
+    exact_names = ('k_scaler_lstm', 'k_demux_l1', 'k_demux_l2')
+    overhead_names = ('k_lstm_tc_demux_l2_probe',) + (exact_names if args.mode == 'fast' else ())
+    H_steps = min(args.length, 30000) // 15
+    executed_steps = {'k_lstm_tc_demux_l1': (steps_fwd + steps_bwd) / 2.0, 'k_demux_l1': None}
+    total_alg_flops = 0.0
     for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per_step_ms = ms / args.steps
         ent = {'kernel': name, 'ms_per_step': per_step_ms, 'launches_per_step': cnt / args.steps,
                'share': ms / total_kernel_ms}
         if name in alg:
             bound, per_read = alg[name]
-            # demux kernels only step the compacted, classified reads
+            # units one step of this kernel really processes: the classifier kernels step the
+            # compacted, classified reads; in the fast mode the exact kernels only re-run the
+            # reads the guards flagged
             units = n_classified if 'demux' in name else n
+            if args.mode == 'fast' and name in exact_names:
+                units = max(rechecked, 1)
+            elif args.mode == 'strict' and name in ('k_demux_l1', 'k_demux_l2'):
+                units = max(rechecked, 1)
+            ent['units_per_step'] = units
             if bound == 'hbm':
                 ach = per_read * units / (per_step_ms / 1e3) / 1e9
                 ent.update({'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'],
@@ -399,71 +508,117 @@ def main():
                             'algorithmic_bytes_per_read': per_read})
                 if name == 'k_segment':
                     T = min(args.length, 100000) // 15
-                    fp64 = 250.0 * T * units / (per_step_ms / 1e3) / 1e12
-                    ent.update({'fp64_tops_estimate': fp64,
+                    passes = 3 if args.mode == 'fast' else 1
+                    fp64 = 250.0 * T * units * passes / (per_step_ms / 1e3) / 1e12
+                    ent.update({'fp64_tops_estimate': fp64, 'decodes_per_read': passes,
                                 'note': 'fp64-compute bound (Gaussian/GMM emissions + DP in '
                                         'double); ~250 fp64 ops per pooled sample'})
             else:
                 ach = per_read * units / (per_step_ms / 1e3) / 1e12
-                fp32_peak = 148 * 128 * 2 * (clocks.get('sm_mhz') or 1965.0) * 1e6 / 1e12
                 ent.update({'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_tflops'],
                             'unit': 'TFLOP/s', 'frac': ach / peaks['tensor_tflops'],
                             'algorithmic_flops_per_read': per_read})
+                if name not in overhead_names:
+                    total_alg_flops += per_read * units
                 if name.startswith('k_lstm_tc'):
                     mp = mufu_per_read(args.length).get(name)
                     if mp:
-                        xu_peak = 148 * 16 * (clocks.get('sm_mhz') or 1965.0) * 1e6
-                        ent.update({'mufu_ops_per_read': mp, 'xu_peak_ops_per_s_at_clock': xu_peak,
-                                    'frac_of_mufu_peak': mp * units / (per_step_ms / 1e3) / xu_peak})
+                        frac_steps = 1.0
+                        if name == 'k_lstm_tc_demux_l1':
+                            # the -1000 left padding is not stepped: table look-ups (forward) and
+                            # a frozen state (backward) stand in for those steps
+                            frac_steps = executed_steps[name] / 300.0
+                            ent.update({'steps_algorithmic': 300, 'steps_executed_mean': executed_steps[name],
+                                        'achieved_executed': ach * frac_steps,
+                                        'frac_executed': ach * frac_steps / peaks['tensor_tflops']})
+                        ent.update({'mufu_ops_per_read_executed': mp * frac_steps,
+                                    'xu_peak_ops_per_s_at_clock': xu_peak,
+                                    'frac_of_mufu_peak': mp * frac_steps * units / (per_step_ms / 1e3) / xu_peak})
                 else:
                     ent.update({'fp32_simt_peak_tflops_at_clock': fp32_peak,
                                 'frac_of_fp32_simt': ach / fp32_peak})
         kernels.append(ent)
-    dom = kernels[0] if kernels else {}
+    useful = [k for k in kernels if k['kernel'] not in overhead_names and 'frac' in k]
+    dom = useful[0] if useful else (kernels[0] if kernels else {})
     roofline = {k: dom.get(k) for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
     # DRAM traffic per launch of the dominant kernel: dram__bytes_read+write per read from the
-    # committed `ncu --set full` capture (profiles/r1_traffic.json) x reads per launch here
+    # committed `ncu --set full` capture (profiles/*_traffic.json, newest round first) x the
+    # reads one launch processes here
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if dom and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        ent = tj.get(dom['kernel'])
-        if ent and dom.get('launches_per_step'):
-            units = n_classified if 'demux' in dom['kernel'] else n
-            traffic = ent['dram_bytes_per_read'] * units / dom['launches_per_step']
-    roofline.update({'kernel': dom.get('kernel'), 'traffic': traffic, 'peak_source': peaks['source'],
-                     'share_of_step': dom.get('share'),
-                     'note': 'k_lstm_tc_*: tcgen05 split-fp16 (3 MMAs per product, fp32 accumulate in '
-                             'TMEM) LSTM layers, algorithmic FLOPs = the f32 products of the '
-                             'reference network (frac_of_mufu_peak: the pipe that actually bounds '
-                             'their gate phase); k_scaler_lstm / k_demux_l1 / k_demux_l2: exact-f32 '
-                             'SIMT kernels (packed FFMA2, see frac_of_fp32_simt), which also re-run '
-                             'the reads the margin test flags'})
+    for tname in ('r2_traffic.json', 'r1_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
+        if dom and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            ent = tj.get(dom['kernel'])
+            if ent and dom.get('launches_per_step'):
+                traffic = ent['dram_bytes_per_read'] * dom['units_per_step'] / dom['launches_per_step']
+                break
+    overhead = [{'kernel': k['kernel'], 'ms_per_step': k['ms_per_step'], 'share': k['share'],
+                 'units_per_step': k.get('units_per_step')} for k in kernels
+                if k['kernel'] in overhead_names]
+    roofline.update({
+        'kernel': dom.get('kernel'), 'traffic': traffic, 'peak_source': peaks['source'],
+        'share_of_step': dom.get('share'),
+        'whole_step': {
+            'algorithmic_tflop_per_step': total_alg_flops / 1e12,
+            'achieved': total_alg_flops / (ms_per_step / 1e3) / 1e12, 'peak': peaks['tensor_tflops'],
+            'unit': 'TFLOP/s', 'frac': total_alg_flops / (ms_per_step / 1e3) / 1e12 / peaks['tensor_tflops'],
+            'note': 'reference-network FLOPs of the reads each layer really processed (scaler: '
+                    'real head steps, classifier: 300 steps of every classified read) over the '
+                    'whole step time, probes and exact re-runs counted as time only'},
+        'hbm_whole_step': {
+            'algorithmic_bytes_per_read': 2 * args.length + (112 if full else 84),
+            'achieved': (2 * args.length + (112 if full else 84)) * n / (ms_per_step / 1e3) / 1e9,
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': (2 * args.length + (112 if full else 84)) * n / (ms_per_step / 1e3) / 1e9 / peaks['hbm_gbs']},
+        'overhead': overhead,
+        'note': 'dominant USEFUL kernel (the sensitivity probes and, in the fast mode, the exact '
+                're-run kernels are listed under overhead).  k_lstm_tc_*: tcgen05 split-fp16 (3 MMAs '
+                'per product, fp32 accumulate in TMEM) LSTM layers, algorithmic FLOPs = the f32 '
+                'products of the reference network (frac_of_mufu_peak: the pipe that bounds their '
+                'gate phase); k_scaler_lstm / k_demux_l1 / k_demux_l2: exact-f32 SIMT kernels '
+                '(packed FFMA2, frac_of_fp32_simt)'})
     for k in ('frac_of_fp32_simt', 'frac_of_mufu_peak'):
         if k in dom:
             roofline[k] = dom[k]
 
+    workload = ('%d synthetic %d-sample int16 reads per GPU per step, adapter segmentation + '
+                '4-way barcode demux (BASELINE configs[1]+[2]), preset %s' % (n, args.length, args.preset))
+    if full:
+        workload = ('%d synthetic %d-sample int16 reads per GPU per step + guppy Move tables, full '
+                    'path --trim-adapter --barcoding --filter-chimera + poly(A) (BASELINE configs[3]), '
+                    'preset %s' % (n, args.length, args.preset))
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 (LSTM; recurrent products as split-fp16 on tensor cores) + f64 (Viterbi)',
         'data': 'synthetic',
-        'config': {'workload': '%d synthetic %d-sample int16 reads per GPU per step, adapter '
-                               'segmentation + 4-way barcode demux (BASELINE configs[1]+[2]), '
-                               'preset %s' % (n, args.length, args.preset),
+        'config': {'workload': workload, 'config': args.config, 'lstm_mode': args.mode,
                    'reads_per_gpu': n, 'read_length': args.length, 'preset': args.preset,
                    'l2_policy': 'inputs (%.1f GB per GPU) larger than L2' % (n * args.length * 2 / 1e9),
                    'status_mix': mix, 'classified_reads': classified,
+                   'barcode_mix_of_classified': barcode_mix, 'best_guess_mix_of_classified': guess_mix,
+                   'phred_histogram_of_classified': phred_hist,
+                   'counts_by_barcode_slot': counts_np.sum(axis=(0, 2)).tolist(),
+                   'adapter_window_note': 'adapters of %d..%d pooled samples: %s of the 300 window '
+                                          'positions are -1000 padding (the stock preset needs >= 260)'
+                                          % (int(wl.min()) if len(wl) else 0, int(wl.max()) if len(wl) else 0,
+                                             'about %d' % int(300 - wl.mean()) if len(wl) else 'n/a'),
                    'exact_reruns_per_step': rechecked, 'exact_rerun_causes': rerun_causes,
+                   'exact_rerun_fraction': rechecked / float(n),
                    'tc_barrier_timeouts': tc_timeouts,
                    'mismatches_vs_exact_only_kernels': mismatches,
                    'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)',
                    'cpus_bound_per_rank': numa},
         'clocks': clocks, 'gpu_launches': launches,
-        'roofline': roofline, 'kernels': kernels,
+        'roofline': roofline, 'modes': modes, 'kernels': kernels,
     }
+    if full:
+        fl = chimera['flag']
+        result['config']['chimera_flags_set'] = int((fl == 1).sum().item())
+        result['config']['polya_found'] = int(out['polya'].view(torch.int32)[:, 0].ne(0).sum().item())
 
     # ---- e2e: host buffers through pb2_analyze_host ---------------------------
     if not args.no_e2e:
@@ -472,16 +627,22 @@ def main():
         h = {k: pin(v) for k, v in work.items()}
         hnp = {k: v.numpy() for k, v in h.items()}
         hout = eng.alloc_host_results(hn, pinned=True)     # results land in pinned host memory
+        if full:
+            hout['polya'] = torch.zeros((hn, out['polya'].shape[1]), dtype=torch.uint8,
+                                        pin_memory=True).numpy().view(_polya_dtype()).reshape(hn)
         torch.cuda.synchronize()
-        eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
-                         hnp['digitisation'], hnp['offset'], barcoding=True, out=hout)      # warm-up
+
+        def host_step():
+            return eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
+                                    hnp['digitisation'], hnp['offset'], barcoding=True, out=hout,
+                                    polya=full)
+        host_step()                                        # warm-up
         if world > 1:
             dist.barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            res = eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
-                                   hnp['digitisation'], hnp['offset'], barcoding=True, out=hout)
+            res = host_step()
             if world > 1:
                 c = torch.from_numpy(res['counts']).to(device)
                 dist.all_reduce(c)
@@ -495,7 +656,9 @@ def main():
         d2h = sum(v.nbytes for v in res.values())
         result['e2e'] = {'value': world * hn / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
-                         'api': 'pb2_analyze_host (pinned host input and result buffers; 5-chunk H2D/compute/D2H pipeline)'}
+                         'api': 'pb2_analyze_host (pinned host input and result buffers; chunked '
+                                'H2D/compute/D2H pipeline)' +
+                                ('; the chimera filter of config full is not part of this call' if full else '')}
         assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------
@@ -506,20 +669,32 @@ def main():
         ns = int(min(max(rate * args.cpu_seconds, 256), 65536, n))
         sample = host_sample(work, ns)
         rate, dt, ref = cpu_reference_rate(args.preset, sample, threads)
+        okseg = np.isin(ref['status'], [0, 5])
+        p = ref['pushed'] == 1
         same = bool(np.array_equal(ref['status'], status[:ns]) and
-                    np.array_equal(ref['seg'][:, :6][np.isin(ref['status'], [0, 5])],
-                                   out['segments'][:ns].cpu().numpy()[:, :6][np.isin(ref['status'], [0, 5])]))
+                    np.array_equal(ref['seg'][:, :6][okseg], seg_np[:ns][:, :6][okseg]) and
+                    np.array_equal(ref['barcode'][p], bc_np[:ns][p]) and
+                    np.array_equal(ref['guess'][p], guess_np[:ns][p]) and
+                    np.array_equal(ref['phred'][p], score_np[:ns][p]))
         result['cpu_baseline'] = {
             'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
             'sample': 'first %d reads of the same workload, %.1f s; C restatement of the '
-                      'reference path (oracle/pb_oracle.c, OpenMP over reads, AVX2+FMA) -- '
-                      'faster than the real Python/TF/pomegranate stack' % (ns, dt),
-            'outputs_match_gpu': same}
+                      'reference path (oracle/pb_oracle.c, OpenMP over reads, AVX2+FMA), stages A-D '
+                      'with barcoding -- faster than the real Python/TF/pomegranate stack; the '
+                      'reference Python over shims measured 6.5 reads/s/core (SURVEY.md section 6; '
+                      'profiles/r2_cpu_reference_python.json)' % (ns, dt),
+            'outputs_match_gpu': same,
+            'compared': 'status, segments, barcode, best guess, phred of the sample'}
 
     if rank == 0:
         emit(result)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _polya_dtype():
+    from poreplex_b200.engine import POLYA_DTYPE
+    return POLYA_DTYPE
 
 
 if __name__ == '__main__':

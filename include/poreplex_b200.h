@@ -181,6 +181,30 @@ typedef struct {
     int32_t block_stride;            /* samples per event row          (mean == NULL) */
 } pb2_event_tables;
 
+/* FASTQ side of a batch of guppy basecalls (Fast5Reader.get_basecall, fast5_file.py:149-151):
+ * what construct_events_from_moves (fast5_file.py:183-207) reads besides the Move table. */
+typedef struct {
+    const uint8_t *sequence;         /* concatenated sequences as basecalled (U or T)          */
+    const uint8_t *qstring;          /* concatenated quality strings, same offsets             */
+    const int64_t *seq_offsets;      /* [n_reads + 1]                                          */
+    const double *qual_table;        /* [256] 1 - 10 ** -((q - 33) / 10) per byte value, built
+                                        by the caller with the reference's numpy expression    */
+} pb2_basecalls;
+
+/* Event-table columns derived on the device (any pointer may be NULL = not wanted); all
+ * arrays are [n_events_total] in the order of pb2_event_tables.event_offsets.
+ * fast5_file.py:183-230 + signal_analyzer.py:311-326. */
+typedef struct {
+    float *mean, *stdv;              /* medfilt(5) block mean / np.std, float32                */
+    float *scaled_mean;              /* poly1d(scale, shift)(mean), float32 (needs scale_shift) */
+    int64_t *start, *end, *length;   /* arange(first, ., stride); start + diff, last + 1; stride */
+    int64_t *pos;                    /* cumsum(move)                                            */
+    double *p_model_state;           /* qual[cumsum(move) - 1 + posshift]                      */
+    uint8_t *model_state;            /* [.][5] k-mer of the reversed sequence, U -> T          */
+    int32_t *error;                  /* [n_reads] 0 ok; 1 unknown k-mer size (fast5_file.py:197);
+                                        2 events / raw strides mismatch (fast5_file.py:221)    */
+} pb2_event_columns;
+
 /* A batch of reads: ragged int16 DAC samples + per-read calibration
  * (Fast5Reader.get_raw_data, fast5_file.py:122-131).  raw_offsets[i] is the element
  * offset of read i in `raw` and must be a multiple of 8 (16-byte aligned reads). */
@@ -307,6 +331,18 @@ int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_batch *batch,
                             const pb2_event_tables *events, int64_t n_reads,
                             const float *scale_shift, const int32_t *status,
                             const int32_t *segments, int32_t max_windows, int32_t *flag);
+/* Fast5Reader.construct_events_from_moves + convert_events_guppy (fast5_file.py:183-230) and the
+ * derived columns of SignalAnalysis.load_events (signal_analyzer.py:311-326) for a batch of
+ * guppy Move tables.  events: event_offsets, move, first_sample, block_stride are read (mean /
+ * start / p_model_state are not).  basecalls may be NULL when pos-dependent columns are not
+ * wanted; scale_shift [n][2] may be NULL when scaled_mean is not wanted.  Device pointers. */
+int pb2_derive_event_tables(pb2_context *ctx, const pb2_batch *batch,
+                            const pb2_event_tables *events, const pb2_basecalls *basecalls,
+                            const float *scale_shift, const pb2_event_columns *out, void *stream);
+/* same with HOST pointers everywhere (copies in, runs, copies the columns out, synchronises) */
+int pb2_derive_event_tables_host(pb2_context *ctx, const pb2_batch *batch,
+                                 const pb2_event_tables *events, const pb2_basecalls *basecalls,
+                                 const float *scale_shift, const pb2_event_columns *out);
 /* io.py:274-278 */
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream);
@@ -327,7 +363,11 @@ int pb2_set_exact_division(pb2_context *ctx, int on);
  * logits is  demux_margin_delta + demux_probe_gain * s,  s being the shift of the logits
  * under a deliberately coarse second evaluation of layer 2 (the classifier's second LSTM
  * amplifies perturbations by orders of magnitude for a small fraction of windows, so the
- * sensitivity is measured per window).  Pass 0 to keep a value.  on = 0: exact kernels only. */
+ * sensitivity is measured per window).  Pass 0 to keep a value.  on = 0: exact kernels only.
+ * on = 2 ("strict"): scaler, segmentation and barcode windows through the exact kernels for
+ * every read -- (scale, shift) and the normalised signal are then the reference's float32
+ * values bit for bit -- and only the classifier on the tensor cores (margin test + exact
+ * re-run of the windows it flags). */
 int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta,
                       double demux_probe_gain);
 /* Verification: the tensor-core demultiplexer WITHOUT the exact re-run -- approximate class

@@ -356,7 +356,11 @@ def install():
     install_fake_h5py()
     sys.modules['pomegranate'] = make_pomegranate()
     sys.modules.update(make_tensorflow())
-    sys.modules.setdefault('pysam', _stub('pysam', BGZFile=None, FUNMAP=4))
+    import gzip
+    sys.modules.setdefault('pysam', _stub(
+        'pysam', BGZFile=lambda path, mode='r': gzip.open(path, mode), faidx=None,
+        FUNMAP=4, FREVERSE=16, FSECONDARY=256, FSUPPLEMENTARY=2048,
+        AlignmentFile=None, AlignedSegment=None))
     sys.modules.setdefault('mappy', _stub('mappy'))
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

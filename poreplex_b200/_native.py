@@ -105,6 +105,16 @@ class EventTables(C.Structure):
                 ('first_sample', C.c_void_p), ('block_stride', C.c_int32)]
 
 
+class Basecalls(C.Structure):
+    _fields_ = [('sequence', C.c_void_p), ('qstring', C.c_void_p), ('seq_offsets', C.c_void_p),
+                ('qual_table', C.c_void_p)]
+
+
+class EventColumns(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ('mean', 'stdv', 'scaled_mean', 'start', 'end', 'length',
+                                           'pos', 'p_model_state', 'model_state', 'error')]
+
+
 class Batch(C.Structure):
     _fields_ = [('n_reads', C.c_int64), ('n_raw_total', C.c_int64),
                 ('max_raw_length', C.c_int64),
@@ -130,7 +140,8 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
            'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
-           'pb2_audit_stats', 'pb2_detect_events']
+           'pb2_audit_stats', 'pb2_detect_events', 'pb2_derive_event_tables',
+           'pb2_derive_event_tables_host']
 
 
 def sources():
@@ -209,6 +220,10 @@ def load():
                                      vp, vp, C.c_int32, vp, vp]
     L.pb2_detect_unsplit_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables), C.c_int64,
                                           vp, vp, vp, C.c_int32, vp]
+    L.pb2_derive_event_tables.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables),
+                                          C.POINTER(Basecalls), vp, C.POINTER(EventColumns), vp]
+    L.pb2_derive_event_tables_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables),
+                                               C.POINTER(Basecalls), vp, C.POINTER(EventColumns)]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

@@ -78,7 +78,7 @@ static const char *const kKernelNames[K_NUM] = {
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
     "k_unsplit_windows", "k_unsplit_decide", "k_event_means", "k_lstm_tc_demux_l1",
     "k_lstm_tc_demux_l2", "k_demux_head_tc", "k_lstm_tc_scaler_l1", "k_lstm_tc_scaler_l2",
-    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe"};
+    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe", "k_event_pos"};
 
 static void ws_free(Workspace &w)
 {
@@ -222,7 +222,8 @@ int pb2_set_exact_division(pb2_context *ctx, int on)
 int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta, double demux_probe_gain)
 {
     if (!ctx) return PB2_EINVAL;
-    ctx->fast_lstm = on != 0;
+    ctx->fast_lstm = on == 1;
+    ctx->strict_tc_demux = on == 2;
     if (demux_margin_delta > 0) ctx->demux_margin_delta = demux_margin_delta;
     if (demux_probe_gain > 0) ctx->demux_probe_gain = demux_probe_gain;
 
@@ -372,6 +373,11 @@ int pb2_set_demux(pb2_context *ctx, const pb2_demux_params *p)
         return fail(ctx, PB2_EINVAL, "bad demux class / calibration sizes");
     if (p->trim_length < 1 || p->trim_length > PB2_WINDOW_MAX)
         return fail(ctx, PB2_EINVAL, "signal_trim_length out of range");
+    // the count tensor has one slot per barcode (io.py:269-278): more barcode classes than
+    // slots would be folded into "undetermined" silently
+    if (p->n_decoy < 0 || p->n_classes - p->n_decoy > PB2_N_BARCODE_SLOTS - 1)
+        return fail(ctx, PB2_EUNSUPPORTED, "%d barcode classes, the count tensor holds %d",
+                    p->n_classes - p->n_decoy, PB2_N_BARCODE_SLOTS - 1);
     int rc;
     if ((rc = upload_lstm(ctx, p->fwd, D.fwd))) return rc;
     if ((rc = upload_lstm(ctx, p->bwd, D.bwd))) return rc;
@@ -599,6 +605,92 @@ int pb2_detect_unsplit_host(pb2_context *ctx, const pb2_batch *hb, const pb2_eve
                             (const int32_t *)(base + o_seg), max_windows, (int32_t *)(base + o_fl), st);
     if (rc) return rc;
     PB_CUDA(ctx, cudaMemcpyAsync(flag, base + o_fl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
+}
+
+int pb2_derive_event_tables(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tables *events,
+                            const pb2_basecalls *basecalls, const float *scale_shift,
+                            const pb2_event_columns *out, void *stream)
+{
+    int rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!events || !out) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    return launch_derive_events(ctx, *batch, *events, basecalls, scale_shift, *out, (cudaStream_t)stream);
+}
+
+int pb2_derive_event_tables_host(pb2_context *ctx, const pb2_batch *hb, const pb2_event_tables *hev,
+                                 const pb2_basecalls *hbc, const float *scale_shift,
+                                 const pb2_event_columns *hout)
+{
+    int rc = check_batch(ctx, hb);
+    if (rc) return rc;
+    if (!hev || !hout || !hev->event_offsets || !hev->first_sample) return PB2_EINVAL;
+    const int64_t n = hb->n_reads;
+    if (n <= 0) return PB2_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->host_stream;
+    const size_t E = (size_t)hev->n_events_total;
+    const size_t S = hbc ? (size_t)hbc->seq_offsets[n] : 0;
+    const size_t R = (size_t)hb->n_raw_total;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align(bytes + 16); return o; };
+    const size_t o_raw = take(2 * R), o_ro = take(8 * n), o_rl = take(8 * n), o_rg = take(8 * n);
+    const size_t o_dg = take(8 * n), o_of = take(8 * n), o_eo = take(8 * (n + 1)), o_fs = take(8 * n);
+    const size_t o_mv = take(4 * E), o_sq = take(S), o_qs = take(S), o_so = take(8 * (n + 1));
+    const size_t o_qt = take(8 * 256), o_ss = take(8 * n);
+    const size_t o_mean = take(4 * E), o_stdv = take(4 * E), o_sm = take(4 * E), o_start = take(8 * E);
+    const size_t o_end = take(8 * E), o_len = take(8 * E), o_pos = take(8 * E), o_pm = take(8 * E);
+    const size_t o_ms = take(5 * E), o_err = take(4 * n);
+    char *base = (char *)ws_get(ctx, ctx->ws_unsplit_host, off);
+    if (!base) return PB2_ENOMEM;
+#define PB_H2D(o, src, bytes) if ((src) && (bytes)) PB_CUDA(ctx, cudaMemcpyAsync(base + (o), (src), (bytes), cudaMemcpyHostToDevice, st))
+    PB_H2D(o_raw, hb->raw, 2 * R); PB_H2D(o_ro, hb->raw_offsets, 8 * n); PB_H2D(o_rl, hb->raw_lengths, 8 * n);
+    PB_H2D(o_rg, hb->range, 8 * n); PB_H2D(o_dg, hb->digitisation, 8 * n); PB_H2D(o_of, hb->offset, 8 * n);
+    PB_H2D(o_eo, hev->event_offsets, 8 * (n + 1)); PB_H2D(o_fs, hev->first_sample, 8 * n);
+    PB_H2D(o_mv, hev->move, 4 * E);
+    if (hbc) {
+        PB_H2D(o_sq, hbc->sequence, S); PB_H2D(o_qs, hbc->qstring, S);
+        PB_H2D(o_so, hbc->seq_offsets, 8 * (n + 1)); PB_H2D(o_qt, hbc->qual_table, 8 * 256);
+    }
+    PB_H2D(o_ss, scale_shift, 8 * n);
+#undef PB_H2D
+    pb2_batch db = *hb;
+    db.raw = (const int16_t *)(base + o_raw); db.raw_offsets = (const int64_t *)(base + o_ro);
+    db.raw_lengths = (const int64_t *)(base + o_rl); db.range = (const double *)(base + o_rg);
+    db.digitisation = (const double *)(base + o_dg); db.offset = (const double *)(base + o_of);
+    pb2_event_tables dev = *hev;
+    dev.event_offsets = (const int64_t *)(base + o_eo); dev.first_sample = (const int64_t *)(base + o_fs);
+    dev.move = hev->move ? (const int32_t *)(base + o_mv) : nullptr;
+    pb2_basecalls dbc = {};
+    if (hbc) {
+        dbc.sequence = hbc->sequence ? (const uint8_t *)(base + o_sq) : nullptr;
+        dbc.qstring = hbc->qstring ? (const uint8_t *)(base + o_qs) : nullptr;
+        dbc.seq_offsets = (const int64_t *)(base + o_so);
+        dbc.qual_table = hbc->qual_table ? (const double *)(base + o_qt) : nullptr;
+    }
+    pb2_event_columns d = {};
+    d.mean = hout->mean ? (float *)(base + o_mean) : nullptr;
+    d.stdv = hout->stdv ? (float *)(base + o_stdv) : nullptr;
+    d.scaled_mean = hout->scaled_mean ? (float *)(base + o_sm) : nullptr;
+    d.start = hout->start ? (int64_t *)(base + o_start) : nullptr;
+    d.end = hout->end ? (int64_t *)(base + o_end) : nullptr;
+    d.length = hout->length ? (int64_t *)(base + o_len) : nullptr;
+    // pos is needed on the device by the columns that hang off it
+    d.pos = (hout->pos || hout->p_model_state || hout->model_state) ? (int64_t *)(base + o_pos) : nullptr;
+    d.p_model_state = hout->p_model_state ? (double *)(base + o_pm) : nullptr;
+    d.model_state = hout->model_state ? (uint8_t *)(base + o_ms) : nullptr;
+    d.error = hout->error ? (int32_t *)(base + o_err) : nullptr;
+    if (d.model_state) PB_CUDA(ctx, cudaMemsetAsync(d.model_state, 0, 5 * E + 1, st));
+    rc = launch_derive_events(ctx, db, dev, hbc ? &dbc : nullptr, scale_shift ? (const float *)(base + o_ss) : nullptr, d, st);
+    if (rc) return rc;
+#define PB_D2H(field, bytes) if (hout->field && (bytes)) PB_CUDA(ctx, cudaMemcpyAsync(hout->field, d.field, (bytes), cudaMemcpyDeviceToHost, st))
+    PB_D2H(mean, 4 * E); PB_D2H(stdv, 4 * E); PB_D2H(scaled_mean, 4 * E); PB_D2H(start, 8 * E);
+    PB_D2H(end, 8 * E); PB_D2H(length, 8 * E); PB_D2H(pos, 8 * E); PB_D2H(p_model_state, 8 * E);
+    PB_D2H(model_state, 5 * E); PB_D2H(error, 4 * n);
+#undef PB_D2H
     PB_CUDA(ctx, cudaStreamSynchronize(st));
     return PB2_OK;
 }
@@ -905,8 +997,15 @@ int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_resul
                                          sizeof(float) * PB2_MAX_CLASSES * (size_t)n, st));
         if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows,
                                  pushed, slot_count, slot_read, st))) return rc;
-        if ((rc = launch_demux(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
-                               barcode, guess, score, st))) return rc;
+        if (ctx->strict_tc_demux && !ctx->exact_division) {
+            // "strict" mode: (scale, shift), the normalised signal, segments and windows above are
+            // the exact kernels' for every read; only the classifier runs on the tensor cores,
+            // with the margin test and an exact re-run of the windows it flags
+            if ((rc = launch_demux_tc(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
+                                      barcode, guess, score, nullptr, nullptr, nullptr, /*recheck=*/true,
+                                      st, nullptr))) return rc;
+        } else if ((rc = launch_demux(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
+                                      barcode, guess, score, st))) return rc;
     } else {
         barcode = res->barcode; guess = res->barcode_guess; score = res->barcode_score;
     }
@@ -1209,6 +1308,16 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
     if (n < min_reads || keep || hb->n_raw_total < min_elems || nchunks < 2)
         return analyze_host_single(ctx, hb, hr, flags);
+    // the pipelined path uploads each chunk as ONE span of the raw buffer and rebases its
+    // offsets: that needs reads laid out in ascending, non-overlapping order inside the
+    // buffer.  Any other layout is legal for the ABI and takes the single-arena path.
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t o = hb->raw_offsets[i], l = hb->raw_lengths[i];
+        if (o < 0 || l < 0 || o + l > hb->n_raw_total)
+            return fail(ctx, PB2_EINVAL, "read %lld lies outside the raw buffer", (long long)i);
+        if (i > 0 && o < hb->raw_offsets[i - 1] + hb->raw_lengths[i - 1])
+            return analyze_host_single(ctx, hb, hr, flags);
+    }
     std::vector<int64_t> bounds;
     // The first upload and the last download are not hidden behind kernels: make the first and
     // the last chunk half as large as the others (weights 1 2 2 ... 2 1).

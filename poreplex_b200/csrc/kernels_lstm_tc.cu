@@ -211,7 +211,7 @@ __device__ __forceinline__ uint32_t split_pair(float2 h, uint32_t &lo) {
 // has a component that is independent of probe 1's, so that the two probes do not both
 // under-estimate a window's sensitivity by an unlucky projection.
 template <int H, int KX, bool SEQ_OUT, int COARSE = 0>
-__global__ void __launch_bounds__(tc_threads<H, KX>(), (KX == 0 ? 2 : 1))
+__global__ void __maxnreg__((KX == 0 ? 112 : 120))
 k_lstm_tc(const TcArgs A)
 {
     constexpr int N = 4 * H;
@@ -243,7 +243,12 @@ k_lstm_tc(const TcArgs A)
     constexpr int G0_PARTS = (NGRP == 2) ? 2 : NP;           // parts in group 0
     constexpr int N0 = G0_PARTS * UPT * 4, N1 = N - N0;      // accumulator columns of the groups
     static_assert(N0 % 16 == 0 && N1 % 16 == 0, "bad column grouping");
-    __shared__ __align__(8) uint64_t bar_d[2], bar_h;
+    // Vector-input layers are software pipelined: the x(t+1) W products do not depend on the
+    // recurrence, so they are issued into the accumulator as soon as every gate warp has pulled
+    // its D(t) columns into registers (bar_x) and run on the tensor pipe WHILE the gate warps
+    // evaluate step t; only the h(t) U products (K = H) stay on the critical path.
+    constexpr bool PIPE = KX > 0;
+    __shared__ __align__(8) uint64_t bar_d[2], bar_h, bar_x;
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead, s_tstart;
 
@@ -264,6 +269,7 @@ k_lstm_tc(const TcArgs A)
         mbar_init(&bar_d[0], 1);
         mbar_init(&bar_d[1], 1);
         mbar_init(&bar_h, NGW);
+        mbar_init(&bar_x, NGW);
         mbar_fence_init();
         s_dead = 0;
         s_tstart = (dir.skip_mode != 0) ? T : 0;
@@ -334,31 +340,34 @@ k_lstm_tc(const TcArgs A)
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t ph = 0;
+            constexpr uint32_t BOFS = (N0 / 8) * 128;                  // bytes into each k-chunk
             for (int s = t_start; s < s_end; s++) {
+                bool first0 = true, first1 = true;
+                if (PIPE) {
+                    // D(t-1) is in the gate warps' registers and x(t) in TMEM: the input products
+                    // of both column groups go first and overlap the gate phase of step t-1
+                    mbar_wait(&bar_x, ph, &s_dead);
+                    fence_after_sync();
+                    issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
+                                                                tbase + col_x + KX / 2,
+                                                                smem_u32(bW_hi), smem_u32(bW_lo), first0,
+                                                                COARSE == 0);
+                    issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
+                        tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
+                        smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first1, COARSE == 0);
+                }
                 mbar_wait(&bar_h, ph, &s_dead);
                 ph ^= 1;
                 fence_after_sync();
                 // h(t-1) sits in buffer (s - t_start) & 1 (the initial state is written to buffer 0)
                 const uint32_t hcol = tbase + col_h + (HB == 2 ? ((s - t_start) & 1) * H : 0);
-                bool first = true;
-                if (KX > 0)
-                    issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
-                                                                tbase + col_x + KX / 2,
-                                                                smem_u32(bW_hi), smem_u32(bW_lo), first,
-                                                                COARSE == 0);
                 issue_split_gemm<H, N, N0>(tbase + col_d, hcol, hcol + H / 2,
-                                           smem_u32(bU_hi), smem_u32(bU_lo), first, COARSE == 0);
+                                           smem_u32(bU_hi), smem_u32(bU_lo), first0, COARSE == 0);
                 mma_commit(&bar_d[0]);
                 if (NGRP == 2) {
-                    constexpr uint32_t BOFS = (N0 / 8) * 128;          // bytes into each k-chunk
-                    first = true;
-                    if (KX > 0)
-                        issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
-                            tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
-                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first, COARSE == 0);
                     issue_split_gemm<H, N, (N1 > 0 ? N1 : 16)>(tbase + col_d + N0, hcol, hcol + H / 2,
                                                                smem_u32(bU_hi) + BOFS, smem_u32(bU_lo) + BOFS,
-                                                               first, COARSE == 0);
+                                                               first1, COARSE == 0);
                     mma_commit(&bar_d[1]);
                 }
             }
@@ -420,7 +429,16 @@ k_lstm_tc(const TcArgs A)
         tmem_st_wait();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_h);
+        if (lane == 0) {
+            mbar_arrive(&bar_h);
+            if (PIPE) mbar_arrive(&bar_x);
+        }
+        if (PIPE && t_start + 1 < T) {                     // the second step's input, on its way
+            const int tn = dir.reverse ? (T - 2 - t_start) : (t_start + 1);
+            const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+            for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+        }
 
         uint32_t ph = 0;
         uint32_t rng = ((uint32_t)(A.row0 + tile0 + m) * 2654435761u) ^ ((uint32_t)part * 0x9E3779B9u) ^ 0x85EBCA6Bu;
@@ -430,12 +448,6 @@ k_lstm_tc(const TcArgs A)
             const int t = dir.reverse ? (T - 1 - s) : s;
             float xv = 0.f;
             if (KX == 0) xv = (t >= pad) ? __ldg(xbase + t) : A.padval;
-            if (KX > 0 && s + 1 < T) {                     // prefetch the next step's input
-                const int tn = dir.reverse ? (T - 2 - s) : (s + 1);
-                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
-#pragma unroll
-                for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
-            }
             // this thread's slots in the sequence scratch at step t (constant offsets from here)
             uint32_t *g_hi_t = nullptr, *g_lo_t = nullptr;
             if (SEQ_OUT) {
@@ -450,11 +462,37 @@ k_lstm_tc(const TcArgs A)
             mbar_wait(&bar_d[grp], ph, &s_dead);
             __syncwarp();
             fence_after_sync();
+            uint32_t va[PIPE ? NCH : 1][32];
+            if (PIPE) {
+                // every pre-activation of this thread -> registers; then the accumulator columns
+                // and the x operand are free for the next step's input products
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) tmem_ld32(d_addr + ch * 32, va[ch]);
+                tmem_ld_wait();
+                if (s + 1 < T) {
+#pragma unroll
+                    for (int j = 0; j < XW; j += 4)
+                        tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+                    tmem_st_wait();
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_x);
+                if (s + 2 < T) {                           // x(t+2): a whole step to arrive
+                    const int tn = dir.reverse ? (T - 3 - s) : (s + 2);
+                    const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+                    for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+                }
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
-                uint32_t vv[32];
-                tmem_ld32(d_addr + ch * 32, vv);
-                tmem_ld_wait();
+                uint32_t vl[32];
+                if (!PIPE) {
+                    tmem_ld32(d_addr + ch * 32, vl);
+                    tmem_ld_wait();
+                }
+                const uint32_t (&vv)[32] = PIPE ? va[ch] : vl;
                 uint32_t hi[4], lo[4];
                 float2 hn[4];
 #pragma unroll
@@ -501,17 +539,6 @@ k_lstm_tc(const TcArgs A)
 #pragma unroll
                     for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
                 }
-            }
-            if (KX > 0 && s + 1 < T) {
-                // the x operand may be replaced only when every MMA of this step is done
-                if (NGRP > 1 && grp != NGRP - 1) {
-                    mbar_wait(&bar_d[NGRP - 1], ph, &s_dead);
-                    __syncwarp();
-                    fence_after_sync();
-                }
-#pragma unroll
-                for (int j = 0; j < XW; j += 4)
-                    tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
             }
             ph ^= 1;
             tmem_st_wait();

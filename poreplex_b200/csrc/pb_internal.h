@@ -70,7 +70,7 @@ namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
                 K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_DEMUX_TC_L1, K_DEMUX_TC_L2, K_DEMUX_TC_HEAD,
-                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_NUM };
+                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_EVENT_POS, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 
@@ -82,6 +82,7 @@ struct pb2_context {
     // tensor-core LSTM path (kernels_lstm_tc.cu): approximate outputs + margin test + exact
     // re-run of the reads whose decisions are not safe.  Off = exact kernels only.
     bool fast_lstm = true;
+    bool strict_tc_demux = false;    // exact scaler / segmentation / windows, tensor-core classifier
     // per-window bound on the logit error = delta + probe_gain * (logit shift of the coarse probe)
     double demux_margin_delta = 1e-3;
     double demux_probe_gain = 0.1;
@@ -215,6 +216,9 @@ int launch_detect_events(pb2_context *ctx, const float *signal, const int64_t *o
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);
+int launch_derive_events(pb2_context *ctx, const pb2_batch &b, const pb2_event_tables &ev,
+                         const pb2_basecalls *bc, const float *scale_shift,
+                         const pb2_event_columns &out, cudaStream_t st);
 int launch_unsplit(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tables &ev,
                    int64_t n, const float *scale_shift, const int32_t *status,
                    const int32_t *segments, int32_t max_windows, int32_t *flag, cudaStream_t st);

@@ -217,12 +217,22 @@ struct pb2f_file {
         // depth-first, children in order: names come out sorted as the file stores them
         struct Walk {
             const pb2f_file &f; uint64_t heap; std::vector<std::string> &out;
-            void go(uint64_t node, int depth) {
+            // A crafted node that names itself (or an ancestor) as its child must not hang the
+            // loader: node levels have to fall by one per step (level 0 points at symbol nodes),
+            // which rules out cycles, and the whole walk has a node budget.
+            uint64_t visited = 0;
+            void go(uint64_t node, int depth, int want_level = -1) {
                 if (depth > 64) bad("group B-tree too deep");
+                if (++visited > (1u << 22)) bad("group B-tree has too many nodes");
                 if (f.m.sig(node, "TREE")) {
+                    const int level = f.m.u8(node + 5);
+                    if (want_level == -2 || (want_level >= 0 && level != want_level))
+                        bad("group B-tree levels are inconsistent");
                     const unsigned used = f.m.u16(node + 6);
-                    for (unsigned i = 0; i < used; i++) go(f.m.u64(node + 24 + 16ull * i + 8), depth + 1);
+                    for (unsigned i = 0; i < used; i++)
+                        go(f.m.u64(node + 24 + 16ull * i + 8), depth + 1, level > 0 ? level - 1 : -2);
                 } else if (f.m.sig(node, "SNOD")) {
+                    if (want_level >= 0) bad("group B-tree levels are inconsistent");
                     const unsigned nsym = f.m.u16(node + 6);
                     for (unsigned i = 0; i < nsym; i++)
                         out.push_back(f.m.cstr(heap + f.m.u64(node + 8 + 40ull * i)));
@@ -230,7 +240,7 @@ struct pb2f_file {
                     bad("bad group node signature");
                 }
             }
-        } w{*this, heap, out};
+        } w{*this, heap, out, 0};
         w.go(root_node, 0);
     }
 
@@ -582,16 +592,19 @@ void read_int16(const pb2f_file &f, const Dataset &d, int16_t *dst, Scratch &s)
     if (d.btree == UNDEF) return;
     struct Walk {
         const pb2f_file &f; const Dataset &d; int16_t *dst; Scratch &s; uint64_t n, clen;
-        void go(uint64_t node, int depth) {
+        uint64_t visited = 0;
+        void go(uint64_t node, int depth, int want_level = -1) {
             if (depth > 32) bad("chunk B-tree too deep");
+            if (++visited > (1u << 22)) bad("chunk B-tree has too many nodes");
             if (!f.m.sig(node, "TREE") || f.m.u8(node + 4) != 1) bad("bad chunk B-tree node");
             const unsigned level = f.m.u8(node + 5), used = f.m.u16(node + 6);
+            if (want_level >= 0 && (int)level != want_level) bad("chunk B-tree levels are inconsistent");
             const uint64_t klen = 8 + 8 * 2;               // size, mask, offset[rank + 1], rank 1
             uint64_t p = node + 24;
             for (unsigned i = 0; i < used; i++, p += klen + 8) {
                 const uint32_t size = f.m.u32(p), mask = f.m.u32(p + 4);
                 const uint64_t off = f.m.u64(p + 8), child = f.m.u64(p + klen);
-                if (level) { go(child, depth + 1); continue; }
+                if (level) { go(child, depth + 1, (int)level - 1); continue; }
                 if (off >= n) continue;
                 const uint64_t take = off + clen <= n ? clen : n - off;
                 const uint8_t *src = f.m.at(child, size);
@@ -606,7 +619,7 @@ void read_int16(const pb2f_file &f, const Dataset &d, int16_t *dst, Scratch &s)
                 }
             }
         }
-    } w{f, d, dst, s, n, clen};
+    } w{f, d, dst, s, n, clen, 0};
     w.go(d.btree, 0);
 }
 

@@ -14,7 +14,8 @@ import numpy as np
 from . import _native as N
 from . import params as P
 
-__all__ = ['SignalEngine', 'get_engine', 'POLYA_DTYPE', 'polya_to_dict']
+__all__ = ['SignalEngine', 'get_engine', 'close_engines', 'config_digest', 'POLYA_DTYPE',
+           'polya_to_dict']
 
 POLYA_DTYPE = np.dtype([('found', 'i4'), ('n_spikes', 'i4'), ('begin', 'i8'), ('end', 'i8'),
                         ('dwell_samples', 'i8'), ('extensions', 'i4'), ('flags', 'i4'),
@@ -24,8 +25,17 @@ assert POLYA_DTYPE.itemsize == C.sizeof(N.PolyaResult)
 
 def polya_to_dict(rec, sampling_rate):
     """pb2_polya_result -> the dict of NanoporeRead.set_polya_tail (polya.py:116-121)."""
+    # Capacity limits of the kernel's fixed-size buffers are never silent: the reference would
+    # report the full record, so a read that exceeds them becomes an error for that read
+    # (the drop-in turns it into `unknown_error` with this message).
+    if int(rec['flags']) & 1:
+        raise OverflowError('poly(A) recalibration met more anchor events than the kernel '
+                            'buffers (polya_core.cuh POLYA_MAX_ANCHORS)')
     if not rec['found']:
         return None
+    if int(rec['n_spikes']) > N.POLYA_MAX_SPIKES:
+        raise OverflowError('poly(A) tail holds {} spikes, more than the {} the result record '
+                            'carries'.format(int(rec['n_spikes']), N.POLYA_MAX_SPIKES))
     spikes = []
     for k in range(min(int(rec['n_spikes']), N.POLYA_MAX_SPIKES)):
         row = rec['spikes'][k]
@@ -96,7 +106,6 @@ class SignalEngine:
     def __init__(self, config, device=0, barcoding=None, barcoding_quality_filter=None):
         from scipy.stats import norm
         self.lib = N.load()
-        self.config = config
         self._keep = []
         handle = C.c_void_p()
         rc = self.lib.pb2_create(int(device), C.byref(handle))
@@ -222,9 +231,14 @@ class SignalEngine:
         self._check(self.lib.pb2_set_exact_division(self.handle, 1 if on else 0))
 
     def set_fast_lstm(self, on=True, demux_margin_delta=0.0, demux_probe_gain=0.0):
-        """Tensor-core LSTM path with margin test + exact re-run (default on); off = exact
-        f32 kernels only."""
-        self._check(self.lib.pb2_set_fast_lstm(self.handle, 1 if on else 0,
+        """True / 'fast': tensor-core scaler and classifier with margin tests + exact re-run (the
+        library default); 'strict': exact scaler, segmentation and windows for every read (all
+        float outputs but the class probabilities bit-exact), tensor-core classifier with
+        margin test + exact re-run; False / 'exact': exact f32 kernels only."""
+        mode = {'fast': 1, 'strict': 2, 'exact': 0}.get(on, 1 if on else 0) if isinstance(on, str) \
+            else (2 if on == 2 else (1 if on else 0))
+        self.lstm_mode = ('exact', 'fast', 'strict')[mode]
+        self._check(self.lib.pb2_set_fast_lstm(self.handle, mode,
                                                float(demux_margin_delta), float(demux_probe_gain)))
 
     def recheck_stats(self):
@@ -339,7 +353,8 @@ class SignalEngine:
         if polya:
             if not self.polya_ready:
                 raise ValueError("config has no 'polya_dwell' section")
-            out['polya'] = np.zeros(n, POLYA_DTYPE)
+            if 'polya' not in out or out['polya'].shape != (n,):
+                out['polya'] = np.zeros(n, POLYA_DTYPE)
         b = N.Batch(n, raw.size, int(lengths.max()) if n else 0, _np_ptr(raw), _np_ptr(offsets),
                     _np_ptr(lengths), _np_ptr(rng), _np_ptr(digitisation), _np_ptr(offset))
         r = N.Results(_np_ptr(out['status']), _np_ptr(out['label']), _np_ptr(out['scale_shift']),
@@ -422,6 +437,75 @@ class SignalEngine:
             self.handle, bptr, C.byref(ev), n, _np_ptr(scale_shift), _np_ptr(status),
             _np_ptr(segments), int(maxw), _np_ptr(flag)))
         return flag
+
+    @staticmethod
+    def quality_table():
+        """qual[byte] = 1 - 10 ** -((byte - 33) / 10) with the reference's own numpy expression
+        (fast5_file.py:188) for every byte value; the device only gathers from it."""
+        with np.errstate(over='ignore'):
+            return np.ascontiguousarray(
+                1 - 10 ** -((np.arange(256, dtype=np.uint8) - 33) / 10), np.float64)
+
+    def derive_event_tables_host(self, batch, moves, first_sample, block_stride, sequences=None,
+                                 qstrings=None, scale_shift=None,
+                                 columns=('mean', 'stdv', 'start', 'end', 'length', 'pos',
+                                          'p_model_state', 'model_state', 'scaled_mean')):
+        """Guppy ``Move`` tables -> event-table columns for a batch of reads, on the device
+        (Fast5Reader.construct_events_from_moves / convert_events_guppy, fast5_file.py:183-230,
+        plus the derived columns of SignalAnalysis.load_events, signal_analyzer.py:311-326).
+
+        ``batch`` = (raw, offsets, lengths, range, digitisation, offset) host arrays; ``moves``:
+        per read a uint8 / int array; ``sequences`` / ``qstrings``: per read ``str`` (FASTQ
+        lines 2 and 4).  Returns (list of per-read dicts of numpy columns, int32 error codes):
+        1 = unknown k-mer size, 2 = events / raw strides mismatch (the reference raises)."""
+        n = len(moves)
+        counts = np.array([len(m) for m in moves], np.int64)
+        ev_off = np.zeros(n + 1, np.int64)
+        ev_off[1:] = np.cumsum(counts)
+        E = int(ev_off[-1])
+        move = (np.concatenate([np.asarray(m).astype(np.int32) for m in moves])
+                if E else np.zeros(0, np.int32))
+        first = np.ascontiguousarray(first_sample, np.int64)
+        raw, roff, rlen, rng, dig, off = (np.ascontiguousarray(a) for a in batch)
+        b = N.Batch(n, raw.size, int(rlen.max()) if n else 0, _np_ptr(raw), _np_ptr(roff),
+                    _np_ptr(rlen), _np_ptr(rng), _np_ptr(dig), _np_ptr(off))
+        ev = N.EventTables(E, _np_ptr(ev_off), None, None, _np_ptr(move), None, None,
+                           _np_ptr(first), int(block_stride))
+        bc = None
+        keep = []
+        if sequences is not None:
+            seq_off = np.zeros(n + 1, np.int64)
+            seq_off[1:] = np.cumsum([len(s) for s in sequences])
+            seq = np.frombuffer(''.join(sequences).encode('ascii'), np.uint8).copy()
+            qs = np.frombuffer(''.join(qstrings).encode('ascii'), np.uint8).copy()
+            if len(qs) != len(seq):
+                raise ValueError('sequence and quality strings differ in length')
+            qt = self.quality_table()
+            keep += [seq_off, seq, qs, qt]
+            bc = N.Basecalls(_np_ptr(seq), _np_ptr(qs), _np_ptr(seq_off), _np_ptr(qt))
+        dt = {'mean': np.float32, 'stdv': np.float32, 'scaled_mean': np.float32, 'start': np.int64,
+              'end': np.int64, 'length': np.int64, 'pos': np.int64, 'p_model_state': np.float64}
+        cols = {}
+        for c in columns:
+            if c in ('pos', 'p_model_state', 'model_state') and bc is None and c != 'pos':
+                continue
+            if c == 'scaled_mean' and scale_shift is None:
+                continue
+            cols[c] = np.zeros((E, 5), np.uint8) if c == 'model_state' else np.zeros(E, dt[c])
+        err = np.zeros(n, np.int32)
+        out = N.EventColumns(*[(_np_ptr(cols[k]) if k in cols else None) for k in
+                               ('mean', 'stdv', 'scaled_mean', 'start', 'end', 'length', 'pos',
+                                'p_model_state', 'model_state')], _np_ptr(err))
+        ss = None
+        if scale_shift is not None:
+            ss = np.ascontiguousarray(scale_shift, np.float32)
+        self._check(self.lib.pb2_derive_event_tables_host(
+            self.handle, C.byref(b), C.byref(ev), C.byref(bc) if bc is not None else None,
+            _np_ptr(ss) if ss is not None else None, C.byref(out)))
+        if 'model_state' in cols:
+            cols['model_state'] = cols['model_state'].reshape(E, 5).view('S5').reshape(E)
+        tables = [{k: v[ev_off[i]:ev_off[i + 1]] for k, v in cols.items()} for i in range(n)]
+        return tables, err
 
     # ----------------------------------------------------- device-resident API
     def _batch_from_tensors(self, raw, offsets, lengths, rng, digitisation, offset,
@@ -624,17 +708,48 @@ class SignalEngine:
         return counts
 
 
-_engines = {}
+_engines = {}          # device -> (config digest, SignalEngine)
+
+# every config entry SignalEngine.__init__ (and the analyzer's engine set-up) reads
+_ENGINE_KEYS = ('signal_processing', 'segmentation', 'segmentation_model', 'polya_dwell',
+                'unsplit_read_detection_model', 'unsplit_read_detection', 'demultiplexing',
+                'barcoding', 'barcoding_quality_filter', 'fast_lstm')
+
+
+def config_digest(config):
+    """Content hash of the parameters an engine is built from.  ``pipeline.py:204`` pickles
+    ``config`` anew for every batch, so object identity says nothing: two configs with the
+    same content must map to the same engine, and a changed parameter must not."""
+    import hashlib
+    import json
+    doc = {k: config.get(k) for k in _ENGINE_KEYS}
+    doc['barcoding'] = bool(doc['barcoding'])
+    blob = json.dumps(doc, sort_keys=True, default=repr)
+    return hashlib.sha1(blob.encode()).hexdigest()
 
 
 def get_engine(config, device=0):
-    """Process-lifetime engine cache, the analogue of the reference's
-    ``sys.modules['__poreplex_persistence']`` singleton (worker_persistence.py:46-58)."""
-    key = (id(config.get('segmentation_model')), device, bool(config.get('barcoding')),
-           config.get('barcoding_quality_filter', 18),
-           config['signal_processing'].get('scaler_min_length_override'),
-           config.get('demultiplexing', {}).get('minimum_dna_length'))
-    eng = _engines.get(key)
-    if eng is None:
-        eng = _engines[key] = SignalEngine(config, device=device)
+    """Process-lifetime engine, the analogue of the reference's
+    ``sys.modules['__poreplex_persistence']`` singleton (worker_persistence.py:46-58):
+    one engine per (process, device), rebuilt -- and the superseded one closed, its device
+    arenas freed -- only when the content of the configuration changes."""
+    digest = config_digest(config)
+    held = _engines.get(device)
+    if held is not None and held[0] == digest:
+        return held[1]
+    if held is not None:
+        held[1].close()
+        del _engines[device]
+    eng = SignalEngine(config, device=device)
+    # The drop-in defaults to the exact kernels: every float and integer output is then the
+    # oracle's bit for bit.  config['fast_lstm'] opts into the tensor-core path, whose
+    # integer outputs are guarded (DESIGN.md section 3a) and whose floats are approximate.
+    eng.set_fast_lstm(config.get('fast_lstm') or False)
+    _engines[device] = (digest, eng)
     return eng
+
+
+def close_engines():
+    """Release every cached engine (tests; worker shutdown)."""
+    for dev in list(_engines):
+        _engines.pop(dev)[1].close()

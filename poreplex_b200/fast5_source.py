@@ -138,6 +138,10 @@ class Fast5Source:
         self.run_id = trackattrs['run_id'].decode()
         self.sample_id = trackattrs['sample_id'].decode()
 
+    def signal_length(self):
+        """len() of the Signal dataset (what get_raw_data clips to, fast5_file.py:123-125)."""
+        return len(self.handle[self.read_node + '/Signal'])
+
     def raw_int16(self):
         """The whole Signal dataset as int16 (no conversion; fast5_file.py:123-128)."""
         node = self.handle[self.read_node + '/Signal']

@@ -115,7 +115,11 @@ class NanoporeRead:
         """The length test of load_padded_signal_head (signal_loader.py:212-222)."""
         sigload_length = min(length_limit, self.fast5.duration)
         sigload_length = sigload_length - sigload_length % stride
-        return sigload_length < min_length
+        # get_raw_data(end=...) clips to the Signal dataset itself (fast5_file.py:124-125):
+        # a dataset shorter than its `duration` attribute is judged by what was actually read
+        got = min(sigload_length, self.fast5.signal_length())
+        got -= got % stride
+        return got < min_length
 
     def report(self):
         rep = {'filename': self.filename, 'read_id': self.read_id, 'status': self.status}
@@ -258,8 +262,11 @@ class SignalAnalyzer:
                 if 'polya' in out:
                     npread._gpu['polya'] = out['polya'][i]
                 st = STATUS_NAMES[int(out['status'][i])]
-                if st == 'scaling_qc_fail':            # fit_scalers, signal_loader.py:104-109
-                    npread.set_status('scaling_qc_fail', stop=True)
+                if st in ('scaling_qc_fail', 'scaler_signal_too_short'):
+                    # fit_scalers (signal_loader.py:104-109); a too-short head is normally
+                    # caught in stage A -- if the device still reports one, it stops the read
+                    # here rather than letting it continue with no scaling parameters
+                    npread.set_status(st, stop=True)
                 else:
                     npread.set_scaling_params(np.array(out['scale_shift'][i], dtype=np.float32))
 

@@ -27,6 +27,59 @@ from .params import STATUS_NAMES
 LABEL_NAMES = ('pass', 'fail', 'artifact')          # k_finalize label codes 0, 1, 2 (3 = none)
 
 
+def output_name_mapping(config):
+    """(label_names, barcode_names, output_layout) as commandline.py:137-159 builds them:
+    the keys every writer indexes its streams with -- 'artifact' exists only with the
+    chimera filter on, barcode keys only with barcoding on."""
+    label_names = {'fail': 'fail', 'pass': 'pass'}
+    if config['filter_unsplit_reads']:
+        label_names['artifact'] = 'artifact'
+    if config['barcoding']:
+        barcode_names = {None: 'undetermined'}
+        for i in range(config['demultiplexing']['number_of_barcodes']):
+            barcode_names[i] = 'BC{n}'.format(n=i + 1)
+        layout = {(label, bc): os.path.join(labelname, bcname)
+                  for label, labelname in label_names.items()
+                  for bc, bcname in barcode_names.items()}
+    else:
+        barcode_names = {None: '-'}
+        layout = {(label, None): labelname for label, labelname in label_names.items()}
+    return label_names, barcode_names, layout
+
+
+class FASTQWriter:
+    """io.py:38-71: one gzip stream per (label, barcode) output; a read is written with its
+    adapter_length trailing bases removed.  (The reference writes BGZF through pysam, a
+    gzip-compatible container: the decompressed bytes are what is compared.)"""
+
+    def __init__(self, output_dir, output_layout):
+        import gzip
+        self.output_dir = output_dir
+        self.output_layout = output_layout
+        self.lock = Lock()
+        self.streams = {}
+        for int_name, name in output_layout.items():
+            path = os.path.join(output_dir, 'fastq', name + '.fastq.gz')
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            self.streams[int_name] = gzip.open(path, 'wb')
+
+    def close(self):
+        for stream in self.streams.values():
+            stream.close()
+
+    def write_sequences(self, procresult):
+        with self.lock:
+            for entry in procresult:
+                if entry.get('sequence') is not None:
+                    seq, qual, adapter_length = entry['sequence']
+                    if adapter_length > 0:
+                        seq = seq[:-adapter_length]
+                        qual = qual[:-adapter_length]
+                    output_name = entry['label'], entry.get('barcode')
+                    formatted = '@{}\n{}\n+\n{}\n'.format(entry['read_id'], seq, qual)
+                    self.streams[output_name].write(formatted.encode('ascii'))
+
+
 class SequencingSummaryWriter:
     """io.py:120-184."""
 

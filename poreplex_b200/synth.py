@@ -20,11 +20,17 @@ __all__ = ['SynthSpec', 'generate_reads']
 _ORDER = ['pre-leader', 'leader-low', 'leader-high', 'adapter', 'polya-tail', 'transcript']
 
 
+# pA centre / spread a prototype unit maps to: 74 - 3.0 * 5.5 .. 74 + 2.2 * 5.5 stays where the adapter emission of
+# the segmentation HMM beats the transcript mixture (above ~90 pA the transcript state wins)
+ADAPTER_LEVEL = (74.0, 5.5)
+
 class SynthSpec:
     def __init__(self, read_length=4000, adapter_pooled=(110, 190), polya_pooled=(8, 40),
                  lead_pooled=((4, 12), (6, 14), (6, 14)), compress=0.78,
                  scale_dist=(0.955, 0.05), shift_dist=(5.5, 4.0), sample_noise=1.5,
-                 frac_no_adapter=0.01, frac_qc_fail=0.01, stride=15, transcript_level=None):
+                 frac_no_adapter=0.01, frac_qc_fail=0.01, stride=15, transcript_level=None,
+                 frac_barcoded=0.8, frac_weak_barcode=0.3, weak_alpha=(0.35, 0.95),
+                 prototypes=None, adapter_level=None):
         self.read_length = read_length
         self.adapter_pooled = adapter_pooled
         self.polya_pooled = polya_pooled
@@ -39,6 +45,18 @@ class SynthSpec:
         # (mean, sd) of a single-Gaussian transcript level, or None to sample the
         # preset's two-component transcript mixture
         self.transcript_level = transcript_level
+        # Barcodes: a fraction of the reads carries one of the four class prototypes of
+        # presets/synth_barcode_prototypes.npz (tools/make_barcode_prototypes.py) in its
+        # adapter, the rest an adapter sampled from the HMM emission (which the
+        # demultiplexer calls decoy).  A planted adapter is alpha * prototype +
+        # sqrt(1 - alpha^2) * noise: alpha = 1 for most, drawn from `weak_alpha` for
+        # `frac_weak_barcode` of them so that scores spread over the calibration bins and
+        # both sides of the acceptance threshold (barcoding.py:108-118).
+        self.frac_barcoded = frac_barcoded
+        self.frac_weak_barcode = frac_weak_barcode
+        self.weak_alpha = weak_alpha
+        self.prototypes = prototypes              # 'short' | 'stock' | None (by read length)
+        self.adapter_level = adapter_level or ADAPTER_LEVEL   # (pA centre, pA per unit)
 
     @classmethod
     def for_length(cls, L, **kw):
@@ -50,7 +68,13 @@ class SynthSpec:
         if T >= 700:                       # stock preset: adapter must be 260..3000 pooled
             d = dict(adapter_pooled=(270, max(280, min(330, T // 3))), polya_pooled=(20, 60),
                      compress=1.0, transcript_level=(105.0, 12.0))
-        elif T >= 200:                     # bench-short: 100..3000 pooled
+        elif T >= 250:                     # bench-short: 100..3000 pooled
+            # (adapters of 172..178 pooled samples: the barcode prototypes need that much
+            # signal, shorter windows are decoys to the network whatever they hold)
+            d = dict(adapter_pooled=(172, min(178, T - 80)), polya_pooled=(15, 30),
+                     lead_pooled=((3, 6), (4, 8), (4, 8)), adapter_level=(76.0, 3.5),
+                     compress=0.85, transcript_level=(112.0, 8.0))
+        elif T >= 200:
             d = dict(adapter_pooled=(105, min(135, T - 110)), polya_pooled=(20, 50),
                      compress=0.85, transcript_level=(112.0, 8.0))
         else:                              # too short for demux under any preset
@@ -81,6 +105,20 @@ def _emission_table(preset, transcript_level=None):
     return mu, sd, w0
 
 
+_PROTO_FILE = 'synth_barcode_prototypes.npz'
+_proto_cache = {}
+
+
+def load_prototypes(which):
+    """[4][P] float32 class prototypes in normalised units, right-aligned at the adapter end."""
+    import os
+    if which not in _proto_cache:
+        from .params import PRESET_DIR
+        z = np.load(os.path.join(PRESET_DIR, _PROTO_FILE))
+        _proto_cache[which] = np.ascontiguousarray(z[which], np.float32)
+    return _proto_cache[which]
+
+
 def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
     """Return a dict of tensors on ``device``:
 
@@ -103,6 +141,9 @@ def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
     p_scale = torch.empty(n, dtype=torch.float32, device=dev)
     p_shift = torch.empty(n, dtype=torch.float32, device=dev)
     bounds = torch.empty((n, 5), dtype=torch.int32, device=dev)
+    planted_bc = torch.zeros(n, dtype=torch.int32, device=dev)     # 0 none, 1..4 class
+    which = spec.prototypes or ('stock' if T >= 700 else 'short')
+    proto = torch.from_numpy(load_prototypes(which)).to(dev) if spec.frac_barcoded > 0 else None
 
     def randint(lo, hi, m):
         return torch.randint(int(lo), int(hi) + 1, (m,), generator=g, device=dev)
@@ -122,6 +163,23 @@ def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
         state = (t[:, :, None] >= b[:, None, :]).sum(dim=2)         # [m, T] in 0..5
         comp = (torch.rand((m, T), generator=g, device=dev) >= w0[state]).long()
         level = mu[state, comp] + sd[state, comp] * torch.randn((m, T), generator=g, device=dev)
+        if proto is not None:
+            # class prototype over the last P pooled samples of the adapter
+            P = proto.shape[1]
+            cls = torch.randint(1, proto.shape[0] + 1, (m,), generator=g, device=dev)
+            cls = torch.where(torch.rand(m, generator=g, device=dev) < spec.frac_barcoded,
+                              cls, torch.zeros_like(cls))
+            weak = torch.rand(m, generator=g, device=dev) < spec.frac_weak_barcode
+            alpha = spec.weak_alpha[0] + (spec.weak_alpha[1] - spec.weak_alpha[0]) * \
+                torch.rand(m, generator=g, device=dev)
+            alpha = torch.where(weak, alpha, torch.ones_like(alpha))
+            j = P - (b[:, 3:4] - t)                                     # [m, T] prototype index
+            inside = (state == 3) & (j >= 0) & (j < P) & (cls[:, None] > 0)
+            pv = proto[(cls[:, None] - 1).clamp(min=0), j.clamp(0, P - 1)]
+            mix = alpha[:, None] * pv + torch.sqrt(1 - alpha[:, None] ** 2) * \
+                torch.randn((m, T), generator=g, device=dev)
+            level = torch.where(inside, spec.adapter_level[0] + spec.adapter_level[1] * mix, level)
+            planted_bc[c0:c0 + m] = torch.where(no_ad, torch.zeros_like(cls), cls).to(torch.int32)
         # up-sample to the raw rate (+ remainder) and add per-sample noise
         sig = level.repeat_interleave(st, dim=1)
         if L > T * st:
@@ -151,7 +209,8 @@ def generate_reads(n, spec, preset, seed=0, device='cpu', chunk=32768):
         'raw': raw, 'gain': gain, 'offset': offset, 'range': rng_pa,
         'digitisation': torch.full((n,), 8192.0, dtype=torch.float64, device=dev),
         'sampling_rate': torch.full((n,), 3012.0, dtype=torch.float64, device=dev),
-        'planted': {'scale': p_scale, 'shift': p_shift, 'bounds': bounds},
+        'planted': {'scale': p_scale, 'shift': p_shift, 'bounds': bounds,
+                    'barcode': planted_bc},
     }
 
 

@@ -62,11 +62,17 @@ def build_inputs(variant, L, n, seed):
     if variant == 'bench-short':
         preset = params.bench_short_preset(preset)
     spec = synth.SynthSpec.for_length(L, frac_no_adapter=0.07, frac_qc_fail=0.07)
-    if variant == 'stock':
-        spec.adapter_pooled = (245, 340)     # straddles minimum_dna_length = 260
-    else:
-        spec.adapter_pooled = (90, 140)      # straddles the bench-short minimum of 100
     rd = synth.to_numpy(synth.generate_reads(n, spec, preset, seed=seed))
+    # every sixth read gets an adapter whose length straddles the demultiplexer's minimum
+    # (260 pooled samples, 100 under bench-short): the length gate of barcoding.py:84-98
+    spec2 = synth.SynthSpec.for_length(L, frac_no_adapter=0.0, frac_qc_fail=0.0)
+    spec2.adapter_pooled = (245, 275) if variant == 'stock' else (90, 110)
+    rd2 = synth.to_numpy(synth.generate_reads(n, spec2, preset, seed=seed + 7))
+    for i in range(4, n, 6):
+        for k in ('raw', 'range', 'digitisation', 'offset', 'gain', 'sampling_rate'):
+            rd[k][i] = rd2[k][i]
+        for k in rd['planted']:
+            rd['planted'][k][i] = rd2['planted'][k][i]
     rng = np.random.default_rng(seed)
     if L >= 30000:
         plant_chimeras(rd, np.random.default_rng(seed + 1))

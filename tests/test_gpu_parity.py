@@ -65,6 +65,72 @@ def _compare(out, ref, n_states=6, check_probs=True):
                            rtol=0, atol=PROB_ATOL), 'softmax outside tolerance'
 
 
+def _assert_barcodes_exercised(ref, min_accepted, classes):
+    """The accept branch (barcoding.py:108-118) must really be on the path of the test."""
+    pushed = ref['pushed'] == 1
+    acc = ref['barcode'][pushed]
+    assert (acc >= 0).sum() >= min_accepted, np.bincount(acc + 1)
+    assert len(set(acc[acc >= 0].tolist())) >= classes, np.bincount(acc + 1)
+    # ... and so must the reject-below-threshold branch (a barcode guess, no barcode)
+    assert ((ref['guess'][pushed] >= 0) & (acc < 0)).sum() >= 1
+
+
+@pytest.mark.parametrize('mode', ['exact', 'strict'])
+@pytest.mark.parametrize('which', ['short', 'stock'])
+def test_whole_path_bit_exact_modes(which, mode, eng_short, eng_stock, orc_short, orc_stock,
+                                    preset_short, preset):
+    """The exact kernels end to end against the oracle: status, (scale, shift), segments, barcode
+    calls AND class probabilities as raw bit patterns.  `strict` (exact scaler, segmentation and
+    windows; tensor-core classifier + guard + exact re-run) must give the same bits for everything
+    but the class probabilities of guard-passing windows."""
+    eng, orc, pr = (eng_short, orc_short, preset_short) if which == 'short' else (eng_stock, orc_stock, preset)
+    L, n = (4000, 256) if which == 'short' else (16000, 96)
+    rd = _reads(pr, n, L, seed=21, frac_no_adapter=0.04, frac_qc_fail=0.04)
+    raw, off, ln = _dense_batch(rd)
+    eng.set_fast_lstm(mode)
+    try:
+        out = eng.analyze_host(raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
+    finally:
+        eng.set_fast_lstm('fast')
+    ref = _oracle_batch(orc, raw, off, ln, rd)
+    if mode == 'exact':
+        _compare(out, ref, check_probs='exact')
+    else:
+        has_ss = ref['status'] != 3
+        ss_ref = np.stack([ref['scale'], ref['shift']], axis=1)
+        assert np.array_equal(out['scale_shift'][has_ss].view(np.uint32), ss_ref[has_ss].view(np.uint32))
+        _compare(out, ref, check_probs=True)
+    _assert_barcodes_exercised(ref, 20 if which == 'short' else 30, 2 if which == 'short' else 4)
+
+
+@pytest.mark.parametrize('name', ['stock16k', 'short4k', 'chimera40k'])
+def test_barcode_windows_match_reference_capture(name, eng_short, eng_stock):
+    """A6 directly: the normalised, padded windows k_windows builds (barcoding.py:77-101) against
+    the windows captured from inside the REFERENCE's own BarcodeDemultiplexer.push when the
+    golden fixtures were made -- raw bit patterns."""
+    import torch
+    from golden_util import load_golden, pack_golden
+    z, doc = load_golden(name)
+    eng = eng_short if doc['preset'] == 'bench-short' else eng_stock
+    raw, off, ln = pack_golden(z)
+    dev = torch.device('cuda', 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (t(raw), t(off), t(ln), t(z['range']), t(z['digitisation']), t(z['offset']))
+    pooled = eng.pool_signal(*args, max_raw_length=int(ln.max()))
+    status, ss, _ = eng.fit_scalers(*args, pooled)
+    seg, _ = eng.detect_segments(*args, pooled, ss, status, max_raw_length=int(ln.max()))
+    win, pushed = eng.barcode_windows(*args, pooled, ss, status, seg)
+    torch.cuda.synchronize()
+    win, pushed = win.cpu().numpy(), pushed.cpu().numpy()
+    ids = [str(s) for s in z['read_ids']]
+    want_ids = [str(s) for s in z['window_ids']]
+    assert sorted(ids[i] for i in np.nonzero(pushed)[0]) == sorted(want_ids)
+    for k, rid in enumerate(want_ids):
+        i = ids.index(rid)
+        assert np.array_equal(win[i].view(np.uint32), z['window_bits'][k]), rid
+    assert len(want_ids) >= 10
+
+
 def test_whole_path_short_reads(eng_short, orc_short, preset_short):
     rd = _reads(preset_short, 200, 4000, seed=11, frac_no_adapter=0.05, frac_qc_fail=0.05)
     raw, off, ln = _dense_batch(rd)
@@ -73,6 +139,7 @@ def test_whole_path_short_reads(eng_short, orc_short, preset_short):
     _compare(out, ref)
     assert (ref['status'] == 0).sum() > 150 and (ref['pushed'] == 1).sum() > 100
     assert set(np.unique(ref['status'])) >= {0, 4, 5}
+    _assert_barcodes_exercised(ref, 15, 2)
 
 
 def test_whole_path_stock_16k(eng_stock, orc_stock, preset):
@@ -82,6 +149,7 @@ def test_whole_path_stock_16k(eng_stock, orc_stock, preset):
     ref = _oracle_batch(orc_stock, raw, off, ln, rd)
     _compare(out, ref)
     assert (ref['pushed'] == 1).sum() > 40 and (ref['status'] == 0).sum() > 55
+    _assert_barcodes_exercised(ref, 20, 4)
 
 
 def test_ragged_lengths_and_exit_paths(eng_stock, orc_stock, preset):

@@ -426,3 +426,51 @@ def test_unsplit_restatement_matches_reference(oracle_mod):
         n_false += not want
         npread.close()
     assert n_true >= 4 and n_false >= 6
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree not present')
+@pytest.mark.parametrize('name', ['stock16k', 'chimera40k'])
+def test_event_table_restatement_matches_reference(oracle_mod, name):
+    """oracle/events_restated.py vs the reference's own Fast5Reader.get_basecall (Move table ->
+    events, fast5_file.py:183-230) + SignalAnalysis.load_events (signal_analyzer.py:311-326)
+    running verbatim over the fake FAST5: every column, floats as raw bit patterns."""
+    import tempfile
+    from golden_util import golden_reads, golden_basecalls
+    from oracle import refshim, fake_fast5, events_restated as ER
+    sa, sl, _, _, _ = refshim.reference_modules()
+    z, doc = load_golden(name)
+    ids = [str(s) for s in z['read_ids']]
+    bcs = golden_basecalls(z)
+    tmp = tempfile.mkdtemp()
+    refshim.clear_fast5()
+    fake_fast5.build_fast5(tmp, 'reads.fast5', golden_reads(z), ids, bcs)
+
+    class Analyzer:
+        pass
+    an = Analyzer()
+    an.config = {'albacore_onthefly': False}
+    checked = 0
+    for i, rid in enumerate(ids):
+        if bcs[i] is None or i % 3:
+            continue
+        npread = sl.NanoporeRead('reads.fast5', tmp, rid)
+        ss = np.array([0.93 + 0.001 * i, 4.5 - 0.01 * i], np.float32)
+        npread.set_scaling_params(ss)
+        events = sa.SignalAnalysis(npread, an).load_events()
+        raw = z['raw'][i][:int(z['length'][i])]
+        got = ER.derive_event_table(raw, z['range'][i], z['digitisation'][i], z['offset'][i],
+                                    bcs[i]['moves'], bcs[i]['sequence'], bcs[i]['qstring'],
+                                    bcs[i]['first_sample'], bcs[i]['block_stride'], ss)
+        for col in ('mean', 'stdv', 'scaled_mean'):
+            a = np.asarray(events[col].values, np.float32)
+            assert events[col].values.dtype == np.float32, col
+            assert np.array_equal(a.view(np.uint32), np.asarray(got[col], np.float32).view(np.uint32)), col
+        for col in ('start', 'length', 'move', 'pos', 'end'):
+            assert np.array_equal(np.asarray(events[col].values, np.int64), np.asarray(got[col], np.int64)), col
+        assert np.array_equal(np.asarray(events['p_model_state'].values, np.float64).view(np.uint64),
+                              got['p_model_state'].view(np.uint64))
+        assert [s.encode() if isinstance(s, str) else s for s in events['model_state'].values] == \
+            list(got['model_state'])
+        npread.close()
+        checked += 1
+    assert checked >= 5

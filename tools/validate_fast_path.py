@@ -25,11 +25,13 @@ def main():
     ap.add_argument('--reads', type=int, default=1000000)
     ap.add_argument('--length', type=int, default=4000)
     ap.add_argument('--seed0', type=int, default=777000)
+    ap.add_argument('--mode', default='fast', choices=['fast', 'strict'])
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     base = params.load_preset()
     preset = params.bench_short_preset(base) if args.length < 10500 else base
     eng = SignalEngine(dict(preset, barcoding=True), device=0)
+    eng.set_fast_lstm(args.mode)
     n, L = args.reads, args.length
     Lp = (L + 7) // 8 * 8
     keys = ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'label')
@@ -51,11 +53,18 @@ def main():
         eng.set_fast_lstm(False)
         eng.analyze_device(*work, out=out, barcoding=True, max_raw_length=L)
         torch.cuda.synchronize()
-        eng.set_fast_lstm(True)
+        eng.set_fast_lstm(args.mode)
         mism = {k: int((fast[k] != out[k]).sum().item()) for k in keys}
         okay = out['status'] == 0
         d = (fast_ss.double() - out['scale_shift'].double()).abs()[okay]
+        bc = out['barcode'][out['barcode_score'] >= 0]
+        ex = out['scale_shift'].double()[okay]
+        rel = (d[:, 0] * 100.0 + d[:, 1]) / (ex[:, 0] * 100.0 + ex[:, 1]).abs()
         ent = {'seed': args.seed0 + b, 'exact_reruns': rerun, 'causes': causes, 'tc_timeouts': timeouts,
+               'accepted_by_barcode': [int((bc == k).sum().item()) for k in range(4)],
+               'undetermined': int((bc < 0).sum().item()),
+               'max_rel_error_normalised_signal_at_100pA': float(rel.max().item()) if rel.numel() else 0.0,
+               'reads_over_1e-5_rel': int((rel > 1e-5).sum().item()),
                'mismatches': mism, 'classified': int((out['barcode_score'] >= 0).sum().item()),
                'max_scaler_z0_error_okay_reads': float((d[:, 0] / 0.13295630234669656).max().item()),
                'max_scaler_z1_error_okay_reads': float((d[:, 1] / 9.82564593783874).max().item())}
@@ -65,6 +74,11 @@ def main():
         print(json.dumps(ent), file=sys.stderr)
         del raw, rd, work
     doc['total_reads'] = n * args.batches
+    doc['mode'] = args.mode
+    doc['accepted_by_barcode'] = [sum(e['accepted_by_barcode'][k] for e in doc['batches']) for k in range(4)]
+    doc['exact_rerun_fraction'] = sum(e['exact_reruns'] for e in doc['batches']) / float(n * args.batches)
+    doc['max_rel_error_normalised_signal_at_100pA'] = max(e['max_rel_error_normalised_signal_at_100pA'] for e in doc['batches'])
+    doc['reads_over_1e-5_rel'] = sum(e['reads_over_1e-5_rel'] for e in doc['batches'])
     doc['total_mismatches'] = total
     doc['max_scaler_z0_error'] = max(e['max_scaler_z0_error_okay_reads'] for e in doc['batches'])
     doc['max_scaler_z1_error'] = max(e['max_scaler_z1_error_okay_reads'] for e in doc['batches'])
