@@ -211,7 +211,7 @@ __device__ __forceinline__ uint32_t split_pair(float2 h, uint32_t &lo) {
 // has a component that is independent of probe 1's, so that the two probes do not both
 // under-estimate a window's sensitivity by an unlucky projection.
 template <int H, int KX, bool SEQ_OUT, int COARSE = 0>
-__global__ void __maxnreg__((KX == 0 ? 112 : 120))
+__global__ void __launch_bounds__(tc_threads<H, KX>(), (KX == 0 ? 2 : 1))
 k_lstm_tc(const TcArgs A)
 {
     constexpr int N = 4 * H;
@@ -247,7 +247,11 @@ k_lstm_tc(const TcArgs A)
     // recurrence, so they are issued into the accumulator as soon as every gate warp has pulled
     // its D(t) columns into registers (bar_x) and run on the tensor pipe WHILE the gate warps
     // evaluate step t; only the h(t) U products (K = H) stay on the critical path.
-    constexpr bool PIPE = KX > 0;
+    // Used where the 64 pre-activations of a thread fit next to its state in the register file
+    // (H = 48: 416 threads, 127 registers); with H = 64 the CTA's 17 warps cap a thread at 96
+    // registers, the hoisted loads spill and the spill traffic costs more than the overlap wins
+    // (measured on B200: classifier layer 2 65.3 vs 65.0 ms, probes 106 vs 81 ms).
+    constexpr bool PIPE = KX > 0 && H <= 48;
     __shared__ __align__(8) uint64_t bar_d[2], bar_h, bar_x;
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead, s_tstart;
@@ -361,10 +365,19 @@ k_lstm_tc(const TcArgs A)
                 fence_after_sync();
                 // h(t-1) sits in buffer (s - t_start) & 1 (the initial state is written to buffer 0)
                 const uint32_t hcol = tbase + col_h + (HB == 2 ? ((s - t_start) & 1) * H : 0);
+                if (!PIPE && KX > 0)
+                    issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
+                                                                tbase + col_x + KX / 2,
+                                                                smem_u32(bW_hi), smem_u32(bW_lo), first0,
+                                                                COARSE == 0);
                 issue_split_gemm<H, N, N0>(tbase + col_d, hcol, hcol + H / 2,
                                            smem_u32(bU_hi), smem_u32(bU_lo), first0, COARSE == 0);
                 mma_commit(&bar_d[0]);
                 if (NGRP == 2) {
+                    if (!PIPE && KX > 0)
+                        issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
+                            tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
+                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first1, COARSE == 0);
                     issue_split_gemm<H, N, (N1 > 0 ? N1 : 16)>(tbase + col_d + N0, hcol, hcol + H / 2,
                                                                smem_u32(bU_hi) + BOFS, smem_u32(bU_lo) + BOFS,
                                                                first1, COARSE == 0);
@@ -455,6 +468,12 @@ k_lstm_tc(const TcArgs A)
                 g_hi_t = gt + (size_t)(dir.g_hi + u0 / 2) * TCM;
                 g_lo_t = gt + (size_t)(dir.g_lo + u0 / 2) * TCM;
             }
+            if (!PIPE && KX > 0 && s + 1 < T) {            // prefetch the next step's input
+                const int tn = dir.reverse ? (T - 2 - s) : (s + 1);
+                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+                for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+            }
             const float2 xv2 = splat(xv);
             // h(t) goes to the buffer the MMAs of this step do not read
             const uint32_t hh_addr = lane_addr + col_h + (HB == 2 ? ((s - t_start + 1) & 1) * H : 0) + u0 / 2;
@@ -539,6 +558,17 @@ k_lstm_tc(const TcArgs A)
 #pragma unroll
                     for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
                 }
+            }
+            if (!PIPE && KX > 0 && s + 1 < T) {
+                // the x operand may be replaced only when every MMA of this step is done
+                if (NGRP > 1 && grp != NGRP - 1) {
+                    mbar_wait(&bar_d[NGRP - 1], ph, &s_dead);
+                    __syncwarp();
+                    fence_after_sync();
+                }
+#pragma unroll
+                for (int j = 0; j < XW; j += 4)
+                    tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
             }
             ph ^= 1;
             tmem_st_wait();

@@ -302,7 +302,7 @@ def test_polya_kernel_matches_host_core(eng_stock, orc_stock, preset):
     from poreplex_b200.engine import polya_to_dict
     hc = H.load()
     Pc = H.polya_params(preset['polya_dwell'])
-    found = 0
+    found = overflowed = 0
     for L, polya_len, seed in ((16000, (20, 60), 31), (24000, (5, 300), 32), (20000, (100, 500), 33)):
         from poreplex_b200 import synth
         spec = synth.SynthSpec.for_length(L, frac_no_adapter=0.05, frac_qc_fail=0.05)
@@ -314,9 +314,8 @@ def test_polya_kernel_matches_host_core(eng_stock, orc_stock, preset):
         names = eng_stock.state_names
         ia, ip = names.index('adapter'), names.index('polya-tail')
         for i in range(len(ln)):
-            got = polya_to_dict(out['polya'][i], 3012.0)
             if out['status'][i] != 0:
-                assert got is None
+                assert polya_to_dict(out['polya'][i], 3012.0) is None
                 continue
             seg = out['segments'][i]
             rb, re = (int(seg[ip, 0]), int(seg[ip, 1])) if seg[ip, 0] >= 0 else (int(seg[ia, 1]) + 1, -1)
@@ -326,10 +325,22 @@ def test_polya_kernel_matches_host_core(eng_stock, orc_stock, preset):
                         C.c_double(rd['range'][i] / rd['digitisation'][i]), C.c_double(rd['offset'][i]),
                         C.c_float(out['scale_shift'][i, 0]), C.c_float(out['scale_shift'][i, 1]),
                         C.c_int32(rb), C.c_int32(re), C.byref(R))
+            rec = out['polya'][i]
+            # the fixed-size buffers of the kernel (48 spikes, 64 recalibration anchors) are never
+            # silent: a record that exceeds them raises, and the host core agrees that it does
+            over = bool(R.flags & 1) or (R.found and R.n_spikes > H.MAX_SPIKES)
+            if over:
+                with pytest.raises(OverflowError):
+                    polya_to_dict(rec, 3012.0)
+                assert (int(rec['flags']), int(rec['n_spikes'])) == (R.flags, R.n_spikes)
+                overflowed += 1
+                continue
+            got = polya_to_dict(rec, 3012.0)
             want = H.result_to_dict(R, 3012.0)
             assert want == got, (L, i, want, got)
             found += got is not None
     assert found > 150
+    assert overflowed >= 1          # the 100..500-sample tails do reach the spike capacity
 
 
 def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
