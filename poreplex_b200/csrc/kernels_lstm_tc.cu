@@ -231,28 +231,30 @@ k_lstm_tc(const TcArgs A)
     __half *bW_lo = bW_hi + KX * N;
     float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);       // [N], accumulator column order
     float *s_win = s_bias + N;                                        // [N] scalar input kernel
-    // Column groups = the accumulator columns of one gate-warp part.  The MMAs of a step are
-    // issued group by group, each with its own commit barrier, so the gate warps of group 0
-    // start while the tensor pipe still works on the later groups (vector-input layers, which
-    // are alone on their SM; scalar-input layers have one group and a second CTA instead).
-    // Two groups measured best on B200 (N = 128 + 128 for H = 64, 128 + 64 for H = 48): with one
-    // group per part the N = 64 MMAs are issued too slowly to keep the tensor pipe fed.
-    constexpr int NGRP = (KX > 0) ? 2 : 1;
-    constexpr int HB = (KX > 0) ? 2 : 1;      // h operand buffers (group 1's MMAs still read
-                                              // h(t-1) while group 0's gate warps write h(t))
-    constexpr int G0_PARTS = (NGRP == 2) ? 2 : NP;           // parts in group 0
-    constexpr int N0 = G0_PARTS * UPT * 4, N1 = N - N0;      // accumulator columns of the groups
+    // Vector-input layers (alone on their SM: all 512 TMEM columns) hide most of their MMAs
+    // behind the gate arithmetic.  A gate thread works through its units in NCH chunks of 8; the
+    // accumulator columns are ordered chunk-major (tc_core.cuh unit_slot), so "chunk c of every
+    // thread" is one contiguous column group with its own MMAs and barriers:
+    //   * the x(t+1) W products of group c do not depend on the recurrence: they are issued as
+    //     soon as every gate warp has pulled its chunk-c columns of D(t) into registers
+    //     (bar_x[c]) and run on the tensor pipe WHILE the gate warps evaluate step t;
+    //   * only the h(t) U products (K = H) wait for the whole of h(t) (bar_h); group 0's are
+    //     committed first (bar_d[0]), so the gate warps start on chunk 0 of step t+1 while the
+    //     tensor pipe finishes group 1.
+    // h is double buffered (group 1's MMAs still read h(t) while chunk 0 of h(t+1) is written);
+    // x is single buffered: x(t+1) is stored right after bar_d[0] of step t, which (MMAs retire in
+    // issue order) also says that every product that read x(t) is done.
+    // An earlier variant hoisted ALL of a thread's 64 pre-activations into registers at once:
+    // with H = 64 the CTA's 17 warps cap a thread at 96 registers, that spilled, and the spill
+    // traffic cost more than the overlap won (probes 106 vs 81 ms); chunk groups need 32 at a time.
+    constexpr bool PIPE = KX > 0;
+    constexpr int SLOT_NP = PIPE ? NP : 0;                   // accumulator column order
+    constexpr int NGRP = PIPE ? NCH : 1;
+    static_assert(NGRP <= 2, "at most two column groups");
+    constexpr int HB = PIPE ? 2 : 1;                         // h operand buffers
+    constexpr int N0 = PIPE ? NP * 8 * 4 : N, N1 = N - N0;   // accumulator columns of the groups
     static_assert(N0 % 16 == 0 && N1 % 16 == 0, "bad column grouping");
-    // Vector-input layers are software pipelined: the x(t+1) W products do not depend on the
-    // recurrence, so they are issued into the accumulator as soon as every gate warp has pulled
-    // its D(t) columns into registers (bar_x) and run on the tensor pipe WHILE the gate warps
-    // evaluate step t; only the h(t) U products (K = H) stay on the critical path.
-    // Used where the 64 pre-activations of a thread fit next to its state in the register file
-    // (H = 48: 416 threads, 127 registers); with H = 64 the CTA's 17 warps cap a thread at 96
-    // registers, the hoisted loads spill and the spill traffic costs more than the overlap wins
-    // (measured on B200: classifier layer 2 65.3 vs 65.0 ms, probes 106 vs 81 ms).
-    constexpr bool PIPE = KX > 0 && H <= 48;
-    __shared__ __align__(8) uint64_t bar_d[2], bar_h, bar_x;
+    __shared__ __align__(8) uint64_t bar_d[2], bar_h, bar_x[2];
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead, s_tstart;
 
@@ -273,18 +275,19 @@ k_lstm_tc(const TcArgs A)
         mbar_init(&bar_d[0], 1);
         mbar_init(&bar_d[1], 1);
         mbar_init(&bar_h, NGW);
-        mbar_init(&bar_x, NGW);
+        mbar_init(&bar_x[0], NGW);
+        mbar_init(&bar_x[1], NGW);
         mbar_fence_init();
         s_dead = 0;
         s_tstart = (dir.skip_mode != 0) ? T : 0;
     }
     if (warp == NGW) tmem_alloc(&s_tmem, TCOLS);
-    load_b_split<H, H>(dir.U, bU_hi, bU_lo, tid, NTHR);
-    if (KX > 0) load_b_split<(KX > 0 ? KX : 16), H>(dir.W, bW_hi, bW_lo, tid, NTHR);
+    load_b_split<H, H, SLOT_NP>(dir.U, bU_hi, bU_lo, tid, NTHR);
+    if (KX > 0) load_b_split<(KX > 0 ? KX : 16), H, SLOT_NP>(dir.W, bW_hi, bW_lo, tid, NTHR);
     for (int i = tid; i < N; i += NTHR) {
         const int gate = i / H, u = i % H;
-        s_bias[gate_col(u, gate)] = dir.b[i];
-        s_win[gate_col(u, gate)] = (KX == 0) ? dir.W[i] : 0.f;
+        s_bias[gate_col(unit_slot<H, SLOT_NP>(u), gate)] = dir.b[i];
+        s_win[gate_col(unit_slot<H, SLOT_NP>(u), gate)] = (KX == 0) ? dir.W[i] : 0.f;
     }
     fence_proxy_async_smem();
     fence_before_sync();
@@ -348,36 +351,31 @@ k_lstm_tc(const TcArgs A)
             for (int s = t_start; s < s_end; s++) {
                 bool first0 = true, first1 = true;
                 if (PIPE) {
-                    // D(t-1) is in the gate warps' registers and x(t) in TMEM: the input products
-                    // of both column groups go first and overlap the gate phase of step t-1
-                    mbar_wait(&bar_x, ph, &s_dead);
+                    // input products of step s: each column group as soon as its columns of
+                    // D(s-1) are in the gate warps' registers (and x(s) is in TMEM)
+                    mbar_wait(&bar_x[0], ph, &s_dead);
                     fence_after_sync();
                     issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
                                                                 tbase + col_x + KX / 2,
                                                                 smem_u32(bW_hi), smem_u32(bW_lo), first0,
                                                                 COARSE == 0);
-                    issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
-                        tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
-                        smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first1, COARSE == 0);
+                    if (NGRP == 2) {
+                        mbar_wait(&bar_x[1], ph, &s_dead);
+                        fence_after_sync();
+                        issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
+                            tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
+                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first1, COARSE == 0);
+                    }
                 }
                 mbar_wait(&bar_h, ph, &s_dead);
                 ph ^= 1;
                 fence_after_sync();
                 // h(t-1) sits in buffer (s - t_start) & 1 (the initial state is written to buffer 0)
                 const uint32_t hcol = tbase + col_h + (HB == 2 ? ((s - t_start) & 1) * H : 0);
-                if (!PIPE && KX > 0)
-                    issue_split_gemm<(KX > 0 ? KX : 16), N, N0>(tbase + col_d, tbase + col_x,
-                                                                tbase + col_x + KX / 2,
-                                                                smem_u32(bW_hi), smem_u32(bW_lo), first0,
-                                                                COARSE == 0);
                 issue_split_gemm<H, N, N0>(tbase + col_d, hcol, hcol + H / 2,
                                            smem_u32(bU_hi), smem_u32(bU_lo), first0, COARSE == 0);
                 mma_commit(&bar_d[0]);
                 if (NGRP == 2) {
-                    if (!PIPE && KX > 0)
-                        issue_split_gemm<(KX > 0 ? KX : 16), N, (N1 > 0 ? N1 : 16)>(
-                            tbase + col_d + N0, tbase + col_x, tbase + col_x + KX / 2,
-                            smem_u32(bW_hi) + BOFS, smem_u32(bW_lo) + BOFS, first1, COARSE == 0);
                     issue_split_gemm<H, N, (N1 > 0 ? N1 : 16)>(tbase + col_d + N0, hcol, hcol + H / 2,
                                                                smem_u32(bU_hi) + BOFS, smem_u32(bU_lo) + BOFS,
                                                                first1, COARSE == 0);
@@ -444,7 +442,7 @@ k_lstm_tc(const TcArgs A)
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&bar_h);
-            if (PIPE) mbar_arrive(&bar_x);
+            if (PIPE) { mbar_arrive(&bar_x[0]); if (NGRP == 2) mbar_arrive(&bar_x[1]); }
         }
         if (PIPE && t_start + 1 < T) {                     // the second step's input, on its way
             const int tn = dir.reverse ? (T - 2 - t_start) : (t_start + 1);
@@ -455,8 +453,8 @@ k_lstm_tc(const TcArgs A)
 
         uint32_t ph = 0;
         uint32_t rng = ((uint32_t)(A.row0 + tile0 + m) * 2654435761u) ^ ((uint32_t)part * 0x9E3779B9u) ^ 0x85EBCA6Bu;
-        const int grp = (NGRP == 2 && part >= G0_PARTS) ? 1 : 0;
-        const uint32_t d_addr = lane_addr + col_d + u0 * 4;
+        // accumulator columns of this thread's chunk ch start at slot(ch) * 4 (tc_core.cuh unit_slot)
+        auto slot0 = [&](int ch) { return PIPE ? ch * (NP * 8) + part * 8 : u0 + ch * 8; };
         for (int s = t_start; s < s_end; s++) {
             const int t = dir.reverse ? (T - 1 - s) : s;
             float xv = 0.f;
@@ -468,55 +466,52 @@ k_lstm_tc(const TcArgs A)
                 g_hi_t = gt + (size_t)(dir.g_hi + u0 / 2) * TCM;
                 g_lo_t = gt + (size_t)(dir.g_lo + u0 / 2) * TCM;
             }
-            if (!PIPE && KX > 0 && s + 1 < T) {            // prefetch the next step's input
-                const int tn = dir.reverse ? (T - 2 - s) : (s + 1);
-                const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
-#pragma unroll
-                for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
-            }
             const float2 xv2 = splat(xv);
             // h(t) goes to the buffer the MMAs of this step do not read
             const uint32_t hh_addr = lane_addr + col_h + (HB == 2 ? ((s - t_start + 1) & 1) * H : 0) + u0 / 2;
             const uint32_t hl_addr = hh_addr + H / 2;
-            mbar_wait(&bar_d[grp], ph, &s_dead);
-            __syncwarp();
-            fence_after_sync();
-            uint32_t va[PIPE ? NCH : 1][32];
-            if (PIPE) {
-                // every pre-activation of this thread -> registers; then the accumulator columns
-                // and the x operand are free for the next step's input products
-#pragma unroll
-                for (int ch = 0; ch < NCH; ch++) tmem_ld32(d_addr + ch * 32, va[ch]);
-                tmem_ld_wait();
-                if (s + 1 < T) {
-#pragma unroll
-                    for (int j = 0; j < XW; j += 4)
-                        tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
-                    tmem_st_wait();
-                }
-                fence_before_sync();
+            if (!PIPE) {
+                mbar_wait(&bar_d[0], ph, &s_dead);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_x);
-                if (s + 2 < T) {                           // x(t+2): a whole step to arrive
-                    const int tn = dir.reverse ? (T - 3 - s) : (s + 2);
-                    const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
-#pragma unroll
-                    for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
-                }
+                fence_after_sync();
             }
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
-                uint32_t vl[32];
-                if (!PIPE) {
-                    tmem_ld32(d_addr + ch * 32, vl);
-                    tmem_ld_wait();
+                uint32_t vv[32];
+                if (PIPE) {
+                    // the h(t-1) U products of column group ch are done (and, MMAs retiring in
+                    // issue order, so is everything issued before them)
+                    mbar_wait(&bar_d[ch], ph, &s_dead);
+                    __syncwarp();
+                    fence_after_sync();
                 }
-                const uint32_t (&vv)[32] = PIPE ? va[ch] : vl;
+                tmem_ld32(lane_addr + col_d + slot0(ch) * 4, vv);
+                tmem_ld_wait();
+                if (PIPE) {
+                    if (ch == 0 && s + 1 < T) {
+                        // every product that read x(t) has retired: x(t+1) takes its place
+#pragma unroll
+                        for (int j = 0; j < XW; j += 4)
+                            tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+                        tmem_st_wait();
+                    }
+                    // this thread's chunk-ch columns of D(t) are in registers: once every gate warp
+                    // says so, the x(t+1) W products of the group may overwrite them
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_x[ch]);
+                    if (ch == 0 && s + 2 < T) {            // x(t+2): a whole step to arrive
+                        const int tn = dir.reverse ? (T - 3 - s) : (s + 2);
+                        const uint32_t *gp = gin + (size_t)tn * KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+                        for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+                    }
+                }
                 uint32_t hi[4], lo[4];
                 float2 hn[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {              // four independent pairs of units
-                    const int col = (u0 + ch * 8 + 2 * j) * 4;          // = gate_col(u, 0)
+                    const int col = (slot0(ch) + 2 * j) * 4;            // = gate_col(slot, 0)
                     const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col);
                     const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + col + 4);
                     float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
@@ -558,17 +553,6 @@ k_lstm_tc(const TcArgs A)
 #pragma unroll
                     for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
                 }
-            }
-            if (!PIPE && KX > 0 && s + 1 < T) {
-                // the x operand may be replaced only when every MMA of this step is done
-                if (NGRP > 1 && grp != NGRP - 1) {
-                    mbar_wait(&bar_d[NGRP - 1], ph, &s_dead);
-                    __syncwarp();
-                    fence_after_sync();
-                }
-#pragma unroll
-                for (int j = 0; j < XW; j += 4)
-                    tmem_st4(lane_addr + col_x + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
             }
             ph ^= 1;
             tmem_st_wait();

@@ -163,16 +163,28 @@ __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t &lo) {
 // tcgen05.ld gets aligned register pairs for the packed f32x2 gate arithmetic.
 __host__ __device__ constexpr int gate_col(int u, int gate) { return (u >> 1) * 8 + gate * 2 + (u & 1); }
 
-// src: Keras matrix [K][4H] row-major, gate blocks i|f|c|o.  Output column n = gate_col(u, gate).
-// B_hi / B_lo: fp16 [K/8][N/8][8 (n)][8 (k)], N = 4H.
-template <int K, int H>
+// Chunk-major unit order (NP > 0): a gate thread owns UPT = H / NP consecutive units and works
+// through them in chunks of 8; the accumulator keeps chunk 0 of every thread part first, then
+// chunk 1, ... so that "all first chunks" is ONE contiguous column group that a single set of
+// MMAs produces (and can overwrite as soon as every thread has read its first chunk).
+// NP = 0: natural order.
+template <int H, int NP>
+__host__ __device__ constexpr int unit_slot(int u) {
+    if (NP == 0) return u;
+    const int upt = H / NP, p = u / upt, w = u % upt;
+    return (w / 8) * (NP * 8) + p * 8 + (w % 8);
+}
+
+// src: Keras matrix [K][4H] row-major, gate blocks i|f|c|o.  Output column n =
+// gate_col(unit_slot(u), gate).  B_hi / B_lo: fp16 [K/8][N/8][8 (n)][8 (k)], N = 4H.
+template <int K, int H, int NP = 0>
 __device__ __forceinline__ void load_b_split(const float *__restrict__ src, __half *b_hi,
                                              __half *b_lo, int tid, int nthreads) {
     constexpr int N = 4 * H;
     for (int idx = tid; idx < K * N; idx += nthreads) {
         const int k = idx / N, col = idx % N;          // coalesced read of src
         const int gate = col / H, u = col % H;
-        const int n = gate_col(u, gate);
+        const int n = gate_col(unit_slot<H, NP>(u), gate);
         const float v = src[idx];
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
