@@ -379,6 +379,28 @@ class SignalEngine:
         1 unsplit, 0 not, < 0 internal error for that read."""
         if not self.unsplit_ready:
             raise ValueError('config has no unsplit-read detection model')
+        # guppy Move tables as Fast5Source hands them over (move + FASTQ strings): the event
+        # columns are derived on the device first
+        need = [i for i, t in enumerate(tables)
+                if t is not None and t.get('guppy_move') and 'start' not in t]
+        if need:
+            if batch is None:
+                raise ValueError('guppy Move tables need the batch of the same reads')
+            raw, roff, rlen, rng, dig, off = (np.ascontiguousarray(a) for a in batch)
+            sub = (raw, roff[need], rlen[need], rng[need], dig[need], off[need])
+            strides = {int(tables[i]['block_stride']) for i in need}
+            if len(strides) != 1:
+                raise ValueError('reads of one batch must share block_stride')
+            derived, err = self.derive_event_tables_host(
+                sub, [tables[i]['move'] for i in need], [int(tables[i]['first_sample']) for i in need],
+                strides.pop(), sequences=[tables[i]['sequence'] for i in need],
+                qstrings=[tables[i]['qstring'] for i in need],
+                columns=('mean', 'start', 'p_model_state'))
+            if err.any():
+                raise ValueError('event-table derivation failed for reads %r' % (np.nonzero(err)[0].tolist(),))
+            tables = list(tables)
+            for k, i in enumerate(need):
+                tables[i] = dict(tables[i], **derived[k])
         has = [t is not None and len(t['start']) > 0 for t in tables]
         with_mean = [h and 'mean' in t for h, t in zip(has, tables)]
         derived = [h and 'mean' not in t for h, t in zip(has, tables)]

@@ -180,25 +180,27 @@ class Fast5Source:
             table = analyses['BaseCalled_template/Events'][()]
             names = table.dtype.names or ()
             if len(names) <= 3 and 'move' in names:            # old guppy
-                return self._convert_guppy({'move': np.asarray(table['move'])}, summary,
-                                           want_events)
+                cols = {'move': np.asarray(table['move'])}
+                for extra in ('model_state', 'p_model_state'):
+                    if extra in names:
+                        cols[extra] = np.asarray(table[extra])
+                return self._convert_guppy(cols, summary, want_events)
             if len(names) == 14:                               # albacore >= 2.3.0
                 return {n: np.asarray(table[n]) for n in names}
             raise Exception('Unsupported event table found.')
         if 'BaseCalled_template/Move' in analyses:
             moves = analyses['BaseCalled_template/Move'][()]
             kmer_size = len(summary['sequence']) - int(moves.sum()) + 1
-            if kmer_size == 5:
-                posshift = 2
-            elif kmer_size == 1:
-                posshift = 0
-            else:
+            if kmer_size not in (5, 1):
                 raise Exception('Move table is encoded with an unknown kmer-size.')
             cols = {'move': np.asarray(moves)}
             if want_events:
-                pos = moves.cumsum() - 1
-                qual = 1 - 10 ** -((np.frombuffer(summary['qstring'].encode(), 'B') - 33) / 10)
-                cols['p_model_state'] = qual[pos.astype(np.int64) + posshift]
+                # construct_events_from_moves (fast5_file.py:183-207): pos, p_model_state and
+                # model_state are derived on the GPU for the whole batch
+                # (SignalEngine.derive_event_tables_host); what they are derived from:
+                cols['guppy_move'] = True
+                cols['sequence'] = summary['sequence']
+                cols['qstring'] = summary['qstring']
             return self._convert_guppy(cols, summary, want_events)
         raise Exception("Neither `Events' or `Move' table found in the basecall.")
 
@@ -208,7 +210,8 @@ class Fast5Source:
         first_sample = summary['first_sample_template']
         block_stride = summary['block_stride']
         last_sample = first_sample + block_stride * n
-        cols['start'] = np.arange(first_sample, last_sample, block_stride)
+        if not cols.get('guppy_move'):
+            cols['start'] = np.arange(first_sample, last_sample, block_stride)
         node = self.handle[self.read_node + '/Signal']
         end = min(last_sample, len(node))
         nraw = max(end - first_sample, 0)
@@ -216,10 +219,11 @@ class Fast5Source:
         if padded // block_stride != n:
             raise Exception('Numbers of events and raw data strides does not match.')
         if want_events:
-            # the `mean` column (medfilt(5) + per-block mean of the pA signal,
-            # fast5_file.py:217-227) is derived on the GPU from the raw signal
-            # (k_event_means); only its coordinates are recorded here
+            # the `mean` / `stdv` columns (medfilt(5) + per-block statistics of the pA signal,
+            # fast5_file.py:217-227) are derived on the GPU from the raw signal
+            # (k_event_stats); only their coordinates are recorded here
             cols['first_sample'] = first_sample
             cols['block_stride'] = block_stride
-        cols['length'] = np.full(n, block_stride)
+        if not cols.get('guppy_move'):
+            cols['length'] = np.full(n, block_stride)
         return cols

@@ -9,11 +9,13 @@ run as ONE batched GPU pass over all reads of the batch through the C ABI
 TensorFlow / pomegranate calls.  ``pipeline.py:204`` can call this ``process_batch``
 unchanged.
 
-Switch coverage this round: ``trim_adapter`` (a no-op in the reference at this commit,
-SURVEY.md F6 -- reproduced), ``barcoding``, ``measure_polya`` and
-``filter_unsplit_reads``.  The dump switches and on-the-fly albacore raise ``NotImplementedError`` when the
-analyzer is built, which ``process_batch`` reports as a batch-level failure exactly like
-any other unhandled exception -- never a silent CPU fallback.
+Switch coverage: ``trim_adapter`` (a no-op in the reference at this commit, SURVEY.md F6 --
+reproduced), ``barcoding``, ``measure_polya``, ``filter_unsplit_reads``, and the two dump
+switches ``dump_adapter_signals`` / ``dump_basecalls`` (signal_analyzer.py:155-211,450-466:
+HDF5 part files under ``outputdir/adapter-dumps`` and ``outputdir/events``).  On-the-fly
+albacore raises ``NotImplementedError`` when the analyzer is built, which ``process_batch``
+reports as a batch-level failure exactly like any other unhandled exception -- never a
+silent CPU fallback.
 """
 import os
 import sys
@@ -164,10 +166,16 @@ class NanoporeRead:
 class SignalAnalyzer:
 
     UNSUPPORTED_SWITCHES = {
-        'dump_adapter_signals': 'adapter signal dumps',
-        'dump_basecalls': 'basecalled event dumps',
         'albacore_onthefly': 'on-the-fly albacore basecalling',
     }
+
+    # signal_analyzer.py:62-68 (model_state becomes 'S<kmersize>' in open_dumps, :156)
+    _EVENT_DUMP_FIELD_NAMES = [
+        'mean', 'start', 'stdv', 'length', 'model_state',
+        'move', 'pos', 'end', 'scaled_mean']
+    _EVENT_DUMP_FIELD_DTYPES = [
+        '<f4', '<u8', '<f4', '<u8', None,
+        '<i4', '<u8', '<u8', '<f8']
 
     def __init__(self, config, batchid):
         for key, what in self.UNSUPPORTED_SWITCHES.items():
@@ -183,15 +191,72 @@ class SignalAnalyzer:
         device = int(os.environ.get('POREPLEX_B200_DEVICE', config.get('cuda_device', 0)))
         self.engine = get_engine(config, device)
         self.kmersize = config.get('kmersize', 5)
+        self.open_dumps()
+
+    # ---- HDF5 dumps (signal_analyzer.py:155-211) ------------------------------------------
+    # The reference appends to one file per worker process ('part-<workerid>.h5', h5py mode
+    # 'a').  The writer here produces whole files, so every batch writes its own
+    # 'part-<workerid>-<batchid>.h5' with the same internal layout; the inventories
+    # (io.py:334-376) glob 'part-*.h5' and walk every batch group of every file, so they see
+    # the same objects.
+    def open_dumps(self):
+        import multiprocessing as mp
+        from hashlib import sha1
+        self.workerid = sha1(mp.current_process().name.encode()).hexdigest()[:16]
+        self.EVENT_DUMP_FIELDS = [
+            (n, d if d is not None else 'S{}'.format(self.kmersize))
+            for n, d in zip(self._EVENT_DUMP_FIELD_NAMES, self._EVENT_DUMP_FIELD_DTYPES)]
+        self.adapter_dump = {} if self.config.get('dump_adapter_signals') else None
+        self.adapter_dump_list = []
+        self.basecall_dump = {} if self.config.get('dump_basecalls') else None
+
+    def dump_path(self, subdir):
+        path = os.path.join(self.outputdir, subdir,
+                            'part-{}-{}.h5'.format(self.workerid, self.formatted_batchid))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        return path
+
+    def dump_adapter_signal(self, read_id, adapter_signal, segments, stride):
+        """SignalAnalysis.dump_adapter_signal (signal_analyzer.py:450-466)."""
+        if len(adapter_signal) > 0 and read_id not in self.adapter_dump:
+            self.adapter_dump[read_id] = np.array(adapter_signal, dtype=np.float32)
+            self.adapter_dump_list.append((read_id, segments['adapter'][0] * stride,
+                                           (segments['adapter'][1] + 1) * stride))
+
+    def write_basecalled_events(self, read_id, events, attrs):
+        """signal_analyzer.py:184-196."""
+        dataset = np.empty(len(events['start']), dtype=self.EVENT_DUMP_FIELDS)
+        for name, _ in self.EVENT_DUMP_FIELDS:
+            dataset[name] = events[name]
+        if read_id not in self.basecall_dump:
+            self.basecall_dump[read_id] = (dataset, attrs)
+
+    def close(self):
+        """signal_analyzer.py:198-211."""
+        from . import hdf5_write as W
+        if self.adapter_dump is not None:
+            root = W.Group()
+            grp = root.group('adapter').group(self.formatted_batchid)
+            for read_id, sig in self.adapter_dump.items():
+                grp.dataset(read_id, sig)
+            catalog = np.array(self.adapter_dump_list,
+                               dtype=[('read_id', 'S36'), ('start', 'i8'), ('end', 'i8')])
+            root.group('catalog').group('adapter').dataset(self.formatted_batchid, catalog)
+            W.write_file(self.dump_path('adapter-dumps'), root)
+            self.adapter_dump = None
+        if self.basecall_dump is not None:
+            root = W.Group()
+            grp = root.group('basecalled_events').group(self.formatted_batchid)
+            for read_id, (dataset, attrs) in self.basecall_dump.items():
+                grp.dataset(read_id, dataset, attrs=dict(attrs))
+            W.write_file(self.dump_path('events'), root)
+            self.basecall_dump = None
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         self.close()
-
-    def close(self):
-        pass
 
     def prefetch_signals(self, reads):
         """Raw signals of the whole batch through the native FAST5 loader (thread pool, one open
@@ -252,10 +317,17 @@ class SignalAnalyzer:
                 *batch,
                 barcoding=bool(self.config['barcoding']),
                 polya=bool(self.config['measure_polya']),
-                # the chimera filter decodes the scaled event means: exact scale/shift
-                exact_scaler=bool(self.config.get('filter_unsplit_reads')))
+                # the adapter dump stores the scaled pooled signal itself
+                keep_pooled=self.adapter_dump is not None,
+                # the chimera filter and the event dump use the scaled event means: exact scale/shift
+                exact_scaler=bool(self.config.get('filter_unsplit_reads')) or
+                self.basecall_dump is not None)
+            pooled_at = eng.pooled_offsets(offsets)
             for i, npread in enumerate(loaded):
                 npread._raw = None
+                if self.adapter_dump is not None:
+                    T = int(lengths[i]) // eng.stride
+                    npread._pooled = out['pooled'][pooled_at[i]:pooled_at[i] + T]
                 npread._gpu = {k: out[k][i] for k in ('status', 'scale_shift', 'segments',
                                                       'barcode', 'barcode_guess',
                                                       'barcode_score')}
@@ -283,8 +355,11 @@ class SignalAnalyzer:
                     error = self.pack_unhandled_exception(f5file, read_id, exc, sys.exc_info())
                     siganal.set_error(error)
                     siganal.failed = True
-            if phase == 1 and self.config['filter_unsplit_reads'] and loaded:
-                self.detect_unsplit_reads(nextprocs, batch)
+            if phase == 1 and loaded:
+                if self.config['filter_unsplit_reads'] or self.basecall_dump is not None:
+                    self.derive_event_tables(nextprocs, batch)
+                if self.config['filter_unsplit_reads']:
+                    self.detect_unsplit_reads(nextprocs, batch)
         for siganal in nextprocs:
             siganal.clear_cache()
 
@@ -292,6 +367,45 @@ class SignalAnalyzer:
         for npread in loaded:
             results.append(npread.report())
         return results
+
+    def derive_event_tables(self, analyses, batch):
+        """Event tables of every guppy ``Move`` basecall of the batch in one device call
+        (Fast5Reader.construct_events_from_moves / convert_events_guppy, fast5_file.py:183-230,
+        and the derived columns of SignalAnalysis.load_events, signal_analyzer.py:311-326);
+        `analyses` is aligned with the packed `batch`."""
+        eng = self.engine
+        idx = [i for i, a in enumerate(analyses)
+               if not (a.is_stopped() or a.failed) and a.events is not None
+               and a.events.get('guppy_move')]
+        if not idx:
+            return
+        raw, offsets, lengths, rng, dig, off = batch
+        sub = (raw, offsets[idx], lengths[idx], rng[idx], dig[idx], off[idx])
+        ev = [analyses[i].events for i in idx]
+        strides = {int(e['block_stride']) for e in ev}
+        if len(strides) != 1:
+            raise ValueError('reads of one batch must share block_stride')
+        cols = ('mean', 'start', 'p_model_state')
+        if self.basecall_dump is not None:
+            cols = ('mean', 'stdv', 'start', 'end', 'length', 'pos', 'p_model_state',
+                    'model_state', 'scaled_mean')
+        tables, err = eng.derive_event_tables_host(
+            sub, [e['move'] for e in ev], [int(e['first_sample']) for e in ev], strides.pop(),
+            sequences=[e['sequence'] for e in ev], qstrings=[e['qstring'] for e in ev],
+            scale_shift=np.array([analyses[i].npread._gpu['scale_shift'] for i in idx], np.float32),
+            columns=cols)
+        for k, i in enumerate(idx):
+            a = analyses[i]
+            if err[k]:
+                # both conditions are checked when the table is loaded (Fast5Source); the device
+                # disagreeing is an internal error of this read, never silent
+                a.set_error(self.pack_unhandled_exception(
+                    a.npread.filename, a.npread.read_id,
+                    Exception('event-table derivation failed on the device (code {})'.format(int(err[k]))),
+                    (None, None, None)))
+                a.failed = True
+                continue
+            a.events.update(tables[k])
 
     def detect_unsplit_reads(self, analyses, batch):
         """Batched SignalAnalysis.detect_unsplit_read (signal_analyzer.py:366-443); `analyses`
@@ -312,12 +426,16 @@ class SignalAnalyzer:
 
     def pack_unhandled_exception(self, f5filename, read_id, exc, excinfo):
         exc_type, exc_obj, exc_tb = excinfo
-        srcfilename = os.path.split(exc_tb.tb_frame.f_code.co_filename)[-1]
+        if exc_tb is None:                                  # not raised: report this frame
+            srcfilename, lineno = os.path.basename(__file__), sys._getframe().f_lineno
+        else:
+            srcfilename = os.path.split(exc_tb.tb_frame.f_code.co_filename)[-1]
+            lineno = exc_tb.tb_lineno
         errorf = StringIO()
         traceback.print_exc(file=errorf)
         errmsg = ('[{srcfilename}:{lineno}] ({f5filename}#{read_id}) Unhandled '
                   'exception {name}: {msg}\n{exc}'.format(
-            srcfilename=srcfilename, lineno=exc_tb.tb_lineno,
+            srcfilename=srcfilename, lineno=lineno,
             f5filename=f5filename, read_id=read_id, name=type(exc).__name__, msg=str(exc),
             exc=errorf.getvalue()))
         return {
@@ -364,6 +482,11 @@ class SignalAnalysis:
                 if 'adapter' not in segments:
                     raise SignalAnalysisError('adapter_not_detected')
 
+                if self.analyzer.adapter_dump is not None:     # signal_analyzer.py:243-244
+                    a0, a1 = segments['adapter']
+                    self.analyzer.dump_adapter_signal(npread.read_id, npread._pooled[a0:a1 + 1],
+                                                      segments, eng.stride)
+
                 if self.config['barcoding'] and int(gpu['barcode_score']) >= 0:
                     bc = int(gpu['barcode'])
                     npread.set_barcode(None if bc < 0 else bc, int(gpu['barcode_guess']),
@@ -377,6 +500,11 @@ class SignalAnalysis:
                 self.events = self.load_events()
 
             if phase in (None, 2):
+                if self.analyzer.basecall_dump is not None:    # signal_analyzer.py:259-263
+                    self.analyzer.write_basecalled_events(
+                        npread.read_id, self.dump_columns(self.events),
+                        self.get_dump_attributes(npread.segments, eng.stride))
+
                 if self.config['trim_adapter']:
                     self.trim_adapter(self.events, npread.segments, eng.stride)
 
@@ -398,6 +526,42 @@ class SignalAnalysis:
             npread.set_status(exc.args[0], stop=True)
             npread.set_label(outname)
 
+    def dump_columns(self, events):
+        """The event table with the derived columns of load_events (signal_analyzer.py:311-326).
+        Guppy Move tables come complete from the device; tables stored in the file (albacore,
+        old guppy) get the three derived columns here, as numpy computes them in the
+        reference."""
+        if 'scaled_mean' in events and 'pos' in events and 'end' in events:
+            return events
+        ev = dict(events)
+        if 'mean' not in ev:
+            raise Exception('event dump of a table without a mean column is not supported')
+        ev['scaled_mean'] = np.poly1d(self.npread.scaling_params)(np.asarray(ev['mean']))
+        ev['pos'] = np.cumsum(ev['move'])
+        duration = np.hstack((np.diff(ev['start']), [1])).astype(np.int64)
+        ev['end'] = ev['start'] + duration
+        return ev
+
+    def get_dump_attributes(self, segments, stride):
+        """signal_analyzer.py:288-309."""
+        attrlist = []
+        if self.npread.scaling_params is not None:
+            sp_scale, sp_shift = self.npread.scaling_params
+            attrlist.append(('signal_scale', sp_scale))
+            attrlist.append(('signal_shift', sp_shift))
+        if 'adapter' in segments:
+            attrlist.append(('adapter_begin', np.uint32(segments['adapter'][0] * stride)))
+            attrlist.append(('adapter_end', np.uint32((segments['adapter'][1] + 1) * stride)))
+        if self.npread.polya is not None:
+            polya = self.npread.polya
+            if 'polya-tail' in segments:
+                attrlist.append(('polya_end_debug',
+                                 np.uint32((segments['polya-tail'][1] + 1) * stride)))
+            attrlist.append(('polya_begin', np.uint32(polya['begin'])))
+            attrlist.append(('polya_end', np.uint32(polya['end'])))
+            attrlist.append(('spikes', repr(polya['spikes']).encode()))
+        return attrlist
+
     def detect_segments(self):
         """{state name: (first, last)} from the kernel's baked-order table
         (signal_analyzer.py:355-362)."""
@@ -408,7 +572,8 @@ class SignalAnalysis:
 
     def load_events(self):
         events = self.npread.load_fast5_events(
-            want_events=bool(self.config['filter_unsplit_reads']))
+            want_events=bool(self.config['filter_unsplit_reads']) or
+            self.analyzer.basecall_dump is not None)
         if self.npread.scaling_params is None:
             raise Exception('Signal scaling is not available yet.')
         return events

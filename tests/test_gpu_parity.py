@@ -369,24 +369,24 @@ def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
     flags = eng_stock.detect_unsplit_host(tables, np.array(rates), out['scale_shift'], status,
                                           out['segments'],
                                           batch=(raw, off, ln, z['range'], z['digitisation'], z['offset']))
-    from scipy.signal import medfilt
+    from oracle import events_restated as ER
+    bcs = golden_basecalls(z)
     ia = eng_stock.adapter_state
     n_true = 0
     for i, t in enumerate(tables):
         if t is None:
             assert flags[i] == 0
             continue
-        # the reference's own numpy recipe for the mean column (fast5_file.py:217-227)
-        sig = z['raw'][i][:ln[i]]
-        pa = np.array(z['range'][i] / z['digitisation'][i] * (sig + z['offset'][i]), dtype=np.float32)
-        E = len(t['start'])
-        mean = medfilt(pa[t['first_sample']:t['first_sample'] + 15 * E], 5).reshape(E, 15).mean(axis=1)
-        scaled, pos, end = UR.derive_event_columns(t['start'], mean, t['move'],
+        # the event table as the reference's own numpy recipe builds it (fast5_file.py:183-230)
+        ev = ER.derive_event_table(z['raw'][i][:ln[i]], z['range'][i], z['digitisation'][i],
+                                   z['offset'][i], bcs[i]['moves'], bcs[i]['sequence'],
+                                   bcs[i]['qstring'], 0, 15)
+        scaled, pos, end = UR.derive_event_columns(ev['start'], ev['mean'], ev['move'],
                                                    out['scale_shift'][i, 0], out['scale_shift'][i, 1])
         want = UR.detect_unsplit_read(
             preset['unsplit_read_detection'], lambda x: orc_stock.viterbi(x, 'unsplit')[1],
-            orc_stock.unsplit_names, np.asarray(t['start'], np.int64), end, scaled, pos,
-            np.asarray(t['p_model_state'], np.float64), int(out['segments'][i, ia, 1]), rates[i])
+            orc_stock.unsplit_names, np.asarray(ev['start'], np.int64), end, scaled, pos,
+            np.asarray(ev['p_model_state'], np.float64), int(out['segments'][i, ia, 1]), rates[i])
         assert int(flags[i]) == int(want), (i, flags[i], want)
         n_true += want
     assert n_true >= 4

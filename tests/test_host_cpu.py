@@ -125,3 +125,25 @@ def test_world_size_2_count_reduce_gloo():
         p.join(timeout=60)
     assert res[0][1:3] == (0, 500) and res[1][1:3] == (500, 1001)
     assert all(r[3] for r in res)
+
+
+def test_config_digest_is_content_based():
+    """get_engine keys on the CONTENT of the configuration (pipeline.py:204 re-pickles it for
+    every batch), not on object identity."""
+    import pickle
+    from poreplex_b200 import engine, params
+    cfg = dict(params.load_preset(), barcoding=True, barcoding_quality_filter=18, inputdir='/a')
+    again = pickle.loads(pickle.dumps(cfg))
+    assert again['segmentation_model'] is not cfg['segmentation_model']
+    assert engine.config_digest(again) == engine.config_digest(cfg)
+    again['inputdir'] = '/b'                                   # not an engine parameter
+    assert engine.config_digest(again) == engine.config_digest(cfg)
+    for change in (lambda c: c.__setitem__('barcoding_quality_filter', 20),
+                   lambda c: c['signal_processing'].__setitem__('scaler_qc_threshold', 0.05),
+                   lambda c: c['polya_dwell'].__setitem__('spike_weight', 2.0),
+                   lambda c: c['unsplit_read_detection'].__setitem__('window_size', 9.0),
+                   lambda c: c['demultiplexing'].__setitem__('minimum_dna_length', 100),
+                   lambda c: c.__setitem__('barcoding', False)):
+        other = pickle.loads(pickle.dumps(cfg))
+        change(other)
+        assert engine.config_digest(other) != engine.config_digest(cfg)
