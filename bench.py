@@ -432,6 +432,7 @@ def main():
     # every integer output of every read must be identical (outside the timed region)
     rechecked, tc_timeouts = eng.recheck_stats()
     rerun_causes = eng.rerun_causes()
+    probe2_rows = eng.probe2_rows()
     int_keys = ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'label', 'counts')
     fast_int = {k: out[k].clone() for k in int_keys}
     fast_ss = out['scale_shift'].clone()
@@ -608,6 +609,7 @@ def main():
                                              'about %d' % int(300 - wl.mean()) if len(wl) else 'n/a'),
                    'exact_reruns_per_step': rechecked, 'exact_rerun_causes': rerun_causes,
                    'exact_rerun_fraction': rechecked / float(n),
+                   'windows_needing_second_probe': probe2_rows,
                    'tc_barrier_timeouts': tc_timeouts,
                    'mismatches_vs_exact_only_kernels': mismatches,
                    'collective': 'all_reduce(int64[4,5,11]) per step' if world > 1 else 'none (N=1)',

@@ -368,6 +368,9 @@ int pb2_set_exact_division(pb2_context *ctx, int on);
  * every read -- (scale, shift) and the normalised signal are then the reference's float32
  * values bit for bit -- and only the classifier on the tensor cores (margin test + exact
  * re-run of the windows it flags). */
+/* Diagnostics: windows of the last classifier launch that needed the second sensitivity probe
+ * (the others were settled by the first probe under the wide screening bound). */
+int pb2_probe2_rows(pb2_context *ctx, int64_t *rows);
 int pb2_set_fast_lstm(pb2_context *ctx, int on, double demux_margin_delta,
                       double demux_probe_gain);
 /* Verification: the tensor-core demultiplexer WITHOUT the exact re-run -- approximate class

@@ -141,7 +141,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
            'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
            'pb2_audit_stats', 'pb2_detect_events', 'pb2_derive_event_tables',
-           'pb2_derive_event_tables_host']
+           'pb2_derive_event_tables_host', 'pb2_probe2_rows']
 
 
 def sources():
@@ -224,6 +224,7 @@ def load():
                                           C.POINTER(Basecalls), vp, C.POINTER(EventColumns), vp]
     L.pb2_derive_event_tables_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables),
                                                C.POINTER(Basecalls), vp, C.POINTER(EventColumns)]
+    L.pb2_probe2_rows.argtypes = [vp, _i64p]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

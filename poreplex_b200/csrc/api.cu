@@ -148,6 +148,10 @@ int pb2_create(int device, pb2_context **out)
         delete ctx;
         return PB2_ECUDA;
     }
+    if (const char *env = getenv("POREPLEX_B200_SCREEN_GAIN")) {       // tuning / measurements
+        const double v = atof(env);
+        if (v >= 0) ctx->demux_screen_gain = v;
+    }
     if (const char *env = getenv("POREPLEX_B200_DEMUX_PROBES")) {      // tuning / measurements
         const int v = atoi(env);
         if (v == 1 || v == 2) ctx->demux_probes = v;
@@ -186,7 +190,7 @@ void pb2_destroy(pb2_context *ctx)
                         &ctx->ws_unsplit, &ctx->ws_unsplit_host, &ctx->ws_tstart, &ctx->ws_evmean,
                         &ctx->ws_hlast, &ctx->ws_recheck, &ctx->ws_win2, &ctx->ws_read2,
                         &ctx->ws_tcmisc, &ctx->ws_fast, &ctx->ws_sub,
-                        &ctx->ws_slotof};
+                        &ctx->ws_slotof, &ctx->ws_probe2};
     for (Workspace *w : all) ws_free(*w);
     for (const ProfEvent &pe : ctx->prof_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -266,6 +270,19 @@ int pb2_audit_stats(pb2_context *ctx, int64_t *audited, int64_t *mismatched)
     PB_CUDA(ctx, cudaMemset(ctx->tc_err + 2, 0, sizeof(v)));
     if (audited) *audited = v[0];
     if (mismatched) *mismatched = v[1];
+    return PB2_OK;
+}
+
+int pb2_probe2_rows(pb2_context *ctx, int64_t *rows)
+{
+    if (!ctx || !rows) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    int v = 0;
+    if (ctx->probe2_count_dev) {
+        PB_CUDA(ctx, cudaDeviceSynchronize());
+        PB_CUDA(ctx, cudaMemcpy(&v, ctx->probe2_count_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    *rows = v;
     return PB2_OK;
 }
 

@@ -603,6 +603,13 @@ struct TcHeadArgs {
     const float *h_probe;          // [rows][H2] the coarse (perturbed) evaluation
     const float *h_probe2;         // second, independently perturbed probe (or nullptr)
     double delta0, probe_gain;     // per-window error bound = delta0 + probe_gain * |logit shift|
+    // Two-stage use of the probes (stage 0 = both probes for every row, the plain rule):
+    //  stage 1: only probe 1 is available; a row is final if its call is safe under the much wider
+    //           bound delta0 + screen_gain * s1, else it goes on `probe2_rows` (no unsafe flag yet);
+    //  stage 2: row k of this launch is probe2_rows[k], h_probe2 is indexed by k; the plain rule.
+    int stage;
+    double screen_gain;
+    int *probe2_count; int32_t *probe2_rows;
     float *sens_out;               // optional [rows]: the measured logit shift
     int64_t n;
     const int *slot_count;
@@ -622,10 +629,15 @@ struct TcHeadArgs {
 template <int H2>
 __global__ void k_demux_head_tc(const TcHeadArgs A)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t n_eff = A.n;
-    if (A.slot_count && (int64_t)*A.slot_count < n_eff) n_eff = *A.slot_count;
-    if (row >= n_eff) return;
+    if (A.stage == 2) {
+        if (k >= (int64_t)*A.probe2_count) return;
+    } else {
+        if (A.slot_count && (int64_t)*A.slot_count < n_eff) n_eff = *A.slot_count;
+        if (k >= n_eff) return;
+    }
+    const int64_t row = (A.stage == 2) ? (int64_t)A.probe2_rows[k] : k;
     const int64_t r = A.slot_read ? (int64_t)A.slot_read[row] : row;
     if (A.pushed && !A.pushed[r]) return;
     DemuxCall call;
@@ -642,8 +654,9 @@ __global__ void k_demux_head_tc(const TcHeadArgs A)
         if (j < A.n_classes)
             shift = fmaxf(shift, fabsf((call.logit[j] - call.logit[call.arg]) -
                                        (probe.logit[j] - probe.logit[call.arg])));
-    if (A.h_probe2) {
-        demux_head<H2>(A.h_probe2 + (size_t)row * H2, 1, A.Wd, A.bd, A.n_classes, A.n_decoy,
+    if (A.h_probe2 && A.stage != 1) {
+        const int64_t prow = (A.stage == 2) ? k : row;
+        demux_head<H2>(A.h_probe2 + (size_t)prow * H2, 1, A.Wd, A.bd, A.n_classes, A.n_decoy,
                        A.score_threshold, A.calibration, A.n_calibration, probe);
 #pragma unroll
         for (int j = 0; j < PB2_MAX_CLASSES; j++)
@@ -652,26 +665,35 @@ __global__ void k_demux_head_tc(const TcHeadArgs A)
                                            (probe.logit[j] - probe.logit[call.arg])));
     }
     if (!(shift == shift)) shift = INFINITY;
-    const double delta = A.delta0 + A.probe_gain * (double)shift;
+    const double gain = (A.stage == 1) ? A.screen_gain : A.probe_gain;
+    const double delta = A.delta0 + gain * (double)shift;
     const bool safe = demux_call_is_safe(call, A.n_classes, delta, A.score_threshold,
                                          A.calibration, A.n_calibration);
     if (A.sens_out) A.sens_out[row] = shift;
-    if (A.class_probs) {
+    if (A.stage != 2) {
+        if (A.class_probs) {
 #pragma unroll
-        for (int j = 0; j < PB2_MAX_CLASSES; j++) A.class_probs[r * PB2_MAX_CLASSES + j] = call.probs[j];
+            for (int j = 0; j < PB2_MAX_CLASSES; j++) A.class_probs[r * PB2_MAX_CLASSES + j] = call.probs[j];
+        }
+        if (A.barcode) A.barcode[r] = call.barcode;
+        if (A.guess) A.guess[r] = call.guess;
+        if (A.score) A.score[r] = call.score;
+        if (A.logits_out) {
+#pragma unroll
+            for (int j = 0; j < PB2_MAX_CLASSES; j++) A.logits_out[row * PB2_MAX_CLASSES + j] = call.logit[j];
+        }
     }
-    if (A.barcode) A.barcode[r] = call.barcode;
-    if (A.guess) A.guess[r] = call.guess;
-    if (A.score) A.score[r] = call.score;
-    if (A.logits_out) {
-#pragma unroll
-        for (int j = 0; j < PB2_MAX_CLASSES; j++) A.logits_out[row * PB2_MAX_CLASSES + j] = call.logit[j];
+    if (A.stage == 1) {
+        // not provably safe on one probe alone: the second probe decides
+        if (A.unsafe_out) A.unsafe_out[row] = 0;
+        if (!safe) A.probe2_rows[atomicAdd(A.probe2_count, 1)] = (int32_t)row;
+        return;
     }
     if (A.unsafe_out) A.unsafe_out[row] = safe ? 0 : 1;
     if (A.read_unsafe && !safe) atomicOr(&A.read_unsafe[r], 4);       // cause bit 4: barcode call
     if (!safe && A.recheck_rows) {
-        const int k = atomicAdd(A.recheck_count, 1);
-        A.recheck_rows[k] = (int32_t)row;
+        const int kk = atomicAdd(A.recheck_count, 1);
+        A.recheck_rows[kk] = (int32_t)row;
     }
 }
 
@@ -927,6 +949,9 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     int32_t *rrows = rlist + 4;
     PB_CUDA(ctx, cudaMemsetAsync(rlist, 0, sizeof(int32_t) * 2, st));
     const bool use_pad = D.pad_state && !ctx->no_pad_skip;
+    // probe 2 only for the windows probe 1 cannot settle (not on the verification entry point,
+    // which reports the two-probe sensitivity of every window)
+    const bool screen = ctx->demux_probes >= 2 && ctx->demux_screen_gain > 0 && !sens_out && !unsafe_out;
 
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
         const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
@@ -958,7 +983,7 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         B.dir[1] = B.dir[0];
         PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe>", st,
             k_lstm_tc<H2, KX, false, 1><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
-        if (ctx->demux_probes >= 2) {
+        if (ctx->demux_probes >= 2 && !screen) {
             B.dir[0].h_last = h_probe2;
             B.dir[1] = B.dir[0];
             PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe 2>", st,
@@ -977,8 +1002,56 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     Hd.class_probs = class_probs; Hd.barcode = barcode; Hd.guess = guess; Hd.score = score;
     Hd.recheck_count = rcount; Hd.recheck_rows = recheck ? rrows : nullptr;
     Hd.logits_out = logits_out; Hd.unsafe_out = unsafe_out; Hd.read_unsafe = read_unsafe;
-    PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc", st,
-        k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
+    if (!screen) {
+        PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc", st,
+            k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
+    } else {
+        // ---- stage 1: every window on probe 1 alone, with the wide screening bound
+        int32_t *p2 = (int32_t *)ws_get(ctx, ctx->ws_probe2, sizeof(int32_t) * ((size_t)n + 4));
+        float *win_s = (float *)ws_get(ctx, ctx->ws_win2, sizeof(float) * (size_t)n * T);
+        int32_t *read_s = (int32_t *)ws_get(ctx, ctx->ws_read2, sizeof(int32_t) * (size_t)n);
+        if (!p2 || !win_s || !read_s) return PB2_ENOMEM;
+        int *p2count = (int *)p2;
+        int32_t *p2rows = p2 + 4;
+        PB_CUDA(ctx, cudaMemsetAsync(p2count, 0, sizeof(int), st));
+        Hd.stage = 1; Hd.screen_gain = ctx->demux_screen_gain;
+        Hd.probe2_count = p2count; Hd.probe2_rows = p2rows;
+        PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc<screen>", st,
+            k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
+        // ---- stage 2: the undecided windows, compacted: layer 1 again (their tiles are gone from
+        // the scratch), the second probe, and the two-probe rule.  Grids are sized for the worst
+        // case; CTAs beyond the device-side count leave at once.
+        PB_LAUNCH(ctx, K_MISC, "k_gather_recheck<probe2>", st,
+            k_gather_recheck<<<(unsigned)n, 64, 0, st>>>(windows, T, p2count, p2rows, nullptr, win_s, read_s));
+        for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
+            const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
+            const int64_t r0 = t0 * TCM;
+            TcArgs A = {};
+            A.dir[0] = {D.fwd.recurrent, D.fwd.kernel, D.fwd.bias, 0, use_pad ? 1 : 0, 0, KX / 2, 0, nullptr};
+            A.dir[1] = {D.bwd.recurrent, D.bwd.kernel, D.bwd.bias, 1, use_pad ? 3 : 0, H1 / 2, KX / 2 + H1 / 2, 0, nullptr};
+            A.xsrc = win_s; A.padval = D.pad_value; A.T = T;
+            A.n = (n - r0 < nt * TCM) ? n - r0 : nt * TCM;
+            A.slot_count = p2count; A.row0 = r0;
+            A.tab = use_pad ? D.pad_state : nullptr;
+            A.tab_stride = 2 * H1; A.tab_h = 0; A.tab_c = H1;
+            A.tile_tstart = tstart;
+            A.Gout = G; A.g_words = KX; A.g_t0 = 0; A.g_T = T; A.fill_skipped = 1;
+            A.err = err;
+            PB_LAUNCH(ctx, K_DEMUX_TC_L1, "k_lstm_tc<demux l1, probe-2 rows>", st,
+                k_lstm_tc<H1, 0, true><<<dim3((unsigned)nt, 2), tc_threads<48, 0>(), tc_smem_bytes<H1, 0>(), st>>>(A));
+            TcArgs B = {};
+            B.dir[0] = {D.l2.recurrent, D.l2.kernel, D.l2.bias, 0, 0, 0, 0, 1, h_probe2};   // [k][H2], k = list position
+            B.dir[1] = B.dir[0];
+            B.T = T; B.n = A.n; B.slot_count = p2count; B.row0 = r0;
+            B.Gin = G; B.g_t0 = 0; B.g_T = T; B.err = err;
+            PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe 2, subset>", st,
+                k_lstm_tc<H2, KX, false, 2><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+        }
+        Hd.stage = 2;
+        PB_LAUNCH(ctx, K_DEMUX_TC_HEAD, "k_demux_head_tc<probe 2>", st,
+            k_demux_head_tc<H2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Hd));
+        ctx->probe2_count_dev = p2count;
+    }
     if (!recheck) return PB2_OK;
 
     // exact re-run of the unsafe rows (grids are sized for the worst case; CTAs beyond the

@@ -87,6 +87,17 @@ struct pb2_context {
     double demux_margin_delta = 1e-3;
     double demux_probe_gain = 0.1;
     int demux_probes = 2;                         // coarse probe evaluations of layer 2 (1 or 2)
+    // Probe 2 only where probe 1 cannot settle the call: a call that is safe under the bound
+    // delta + screen_gain * (shift of probe 1 alone) is final; the rest get the second probe and
+    // the two-probe rule.  0 (default) = second probe for every window.  Measured on B200
+    // (POREPLEX_B200_SCREEN_GAIN=10, the smallest gain with a comfortable margin over the worst
+    // single-probe under-estimate seen): 39 % of the windows still need probe 2 -- the 29
+    // calibration edges are close together -- and re-running layer 1 for them costs what the
+    // skipped probes save (334.1 vs 334.9 ms per step); the list order also makes the unsafe
+    // set depend on warp scheduling.  Kept as a knob, off.
+    double demux_screen_gain = 0.0;
+    int64_t last_probe2_rows = 0;
+    int *probe2_count_dev = nullptr;              // device count of the last launch (diagnostics)
     // assumed bounds on the error of the scaler's two raw outputs (z0 -> scale, z1 -> shift); the
     // shift output has the heavier tail (largest seen on 1 M reads: 4.4e-5 / 2.9e-4)
     double scaler_margin_z0 = 2.5e-4, scaler_margin_z1 = 1.5e-3;
@@ -121,7 +132,7 @@ struct pb2_context {
     pb::Workspace ws_pooled, ws_status, ws_label, ws_scale, ws_seg, ws_win, ws_pushed,
         ws_probs, ws_bc, ws_guess, ws_score, ws_h1, ws_bp, ws_counts, ws_batch, ws_misc,
         ws_heads, ws_flags, ws_slots, ws_polya, ws_unsplit, ws_unsplit_host, ws_tstart, ws_evmean,
-        ws_hlast, ws_recheck, ws_win2, ws_read2, ws_tcmisc, ws_fast, ws_sub, ws_slotof;
+        ws_hlast, ws_recheck, ws_win2, ws_read2, ws_tcmisc, ws_fast, ws_sub, ws_slotof, ws_probe2;
     // host staging for pb2_analyze_host
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path

@@ -257,6 +257,12 @@ class SignalEngine:
         self._check(self.lib.pb2_audit_stats(self.handle, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def probe2_rows(self):
+        """Windows of the last classifier launch that needed the second sensitivity probe."""
+        a = C.c_int64(0)
+        self._check(self.lib.pb2_probe2_rows(self.handle, C.byref(a)))
+        return int(a.value)
+
     def rerun_causes(self):
         """{cause: reads} behind the exact re-runs of the last whole-path call."""
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
