@@ -426,7 +426,10 @@ k_lstm_tc(const TcArgs A)
             }
         }
         // vector input of the first step -> TMEM
-        constexpr int XW = (KX > 0) ? KX / NP : 4;         // x words per thread
+        // x words per thread: the (hi | lo) words of the input, or only the hi half for the coarse
+        // probes (their MMAs read nothing else)
+        constexpr int XW = (KX > 0) ? (COARSE != 0 ? KX / 2 : KX) / NP : 4;
+        static_assert(XW % 4 == 0, "x words per thread must be a multiple of 4");
         uint32_t xw[XW];
         if (KX > 0) {
             const int t = dir.reverse ? (T - 1 - t_start) : t_start;

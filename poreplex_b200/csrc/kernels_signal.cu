@@ -104,24 +104,52 @@ int launch_pool(pb2_context *ctx, const pb2_batch &b, int stride, float *pooled,
 // ---------------------------------------------------------------------------
 constexpr int WIN_WARPS = 4;
 
-__device__ __forceinline__ float warp_median(const float *v, int n, int lane,
-                                              float *slot /* [2] shared, per warp */)
+// k-th smallest (0-based) of v[0..n) by a bitwise search on the order-preserving integer image of
+// the floats: the answer is the largest key K with #{key < K} <= k.  32 counting passes of n / 32
+// elements per lane instead of n rank counts of n elements each (n <= 300: ~9x fewer
+// instructions); the value returned is an element of v, exactly the order statistic np.median
+// / np.partition pick.
+__device__ __forceinline__ uint32_t float_key(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ uint32_t warp_select_key(const float *v, int n, int k, int lane)
 {
-    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
-    for (int i = lane; i < n; i += 32) {
-        const float x = v[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            const float y = v[j];
-            rank += (y < x) || (y == x && j < i);
-        }
-        if (rank == k_lo) slot[0] = x;
-        if (rank == k_hi) slot[1] = x;
+    uint32_t res = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t cand = res | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < n; i += 32) c += float_key(v[i]) < cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c <= k) res = cand;
     }
-    __syncwarp();
-    const float lo = slot[0], hi = slot[1];
-    __syncwarp();
-    if (n & 1) return hi;
+    return res;
+}
+
+__device__ __forceinline__ float warp_median(const float *v, int n, int lane,
+                                              float *slot /* [2] shared, per warp; unused */)
+{
+    (void)slot;
+    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
+    const uint32_t key_lo = warp_select_key(v, n, k_lo, lane);
+    if (n & 1) return key_float(key_lo);
+    // the next order statistic: the same value if it occurs often enough, else the smallest
+    // element above it
+    int le = 0;
+    uint32_t above = 0xFFFFFFFFu;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t kx = float_key(v[i]);
+        le += kx <= key_lo;
+        if (kx > key_lo && kx < above) above = kx;
+    }
+    le = __reduce_add_sync(0xffffffffu, le);
+    above = __reduce_min_sync(0xffffffffu, above);
+    const float lo = key_float(key_lo);
+    const float hi = (le > k_hi) ? lo : key_float(above);
     return pb::fdiv(pb::fadd(lo, hi), 2.0f);        // np.mean of the two middle values
 }
 
