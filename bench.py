@@ -157,20 +157,40 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index):
-    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs NVML
-    reports as local to this GPU, so the H2D copies of the host path do not cross sockets."""
+    """One process per GPU: run on the CPUs NVML reports as local to this GPU and ask the kernel
+    to place this process's pages (the pinned host buffers above all) on the GPU's own NUMA
+    node, so that the H2D copies of the host path neither cross sockets nor all read one node's
+    memory.  Returns what happened, for the JSON line."""
+    info = {'cpus_bound': None, 'gpu_numa_node': None, 'mempolicy': 'not tried'}
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return None
+            info['cpus_bound'] = len(cpus)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(':')[0]) == 8:                   # 00000000:17:00.0 -> 0000:17:00.0
+            bdf = bdf[4:]
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        info['gpu_numa_node'] = node
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))   # set_mempolicy
+            info['mempolicy'] = 'preferred node %d' % node if rc == 0 else \
+                'failed (errno %d)' % ctypes.get_errno()
+    except Exception as exc:
+        info['mempolicy'] = 'failed (%s)' % type(exc).__name__
+    return info
 
 
 def make_workload(args, device, seed):
@@ -639,7 +659,22 @@ def main():
                                     hnp['digitisation'], hnp['offset'], barcoding=True, out=hout,
                                     polya=full)
         host_step()                                        # warm-up
+        # what the box can move: the same pinned input buffer copied to the device with nothing
+        # else running, every rank at the same time (N > 1: the ranks share the host's PCIe
+        # uplinks) -- the floor under any host-buffer figure is h2d_bytes / this rate
+        dst = torch.empty_like(work['raw'])
         if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tc0 = time.perf_counter()
+        dst.copy_(h['raw'], non_blocking=True)
+        torch.cuda.synchronize()
+        copy_rate = h['raw'].numel() * 2 / (time.perf_counter() - tc0) / 1e9
+        del dst
+        if world > 1:
+            t = torch.tensor([copy_rate], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            copy_rate = float(t.item())
             dist.barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
@@ -658,6 +693,8 @@ def main():
         d2h = sum(v.nbytes for v in res.values())
         result['e2e'] = {'value': world * hn / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+                         'pinned_h2d_gb_per_s_per_gpu_all_ranks_copying': copy_rate,
+                         'ms_per_step_floor_from_h2d': h2d / copy_rate / 1e6,
                          'api': 'pb2_analyze_host (pinned host input and result buffers; chunked '
                                 'H2D/compute/D2H pipeline)' +
                                 ('; the chimera filter of config full is not part of this call' if full else '')}
