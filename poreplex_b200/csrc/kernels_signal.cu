@@ -9,10 +9,20 @@
 namespace pb {
 
 // ---------------------------------------------------------------------------
-// k_pool: one warp produces 32 pooled samples per iteration.
-//   raw tile   32*stride int16 staged in shared memory with 16-byte loads
-//              (reads start 16-byte aligned; a tile is 32*stride*2 bytes which is a
-//              multiple of 16 for every stride)
+// k_pool: one warp per read chunk; 32 pooled samples (= one 32*stride int16 tile, 960 bytes for
+// stride 15) per iteration.
+//   raw tiles  staged in shared memory by the TMA unit: lane 0 issues one bulk asynchronous copy
+//              per tile (cp.async.bulk.shared.global, completion counted in bytes on an
+//              mbarrier) POOL_STAGES tiles ahead of the arithmetic, so a warp always has
+//              several 960-byte requests in flight instead of one load-use round trip per tile
+//              (reads start 16-byte aligned and a tile is a multiple of 16 bytes for every
+//              stride; the ragged last tile of a read is rounded up to 16 bytes when that stays
+//              inside the buffer, else it is fetched with plain loads);
+//              What bounds the kernel after that is not the stream but the conversion: per raw
+//              sample one I2F.F64 and one F2F.F32.F64 (XU pipe, 16 lanes / SM / clock: 1.8 ms
+//              per 4e9 samples) next to the DADD / DMUL.  Measured and rejected on B200: the
+//              conversions by hand (2^52 magic add + integer rounding: 4.98 ms instead of
+//              2.46), integer addition of whole-number offsets (2.60 ms).
 //   lane l     converts its `stride` samples in fp64 (fast5_file.py:130-131), sums
 //              them in numpy's pairwise order (signal_loader.py:224-225) and stores
 //              one f32 -- 128-byte coalesced store per warp.
@@ -20,8 +30,30 @@ namespace pb {
 // samples so that long reads are spread over many warps.
 // ---------------------------------------------------------------------------
 constexpr int POOL_WARPS = 8;
-constexpr int POOL_CHUNK = 256;         // pooled samples per (warp, blockIdx.y)
+constexpr int POOL_CHUNK = 512;         // pooled samples per (warp, blockIdx.y)
 constexpr int POOL_MAX_STRIDE = 32;
+constexpr int POOL_STAGES = 4;
+
+__device__ __forceinline__ uint32_t pool_smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pool_bar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pool_smem_u32(bar)) : "memory");
+}
+// arm the barrier for `bytes` and start the bulk copy global -> shared that will complete it
+__device__ __forceinline__ void pool_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(pool_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pool_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pool_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pool_bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra WAIT_%=;\n\t}"
+                 ::"r"(pool_smem_u32(bar)), "r"(parity) : "memory");
+}
 
 template <int STRIDE>
 __global__ void __launch_bounds__(POOL_WARPS * 32)
@@ -31,10 +63,15 @@ k_pool(const int16_t *__restrict__ raw, const int64_t *__restrict__ raw_offsets,
        int64_t n_reads, int64_t n_raw_total, int limit_pooled, float *__restrict__ pooled)
 {
     constexpr int TILE = 32 * STRIDE;                 // int16 elements per warp tile
-    constexpr int NVEC = TILE / 8;                    // 16-byte vectors per tile
-    __shared__ __align__(16) int16_t stage[POOL_WARPS][TILE];
+    static_assert((TILE * 2) % 16 == 0, "a tile must be a whole number of 16-byte units");
+    __shared__ __align__(128) int16_t stage[POOL_WARPS][POOL_STAGES][TILE];
+    __shared__ __align__(8) uint64_t bars[POOL_WARPS][POOL_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * POOL_WARPS + warp;
+    if (lane == 0)
+        for (int sidx = 0; sidx < POOL_STAGES; sidx++) pool_bar_init(&bars[warp][sidx]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
     if (r >= n_reads) return;
     const int64_t roff = raw_offsets[r];
     const int64_t rlen = raw_lengths[r];
@@ -46,23 +83,33 @@ k_pool(const int16_t *__restrict__ raw, const int64_t *__restrict__ raw_offsets,
     const double gain = pb::ddiv(range[r], digitisation[r]);   // range / digitisation
     const double off = offset[r];
     const int64_t pout = pooled_offset(roff, STRIDE);
-    int16_t *mine = stage[warp];
+    const int ntiles = (int)((t_end - t_begin + 31) / 32);
 
-    for (int64_t t0 = t_begin; t0 < t_end; t0 += 32) {
-        const int64_t e0 = roff + t0 * STRIDE;          // first raw element of the tile
-#pragma unroll
-        for (int v = lane; v < NVEC; v += 32) {
-            const int64_t e = e0 + (int64_t)v * 8;
-            if (e + 8 <= n_raw_total) {
-                *reinterpret_cast<int4 *>(mine + v * 8) =
-                    __ldg(reinterpret_cast<const int4 *>(raw + e));
-            } else {
-                for (int j = 0; j < 8; j++)
-                    mine[v * 8 + j] = (e + j < n_raw_total) ? raw[e + j] : (int16_t)0;
-            }
+    // tile i of this warp: raw elements [e0, e0 + nel); fetched by the TMA unit when its
+    // 16-byte rounded extent lies inside the buffer
+    auto issue = [&](int i) {
+        const int64_t t0 = t_begin + (int64_t)i * 32;
+        const int64_t e0 = roff + t0 * STRIDE;
+        const int64_t np = (t_end - t0 < 32) ? t_end - t0 : 32;
+        const int64_t nel = (np * STRIDE + 7) & ~(int64_t)7;
+        int16_t *dst = stage[warp][i % POOL_STAGES];
+        if (e0 + nel <= n_raw_total) {
+            if (lane == 0) pool_bulk_load(dst, raw + e0, (uint32_t)(nel * 2), &bars[warp][i % POOL_STAGES]);
+        } else {
+            for (int64_t j = lane; j < nel; j += 32) dst[j] = (e0 + j < n_raw_total) ? raw[e0 + j] : (int16_t)0;
+            __syncwarp();
+            if (lane == 0)          // complete the phase by hand so the consumer's wait is uniform
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                             ::"r"(pool_smem_u32(&bars[warp][i % POOL_STAGES])) : "memory");
         }
-        __syncwarp();
-        const int64_t t = t0 + lane;
+    };
+    for (int i = 0; i < POOL_STAGES && i < ntiles; i++) issue(i);
+
+    for (int i = 0; i < ntiles; i++) {
+        const int sidx = i % POOL_STAGES;
+        pool_bar_wait(&bars[warp][sidx], (uint32_t)((i / POOL_STAGES) & 1));
+        const int16_t *mine = stage[warp][sidx];
+        const int64_t t = t_begin + (int64_t)i * 32 + lane;
         if (t < t_end) {
             float a[STRIDE];
 #pragma unroll
@@ -70,7 +117,8 @@ k_pool(const int16_t *__restrict__ raw, const int64_t *__restrict__ raw_offsets,
                 a[j] = pb::dac_to_pa((int)mine[lane * STRIDE + j], gain, off);
             pooled[pout + t] = pb::pool_mean<STRIDE>(a);
         }
-        __syncwarp();
+        __syncwarp();                                  // every lane is done with this stage
+        if (i + POOL_STAGES < ntiles) issue(i + POOL_STAGES);
     }
 }
 
