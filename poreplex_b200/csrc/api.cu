@@ -1336,16 +1336,28 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
             return analyze_host_single(ctx, hb, hr, flags);
     }
     std::vector<int64_t> bounds;
-    // The first upload and the last download are not hidden behind kernels: make the first and
-    // the last chunk half as large as the others (weights 1 2 2 ... 2 1).
-    const int64_t parts = uniform ? nchunks : nchunks + 1;
-    const int64_t wsum = uniform ? nchunks : 2 * nchunks;
-    int64_t acc = 0;
-    for (int64_t c = 0; c <= parts; c++) {
-        int64_t b = (n * acc) / wsum;
-        if (c < parts) b -= b % 128;             // keep chunk starts tile aligned
-        if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
-        acc += uniform ? 1 : ((c == 0 || c == parts - 1) ? 1 : 2);
+    // Only the FIRST upload is not hidden behind kernels (the results of the last chunk are a
+    // few megabytes): a small first chunk, then equal large ones.  Chunk sizes are whole waves
+    // of the tensor-core kernels (one 128-read tile per SM) so that no chunk ends on a partly
+    // filled wave: first chunk = 3 waves (0.45 GB of 4000-sample reads, ~8 ms of PCIe).
+    if (uniform) {
+        for (int64_t c = 0; c <= nchunks; c++) {
+            int64_t b = (n * c) / nchunks;
+            if (c < nchunks) b -= b % 128;       // keep chunk starts tile aligned
+            if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
+        }
+    } else {
+        const int64_t wave = (int64_t)ctx->sm_count * 128;
+        int64_t first = 3 * wave;
+        if (first > n / 8) first = (n / 8) - (n / 8) % 128;
+        bounds.push_back(0);
+        if (first > 0) bounds.push_back(first);
+        const int64_t rest = n - bounds.back();
+        for (int64_t c = 1; c <= nchunks; c++) {
+            int64_t b = bounds[first > 0 ? 1 : 0] + (rest * c) / nchunks;
+            if (c < nchunks) { b -= b % wave; b -= b % 128; }
+            if (b > bounds.back()) bounds.push_back(b);
+        }
     }
     if (bounds.back() != n) bounds.push_back(n);
     if (bounds.size() < 3) return analyze_host_single(ctx, hb, hr, flags);
