@@ -700,6 +700,43 @@ def main():
                                 ('; the chimera filter of config full is not part of this call' if full else '')}
         assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
 
+        # ---- the same call with the compressed upload: the streamvbyte-16 bodies of the reads
+        # (what a VBZ FAST5 holds under its zstd stage) cross the bus instead of int16 samples
+        # and are decoded on the device; encoded once here, outside the timed region, as the
+        # ingest would hand them over
+        from poreplex_b200 import fast5_loader
+        fast5_loader.build()
+        pk, po = fast5_loader.svb16_encode(hnp['raw'], hnp['offsets'], hnp['lengths'], pinned=True)
+
+        def packed_step():
+            return eng.analyze_host(None, hnp['offsets'], hnp['lengths'], hnp['range'],
+                                    hnp['digitisation'], hnp['offset'], barcoding=True, out=hout,
+                                    polya=full, packed=(pk, po))
+        packed_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res2 = packed_step()
+            if world > 1:
+                c = torch.from_numpy(res2['counts']).to(device)
+                dist.all_reduce(c)
+                c.cpu()
+        dt2 = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt2], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt2 = float(t.item())
+        h2d2 = int(po[-1]) + sum(v.numel() * v.element_size() for k, v in h.items() if k != 'raw') + po.nbytes
+        result['e2e_svb16'] = {'value': world * hn / dt2, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d2),
+                               'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt2 * 1e3,
+                               'bytes_per_sample': float(po[-1]) / float(hnp['lengths'].sum()),
+                               'api': 'pb2_analyze_host with pb2_batch.packed: streamvbyte-16 bodies '
+                                      '(VBZ chunks without their zstd stage) uploaded, decoded on the '
+                                      'device (k_svb16_decode)'}
+        assert np.array_equal(res2['status'], status) and np.array_equal(res2['segments'], seg_np), \
+            'packed and int16 host paths disagree'
+
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

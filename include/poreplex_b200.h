@@ -218,6 +218,15 @@ typedef struct {
     const double *range;             /* [n_reads] channel_id attrs */
     const double *digitisation;      /* [n_reads] */
     const double *offset;            /* [n_reads] */
+    /* Optional compressed form of `raw` for the HOST entry points: one streamvbyte-16 stream per
+     * read = the body of an ONT VBZ chunk (HDF5 filter 32020, version 1, 2-byte integers, zigzag
+     * deltas) after its optional zstd stage; read i occupies bytes
+     * [packed_offsets[i], packed_offsets[i + 1]), offsets multiples of 16.  When `packed` is not
+     * NULL pb2_analyze_host uploads these bytes (about 1.13 per sample) instead of `raw`, which
+     * may be NULL, and decodes them on the device (pb2_svb16_decode) into the layout
+     * raw_offsets / raw_lengths describe.  Ignored by the device-resident entry points. */
+    const uint8_t *packed;
+    const int64_t *packed_offsets;   /* [n_reads + 1] */
 } pb2_batch;
 
 /* Per-read results (any pointer may be NULL = not wanted). */
@@ -343,6 +352,12 @@ int pb2_derive_event_tables(pb2_context *ctx, const pb2_batch *batch,
 int pb2_derive_event_tables_host(pb2_context *ctx, const pb2_batch *batch,
                                  const pb2_event_tables *events, const pb2_basecalls *basecalls,
                                  const float *scale_shift, const pb2_event_columns *out);
+/* Device-side half of the VBZ decoder (see pb2_batch.packed): streamvbyte-16 + zigzag + delta
+ * -> int16 samples, one warp per read.  Device pointers; *error (may be NULL) is set to 1 when a
+ * stream is shorter than its key block promises. */
+int pb2_svb16_decode(pb2_context *ctx, const uint8_t *packed, const int64_t *packed_offsets,
+                     const int64_t *raw_offsets, const int64_t *raw_lengths, int64_t n_reads,
+                     int16_t *raw, int32_t *error, void *stream);
 /* io.py:274-278 */
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
                       const int32_t *barcode, int64_t n, int64_t *counts, void *stream);

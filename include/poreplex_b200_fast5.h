@@ -94,6 +94,16 @@ void pb2f_batch_close(pb2f_batch *b);
  * small, PB2F_EFORMAT for truncated / corrupt input or an Adler-32 mismatch. */
 int64_t pb2f_inflate(const void *src, int64_t src_len, void *dst, int64_t dst_capacity);
 
+/* The compressed upload form of a packed int16 batch (include/poreplex_b200.h, pb2_batch.packed):
+ * one streamvbyte-16 stream of zigzag deltas per read -- the body of an ONT VBZ chunk (filter
+ * 32020, version 1, 2-byte integers) without its zstd stage -- each starting on a 16-byte
+ * boundary.  pb2f_svb16_plan fills packed_offsets[n_reads + 1] and returns the buffer size;
+ * pb2f_svb16_encode writes the streams. */
+int64_t pb2f_svb16_plan(const int16_t *raw, const int64_t *raw_offsets, const int64_t *raw_lengths,
+                        int64_t n_reads, int n_threads, int64_t *packed_offsets);
+int pb2f_svb16_encode(const int16_t *raw, const int64_t *raw_offsets, const int64_t *raw_lengths,
+                      int64_t n_reads, int n_threads, const int64_t *packed_offsets, uint8_t *packed);
+
 #ifdef __cplusplus
 }
 #endif

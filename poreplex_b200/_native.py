@@ -119,7 +119,8 @@ class Batch(C.Structure):
     _fields_ = [('n_reads', C.c_int64), ('n_raw_total', C.c_int64),
                 ('max_raw_length', C.c_int64),
                 ('raw', C.c_void_p), ('raw_offsets', C.c_void_p), ('raw_lengths', C.c_void_p),
-                ('range', C.c_void_p), ('digitisation', C.c_void_p), ('offset', C.c_void_p)]
+                ('range', C.c_void_p), ('digitisation', C.c_void_p), ('offset', C.c_void_p),
+                ('packed', C.c_void_p), ('packed_offsets', C.c_void_p)]
 
 
 class Results(C.Structure):
@@ -141,7 +142,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
            'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
            'pb2_audit_stats', 'pb2_detect_events', 'pb2_derive_event_tables',
-           'pb2_derive_event_tables_host', 'pb2_probe2_rows']
+           'pb2_derive_event_tables_host', 'pb2_probe2_rows', 'pb2_svb16_decode']
 
 
 def sources():
@@ -225,6 +226,7 @@ def load():
     L.pb2_derive_event_tables_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(EventTables),
                                                C.POINTER(Basecalls), vp, C.POINTER(EventColumns)]
     L.pb2_probe2_rows.argtypes = [vp, _i64p]
+    L.pb2_svb16_decode.argtypes = [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]
     L.pb2_profile_enable.argtypes = [vp, C.c_int]
     L.pb2_profile_kernel_count.restype = C.c_int
     L.pb2_profile_kernel_name.argtypes = [C.c_int]

@@ -78,7 +78,7 @@ static const char *const kKernelNames[K_NUM] = {
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
     "k_unsplit_windows", "k_unsplit_decide", "k_event_means", "k_lstm_tc_demux_l1",
     "k_lstm_tc_demux_l2", "k_demux_head_tc", "k_lstm_tc_scaler_l1", "k_lstm_tc_scaler_l2",
-    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe", "k_event_pos"};
+    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe", "k_event_pos", "k_svb16_decode"};
 
 static void ws_free(Workspace &w)
 {
@@ -182,6 +182,7 @@ void pb2_destroy(pb2_context *ctx)
     cudaFree(ctx->demux.calibration_dev);
     cudaFree(ctx->tc_err);
     if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     Workspace *all[] = {&ctx->ws_pooled, &ctx->ws_status, &ctx->ws_label, &ctx->ws_scale,
                         &ctx->ws_seg, &ctx->ws_win, &ctx->ws_pushed, &ctx->ws_probs,
                         &ctx->ws_bc, &ctx->ws_guess, &ctx->ws_score, &ctx->ws_h1, &ctx->ws_bp,
@@ -448,7 +449,8 @@ static int check_batch(pb2_context *ctx, const pb2_batch *b)
 {
     if (!ctx || !b) return PB2_EINVAL;
     if (b->n_reads < 0) return fail(ctx, PB2_EINVAL, "negative read count");
-    if (b->n_reads > 0 && (!b->raw || !b->raw_offsets || !b->raw_lengths || !b->range ||
+    if (b->n_reads > 0 && ((!b->raw && !b->packed) || (b->packed && !b->packed_offsets) ||
+                           !b->raw_offsets || !b->raw_lengths || !b->range ||
                            !b->digitisation || !b->offset))
         return fail(ctx, PB2_EINVAL, "null batch pointer");
     return PB2_OK;
@@ -723,6 +725,18 @@ int pb2_detect_events(pb2_context *ctx, const float *signal, const int64_t *offs
     DeviceGuard g(ctx->device);
     return launch_detect_events(ctx, signal, offsets, lengths, n_signals, *p, event_counts,
                                 event_offsets, records, (cudaStream_t)stream);
+}
+
+int pb2_svb16_decode(pb2_context *ctx, const uint8_t *packed, const int64_t *packed_offsets,
+                     const int64_t *raw_offsets, const int64_t *raw_lengths, int64_t n_reads,
+                     int16_t *raw, int32_t *error, void *stream)
+{
+    if (!ctx) return PB2_EINVAL;
+    if (n_reads > 0 && (!packed || !packed_offsets || !raw_offsets || !raw_lengths || !raw))
+        return fail(ctx, PB2_EINVAL, "svb16_decode: null pointer");
+    DeviceGuard g(ctx->device);
+    return launch_svb16_decode(ctx, packed, packed_offsets, raw_offsets, raw_lengths, n_reads, raw,
+                               error, (cudaStream_t)stream);
 }
 
 int pb2_count_results(pb2_context *ctx, const int32_t *status, const int32_t *label,
@@ -1054,6 +1068,9 @@ static int analyze_host_single(pb2_context *ctx, const pb2_batch *hb, const pb2_
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align(bytes); return o; };
     const size_t o_raw = take(sizeof(int16_t) * (size_t)hb->n_raw_total + 16);
+    const bool packed = hb->packed != nullptr;
+    const size_t packed_bytes = packed && n > 0 ? (size_t)hb->packed_offsets[n] : 0;
+    const size_t o_pk = take(packed ? packed_bytes + 16 : 16), o_po = take(packed ? 8 * (size_t)(n + 1) : 16);
     const size_t o_off = take(sizeof(int64_t) * n), o_len = take(sizeof(int64_t) * n);
     const size_t o_rng = take(sizeof(double) * n), o_dig = take(sizeof(double) * n);
     const size_t o_ofs = take(sizeof(double) * n);
@@ -1081,11 +1098,22 @@ static int analyze_host_single(pb2_context *ctx, const pb2_batch *hb, const pb2_
     if (db.max_raw_length <= 0)
         for (int64_t i = 0; i < n; i++)
             if (hb->raw_lengths[i] > db.max_raw_length) db.max_raw_length = hb->raw_lengths[i];
+    db.packed = nullptr; db.packed_offsets = nullptr;
     if (n > 0) {
-        PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw, hb->raw, sizeof(int16_t) * (size_t)hb->n_raw_total,
-                                     cudaMemcpyHostToDevice, st));
         PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw_offsets, hb->raw_offsets, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
         PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw_lengths, hb->raw_lengths, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+        if (packed) {
+            // compressed upload: the streamvbyte bodies cross the bus, the samples are rebuilt here
+            PB_CUDA(ctx, cudaMemcpyAsync(base + o_pk, hb->packed, packed_bytes, cudaMemcpyHostToDevice, st));
+            PB_CUDA(ctx, cudaMemcpyAsync(base + o_po, hb->packed_offsets, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+            PB_CUDA(ctx, cudaMemsetAsync(ctx->tc_err + 1, 0, sizeof(int), st));
+            if ((rc = launch_svb16_decode(ctx, (const uint8_t *)(base + o_pk), (const int64_t *)(base + o_po),
+                                          db.raw_offsets, db.raw_lengths, n, (int16_t *)db.raw,
+                                          ctx->tc_err + 1, st))) return rc;
+        } else {
+            PB_CUDA(ctx, cudaMemcpyAsync((void *)db.raw, hb->raw, sizeof(int16_t) * (size_t)hb->n_raw_total,
+                                         cudaMemcpyHostToDevice, st));
+        }
         PB_CUDA(ctx, cudaMemcpyAsync((void *)db.range, hb->range, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         PB_CUDA(ctx, cudaMemcpyAsync((void *)db.digitisation, hb->digitisation, sizeof(double) * n, cudaMemcpyHostToDevice, st));
         PB_CUDA(ctx, cudaMemcpyAsync((void *)db.offset, hb->offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
@@ -1127,7 +1155,10 @@ static int analyze_host_single(pb2_context *ctx, const pb2_batch *hb, const pb2_
     if (keep) PB_D2H(pooled, sizeof(float) * n_pooled);
     if (want_polya) PB_D2H(polya, sizeof(pb2_polya_result) * (size_t)n);
 #undef PB_D2H
+    int svb_err = 0;
+    if (packed) PB_CUDA(ctx, cudaMemcpyAsync(&svb_err, ctx->tc_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     PB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (svb_err) return fail(ctx, PB2_EINVAL, "packed input: a streamvbyte stream is shorter than its keys promise");
     return PB2_OK;
 }
 
@@ -1145,18 +1176,22 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
     if (!ctx->copy_in) PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     if (!ctx->copy_out) PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     cudaStream_t compute = ctx->host_stream;
-    int64_t max_reads = 0, max_span = 0;
+    const bool packed = hb->packed != nullptr;
+    int64_t max_reads = 0, max_span = 0, max_pk = 0;
     for (int c = 0; c < nchunks; c++) {
         const int64_t c0 = bounds[c], c1 = bounds[c + 1];
         const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - hb->raw_offsets[c0];
         if (c1 - c0 > max_reads) max_reads = c1 - c0;
         if (span > max_span) max_span = span;
+        if (packed && hb->packed_offsets[c1] - hb->packed_offsets[c0] > max_pk)
+            max_pk = hb->packed_offsets[c1] - hb->packed_offsets[c0];
     }
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t m = (size_t)max_reads;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align(bytes); return o; };
     const size_t o_raw = take(sizeof(int16_t) * (size_t)max_span + 32);
+    const size_t o_pk = take(packed ? (size_t)max_pk + 32 : 16), o_po = take(packed ? 8 * (m + 1) : 16);
     const size_t o_off = take(8 * m), o_len = take(8 * m), o_rng = take(8 * m), o_dig = take(8 * m);
     const size_t o_ofs = take(8 * m), o_status = take(4 * m), o_label = take(4 * m);
     const size_t o_ss = take(8 * m), o_seg = take(4 * 2 * PB2_MAX_STATES * m);
@@ -1177,13 +1212,26 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
         ctx->counts_host_bytes = counts_bytes;
     }
     int64_t *counts_host = ctx->counts_host;
+    // pinned staging for the per-chunk rebased offsets: a copy from pageable memory makes the
+    // host wait for everything queued before it on the upload stream (the previous chunk's
+    // kernels included, through the arena hand-over event), and while the host waits the next
+    // chunk's kernels are not queued -- uploads then stop overlapping compute
+    const size_t stage_per_arena = 2 * (m + 2);
+    if (ctx->stage_host_bytes < 2 * stage_per_arena * 8) {
+        if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+        ctx->stage_host = nullptr; ctx->stage_host_bytes = 0;
+        PB_CUDA(ctx, cudaMallocHost(&ctx->stage_host, 2 * stage_per_arena * 8));
+        ctx->stage_host_bytes = 2 * stage_per_arena * 8;
+    }
     cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming);
     }
-    std::vector<int64_t> rebased[2];
+    int64_t *rebased[2] = {ctx->stage_host, ctx->stage_host + stage_per_arena};
+    int64_t *rebased_pk[2] = {rebased[0] + m + 1, rebased[1] + m + 1};
+    if (packed) PB_CUDA(ctx, cudaMemsetAsync(ctx->tc_err + 1, 0, sizeof(int), compute));
     int rc = PB2_OK;
     auto run = [&]() -> int {
         // results of chunk c leave on the third stream.  Issued one chunk LATE: the caller's
@@ -1231,8 +1279,11 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             const int64_t c0 = bounds[c], c1 = bounds[c + 1], nc = c1 - c0;
             const int64_t roff0 = hb->raw_offsets[c0];
             const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - roff0;
-            if (c >= 2) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[a], 0));
-            rebased[a].resize((size_t)nc);
+            if (c >= 2) {
+                // the staging slot of this arena was last read by the upload of chunk c - 2
+                PB_CUDA(ctx, cudaEventSynchronize(ev_h2d[a]));
+                PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[a], 0));
+            }
             int64_t max_len = 0;
             for (int64_t i = 0; i < nc; i++) {
                 rebased[a][i] = hb->raw_offsets[c0 + i] - roff0;
@@ -1240,8 +1291,14 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             }
             spans[c] = span; max_lens[c] = max_len;
             cudaStream_t ci = ctx->copy_in;
+            if (packed) {
+                const int64_t p0 = hb->packed_offsets[c0];
+                for (int64_t i = 0; i <= nc; i++) rebased_pk[a][i] = hb->packed_offsets[c0 + i] - p0;
+                PB_CUDA(ctx, cudaMemcpyAsync(A + o_pk, hb->packed + p0, (size_t)(hb->packed_offsets[c1] - p0), cudaMemcpyHostToDevice, ci));
+                PB_CUDA(ctx, cudaMemcpyAsync(A + o_po, rebased_pk[a], 8 * (size_t)(nc + 1), cudaMemcpyHostToDevice, ci));
+            } else
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_raw, hb->raw + roff0, sizeof(int16_t) * (size_t)span, cudaMemcpyHostToDevice, ci));
-            PB_CUDA(ctx, cudaMemcpyAsync(A + o_off, rebased[a].data(), 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_off, rebased[a], 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_len, hb->raw_lengths + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_rng, hb->range + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
             PB_CUDA(ctx, cudaMemcpyAsync(A + o_dig, hb->digitisation + c0, 8 * (size_t)nc, cudaMemcpyHostToDevice, ci));
@@ -1281,6 +1338,12 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
                 PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_score, 0xFF, 4 * (size_t)nc, compute));
                 PB_CUDA(ctx, cudaMemsetAsync(dr.class_probs, 0, 4 * PB2_MAX_CLASSES * (size_t)nc, compute));
             }
+            if (packed) {
+                int rd = launch_svb16_decode(ctx, (const uint8_t *)(A + o_pk), (const int64_t *)(A + o_po),
+                                             db.raw_offsets, db.raw_lengths, nc, (int16_t *)(A + o_raw),
+                                             ctx->tc_err + 1, compute);
+                if (rd) return rd;
+            }
             int r2 = pb2_analyze_device(ctx, &db, &dr, flags & ~PB2_FLAG_KEEP_POOLED, compute);
             if (r2) return r2;
             PB_CUDA(ctx, cudaEventRecord(ev_comp[a], compute));
@@ -1288,8 +1351,11 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
             if (c >= 1) { int r3 = drain(c - 1); if (r3) return r3; }
         }
         { int r3 = drain(nchunks - 1); if (r3) return r3; }
+        int svb_err = 0;
+        if (packed) PB_CUDA(ctx, cudaMemcpyAsync(&svb_err, ctx->tc_err + 1, sizeof(int), cudaMemcpyDeviceToHost, compute));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
         PB_CUDA(ctx, cudaStreamSynchronize(compute));
+        if (svb_err) return fail(ctx, PB2_EINVAL, "packed input: a streamvbyte stream is shorter than its keys promise");
         return PB2_OK;
     };
     rc = run();

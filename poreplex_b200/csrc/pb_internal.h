@@ -70,7 +70,7 @@ namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
                 K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_DEMUX_TC_L1, K_DEMUX_TC_L2, K_DEMUX_TC_HEAD,
-                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_EVENT_POS, K_NUM };
+                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_EVENT_POS, K_SVB_DECODE, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 
@@ -138,6 +138,8 @@ struct pb2_context {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pipelined host path
     int64_t *counts_host = nullptr;                       // pinned, per-chunk counts
     size_t counts_host_bytes = 0;
+    int64_t *stage_host = nullptr;                        // pinned, per-chunk rebased offsets (2 arenas)
+    size_t stage_host_bytes = 0;
 };
 
 namespace pb {
@@ -227,6 +229,9 @@ int launch_detect_events(pb2_context *ctx, const float *signal, const int64_t *o
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
                  const int32_t *status, const int32_t *segments, pb2_polya_result *out,
                  cudaStream_t st);
+int launch_svb16_decode(pb2_context *ctx, const uint8_t *packed, const int64_t *packed_offsets,
+                        const int64_t *raw_offsets, const int64_t *raw_lengths, int64_t n,
+                        int16_t *raw, int32_t *error, cudaStream_t st);
 int launch_derive_events(pb2_context *ctx, const pb2_batch &b, const pb2_event_tables &ev,
                          const pb2_basecalls *bc, const float *scale_shift,
                          const pb2_event_columns &out, cudaStream_t st);

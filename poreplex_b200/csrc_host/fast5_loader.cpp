@@ -963,4 +963,59 @@ int64_t pb2f_inflate(const void *src, int64_t src_len, void *dst, int64_t dst_ca
     return got < 0 ? PB2F_EFORMAT : got;
 }
 
+// ---- streamvbyte-16 streams for the compressed upload (pb2_batch.packed) --------------------
+// size of the stream of `count` samples is ceil(count / 8) + count + #(values > 255); streams
+// start on 16-byte boundaries.
+static inline uint16_t svb16_code(int16_t x, int16_t prev)
+{
+    const uint16_t d = (uint16_t)((uint16_t)x - (uint16_t)prev);
+    return (uint16_t)((d << 1) ^ (uint16_t)(0 - (d >> 15)));          // zigzag of the 16-bit delta
+}
+
+int64_t pb2f_svb16_plan(const int16_t *raw, const int64_t *raw_offsets, const int64_t *raw_lengths,
+                        int64_t n_reads, int n_threads, int64_t *packed_offsets)
+{
+    if (n_reads < 0 || !packed_offsets || (n_reads > 0 && (!raw || !raw_offsets || !raw_lengths)))
+        return PB2F_EINVAL;
+    std::vector<int64_t> size((size_t)n_reads);
+    parallel_for(n_reads, n_threads, [&](int64_t i, Scratch &) {
+        const int16_t *x = raw + raw_offsets[i];
+        const int64_t n = raw_lengths[i];
+        int64_t wide = 0;
+        int16_t prev = 0;
+        for (int64_t k = 0; k < n; k++) { wide += svb16_code(x[k], prev) > 0xFF; prev = x[k]; }
+        size[(size_t)i] = (n + 7) / 8 + n + wide;
+    });
+    int64_t pos = 0;
+    for (int64_t i = 0; i < n_reads; i++) {
+        packed_offsets[i] = pos;
+        pos += (size[(size_t)i] + 15) & ~(int64_t)15;
+    }
+    packed_offsets[n_reads] = pos;
+    return pos;
+}
+
+int pb2f_svb16_encode(const int16_t *raw, const int64_t *raw_offsets, const int64_t *raw_lengths,
+                      int64_t n_reads, int n_threads, const int64_t *packed_offsets, uint8_t *packed)
+{
+    if (n_reads < 0 || (n_reads > 0 && (!raw || !raw_offsets || !raw_lengths || !packed_offsets || !packed)))
+        return PB2F_EINVAL;
+    parallel_for(n_reads, n_threads, [&](int64_t i, Scratch &) {
+        const int16_t *x = raw + raw_offsets[i];
+        const int64_t n = raw_lengths[i], nkeys = (n + 7) / 8;
+        uint8_t *keys = packed + packed_offsets[i], *data = keys + nkeys;
+        uint8_t *end = packed + packed_offsets[i + 1];
+        memset(keys, 0, (size_t)nkeys);
+        int16_t prev = 0;
+        for (int64_t k = 0; k < n; k++) {
+            const uint16_t v = svb16_code(x[k], prev);
+            prev = x[k];
+            *data++ = (uint8_t)v;
+            if (v > 0xFF) { *data++ = (uint8_t)(v >> 8); keys[k >> 3] |= (uint8_t)(1u << (k & 7)); }
+        }
+        while (data < end) *data++ = 0;                               // alignment padding
+    });
+    return PB2F_OK;
+}
+
 }  // extern "C"

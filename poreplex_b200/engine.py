@@ -317,27 +317,41 @@ class SignalEngine:
         }
 
     def analyze_host(self, raw, offsets, lengths, rng, digitisation, offset, barcoding=None,
-                     keep_pooled=False, polya=False, exact_scaler=False, out=None):
+                     keep_pooled=False, polya=False, exact_scaler=False, out=None, packed=None):
         """SignalAnalyzer.process stages A-D over HOST numpy buffers (H2D, kernels, D2H).
 
         Returns a dict of numpy arrays: status, label, scale_shift [n,2], segments
         [n,8,2] (baked state order = ``state_names``), barcode, barcode_guess,
         barcode_score, class_probs [n,8], counts [4,5,11], and ``pooled`` when asked.
+
+        ``packed`` = (uint8 buffer, packed_offsets[n + 1]) from ``fast5_loader.svb16_encode``: the
+        compressed upload form of the same batch (streamvbyte-16 bodies of VBZ chunks; ``raw`` may
+        then be None, ``offsets`` / ``lengths`` still describe the int16 layout the streams decode
+        into on the device).
         """
         if barcoding is None:
             barcoding = self.barcoding
         if barcoding and self.demux_model is None:
             raise ValueError('engine was created without the demultiplexer')
-        raw = np.ascontiguousarray(raw, np.int16).reshape(-1)
         offsets = np.ascontiguousarray(offsets, np.int64)
         lengths = np.ascontiguousarray(lengths, np.int64)
+        if packed is not None:
+            pk = np.ascontiguousarray(packed[0], np.uint8)
+            pko = np.ascontiguousarray(packed[1], np.int64)
+            if len(pko) != len(lengths) + 1 or np.any(pko % 16):
+                raise ValueError('packed_offsets must hold n + 1 multiples of 16')
+            n_raw_total = int((offsets + (lengths + 7) // 8 * 8).max()) + 8 if len(lengths) else 0
+            raw = None if raw is None else np.ascontiguousarray(raw, np.int16).reshape(-1)
+        else:
+            raw = np.ascontiguousarray(raw, np.int16).reshape(-1)
+            n_raw_total = raw.size
         rng = np.ascontiguousarray(rng, np.float64)
         digitisation = np.ascontiguousarray(digitisation, np.float64)
         offset = np.ascontiguousarray(offset, np.float64)
         n = len(lengths)
         if np.any(offsets % 8):
             raise ValueError('raw_offsets must be multiples of 8 samples (see pack_reads)')
-        if n and int((offsets + lengths).max()) > raw.size:
+        if n and int((offsets + lengths).max()) > n_raw_total:
             raise ValueError('read extends past the raw buffer')
         if out is not None:
             # caller-owned buffers (alloc_host_results): same keys, shapes and dtypes
@@ -355,14 +369,17 @@ class SignalEngine:
                 'counts': np.zeros((N.N_LABEL, N.N_BARCODE_SLOTS, N.N_STATUS), np.int64),
             }
         if keep_pooled:
-            out['pooled'] = np.zeros(raw.size // self.stride + 2, np.float32)
+            out['pooled'] = np.zeros(n_raw_total // self.stride + 2, np.float32)
         if polya:
             if not self.polya_ready:
                 raise ValueError("config has no 'polya_dwell' section")
             if 'polya' not in out or out['polya'].shape != (n,):
                 out['polya'] = np.zeros(n, POLYA_DTYPE)
-        b = N.Batch(n, raw.size, int(lengths.max()) if n else 0, _np_ptr(raw), _np_ptr(offsets),
-                    _np_ptr(lengths), _np_ptr(rng), _np_ptr(digitisation), _np_ptr(offset))
+        b = N.Batch(n, n_raw_total, int(lengths.max()) if n else 0,
+                    _np_ptr(raw) if raw is not None else None, _np_ptr(offsets),
+                    _np_ptr(lengths), _np_ptr(rng), _np_ptr(digitisation), _np_ptr(offset),
+                    _np_ptr(pk) if packed is not None else None,
+                    _np_ptr(pko) if packed is not None else None)
         r = N.Results(_np_ptr(out['status']), _np_ptr(out['label']), _np_ptr(out['scale_shift']),
                       _np_ptr(out['segments']), _np_ptr(out['barcode']),
                       _np_ptr(out['barcode_guess']), _np_ptr(out['barcode_score']),
@@ -724,6 +741,19 @@ class SignalEngine:
         self._check(self.lib.pb2_scaler_predict(self.handle, heads.data_ptr(), n, z.data_ptr(),
                                                 self._stream(stream)))
         return z
+
+    def svb16_decode(self, packed, packed_offsets, raw_offsets, raw_lengths, n_raw_total, stream=None):
+        """Device half of the VBZ decoder over tensors in HBM (pb2_svb16_decode): streamvbyte-16
+        bodies -> int16 samples in the layout raw_offsets / raw_lengths describe.  Returns
+        (raw int16 tensor, error flag tensor)."""
+        import torch
+        raw = torch.zeros(int(n_raw_total), dtype=torch.int16, device=packed.device)
+        err = torch.zeros(1, dtype=torch.int32, device=packed.device)
+        self._check(self.lib.pb2_svb16_decode(
+            self.handle, packed.data_ptr(), packed_offsets.data_ptr(), raw_offsets.data_ptr(),
+            raw_lengths.data_ptr(), int(raw_lengths.numel()), raw.data_ptr(), err.data_ptr(),
+            self._stream(stream)))
+        return raw, err
 
     def count_results(self, status, label, barcode, stream=None):
         import torch

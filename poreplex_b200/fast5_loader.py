@@ -26,7 +26,8 @@ STATUS_NAMES = {READ_OK: 'okay', READ_DISAPPEARED: 'disappeared', READ_IRREGULAR
 EXPORTS = ['pb2f_abi_version', 'pb2f_last_error', 'pb2f_open', 'pb2f_close', 'pb2f_is_multiread',
            'pb2f_num_reads', 'pb2f_read_name', 'pb2f_read_meta_get', 'pb2f_read_signal',
            'pb2f_batch_open', 'pb2f_batch_meta', 'pb2f_batch_meta_full', 'pb2f_batch_plan',
-           'pb2f_batch_read', 'pb2f_batch_close', 'pb2f_inflate']
+           'pb2f_batch_read', 'pb2f_batch_close', 'pb2f_inflate', 'pb2f_svb16_plan',
+           'pb2f_svb16_encode']
 
 
 class Fast5Error(Exception):
@@ -95,6 +96,9 @@ def load():
         L.pb2f_batch_close.restype = None
         L.pb2f_inflate.argtypes = [vp, C.c_int64, vp, C.c_int64]
         L.pb2f_inflate.restype = C.c_int64
+        L.pb2f_svb16_plan.argtypes = [vp, i64p, i64p, C.c_int64, C.c_int, i64p]
+        L.pb2f_svb16_plan.restype = C.c_int64
+        L.pb2f_svb16_encode.argtypes = [vp, i64p, i64p, C.c_int64, C.c_int, i64p, vp]
         if L.pb2f_abi_version() != 1:
             raise RuntimeError('libpb_fast5.so: ABI version mismatch')
         _lib = L
@@ -214,3 +218,29 @@ def load_batch(reads, inputdir=None, threads=None, pinned=False, full_meta=False
         return out
     finally:
         lib.pb2f_batch_close(handle)
+
+
+def svb16_encode(raw, offsets, lengths, threads=None, pinned=False):
+    """int16 batch -> (packed uint8 buffer, packed_offsets[n + 1]): one streamvbyte-16 stream of
+    zigzag deltas per read (the body of an ONT VBZ chunk without its zstd stage), the compressed
+    upload form ``SignalEngine.analyze_host(..., packed=...)`` / ``pb2_batch.packed`` take."""
+    import numpy as np
+    L = load()
+    raw = np.ascontiguousarray(raw, np.int16)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    lengths = np.ascontiguousarray(lengths, np.int64)
+    n = len(lengths)
+    threads = int(threads or min(32, os.cpu_count() or 1))
+    i64p = C.POINTER(C.c_int64)
+    poff = np.zeros(n + 1, np.int64)
+    total = _check(L.pb2f_svb16_plan(raw.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(i64p),
+                                     lengths.ctypes.data_as(i64p), n, threads, poff.ctypes.data_as(i64p)))
+    if pinned:
+        import torch
+        packed = torch.empty(total + 16, dtype=torch.uint8, pin_memory=True).numpy()
+    else:
+        packed = np.empty(total + 16, np.uint8)
+    _check(L.pb2f_svb16_encode(raw.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(i64p),
+                               lengths.ctypes.data_as(i64p), n, threads, poff.ctypes.data_as(i64p),
+                               packed.ctypes.data_as(C.c_void_p)))
+    return packed, poff

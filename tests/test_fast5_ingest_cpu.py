@@ -473,3 +473,31 @@ def test_inflater_survives_corruption(lib):
                 m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
             n, out = _inflate(lib, bytes(m), len(data) + 300)
             assert n < 0 or out == data
+
+
+def test_svb16_encoder_writes_vbz_chunk_bodies():
+    """fast5_loader.svb16_encode (the compressed upload form, pb2_batch.packed) produces exactly
+    the streamvbyte body of a VBZ version-1 chunk without the zstd stage: the same bytes as the
+    test suite's own VBZ encoder at level 0 after its 4-byte size header."""
+    from fast5_files import vbz_encoder
+    from poreplex_b200 import fast5_loader
+    fast5_loader.build()
+    rng = np.random.default_rng(11)
+    sigs = [rng.integers(-32768, 32768, size=n).astype(np.int16) for n in (1, 8, 9, 4000, 4099)]
+    sigs.append((np.cumsum(rng.integers(-30, 31, size=6000)) + 400).astype(np.int16))
+    lens = np.array([len(s) for s in sigs], np.int64)
+    pad = (lens + 7) // 8 * 8
+    off = np.zeros(len(sigs), np.int64)
+    off[1:] = np.cumsum(pad)[:-1]
+    raw = np.zeros(int(pad.sum()) + 8, np.int16)
+    for s, o in zip(sigs, off):
+        raw[o:o + len(s)] = s
+    pk, po = fast5_loader.svb16_encode(raw, off, lens, threads=3)
+    assert np.all(po % 16 == 0) and len(po) == len(sigs) + 1
+    encode = vbz_encoder(np.int16, version=1, zigzag=True, level=0)[2]
+    for i, s in enumerate(sigs):
+        chunk = encode(s.tobytes())
+        assert chunk[:4] == np.uint32(2 * len(s)).tobytes()
+        body = chunk[4:]
+        assert pk[po[i]:po[i] + len(body)].tobytes() == body
+        assert po[i + 1] - po[i] == (len(body) + 15) // 16 * 16
