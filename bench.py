@@ -756,9 +756,10 @@ def main():
             'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
             'sample': 'first %d reads of the same workload, %.1f s; C restatement of the '
                       'reference path (oracle/pb_oracle.c, OpenMP over reads, AVX2+FMA), stages A-D '
-                      'with barcoding -- faster than the real Python/TF/pomegranate stack; the '
-                      'reference Python over shims measured 6.5 reads/s/core (SURVEY.md section 6; '
-                      'profiles/r2_cpu_reference_python.json)' % (ns, dt),
+                      'with barcoding -- faster than the real Python/TF/pomegranate stack: the '
+                      "reference's own Python over shims (its TF / pomegranate calls served by this "
+                      'same C code) ran at 429 reads/s on 8 cores, 54 reads/s/core '
+                      '(profiles/r2_cpu_reference_python.json, build container)' % (ns, dt),
             'outputs_match_gpu': same,
             'compared': 'status, segments, barcode, best guess, phred of the sample'}
 

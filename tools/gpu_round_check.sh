@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -8 > gpurun_out/tests.log
 timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 timeout 300 python bench.py --config full > gpurun_out/bench_full_n1.json 2> gpurun_out/bench_full_n1.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_' -c 400 --csv \
     --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-verify > gpurun_out/ncu_launches.log 2>&1
 # full-set capture: ncu replays each kernel ~40 times, so a smaller batch and one launch of each
