@@ -311,6 +311,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--reads', type=int, default=1000000, help='reads per GPU per step')
+    ap.add_argument('--total-reads', type=int, default=0,
+                    help='a fixed job of this many reads sharded over the ranks (contiguous blocks, '
+                         'sharding.shard_range); overrides --reads, e.g. 10000000 on 8 GPUs')
     ap.add_argument('--length', type=int, default=4000, help='raw samples per read')
     ap.add_argument('--preset', default=None, choices=['bench-short', 'stock'],
                     help='default: bench-short below 10500 samples, stock from there')
@@ -342,6 +345,12 @@ def main():
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + '\n').encode())
 
+    from poreplex_b200.sharding import shard_range, reduce_counts
+    total_reads = 0
+    if args.total_reads > 0:
+        lo, hi = shard_range(args.total_reads, rank, world)
+        args.reads = hi - lo
+        total_reads = args.total_reads
     if args.impl == 'reference':
         run_reference(args, rank, world, emit)
         return
@@ -385,8 +394,7 @@ def main():
                 batch, ev['ev_offsets'], ev['start'], ev['move'], ev['p_model_state'],
                 ev['sampling_rate'], ev['first_sample'], ev['block_stride'], out['scale_shift'],
                 out['status'], out['segments'], ev['max_windows'])
-        if world > 1:
-            dist.all_reduce(out['counts'])        # the one collective of the path
+        reduce_counts(out['counts'])              # the one collective of the path (N > 1)
 
     def timed(k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -420,7 +428,8 @@ def main():
     prof = eng.profile_read()
     eng.profile_enable(False)
     launches = eng.kernel_launches - launches0
-    value = world * n / (ms_per_step / 1e3)
+    reads_all_ranks = total_reads if total_reads else world * n
+    value = reads_all_ranks / (ms_per_step / 1e3)
 
     # status / barcode mix of the workload (from the last step)
     status = out['status'].cpu().numpy()
@@ -465,7 +474,7 @@ def main():
             eng.set_fast_lstm(mode)
             step()
             ms = timed(2)
-            modes[mode] = {'value': world * n / (ms / 1e3), 'ms_per_step': ms, 'timed': False}
+            modes[mode] = {'value': reads_all_ranks / (ms / 1e3), 'ms_per_step': ms, 'timed': False}
             modes[mode]['mismatches_vs_timed_mode'] = \
                 {k: int((fast_int[k] != out[k]).sum().item()) for k in int_keys}
             if mode == 'exact':
@@ -613,11 +622,11 @@ def main():
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None,
+        'scaling': 'strong' if total_reads else 'weak', 'vs_baseline': None,
         'dtype': 'f32 (LSTM; recurrent products as split-fp16 on tensor cores) + f64 (Viterbi)',
         'data': 'synthetic',
         'config': {'workload': workload, 'config': args.config, 'lstm_mode': args.mode,
-                   'reads_per_gpu': n, 'read_length': args.length, 'preset': args.preset,
+                   'reads_per_gpu': n, 'reads_all_ranks': reads_all_ranks, 'read_length': args.length, 'preset': args.preset,
                    'l2_policy': 'inputs (%.1f GB per GPU) larger than L2' % (n * args.length * 2 / 1e9),
                    'status_mix': mix, 'classified_reads': classified,
                    'barcode_mix_of_classified': barcode_mix, 'best_guess_mix_of_classified': guess_mix,
@@ -691,7 +700,7 @@ def main():
             dt = float(t.item())
         h2d = sum(v.numel() * v.element_size() for v in h.values())
         d2h = sum(v.nbytes for v in res.values())
-        result['e2e'] = {'value': world * hn / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+        result['e2e'] = {'value': reads_all_ranks / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
                          'pinned_h2d_gb_per_s_per_gpu_all_ranks_copying': copy_rate,
                          'ms_per_step_floor_from_h2d': h2d / copy_rate / 1e6,
@@ -728,7 +737,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt2 = float(t.item())
         h2d2 = int(po[-1]) + sum(v.numel() * v.element_size() for k, v in h.items() if k != 'raw') + po.nbytes
-        result['e2e_svb16'] = {'value': world * hn / dt2, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d2),
+        result['e2e_svb16'] = {'value': reads_all_ranks / dt2, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d2),
                                'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt2 * 1e3,
                                'bytes_per_sample': float(po[-1]) / float(hnp['lengths'].sum()),
                                'api': 'pb2_analyze_host with pb2_batch.packed: streamvbyte-16 bodies '
