@@ -97,7 +97,27 @@ def main():
         add('decoy_call', g_ex < 0, ratio, err, bad, unsafe)
         for k in range(4):
             add('accepted_BC%d' % (k + 1), bc_ex == k, ratio, err, bad, unsafe)
+        # what other (delta0, gain) pairs would have done on these windows: largest error / bound,
+        # windows whose error exceeds the bound, and windows whose call would be flagged
+        lg = lg_tc[:, :5].astype(np.float64)
+        top2 = np.sort(lg, axis=1)
+        gap = top2[:, -1] - top2[:, -2]
+        pbest = pt.max(1)
+        edges = np.concatenate([[thr], np.asarray(eng.demux_model.calibration, np.float64)])
+        edge_dist = np.abs(pbest[:, None] - edges[None, :]).min(1)
+        sweep = []
+        for d0 in (1e-3, 5e-4, 2e-4, 1e-4):
+            for gn in (0.1, 0.05):
+                bnd = d0 + gn * sens
+                flagged = (gap <= bnd) | (edge_dist <= bnd * pbest * (1 - pbest) + 1e-6)
+                sweep.append({'delta0': d0, 'gain': gn, 'max_err_over_bound': float((err / bnd).max()),
+                              'err_exceeds_bound': int((err > bnd).sum()),
+                              'flagged_fraction': float(flagged.mean()),
+                              'differing_calls_not_flagged': int((bad & ~flagged).sum())})
         ent = {'seed': a.seed0 + b, 'windows': int(m), 'unsafe_fraction': float(unsafe.mean()),
+               'bound_sweep': sweep,
+               'err_quantiles_50_99_9999_max': np.quantile(err, [0.5, 0.99, 0.9999, 1.0]).tolist(),
+               'sens_quantiles_50_99_9999_max': np.quantile(sens, [0.5, 0.99, 0.9999, 1.0]).tolist(),
                'accepted_by_class': [int((bc_ex == k).sum()) for k in range(4)],
                'planted_by_class': [int((planted == k + 1).sum()) for k in range(4)],
                'phred_hist': np.bincount(s_ex[s_ex >= 0], minlength=30).tolist(),
