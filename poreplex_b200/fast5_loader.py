@@ -169,13 +169,15 @@ def _ptr(a, typ):
     return a.ctypes.data_as(C.POINTER(typ))
 
 
-def load_batch(reads, inputdir=None, threads=None, pinned=False, full_meta=False):
+def load_batch(reads, inputdir=None, threads=None, pinned=False, full_meta=False, packed=False):
     """``reads``: list of ``(path, read_id)`` (``read_id`` None = first read of a single-read
     file); ``inputdir`` is joined in front of relative paths.  Returns a dict with ``raw``
     (int16, packed), ``offsets``, ``lengths`` (0 for unreadable reads), ``range``,
     ``digitisation``, ``offset``, ``sampling_rate``, ``duration``, ``start_time``, ``status``
     (READ_OK / READ_DISAPPEARED / READ_IRREGULAR) and, with ``full_meta``, ``meta`` (list of
-    dicts).  ``pinned=True`` allocates ``raw`` in page-locked memory (needs torch + CUDA)."""
+    dicts).  ``pinned=True`` allocates ``raw`` in page-locked memory (needs torch + CUDA).
+    ``packed=True`` adds ``packed`` = (uint8 buffer, offsets): the batch as streamvbyte-16
+    streams for the compressed upload (``svb16_encode``)."""
     lib = load()
     n = len(reads)
     threads = int(threads or min(32, os.cpu_count() or 1))
@@ -215,6 +217,9 @@ def load_batch(reads, inputdir=None, threads=None, pinned=False, full_meta=False
                 lib.pb2f_batch_meta_full(handle, i, C.byref(m))
                 metas.append(m.as_dict())
             out['meta'] = metas
+        if packed:
+            out['packed'] = svb16_encode(raw, out['offsets'], out['lengths'], threads=threads,
+                                         pinned=pinned)
         return out
     finally:
         lib.pb2f_batch_close(handle)

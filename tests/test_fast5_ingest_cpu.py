@@ -501,3 +501,23 @@ def test_svb16_encoder_writes_vbz_chunk_bodies():
         body = chunk[4:]
         assert pk[po[i]:po[i] + len(body)].tobytes() == body
         assert po[i + 1] - po[i] == (len(body) + 15) // 16 * 16
+
+
+def test_load_batch_can_hand_over_the_compressed_form(tmp_path):
+    """load_batch(packed=True): the same reads as streamvbyte-16 streams beside the int16 batch."""
+    from oracle import fake_fast5, refshim
+    from fast5_files import write_fast5
+    from poreplex_b200 import fast5_loader
+    fast5_loader.build()
+    rng = np.random.default_rng(4)
+    tree = refshim.FakeFile()
+    ids = ['%08x-0000-4000-8000-%012x' % (7, i) for i in range(5)]
+    sigs = [(np.cumsum(rng.integers(-20, 21, size=n)) + 450).astype(np.int16) for n in (4000, 4001, 16, 9000, 123)]
+    for rid, sgn in zip(ids, sigs):
+        fake_fast5.add_read(tree, rid, sgn, 8192.0, 1400.0, 5.0, 3012.0)
+    write_fast5(str(tmp_path / 'r.fast5'), tree, signal_kw=dict(chunks=2048, gzip=1, shuffle=True))
+    b = fast5_loader.load_batch([('r.fast5', r) for r in ids], inputdir=str(tmp_path), threads=2, packed=True)
+    pk, po = b['packed']
+    assert len(po) == 6 and po[-1] < 0.65 * 2 * sum(len(x) for x in sigs) + 16 * 6
+    again, off = fast5_loader.svb16_encode(b['raw'], b['offsets'], b['lengths'])
+    assert np.array_equal(off, po) and np.array_equal(again[:po[-1]], pk[:po[-1]])
