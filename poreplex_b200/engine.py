@@ -585,7 +585,11 @@ class SignalEngine:
                        barcoding=None, keep_pooled=False, max_raw_length=0, stream=None,
                        polya=False, exact_scaler=False):
         """Same path over tensors already resident in HBM; enqueued on ``stream`` (default:
-        torch's current stream), not synchronised."""
+        torch's current stream).  In the ``exact`` and ``strict`` modes the call only enqueues; in
+        the ``fast`` mode it waits once on that stream, for the number of reads the guards sent
+        to the exact re-run (the size of the sub-batch it then enqueues), so the kernels before
+        that point have finished when it returns -- the results are complete only after the
+        caller synchronises the stream, as usual."""
         import torch
         if barcoding is None:
             barcoding = self.barcoding

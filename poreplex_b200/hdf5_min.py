@@ -350,10 +350,14 @@ class Hdf5Dataset(_Node):
         buf, rank = self._h5._buf, len(self.shape)
         klen = 8 + 8 * (rank + 1)
 
-        def walk(node):
+        def walk(node, want_level=None):
             if buf[node:node + 4] != b'TREE' or buf[node + 4] != 1:
                 raise Hdf5FormatError('bad chunk B-tree node')
             level = buf[node + 5]
+            # levels fall by one per step: a node that names itself (or an ancestor) as its child
+            # ends the walk instead of recursing without end
+            if want_level is not None and level != want_level:
+                raise Hdf5FormatError('chunk B-tree levels are inconsistent')
             used = struct.unpack_from('<H', buf, node + 6)[0]
             p = node + 24
             for _ in range(used):
@@ -362,7 +366,7 @@ class Hdf5Dataset(_Node):
                 child = struct.unpack_from('<Q', buf, p + klen)[0]
                 p += klen + 8
                 if level:
-                    yield from walk(child)
+                    yield from walk(child, level - 1)
                 else:
                     yield offs, size, mask, child
 
@@ -572,17 +576,20 @@ class Hdf5File(Hdf5Group):
             start = heap_data + off
             return buf[start:buf.find(b'\0', start)].decode()
 
-        def walk(node):
+        def walk(node, want_level=None):
             if buf[node:node + 4] == b'TREE':
                 level = buf[node + 5]
+                if want_level is not None and level != want_level:      # no cycles: see chunks()
+                    raise Hdf5FormatError('group B-tree levels are inconsistent')
                 used = struct.unpack_from('<H', buf, node + 6)[0]
                 p = node + 8 + 16
                 for i in range(used):
                     child = struct.unpack_from('<Q', buf, p + 8)[0]
                     p += 16
-                    yield from walk(child)
-                del level
+                    yield from walk(child, level - 1)
             elif buf[node:node + 4] == b'SNOD':
+                if want_level is not None and want_level >= 0:
+                    raise Hdf5FormatError('group B-tree levels are inconsistent')
                 nsym = struct.unpack_from('<H', buf, node + 6)[0]
                 p = node + 8
                 for _ in range(nsym):

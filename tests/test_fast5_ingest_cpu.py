@@ -521,3 +521,44 @@ def test_load_batch_can_hand_over_the_compressed_form(tmp_path):
     assert len(po) == 6 and po[-1] < 0.65 * 2 * sum(len(x) for x in sigs) + 16 * 6
     again, off = fast5_loader.svb16_encode(b['raw'], b['offsets'], b['lengths'])
     assert np.array_equal(off, po) and np.array_equal(again[:po[-1]], pk[:po[-1]])
+
+
+def test_self_referencing_btree_nodes_end_the_walk(lib, tmp_path):
+    """A crafted group / chunk B-tree node that names itself as its child must not send the loader
+    into a walk of used ** depth nodes: node levels have to fall by one per step, so the walk
+    stops at the first inconsistency (and has a node budget besides)."""
+    import struct
+    import time
+    f5, ids, sigs = _tree(700, seed=9, lengths=[64] * 700, basecalls=False)   # enough children for a 2-level group tree
+    path = str(tmp_path / 'whole.fast5')
+    write_fast5(path, f5, signal_kw=dict(chunks=16, gzip=1))
+    blob = bytearray(open(path, 'rb').read())
+    pos, patched = 0, {0: 0, 1: 0}
+    while True:
+        pos = blob.find(b'TREE', pos)
+        if pos < 0:
+            break
+        ntype, used = blob[pos + 4], struct.unpack_from('<H', blob, pos + 6)[0]
+        if ntype in (0, 1) and used > 0:
+            # every entry's child pointer -> the node itself, entries used = the maximum
+            klen = 8 if ntype == 0 else 24
+            struct.pack_into('<H', blob, pos + 6, max(used, 16))
+            for i in range(min(max(used, 16), 16)):
+                at = pos + 24 + i * (klen + 8) + klen
+                if at + 8 <= len(blob):
+                    struct.pack_into('<Q', blob, at, pos)
+            blob[pos + 5] = 3                                   # claims to be an inner node
+            patched[ntype] += 1
+        pos += 4
+    assert patched[0] >= 1 and patched[1] >= 1
+    mpath = str(tmp_path / 'loop.fast5')
+    open(mpath, 'wb').write(bytes(blob))
+    t0 = time.perf_counter()
+    out = FL.load_batch([(mpath, r) for r in ids[:40]], threads=2)
+    assert set(out['status']) <= {FL.READ_OK, FL.READ_IRREGULAR}
+    try:
+        with FL.Fast5File(mpath) as f:
+            f.read_names()
+    except FL.Fast5Error:
+        pass
+    assert time.perf_counter() - t0 < 20.0
