@@ -367,8 +367,11 @@ def main():
 
     from poreplex_b200 import _native
     from poreplex_b200.engine import SignalEngine
-    if _native.needs_build() and rank == 0:
-        _native.build()
+    from poreplex_b200 import fast5_loader
+    if rank == 0:                              # one builder; the others wait at the barrier
+        if _native.needs_build():
+            _native.build()
+        fast5_loader.build()                   # host-side svb16 encoder of the compressed upload
     if world > 1:
         dist.barrier()
 
@@ -713,9 +716,8 @@ def main():
         # (what a VBZ FAST5 holds under its zstd stage) cross the bus instead of int16 samples
         # and are decoded on the device; encoded once here, outside the timed region, as the
         # ingest would hand them over
-        from poreplex_b200 import fast5_loader
-        fast5_loader.build()
-        pk, po = fast5_loader.svb16_encode(hnp['raw'], hnp['offsets'], hnp['lengths'], pinned=True)
+        pk, po = fast5_loader.svb16_encode(hnp['raw'], hnp['offsets'], hnp['lengths'], pinned=True,
+                                           threads=max(1, (os.cpu_count() or 1) // max(world, 1)))
 
         def packed_step():
             return eng.analyze_host(None, hnp['offsets'], hnp['lengths'], hnp['range'],

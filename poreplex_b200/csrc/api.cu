@@ -1383,6 +1383,10 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     int64_t min_reads = 65536;
     int64_t nchunks = 4;
     bool uniform = false;
+    if (const char *env = getenv("POREPLEX_B200_HOST_CHUNKS")) {          // tuning: large chunks after the small first one
+        const long long v = atoll(env);
+        if (v >= 1 && v <= 64) nchunks = v;
+    }
     if (const char *env = getenv("POREPLEX_B200_HOST_CHUNK_ELEMS")) {     // tests / tuning
         const long long v = atoll(env);
         if (v > 0) { min_elems = v; min_reads = 2048; nchunks = (hb->n_raw_total + v - 1) / v; uniform = true; }
