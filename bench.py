@@ -707,8 +707,9 @@ def main():
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
                          'pinned_h2d_gb_per_s_per_gpu_all_ranks_copying': copy_rate,
                          'ms_per_step_floor_from_h2d': h2d / copy_rate / 1e6,
-                         'api': 'pb2_analyze_host (pinned host input and result buffers; chunked '
-                                'H2D/compute/D2H pipeline)' +
+                         'api': 'pb2_analyze_host (pinned host input and result buffers; whole batch resident, '
+                                'uploaded in 8 chunks (1 2 4 6 6 4 2 1) whose tensor-core kernels overlap the '
+                                'uploads behind them, one exact re-run over all chunks, one download)' +
                                 ('; the chimera filter of config full is not part of this call' if full else '')}
         assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
 

@@ -845,9 +845,24 @@ __global__ void k_scatter_sub_results(int n_sub, const int32_t *__restrict__ lis
     }
 }
 
-static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
-                               uint32_t flags, cudaStream_t st, float *pooled, int32_t *status,
-                               int32_t *label, float *scale_shift, int32_t *segments)
+// The fast path in two halves so that a host batch cut into chunks can run the tensor-core half
+// chunk by chunk (as its uploads arrive) and resolve the unsafe reads of ALL chunks as one
+// sub-batch at the end: the exact kernels have long CTAs, and a sub-batch per chunk ends on a
+// partly filled wave every time.
+//   analyze_fast_tentative: tensor-core scaler, corner segmentations, windows, tensor-core
+//       classifier; tentative results in the result arrays, cause bits in `unsafe`.  No host
+//       synchronisation.  `unsafe` must be zero on entry.
+//   analyze_fast_resolve:   collect the flagged reads of `batch` (the whole batch), re-run them
+//       exactly, scatter, then label + counts.  One host synchronisation.
+struct FastArrays {
+    int32_t *unsafe;               // [n] cause bits
+    int32_t *pushed;               // [n] window accepted (barcoding)
+    int32_t *barcode, *guess, *score;
+};
+
+static int analyze_fast_tentative(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                                  uint32_t flags, cudaStream_t st, float *pooled, int32_t *status,
+                                  float *scale_shift, int32_t *segments, const FastArrays &fa)
 {
     int rc;
     const int64_t n = batch->n_reads;
@@ -855,22 +870,18 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
     const int T = bcd ? ctx->demux.trim_length : 0;
     const size_t SEG = (size_t)PB2_MAX_STATES * 2;
     // scratch: corner (scale, shift) x3, corner status x2 / segments x2 (corner 0 decodes
-    // straight into the result arrays), unsafe flags, the unsafe list
+    // straight into the result arrays)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t o_ssv = take(sizeof(float) * 6 * n), o_st1 = take(4 * (size_t)n), o_st2 = take(4 * (size_t)n);
-    const size_t o_sg1 = take(4 * SEG * n), o_sg2 = take(4 * SEG * n), o_uns = take(4 * (size_t)n);
-    const size_t o_cnt = take(16), o_list = take(4 * (size_t)n);
+    const size_t o_sg1 = take(4 * SEG * n), o_sg2 = take(4 * SEG * n);
     char *fs = (char *)ws_get(ctx, ctx->ws_fast, off);
     if (!fs) return PB2_ENOMEM;
     float *ssv = (float *)(fs + o_ssv);
     int32_t *st1 = (int32_t *)(fs + o_st1), *st2 = (int32_t *)(fs + o_st2);
     int32_t *sg1 = (int32_t *)(fs + o_sg1), *sg2 = (int32_t *)(fs + o_sg2);
-    int32_t *unsafe = (int32_t *)(fs + o_uns), *list = (int32_t *)(fs + o_list);
-    int *count = (int *)(fs + o_cnt);
-    PB_CUDA(ctx, cudaMemsetAsync(unsafe, 0, 4 * (size_t)n, st));
-    PB_CUDA(ctx, cudaMemsetAsync(count, 0, 16, st));
+    int32_t *unsafe = fa.unsafe;
 
     if ((rc = launch_scaler_tc(ctx, *batch, pooled, status, scale_shift, ssv, unsafe, nullptr, st))) return rc;
     // segmentation at the three corners of the uncertainty triangle
@@ -881,27 +892,37 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
     if ((rc = launch_segment(ctx, *batch, pooled, ssv + 4 * n, st2, sg2, nullptr, st))) return rc;
     if ((rc = launch_compare_corners(ctx, n, status, st1, st2, segments, sg1, sg2, unsafe, st))) return rc;
 
-    int32_t *barcode = res->barcode, *guess = res->barcode_guess, *score = res->barcode_score;
-    float *windows = nullptr;
-    int32_t *pushed = nullptr;
     if (bcd) {
-        windows = (float *)ws_get(ctx, ctx->ws_win, sizeof(float) * (size_t)n * T);
-        pushed = (int32_t *)ws_get(ctx, ctx->ws_pushed, sizeof(int32_t) * (size_t)n);
-        barcode = WS_OR(res->barcode, ws_bc, int32_t, n);
-        guess = WS_OR(res->barcode_guess, ws_guess, int32_t, n);
-        score = WS_OR(res->barcode_score, ws_score, int32_t, n);
+        float *windows = (float *)ws_get(ctx, ctx->ws_win, sizeof(float) * (size_t)n * T);
         int32_t *slots = (int32_t *)ws_get(ctx, ctx->ws_slots, sizeof(int32_t) * ((size_t)n + 4));
-        if (!windows || !pushed || !barcode || !guess || !score || !slots) return PB2_ENOMEM;
+        if (!windows || !slots) return PB2_ENOMEM;
         int *slot_count = (int *)slots;
         int32_t *slot_read = slots + 4;
         if (res->class_probs)
             PB_CUDA(ctx, cudaMemsetAsync(res->class_probs, 0, sizeof(float) * PB2_MAX_CLASSES * (size_t)n, st));
-        if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows, pushed,
+        if ((rc = launch_windows(ctx, *batch, pooled, scale_shift, status, segments, windows, fa.pushed,
                                  slot_count, slot_read, st))) return rc;
         if ((rc = launch_demux_tc(ctx, windows, nullptr, n, slot_count, slot_read, res->class_probs,
-                                  barcode, guess, score, nullptr, nullptr, nullptr, /*recheck=*/false,
-                                  st, unsafe))) return rc;
+                                  fa.barcode, fa.guess, fa.score, nullptr, nullptr, nullptr,
+                                  /*recheck=*/false, st, unsafe))) return rc;
     }
+    return PB2_OK;
+}
+
+// count: device int[4] (zero on entry), list: device int32[n]
+static int analyze_fast_resolve(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                                uint32_t flags, cudaStream_t st, float *pooled, int32_t *status,
+                                int32_t *label, float *scale_shift, int32_t *segments,
+                                const FastArrays &fa, int *count, int32_t *list)
+{
+    int rc;
+    const int64_t n = batch->n_reads;
+    const bool bcd = (flags & PB2_FLAG_BARCODING) != 0;
+    const int T = bcd ? ctx->demux.trim_length : 0;
+    const size_t SEG = (size_t)PB2_MAX_STATES * 2;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    int32_t *unsafe = fa.unsafe, *pushed = fa.pushed;
+    int32_t *barcode = fa.barcode, *guess = fa.guess, *score = fa.score;
 
     // ---- the unsafe reads, exactly ---------------------------------------------------
     PB_LAUNCH(ctx, K_MISC, "k_collect_unsafe", st,
@@ -964,10 +985,47 @@ static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const p
             status, scale_shift, segments,
             bcd ? pushed : nullptr, barcode, guess, score, res->class_probs));
     }
-    if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st))) return rc;
+    if ((rc = launch_finalize(ctx, n, flags, status, label, barcode, guess, score, st, pushed))) return rc;
     if (res->counts)
         if ((rc = launch_counts(ctx, status, label, barcode, n, res->counts, st))) return rc;
     return PB2_OK;
+}
+
+// barcode / guess / score arrays of a fast-path call: the caller's, or scratch when barcoding
+// runs and the caller did not ask for one of them
+static int fast_arrays(pb2_context *ctx, const pb2_results *res, uint32_t flags, int64_t n,
+                       int32_t *unsafe, FastArrays &fa)
+{
+    fa.unsafe = unsafe;
+    fa.pushed = nullptr;
+    fa.barcode = res->barcode; fa.guess = res->barcode_guess; fa.score = res->barcode_score;
+    if (flags & PB2_FLAG_BARCODING) {
+        fa.pushed = (int32_t *)ws_get(ctx, ctx->ws_pushed, sizeof(int32_t) * (size_t)n);
+        fa.barcode = WS_OR(res->barcode, ws_bc, int32_t, n);
+        fa.guess = WS_OR(res->barcode_guess, ws_guess, int32_t, n);
+        fa.score = WS_OR(res->barcode_score, ws_score, int32_t, n);
+        if (!fa.pushed || !fa.barcode || !fa.guess || !fa.score) return PB2_ENOMEM;
+    }
+    return PB2_OK;
+}
+
+static int analyze_device_fast(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
+                               uint32_t flags, cudaStream_t st, float *pooled, int32_t *status,
+                               int32_t *label, float *scale_shift, int32_t *segments)
+{
+    int rc;
+    const int64_t n = batch->n_reads;
+    // unsafe flags, [4] counters, the unsafe list
+    const size_t o_cnt = ((size_t)4 * n + 255) & ~(size_t)255, o_list = o_cnt + 256;
+    char *fl = (char *)ws_get(ctx, ctx->ws_flags, o_list + 4 * (size_t)n);
+    if (!fl) return PB2_ENOMEM;
+    PB_CUDA(ctx, cudaMemsetAsync(fl, 0, o_list, st));
+    FastArrays fa;
+    if ((rc = fast_arrays(ctx, res, flags, n, (int32_t *)fl, fa))) return rc;
+    if ((rc = analyze_fast_tentative(ctx, batch, res, flags, st, pooled, status, scale_shift, segments, fa)))
+        return rc;
+    return analyze_fast_resolve(ctx, batch, res, flags, st, pooled, status, label, scale_shift, segments,
+                                fa, (int *)(fl + o_cnt), (int32_t *)(fl + o_list));
 }
 
 int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
@@ -1371,18 +1429,235 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
     return rc;
 }
 
+// Host-buffer path for large batches, whole batch resident on the device (the default).
+// The raw buffer is uploaded chunk by chunk into ONE device buffer at its own offsets, so a chunk
+// is just a range of reads: no rebasing, no arena hand-over.  The kernels of chunk c start when
+// its upload has landed and overlap the uploads of the chunks behind it.  In `fast` mode only
+// the tensor-core half runs per chunk; the reads any chunk flagged are resolved by the exact
+// kernels as ONE sub-batch at the end (a sub-batch per chunk ends on a partly filled wave of the
+// long exact CTAs every time, which cost 20-30 ms per million reads), then label + counts run
+// over the whole batch and the results go back in one go (124 B per read).
+// Chunks are small at both ends and large in the middle (plan_chunks): a small first chunk
+// because its upload is the one nothing hides, a small last one because its kernels are what
+// nothing hides when the bus is the slower side (several GPUs sharing the host's PCIe uplinks).
+static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr,
+                                 uint32_t flags, const std::vector<int64_t> &bounds)
+{
+    DeviceGuard g(ctx->device);
+    const int n_bins = PB2_N_LABEL * PB2_N_BARCODE_SLOTS * PB2_N_STATUS;
+    const int nchunks = (int)bounds.size() - 1;
+    const int64_t n = hb->n_reads;
+    if (!ctx->scaler.set || !ctx->seg_set) return fail(ctx, PB2_ESTATE, "parameters not set");
+    if ((flags & PB2_FLAG_BARCODING) && !ctx->demux.set)
+        return fail(ctx, PB2_ESTATE, "barcoding requested but demux not set");
+    if (!ctx->copy_in) PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    cudaStream_t compute = ctx->host_stream, ci = ctx->copy_in;
+    const bool packed = hb->packed != nullptr;
+    const size_t packed_bytes = packed ? (size_t)hb->packed_offsets[n] : 0;
+    const bool want_polya = (flags & PB2_FLAG_POLYA) && hr->polya;
+    if ((flags & PB2_FLAG_POLYA) && !want_polya) flags &= ~PB2_FLAG_POLYA;
+    flags &= ~PB2_FLAG_KEEP_POOLED;
+    const bool fast = ctx->fast_lstm && !ctx->exact_division &&
+                      !(flags & (PB2_FLAG_POLYA | PB2_FLAG_EXACT_SCALER));
+    const int stride = ctx->scaler.stride > 0 ? ctx->scaler.stride : 15;
+
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t m = (size_t)n;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align(bytes); return o; };
+    const size_t o_raw = take(sizeof(int16_t) * (size_t)hb->n_raw_total + 32);
+    const size_t o_pk = take(packed ? packed_bytes + 32 : 16), o_po = take(packed ? 8 * (m + 1) : 16);
+    const size_t o_off = take(8 * m), o_len = take(8 * m), o_rng = take(8 * m), o_dig = take(8 * m);
+    const size_t o_ofs = take(8 * m), o_status = take(4 * m), o_label = take(4 * m);
+    const size_t o_ss = take(8 * m), o_seg = take(4 * 2 * PB2_MAX_STATES * m);
+    const size_t o_bc = take(4 * m), o_gs = take(4 * m), o_sc = take(4 * m);
+    const size_t o_pr = take(4 * PB2_MAX_CLASSES * m), o_cnt = take(8 * n_bins);
+    const size_t o_polya = take(want_polya ? sizeof(pb2_polya_result) * m : 16);
+    const size_t o_pushed = take(4 * m);
+    const size_t o_unsafe = take(4 * m), o_fcnt = take(16), o_list = take(4 * m);
+    char *A = (char *)ws_get(ctx, ctx->ws_batch, off);
+    float *pooled = (float *)ws_get(ctx, ctx->ws_pooled,
+                                    sizeof(float) * ((size_t)(hb->n_raw_total / stride) + 2));
+    if (!A || !pooled) return PB2_ENOMEM;
+
+    pb2_batch db = *hb;
+    db.raw = (const int16_t *)(A + o_raw);
+    db.raw_offsets = (const int64_t *)(A + o_off);
+    db.raw_lengths = (const int64_t *)(A + o_len);
+    db.range = (const double *)(A + o_rng);
+    db.digitisation = (const double *)(A + o_dig);
+    db.offset = (const double *)(A + o_ofs);
+    db.packed = nullptr; db.packed_offsets = nullptr;
+    pb2_results dr = {};
+    dr.status = (int32_t *)(A + o_status); dr.label = (int32_t *)(A + o_label);
+    dr.scale_shift = (float *)(A + o_ss); dr.segments = (int32_t *)(A + o_seg);
+    dr.barcode = (int32_t *)(A + o_bc); dr.barcode_guess = (int32_t *)(A + o_gs);
+    dr.barcode_score = (int32_t *)(A + o_sc); dr.class_probs = (float *)(A + o_pr);
+    dr.counts = (int64_t *)(A + o_cnt);
+    dr.polya = want_polya ? (pb2_polya_result *)(A + o_polya) : nullptr;
+    FastArrays fa = {(int32_t *)(A + o_unsafe), (int32_t *)(A + o_pushed), dr.barcode, dr.barcode_guess,
+                     dr.barcode_score};
+
+    std::vector<cudaEvent_t> ev((size_t)nchunks + 1, nullptr);
+    for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    std::vector<int64_t> max_lens((size_t)nchunks, 0);
+    int64_t max_len_all = 0;
+    for (int c = 0; c < nchunks; c++) {
+        int64_t ml = 0;
+        for (int64_t i = bounds[c]; i < bounds[c + 1]; i++)
+            if (hb->raw_lengths[i] > ml) ml = hb->raw_lengths[i];
+        max_lens[c] = ml;
+        if (ml > max_len_all) max_len_all = ml;
+    }
+    db.max_raw_length = max_len_all;
+
+    int svb_err = 0;
+    auto run = [&]() -> int {
+        int rc;
+        // per-read metadata of the whole batch (40 bytes per read), then the samples chunk by chunk
+        PB_CUDA(ctx, cudaMemcpyAsync(A + o_off, hb->raw_offsets, 8 * m, cudaMemcpyHostToDevice, ci));
+        PB_CUDA(ctx, cudaMemcpyAsync(A + o_len, hb->raw_lengths, 8 * m, cudaMemcpyHostToDevice, ci));
+        PB_CUDA(ctx, cudaMemcpyAsync(A + o_rng, hb->range, 8 * m, cudaMemcpyHostToDevice, ci));
+        PB_CUDA(ctx, cudaMemcpyAsync(A + o_dig, hb->digitisation, 8 * m, cudaMemcpyHostToDevice, ci));
+        PB_CUDA(ctx, cudaMemcpyAsync(A + o_ofs, hb->offset, 8 * m, cudaMemcpyHostToDevice, ci));
+        if (packed)
+            PB_CUDA(ctx, cudaMemcpyAsync(A + o_po, hb->packed_offsets, 8 * (m + 1), cudaMemcpyHostToDevice, ci));
+        PB_CUDA(ctx, cudaEventRecord(ev[(size_t)nchunks], ci));
+        auto upload = [&](int c) -> int {
+            const int64_t c0 = bounds[c], c1 = bounds[c + 1];
+            if (packed) {
+                const int64_t p0 = hb->packed_offsets[c0], p1 = hb->packed_offsets[c1];
+                if (p1 > p0)
+                    PB_CUDA(ctx, cudaMemcpyAsync(A + o_pk + p0, hb->packed + p0, (size_t)(p1 - p0),
+                                                 cudaMemcpyHostToDevice, ci));
+            } else {
+                const int64_t r0 = hb->raw_offsets[c0];
+                const int64_t span = hb->raw_offsets[c1 - 1] + hb->raw_lengths[c1 - 1] - r0;
+                if (span > 0)
+                    PB_CUDA(ctx, cudaMemcpyAsync(A + o_raw + 2 * (size_t)r0, hb->raw + r0,
+                                                 sizeof(int16_t) * (size_t)span, cudaMemcpyHostToDevice, ci));
+            }
+            PB_CUDA(ctx, cudaEventRecord(ev[(size_t)c], ci));
+            return PB2_OK;
+        };
+        // uploads are issued two chunks ahead of the kernels: from pageable memory a copy blocks
+        // the host, and the kernels of the chunks before it must already be queued by then
+        if ((rc = upload(0))) return rc;
+        if (nchunks > 1 && (rc = upload(1))) return rc;
+
+        PB_CUDA(ctx, cudaStreamWaitEvent(compute, ev[(size_t)nchunks], 0));
+        if (fast) PB_CUDA(ctx, cudaMemsetAsync(A + o_unsafe, 0, o_list - o_unsafe, compute));
+        if (packed) PB_CUDA(ctx, cudaMemsetAsync(ctx->tc_err + 1, 0, sizeof(int), compute));
+        if (!(flags & PB2_FLAG_BARCODING)) {
+            PB_CUDA(ctx, cudaMemsetAsync(dr.barcode, 0xFF, 4 * m, compute));
+            PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_guess, 0xFF, 4 * m, compute));
+            PB_CUDA(ctx, cudaMemsetAsync(dr.barcode_score, 0xFF, 4 * m, compute));
+            PB_CUDA(ctx, cudaMemsetAsync(dr.class_probs, 0, 4 * PB2_MAX_CLASSES * m, compute));
+        }
+        ctx->last_rerun_reads = 0;
+        for (int c = 0; c < nchunks; c++) {
+            const int64_t c0 = bounds[c], nc = bounds[c + 1] - c0;
+            pb2_batch cb = db;                       // a range of reads of the resident batch
+            cb.n_reads = nc; cb.max_raw_length = max_lens[c];
+            cb.raw_offsets = db.raw_offsets + c0; cb.raw_lengths = db.raw_lengths + c0;
+            cb.range = db.range + c0; cb.digitisation = db.digitisation + c0; cb.offset = db.offset + c0;
+            pb2_results cr = {};
+            cr.status = dr.status + c0; cr.label = dr.label + c0;
+            cr.scale_shift = dr.scale_shift + 2 * c0;
+            cr.segments = dr.segments + 2 * PB2_MAX_STATES * c0;
+            cr.barcode = dr.barcode + c0; cr.barcode_guess = dr.barcode_guess + c0;
+            cr.barcode_score = dr.barcode_score + c0;
+            cr.class_probs = dr.class_probs + (size_t)PB2_MAX_CLASSES * c0;
+            cr.polya = want_polya ? dr.polya + c0 : nullptr;
+            PB_CUDA(ctx, cudaStreamWaitEvent(compute, ev[(size_t)c], 0));
+            if (packed &&
+                (rc = launch_svb16_decode(ctx, (const uint8_t *)(A + o_pk), (const int64_t *)(A + o_po) + c0,
+                                          cb.raw_offsets, cb.raw_lengths, nc, (int16_t *)(A + o_raw),
+                                          ctx->tc_err + 1, compute))) return rc;
+            if (fast) {
+                FastArrays fc = {fa.unsafe + c0, fa.pushed + c0, cr.barcode, cr.barcode_guess, cr.barcode_score};
+                if ((rc = launch_pool(ctx, cb, stride, pooled, compute))) return rc;
+                if ((rc = analyze_fast_tentative(ctx, &cb, &cr, flags, compute, pooled, cr.status,
+                                                 cr.scale_shift, cr.segments, fc))) return rc;
+            } else if ((rc = pb2_analyze_device(ctx, &cb, &cr, flags, compute))) {
+                return rc;
+            }
+            if (c + 2 < nchunks && (rc = upload(c + 2))) return rc;
+        }
+        if (fast) {
+            if ((rc = analyze_fast_resolve(ctx, &db, &dr, flags, compute, pooled, dr.status, dr.label,
+                                           dr.scale_shift, dr.segments, fa, (int *)(A + o_fcnt),
+                                           (int32_t *)(A + o_list)))) return rc;
+        } else if ((rc = launch_counts(ctx, dr.status, dr.label, dr.barcode, n, dr.counts, compute))) {
+            return rc;
+        }
+#define PB_D2H(field, bytes)                                                                 \
+        if (hr->field && (bytes) > 0)                                                        \
+            PB_CUDA(ctx, cudaMemcpyAsync(hr->field, dr.field, (bytes), cudaMemcpyDeviceToHost, compute))
+        PB_D2H(status, 4 * m);
+        PB_D2H(label, 4 * m);
+        PB_D2H(scale_shift, 8 * m);
+        PB_D2H(segments, 4 * 2 * PB2_MAX_STATES * m);
+        PB_D2H(barcode, 4 * m);
+        PB_D2H(barcode_guess, 4 * m);
+        PB_D2H(barcode_score, 4 * m);
+        PB_D2H(class_probs, 4 * PB2_MAX_CLASSES * m);
+        PB_D2H(counts, sizeof(int64_t) * n_bins);
+        if (want_polya) PB_D2H(polya, sizeof(pb2_polya_result) * m);
+#undef PB_D2H
+        if (packed) PB_CUDA(ctx, cudaMemcpyAsync(&svb_err, ctx->tc_err + 1, sizeof(int), cudaMemcpyDeviceToHost, compute));
+        PB_CUDA(ctx, cudaStreamSynchronize(compute));
+        return PB2_OK;
+    };
+    int rc = run();
+    if (rc != PB2_OK) cudaDeviceSynchronize();
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (rc == PB2_OK && svb_err)
+        return fail(ctx, PB2_EINVAL, "packed input: a streamvbyte stream is shorter than its keys promise");
+    return rc;
+}
+
+// chunk boundaries of the streamed host path: K chunks whose sizes rise and fall
+// (1 2 4 6 6 4 2 1 for the largest batches), cut on whole waves of the tensor-core kernels
+static std::vector<int64_t> plan_chunks(int64_t n, int64_t wave)
+{
+    static const int w8[] = {1, 2, 4, 6, 6, 4, 2, 1}, w6[] = {1, 2, 4, 4, 2, 1}, w4[] = {1, 2, 2, 1},
+                     w3[] = {1, 2, 1}, w2[] = {1, 1};
+    const double W = (double)n / (double)wave;
+    const int *w = w2; int K = 2, sum = 2;
+    if (W >= 39) { w = w8; K = 8; sum = 26; }
+    else if (W >= 21) { w = w6; K = 6; sum = 14; }
+    else if (W >= 9) { w = w4; K = 4; sum = 6; }
+    else if (W >= 6) { w = w3; K = 3; sum = 4; }
+    std::vector<int64_t> bounds(1, 0);
+    int acc = 0;
+    for (int c = 0; c < K; c++) {
+        acc += w[c];
+        int64_t b = (int64_t)((double)n * acc / sum);
+        if (c + 1 < K) b -= b % wave; else b = n;
+        if (b > bounds.back()) bounds.push_back(b);
+    }
+    if (bounds.back() != n) bounds.push_back(n);
+    return bounds;
+}
+
 int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *hr, uint32_t flags)
 {
     int rc = check_batch(ctx, hb);
     if (rc) return rc;
     if (!hr) return PB2_EINVAL;
-    // chunking: a few large chunks (small ones lose to wave quantisation in the LSTM
-    // kernels): 4 by default, more only to keep a chunk under ~4 Gi samples
+    // Large batches are cut into chunks of reads whose uploads overlap the kernels.  Default: the
+    // streamed path (whole batch resident, analyze_host_streamed).  POREPLEX_B200_HOST_PIPELINE=arena
+    // selects the two-arena pipeline (device memory for two chunks only; also taken when the batch
+    // would need more than a quarter of the device memory): a small first chunk, then
+    // POREPLEX_B200_HOST_CHUNKS (default 4) large ones.
     const int64_t n = hb->n_reads;
     int64_t min_elems = (int64_t)256 << 20;      // below this the copies are not worth hiding
     int64_t min_reads = 65536;
     int64_t nchunks = 4;
     bool uniform = false;
+    const char *pmode = getenv("POREPLEX_B200_HOST_PIPELINE");
+    bool arena = pmode && !strcmp(pmode, "arena");
     if (const char *env = getenv("POREPLEX_B200_HOST_CHUNKS")) {          // tuning: large chunks after the small first one
         const long long v = atoll(env);
         if (v >= 1 && v <= 64) nchunks = v;
@@ -1391,13 +1666,19 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
         const long long v = atoll(env);
         if (v > 0) { min_elems = v; min_reads = 2048; nchunks = (hb->n_raw_total + v - 1) / v; uniform = true; }
     }
-    while (hb->n_raw_total / nchunks > ((int64_t)4 << 30)) nchunks *= 2;
+    {
+        size_t free_b = 0, total_b = 0;
+        DeviceGuard g(ctx->device);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        if ((size_t)hb->n_raw_total * 2 > total_b / 4) arena = true;
+    }
+    if (arena) while (hb->n_raw_total / nchunks > ((int64_t)4 << 30)) nchunks *= 2;
     const bool keep = (flags & PB2_FLAG_KEEP_POOLED) && hr->pooled;
     if (n < min_reads || keep || hb->n_raw_total < min_elems || nchunks < 2)
         return analyze_host_single(ctx, hb, hr, flags);
-    // the pipelined path uploads each chunk as ONE span of the raw buffer and rebases its
-    // offsets: that needs reads laid out in ascending, non-overlapping order inside the
-    // buffer.  Any other layout is legal for the ABI and takes the single-arena path.
+    // both chunked paths upload each chunk as ONE span of the raw buffer: that needs reads laid
+    // out in ascending, non-overlapping order inside the buffer.  Any other layout is legal for
+    // the ABI and takes the single-arena path.
     for (int64_t i = 0; i < n; i++) {
         const int64_t o = hb->raw_offsets[i], l = hb->raw_lengths[i];
         if (o < 0 || l < 0 || o + l > hb->n_raw_total)
@@ -1406,18 +1687,18 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
             return analyze_host_single(ctx, hb, hr, flags);
     }
     std::vector<int64_t> bounds;
-    // Only the FIRST upload is not hidden behind kernels (the results of the last chunk are a
-    // few megabytes): a small first chunk, then equal large ones.  Chunk sizes are whole waves
-    // of the tensor-core kernels (one 128-read tile per SM) so that no chunk ends on a partly
-    // filled wave: first chunk = 3 waves (0.45 GB of 4000-sample reads, ~8 ms of PCIe).
+    const int64_t wave = (int64_t)ctx->sm_count * 128;
     if (uniform) {
         for (int64_t c = 0; c <= nchunks; c++) {
             int64_t b = (n * c) / nchunks;
             if (c < nchunks) b -= b % 128;       // keep chunk starts tile aligned
             if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
         }
+    } else if (!arena) {
+        bounds = plan_chunks(n, wave);
     } else {
-        const int64_t wave = (int64_t)ctx->sm_count * 128;
+        // Only the FIRST upload is not hidden behind kernels: a small first chunk, then equal
+        // large ones, all whole waves of the tensor-core kernels (one 128-read tile per SM).
         int64_t first = 3 * wave;
         if (first > n / 8) first = (n / 8) - (n / 8) % 128;
         bounds.push_back(0);
@@ -1431,7 +1712,8 @@ int pb2_analyze_host(pb2_context *ctx, const pb2_batch *hb, const pb2_results *h
     }
     if (bounds.back() != n) bounds.push_back(n);
     if (bounds.size() < 3) return analyze_host_single(ctx, hb, hr, flags);
-    return analyze_host_pipelined(ctx, hb, hr, flags, bounds);
+    if (arena) return analyze_host_pipelined(ctx, hb, hr, flags, bounds);
+    return analyze_host_streamed(ctx, hb, hr, flags, bounds);
 }
 
 }  // extern "C"

@@ -403,11 +403,13 @@ __global__ void k_finalize(int64_t n, const int32_t *__restrict__ status,
 
 int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
                     int32_t *label, int32_t *barcode, int32_t *guess, int32_t *score,
-                    cudaStream_t st)
+                    cudaStream_t st, const int32_t *pushed_mask)
 {
     if (n <= 0) return PB2_OK;
-    const int32_t *pushed = (flags & PB2_FLAG_BARCODING) ? (const int32_t *)ctx->ws_pushed.ptr
-                                                          : nullptr;
+    // the accept mask of the window stage: the caller's array, else the context's scratch
+    const int32_t *pushed = (flags & PB2_FLAG_BARCODING)
+                                ? (pushed_mask ? pushed_mask : (const int32_t *)ctx->ws_pushed.ptr)
+                                : nullptr;
     PB_LAUNCH(ctx, K_FINALIZE, "k_finalize", st,
         k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, status, pushed, label, barcode,
                                                            guess, score));

@@ -240,7 +240,7 @@ int launch_unsplit(pb2_context *ctx, const pb2_batch *batch, const pb2_event_tab
                    const int32_t *segments, int32_t max_windows, int32_t *flag, cudaStream_t st);
 int launch_finalize(pb2_context *ctx, int64_t n, uint32_t flags, int32_t *status,
                     int32_t *label, int32_t *barcode, int32_t *guess, int32_t *score,
-                    cudaStream_t st);
+                    cudaStream_t st, const int32_t *pushed_mask = nullptr);
 int launch_counts(pb2_context *ctx, const int32_t *status, const int32_t *label,
                   const int32_t *barcode, int64_t n, int64_t *counts, cudaStream_t st);
 

@@ -392,17 +392,20 @@ def test_unsplit_kernels_match_restatement(eng_stock, orc_stock, preset):
     assert n_true >= 4
 
 
-def test_pipelined_host_path_equals_single_pass(eng_short, orc_short, preset_short, monkeypatch):
-    """pb2_analyze_host cuts big batches into chunks and overlaps H2D / kernels / D2H on three
-    streams; results must equal the single-pass path read for read (and the oracle on a
-    sample), including poly(A) records and the summed counts."""
+@pytest.mark.parametrize('pipeline', ['streamed', 'arena'])
+def test_pipelined_host_path_equals_single_pass(eng_short, orc_short, preset_short, monkeypatch, pipeline):
+    """pb2_analyze_host cuts big batches into chunks whose uploads overlap the kernels -- whole
+    batch resident (`streamed`, the default) or two chunk-sized arenas (`arena`); results must
+    equal the single-pass path read for read, including poly(A) records and the summed counts."""
     rd = _reads(preset_short, 6000, 4000, seed=41, frac_no_adapter=0.03, frac_qc_fail=0.03)
     raw, off, ln = _dense_batch(rd)
     args = (raw, off, ln, rd['range'], rd['digitisation'], rd['offset'])
     single = eng_short.analyze_host(*args, polya=True)
     monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(3_000_000))     # -> 8 chunks
+    monkeypatch.setenv('POREPLEX_B200_HOST_PIPELINE', pipeline)
     piped = eng_short.analyze_host(*args, polya=True)
     monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
+    monkeypatch.delenv('POREPLEX_B200_HOST_PIPELINE')
     for k in single:
         a, b = single[k], piped[k]
         if a.dtype.fields:              # poly(A) records: spikes beyond n_spikes are unset

@@ -102,7 +102,7 @@ def test_tc_demux_with_recheck_equals_exact(eng_stock):
 def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monkeypatch):
     """Default path vs exact-only path through pb2_analyze_host on calibrated synthetic reads."""
     from poreplex_b200 import synth
-    rd = synth.to_numpy(synth.generate_reads(1500, synth.SynthSpec.for_length(4000), preset_short, seed=31))
+    rd = synth.to_numpy(synth.generate_reads(3000, synth.SynthSpec.for_length(4000), preset_short, seed=31))
     n, L = rd['raw'].shape
     args = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int64),
             rd['range'], rd['digitisation'], rd['offset'])
@@ -123,13 +123,27 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monk
     assert np.median(d[:, 0]) < 1e-6 and np.median(d[:, 1]) < 5e-5
     assert (d.max(1) == 0).sum() >= rerun                            # re-run reads are exact
     assert 0 < rerun < 0.35 * n
-    assert (fast['barcode_score'] >= 0).sum() > 1000
-    # chunked host path: same integer outputs whatever the tiling of reads
-    monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(1_000_000))
-    piped = eng_short.analyze_host(*args)
-    monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
-    for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
-        assert np.array_equal(piped[k], exact[k]), k
+    assert (fast['barcode_score'] >= 0).sum() > 2000
+    # chunked host paths: same integer outputs whatever the tiling of reads.  `streamed` keeps the
+    # whole batch resident and resolves the unsafe reads of all chunks as one sub-batch at the end;
+    # `arena` resolves them chunk by chunk.
+    other = synth.to_numpy(synth.generate_reads(n, synth.SynthSpec.for_length(4000), preset_short, seed=32))
+    for pipeline in ('streamed', 'arena'):
+        # a different batch first: nothing may be taken from scratch a previous call left behind
+        eng_short.analyze_host(other['raw'].reshape(-1), *args[1:3], other['range'], other['digitisation'],
+                               other['offset'])
+        monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(1_000_000))
+        monkeypatch.setenv('POREPLEX_B200_HOST_PIPELINE', pipeline)
+        piped = eng_short.analyze_host(*args)
+        rerun_p = eng_short.recheck_stats()[0]
+        monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
+        monkeypatch.delenv('POREPLEX_B200_HOST_PIPELINE')
+        for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
+            assert np.array_equal(piped[k], exact[k]), (pipeline, k)
+        dp = np.abs(piped['scale_shift'].astype(np.float64) - exact['scale_shift'])
+        assert dp[:, 0].max() <= 3.4e-5 and dp[:, 1].max() <= 1.5e-2
+        if pipeline == 'streamed':
+            assert 0 < rerun_p < 0.35 * n and (dp.max(1) == 0).sum() >= rerun_p
 
 
 def test_tc_demux_extreme_windows_equal_exact(eng_stock):
