@@ -28,6 +28,7 @@
 // columns (one CTA per SM): the gate warps of column group 0 start while the tensor pipe still
 // works on group 1, and the h operand is double buffered so that they may write h(t) meanwhile.
 // The gate phase is bound by the MUFU (XU) pipe: 7 MUFU per unit and step at 16 lanes/clk/SM.
+#include <cstdlib>
 #include "pb_internal.h"
 #include "pb_math.cuh"
 #include "tc_core.cuh"
@@ -597,6 +598,223 @@ k_lstm_tc(const TcArgs A)
     if (tid == 0 && s_dead && A.err) *A.err = 1;
 }
 
+// ---- both sensitivity probes of a vector-input layer in ONE kernel ---------------------
+// A coarse probe alone leaves both pipes half idle (ncu: XU 63 %, tensor 31 %): its step is the
+// serial chain MMA -> tcgen05.ld -> gates -> tcgen05.st -> MMA, one CTA per SM, nothing to overlap
+// with.  The two probes are independent recurrences over the same input, so this kernel runs
+// them as a ring of four work items per time step,
+//     (P, group 0)  (Q, group 0)  (P, group 1)  (Q, group 1)         P = probe 1, Q = probe 2,
+// a "group" being one half of the 4H accumulator columns (chunk-major unit order, as in
+// k_lstm_tc).  While the gate warps evaluate item k the tensor pipe computes item k + 1:
+//   * the products of item k + 1 need the hidden state written by item k - 1 at the latest
+//     (group 0 of step t + 1 needs both groups of the same probe at step t, and the other probe's
+//     item lies in between) and an accumulator last read by item k - 1;
+//   * so two 128-column accumulators alternate (item k uses buffer k & 1), instead of the 256
+//     columns per recurrence of k_lstm_tc -- that is what makes room for the second recurrence
+//     (TMEM: 2 x 128 accumulator + 2 x 48 input + 2 x 2 x 32 state = 480 columns);
+//   * h and x are double buffered: the group-1 products of a probe still read h(t - 1) after its
+//     group-0 gates have written their half of h(t), and x(t + 1) is stored while the last
+//     products of step t may still be running.
+// Same MMAs in the same order per accumulator column, same gate code, same rounding and the same
+// pseudo-random sequence as k_lstm_tc<H, KX, false, 1> and <.., 2>: the outputs are bit-identical
+// to theirs (tests/test_gpu_tc.py::test_fused_probes_equal_separate_probes), so the guard
+// statistics of DESIGN.md 3a carry over unchanged.  The input stream is read once instead of twice.
+template <int H, int KX>
+__global__ void __launch_bounds__(tc_threads<H, KX>(), 1)
+k_lstm_tc_probes(const TcArgs A)
+{
+    constexpr int N = 4 * H;
+    constexpr int NP = tc_nparts<H, KX>();
+    constexpr int NGW = 4 * NP;
+    constexpr int NTHR = tc_threads<H, KX>();
+    constexpr int UPT = H / NP;
+    static_assert(UPT == 16 && KX > 0, "two chunks of 8 units per gate thread");
+    constexpr int NG = NP * 8 * 4;                    // accumulator columns of one group
+    static_assert(2 * NG == N, "two equal column groups");
+    constexpr int XW = (KX / 2) / NP;                 // hi words of the input per gate thread
+    static_assert(XW % 4 == 0, "x words per thread must be a multiple of 4");
+    constexpr uint32_t COL_ACC = 0, COL_X = 2 * NG, COL_HP = COL_X + KX, COL_HQ = COL_HP + H;
+    static_assert(COL_HQ + H <= 512, "TMEM budget");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half *bU_hi = reinterpret_cast<__half *>(smem_raw);
+    __half *bU_lo = bU_hi + H * N;
+    __half *bW_hi = bU_lo + H * N;
+    __half *bW_lo = bW_hi + KX * N;
+    float *s_bias = reinterpret_cast<float *>(bW_lo + KX * N);
+    __shared__ __align__(8) uint64_t bar_d[2], bar_g[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_dead;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TcDir &dP = A.dir[0], &dQ = A.dir[1];
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TCM;
+    int64_t n_eff = A.n;
+    if (A.slot_count) {
+        n_eff = (int64_t)*A.slot_count - A.row0;
+        if (n_eff > A.n) n_eff = A.n;
+    }
+    if (tile0 >= n_eff) return;
+    const int T = A.T;
+
+    if (tid == 0) {
+        mbar_init(&bar_d[0], 1);
+        mbar_init(&bar_d[1], 1);
+        mbar_init(&bar_g[0], NGW);
+        mbar_init(&bar_g[1], NGW);
+        mbar_fence_init();
+        s_dead = 0;
+    }
+    if (warp == NGW) tmem_alloc(&s_tmem, 512);
+    load_b_split<H, H, NP>(dP.U, bU_hi, bU_lo, tid, NTHR);
+    load_b_split<KX, H, NP>(dP.W, bW_hi, bW_lo, tid, NTHR);
+    for (int i = tid; i < N; i += NTHR) {
+        const int gate = i / H, u = i % H;
+        s_bias[gate_col(unit_slot<H, NP>(u), gate)] = dP.b[i];
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = s_tmem;
+
+    if (warp == NGW) {
+        // ===== MMA issuer: item k = 4 t + i, i: 0 (P, g0)  1 (Q, g0)  2 (P, g1)  3 (Q, g1) =====
+        if (lane == 0) {
+            constexpr uint32_t BOFS = (NG / 8) * 128;              // group 1's columns of a k-chunk
+            const int64_t items = 4 * (int64_t)T;
+            for (int64_t k = 0; k < items; k++) {
+                const int t = (int)(k >> 2), i = (int)(k & 3), grp = i >> 1, b = (int)(k & 1);
+                // gates of item k - 2 done (completion k >> 1 of bar_g[b]; completion 0 = the set-up)
+                mbar_wait(&bar_g[b], (uint32_t)((k >> 1) & 1), &s_dead);
+                fence_after_sync();
+                const uint32_t acc = tbase + COL_ACC + b * NG;
+                const uint32_t xcol = tbase + COL_X + (t & 1) * (KX / 2);
+                const uint32_t hcol = tbase + ((i & 1) ? COL_HQ : COL_HP) + (t & 1) * (H / 2);
+                bool first = true;
+                issue_split_gemm<KX, N, NG>(acc, xcol, xcol, smem_u32(bW_hi) + grp * BOFS,
+                                            smem_u32(bW_lo) + grp * BOFS, first, false);
+                issue_split_gemm<H, N, NG>(acc, hcol, hcol, smem_u32(bU_hi) + grp * BOFS,
+                                           smem_u32(bU_lo) + grp * BOFS, first, false);
+                mma_commit(&bar_d[b]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== gate warps =====
+        const int q = warp & 3, part = (warp >> 2) % NP;
+        const int m = q * 32 + lane;
+        int64_t row = tile0 + m;
+        if (row >= n_eff) row = n_eff - 1;
+        const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+        const int u0 = part * UPT;
+        float2 cP[UPT / 2], cQ[UPT / 2];
+#pragma unroll
+        for (int j = 0; j < UPT / 2; j++) { cP[j] = f2(0.f, 0.f); cQ[j] = f2(0.f, 0.f); }
+        // initial state (zeros) of both probes in buffer 0
+        {
+            uint32_t lo;
+            const uint32_t z = split_pair(f2(0.f, 0.f), lo);
+#pragma unroll
+            for (int j = 0; j < UPT / 2; j += 4) {
+                tmem_st4(lane_addr + COL_HP + u0 / 2 + j, z, z, z, z);
+                tmem_st4(lane_addr + COL_HQ + u0 / 2 + j, z, z, z, z);
+            }
+        }
+        const uint32_t *gin = A.Gin + ((size_t)tile * A.g_T - A.g_t0) * KX * TCM;
+        uint32_t xw[XW];
+        {
+            const uint32_t *gp = gin + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+            for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+#pragma unroll
+            for (int j = 0; j < XW; j += 4)
+                tmem_st4(lane_addr + COL_X + part * XW + j, xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_g[0]); mbar_arrive(&bar_g[1]); }
+        if (T > 1) {
+            const uint32_t *gp = gin + (size_t)KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+            for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+        }
+        uint32_t rng = ((uint32_t)(A.row0 + tile0 + m) * 2654435761u) ^ ((uint32_t)part * 0x9E3779B9u) ^ 0x85EBCA6Bu;
+
+        for (int t = 0; t < T; t++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int grp = i >> 1, b = i & 1;                 // item k = 4 t + i, buffer k & 1
+                const bool isQ = (i & 1) != 0;
+                mbar_wait(&bar_d[b], (uint32_t)(((4 * t + i) >> 1) & 1), &s_dead);
+                __syncwarp();
+                fence_after_sync();
+                uint32_t vv[32];
+                tmem_ld32(lane_addr + COL_ACC + b * NG + part * 32, vv);
+                tmem_ld_wait();
+                if (i == 0 && t + 1 < T) {
+                    // x(t + 1) into the buffer the products of step t - 1 read (all retired: the
+                    // gates of their last item ran before this one)
+#pragma unroll
+                    for (int j = 0; j < XW; j += 4)
+                        tmem_st4(lane_addr + COL_X + ((t + 1) & 1) * (KX / 2) + part * XW + j,
+                                 xw[j], xw[j + 1], xw[j + 2], xw[j + 3]);
+                    if (t + 2 < T) {
+                        const uint32_t *gp = gin + (size_t)(t + 2) * KX * TCM + (size_t)(part * XW) * TCM + m;
+#pragma unroll
+                        for (int j = 0; j < XW; j++) xw[j] = __ldg(gp + (size_t)j * TCM);
+                    }
+                }
+                uint32_t hi[4];
+                float2 hn[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int col = (grp * (NP * 8) + part * 8 + 2 * j) * 4;
+                    const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + col + 4);
+                    const float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
+                    const float2 zf = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 2]), __uint_as_float(vv[8 * j + 3])), f2(b0.z, b0.w));
+                    const float2 zc = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 4]), __uint_as_float(vv[8 * j + 5])), f2(b1.x, b1.y));
+                    const float2 zo = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 6]), __uint_as_float(vv[8 * j + 7])), f2(b1.z, b1.w));
+                    uint32_t lo;
+                    if (isQ) {
+                        hn[j] = lstm_cell_pair<true>(zi, zf, zc, zo, cQ[grp * 4 + j]);
+                        rng = rng * 1664525u + 1013904223u;
+                        const float2 hd = f2(__uint_as_float(__float_as_uint(hn[j].x) + (rng >> 19)),
+                                             __uint_as_float(__float_as_uint(hn[j].y) + ((rng >> 6) & 0x1FFFu)));
+                        hi[j] = split_pair(hd, lo);
+                    } else {
+                        hn[j] = lstm_cell_pair<true>(zi, zf, zc, zo, cP[grp * 4 + j]);
+                        hi[j] = split_pair(hn[j], lo);
+                    }
+                }
+                // h(t) of this probe goes to the buffer its products of step t do not read
+                tmem_st4(lane_addr + (isQ ? COL_HQ : COL_HP) + ((t + 1) & 1) * (H / 2) + u0 / 2 + grp * 4,
+                         hi[0], hi[1], hi[2], hi[3]);
+                if (t == T - 1 && tile0 + m < n_eff) {
+                    float *hl = (isQ ? dQ.h_last : dP.h_last) + (size_t)(A.row0 + tile0 + m) * H + u0 + grp * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
+                }
+                tmem_st_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_g[b]);
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NGW) {
+        fence_after_sync();
+        tmem_dealloc(tbase, 512);
+    }
+    if (tid == 0 && s_dead && A.err) *A.err = 1;
+}
+
 // ---- demultiplexer head on the approximate layer-2 state -----------------------------
 // One thread per window row: Dense + softmax + decision exactly as the exact kernel does it
 // (same code, demux_head.cuh), then the margin test.  Unsafe rows are appended to the
@@ -929,6 +1147,8 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
         if ((rc = tc_set_attr<H2, KX, false>(ctx))) return rc;
         if ((rc = tc_set_attr<H2, KX, false, 1>(ctx))) return rc;
         if ((rc = tc_set_attr<H2, KX, false, 2>(ctx))) return rc;
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc_probes<H2, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tc_smem_bytes<H2, KX>()));
         ctx->attr_demux_tc = true;
     }
     const int64_t tiles = (n + TCM - 1) / TCM;
@@ -955,6 +1175,9 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     // probe 2 only for the windows probe 1 cannot settle (not on the verification entry point,
     // which reports the two-probe sensitivity of every window)
     const bool screen = ctx->demux_probes >= 2 && ctx->demux_screen_gain > 0 && !sens_out && !unsafe_out;
+    // POREPLEX_B200_SPLIT_PROBES=1: the two probes as two launches of k_lstm_tc (verification)
+    const char *split_env = getenv("POREPLEX_B200_SPLIT_PROBES");
+    const bool fused_probes = !(split_env && split_env[0] == '1');
 
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
         const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
@@ -984,6 +1207,13 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
             k_lstm_tc<H2, KX, false><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
         B.dir[0].coarse = 1; B.dir[0].h_last = h_probe;
         B.dir[1] = B.dir[0];
+        if (ctx->demux_probes >= 2 && !screen && fused_probes) {
+            // both probes as one ring of work items in one kernel (bit-identical outputs)
+            B.dir[1].h_last = h_probe2;
+            PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc_probes<demux l2>", st,
+                k_lstm_tc_probes<H2, KX><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
+            continue;
+        }
         PB_LAUNCH(ctx, K_DEMUX_TC_PROBE, "k_lstm_tc<demux l2 probe>", st,
             k_lstm_tc<H2, KX, false, 1><<<dim3((unsigned)nt, 1), tc_threads<H2, KX>(), tc_smem_bytes<H2, KX>(), st>>>(B));
         if (ctx->demux_probes >= 2 && !screen) {
@@ -995,6 +1225,11 @@ int launch_demux_tc(pb2_context *ctx, const float *windows, const int32_t *pushe
     }
     TcHeadArgs Hd = {};
     Hd.h_last = h_last; Hd.h_probe = h_probe; Hd.h_probe2 = ctx->demux_probes >= 2 ? h_probe2 : nullptr; Hd.n = n;
+    if (const char *env = getenv("POREPLEX_B200_SENS_PROBE")) {
+        // verification: the reported sensitivity from ONE of the probes only
+        if (env[0] == '1') Hd.h_probe2 = nullptr;
+        else if (env[0] == '2' && Hd.h_probe2) { Hd.h_probe = h_probe2; Hd.h_probe2 = nullptr; }
+    }
     Hd.delta0 = ctx->demux_margin_delta; Hd.probe_gain = ctx->demux_probe_gain;
     Hd.sens_out = sens_out; Hd.slot_count = slot_count; Hd.slot_read = slot_read;
     Hd.pushed = slot_read ? nullptr : pushed;

@@ -228,3 +228,30 @@ def test_fast_path_is_reproducible(eng_short, preset_short):
         for k, v in first.items():
             assert np.array_equal(v, again[k], equal_nan=True) if v.dtype.kind == 'f' \
                 else np.array_equal(v, again[k]), k
+
+
+def test_fused_probes_equal_separate_probes(eng_stock, monkeypatch):
+    """k_lstm_tc_probes runs both sensitivity probes as one ring of work items; its outputs must be
+    the bits of the two separate k_lstm_tc launches it replaces (same MMAs per accumulator column,
+    same gate code, same pseudo-random rounding), so that the guard statistics carry over.  The
+    logit shift each probe measures is compared per probe and combined, on ragged tile counts."""
+    import torch
+    dev = torch.device('cuda', 0)
+    win = _windows(148 * 128 + 77, seed=17, min_len=40)       # a full wave of tiles and a ragged one
+    win[5, :] = -1000.0
+    wd = torch.from_numpy(win).to(dev)
+    for which in ('', '1', '2'):
+        if which:
+            monkeypatch.setenv('POREPLEX_B200_SENS_PROBE', which)
+        fused = [o.cpu().numpy() for o in eng_stock.demux_predict_tc(wd)]
+        monkeypatch.setenv('POREPLEX_B200_SPLIT_PROBES', '1')
+        split = [o.cpu().numpy() for o in eng_stock.demux_predict_tc(wd)]
+        monkeypatch.delenv('POREPLEX_B200_SPLIT_PROBES')
+        if which:
+            monkeypatch.delenv('POREPLEX_B200_SENS_PROBE')
+        assert eng_stock.recheck_stats()[1] == 0, 'tensor-core kernel barrier time-out'
+        assert fused[6].max() > 0
+        assert np.array_equal(fused[6].view(np.uint32), split[6].view(np.uint32)), 'probe %r' % which
+        assert np.array_equal(fused[5], split[5])
+        for a, b in zip(fused[:5], split[:5]):
+            assert np.array_equal(a, b)
