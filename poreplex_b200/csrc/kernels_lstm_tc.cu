@@ -815,6 +815,266 @@ k_lstm_tc_probes(const TcArgs A)
     if (tid == 0 && s_dead && A.err) *A.err = 1;
 }
 
+// ---- both layers of the scaler network in ONE kernel -------------------------------------
+// LSTM(H) over a scalar input followed by LSTM(H) over its output sequence (signal_loader.py:89-97).
+// As two launches of k_lstm_tc the first layer's sequence crosses HBM (104 KB per read, written and
+// read back) and the second layer -- one CTA per SM, a single recurrence -- leaves the MUFU pipe
+// 40 % idle.  Here one CTA steps both layers over its tile, layer 2 one step behind layer 1:
+//     phase p :  A_p = gates of layer 1, step p        (needs D1(p) = h1(p-1) U1)
+//                B_p = gates of layer 2, step p - 1    (needs D2(p) = h1(p-1) W2 + h2(p-2) U2)
+// The two gate items alternate and the tensor pipe is always one item ahead: D1(p+1) (needs only
+// A_p) runs under B_p, D2(p+1) (needs B_p) runs under A_{p+1}.  h1 is layer 1's recurrent operand
+// AND layer 2's input operand, in TMEM, never in HBM.  It is single buffered (4H + 4H accumulator
+// columns + h1 + h2 = 10 H = 480 of 512): A_{p+1} keeps its new h1 words in registers until
+// D2(p+1), the last reader of h1(p), has retired -- a wait it would meet at the start of B_{p+1}
+// anyway.
+// Same products in the same order per accumulator column, same gate code as
+// k_lstm_tc<H,0,true> + k_lstm_tc<H,H,false>: bit-identical final states
+// (tests/test_gpu_tc.py::test_fused_scaler_equals_two_kernel_scaler).
+template <int H>
+__global__ void __launch_bounds__(128 * 3 + 32, 1)
+k_lstm_tc_scaler2(const TcArgs A)
+{
+    constexpr int N = 4 * H;
+    constexpr int NP = 3;
+    constexpr int NGW = 4 * NP;
+    constexpr int NTHR = 128 * NP + 32;
+    constexpr int UPT = H / NP;
+    constexpr int NCH = UPT / 8;
+    static_assert(UPT % 8 == 0 && H % 16 == 0, "units per thread must be a multiple of 8");
+    constexpr uint32_t COL_D1 = 0, COL_D2 = N, COL_H1 = 2 * N, COL_H2 = 2 * N + H;
+    static_assert(COL_H2 + H <= 512, "TMEM budget");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half *bU1_hi = reinterpret_cast<__half *>(smem_raw);
+    __half *bU1_lo = bU1_hi + H * N;
+    __half *bW2_hi = bU1_lo + H * N;
+    __half *bW2_lo = bW2_hi + H * N;
+    __half *bU2_hi = bW2_lo + H * N;
+    __half *bU2_lo = bU2_hi + H * N;
+    float *s_b1 = reinterpret_cast<float *>(bU2_lo + H * N);     // [N] accumulator column order
+    float *s_w1 = s_b1 + N;                                       // [N] scalar input kernel of layer 1
+    float *s_b2 = s_w1 + N;
+    __shared__ __align__(8) uint64_t bar_d1, bar_d2, bar_h1, bar_h2;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_dead, s_tstart;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TcDir &L1 = A.dir[0], &L2 = A.dir[1];
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TCM;
+    const int64_t n_eff = A.n;
+    if (tile0 >= n_eff) return;
+    const int T = A.T;
+
+    if (tid == 0) {
+        mbar_init(&bar_d1, 1);
+        mbar_init(&bar_d2, 1);
+        mbar_init(&bar_h1, NGW);
+        mbar_init(&bar_h2, NGW);
+        mbar_fence_init();
+        s_dead = 0;
+        s_tstart = T;
+    }
+    if (warp == NGW) tmem_alloc(&s_tmem, 512);
+    load_b_split<H, H, 0>(L1.U, bU1_hi, bU1_lo, tid, NTHR);
+    load_b_split<H, H, 0>(L2.W, bW2_hi, bW2_lo, tid, NTHR);
+    load_b_split<H, H, 0>(L2.U, bU2_hi, bU2_lo, tid, NTHR);
+    for (int i = tid; i < N; i += NTHR) {
+        const int gate = i / H, u = i % H;
+        s_b1[gate_col(u, gate)] = L1.b[i];
+        s_w1[gate_col(u, gate)] = L1.W[i];
+        s_b2[gate_col(u, gate)] = L2.b[i];
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = s_tmem;
+
+    // ---- per-row input addressing and the common start step (zero head: skip_mode 2) ----
+    const int q = warp & 3, part = (warp >> 2) % NP;
+    const int m = q * 32 + lane;
+    int64_t row = tile0 + m;
+    if (row >= n_eff) row = n_eff - 1;
+    const float *xbase = nullptr;
+    int pad = 0;
+    if (warp < NGW) {
+        const int nr = A.nreal[A.row0 + row];
+        pad = T - nr;
+        xbase = A.xsrc + (nr > 0 ? A.xoff[A.row0 + row] : 0) - pad;
+        if (nr <= 0) pad = T;
+        if (part == 0) atomicMin(&s_tstart, pad);
+    }
+    __syncthreads();
+    int t_start = s_tstart;
+    if (t_start >= T) t_start = T - 1;
+    if (!A.tab) t_start = 0;
+
+    if (warp == NGW) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t ph1 = 0, ph2 = 0;
+            for (int p = t_start; p <= T; p++) {
+                mbar_wait(&bar_h1, ph1, &s_dead);                  // h1(p-1) is in TMEM
+                ph1 ^= 1;
+                fence_after_sync();
+                if (p < T) {
+                    bool first = true;
+                    issue_split_gemm<H, N, N>(tbase + COL_D1, tbase + COL_H1, tbase + COL_H1 + H / 2,
+                                              smem_u32(bU1_hi), smem_u32(bU1_lo), first, true);
+                    mma_commit(&bar_d1);
+                }
+                if (p > t_start) {
+                    mbar_wait(&bar_h2, ph2, &s_dead);              // h2(p-2) is in TMEM
+                    ph2 ^= 1;
+                    fence_after_sync();
+                    bool first = true;
+                    issue_split_gemm<H, N, N>(tbase + COL_D2, tbase + COL_H1, tbase + COL_H1 + H / 2,
+                                              smem_u32(bW2_hi), smem_u32(bW2_lo), first, true);
+                    issue_split_gemm<H, N, N>(tbase + COL_D2, tbase + COL_H2, tbase + COL_H2 + H / 2,
+                                              smem_u32(bU2_hi), smem_u32(bU2_lo), first, true);
+                    mma_commit(&bar_d2);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== gate warps =====
+        const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+        const int u0 = part * UPT;
+        float2 c1[UPT / 2], c2[UPT / 2];
+        {
+            const float *tb = (t_start > 0 && A.tab) ? A.tab + (size_t)t_start * A.tab_stride : nullptr;
+#pragma unroll
+            for (int pr = 0; pr < UPT / 2; pr += 2) {
+                uint32_t hi1[2], lo1[2], hi2[2], lo2[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int u = u0 + 2 * (pr + j);
+                    const float2 a = tb ? f2(tb[u], tb[u + 1]) : f2(0.f, 0.f);                      // h1
+                    c1[pr + j] = tb ? f2(tb[H + u], tb[H + u + 1]) : f2(0.f, 0.f);
+                    const float2 b = tb ? f2(tb[2 * H + u], tb[2 * H + u + 1]) : f2(0.f, 0.f);      // h2
+                    c2[pr + j] = tb ? f2(tb[3 * H + u], tb[3 * H + u + 1]) : f2(0.f, 0.f);
+                    hi1[j] = split_pair(a, lo1[j]);
+                    hi2[j] = split_pair(b, lo2[j]);
+                }
+                tmem_st2(lane_addr + COL_H1 + u0 / 2 + pr, hi1[0], hi1[1]);
+                tmem_st2(lane_addr + COL_H1 + H / 2 + u0 / 2 + pr, lo1[0], lo1[1]);
+                tmem_st2(lane_addr + COL_H2 + u0 / 2 + pr, hi2[0], hi2[1]);
+                tmem_st2(lane_addr + COL_H2 + H / 2 + u0 / 2 + pr, lo2[0], lo2[1]);
+            }
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_h1); mbar_arrive(&bar_h2); }
+
+        uint32_t pd1 = 0, pd2 = 0;
+        for (int p = t_start; p <= T; p++) {
+            uint32_t h1hi[UPT / 2], h1lo[UPT / 2];
+            if (p < T) {
+                // ---- A_p: layer 1, step p
+                const float xv = (p >= pad) ? __ldg(xbase + p) : A.padval;
+                const float2 xv2 = splat(xv);
+                mbar_wait(&bar_d1, pd1, &s_dead);
+                pd1 ^= 1;
+                __syncwarp();
+                fence_after_sync();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    uint32_t vv[32];
+                    tmem_ld32(lane_addr + COL_D1 + (u0 + ch * 8) * 4, vv);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int col = (u0 + ch * 8 + 2 * j) * 4;
+                        const float4 b0 = *reinterpret_cast<const float4 *>(s_b1 + col);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(s_b1 + col + 4);
+                        float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
+                        float2 zf = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 2]), __uint_as_float(vv[8 * j + 3])), f2(b0.z, b0.w));
+                        float2 zc = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 4]), __uint_as_float(vv[8 * j + 5])), f2(b1.x, b1.y));
+                        float2 zo = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 6]), __uint_as_float(vv[8 * j + 7])), f2(b1.z, b1.w));
+                        const float4 w0 = *reinterpret_cast<const float4 *>(s_w1 + col);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(s_w1 + col + 4);
+                        zi = __ffma2_rn(xv2, f2(w0.x, w0.y), zi);
+                        zf = __ffma2_rn(xv2, f2(w0.z, w0.w), zf);
+                        zc = __ffma2_rn(xv2, f2(w1.x, w1.y), zc);
+                        zo = __ffma2_rn(xv2, f2(w1.z, w1.w), zo);
+                        const float2 hn = lstm_cell_pair<false>(zi, zf, zc, zo, c1[ch * 4 + j]);
+                        h1hi[ch * 4 + j] = split_pair(hn, h1lo[ch * 4 + j]);
+                    }
+                }
+            }
+            if (p > t_start) {
+                // D2(p) has retired: nothing reads h1(p-1) any more, and B_p may read its columns
+                mbar_wait(&bar_d2, pd2, &s_dead);
+                pd2 ^= 1;
+                __syncwarp();
+                fence_after_sync();
+            }
+            if (p < T) {
+#pragma unroll
+                for (int j = 0; j < UPT / 2; j += 4) {
+                    tmem_st4(lane_addr + COL_H1 + u0 / 2 + j, h1hi[j], h1hi[j + 1], h1hi[j + 2], h1hi[j + 3]);
+                    tmem_st4(lane_addr + COL_H1 + H / 2 + u0 / 2 + j, h1lo[j], h1lo[j + 1], h1lo[j + 2], h1lo[j + 3]);
+                }
+                tmem_st_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_h1);
+            }
+            if (p > t_start) {
+                // ---- B_p: layer 2, step p - 1
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    uint32_t vv[32];
+                    tmem_ld32(lane_addr + COL_D2 + (u0 + ch * 8) * 4, vv);
+                    tmem_ld_wait();
+                    uint32_t hi[4], lo[4];
+                    float2 hn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int col = (u0 + ch * 8 + 2 * j) * 4;
+                        const float4 b0 = *reinterpret_cast<const float4 *>(s_b2 + col);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(s_b2 + col + 4);
+                        const float2 zi = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 0]), __uint_as_float(vv[8 * j + 1])), f2(b0.x, b0.y));
+                        const float2 zf = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 2]), __uint_as_float(vv[8 * j + 3])), f2(b0.z, b0.w));
+                        const float2 zc = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 4]), __uint_as_float(vv[8 * j + 5])), f2(b1.x, b1.y));
+                        const float2 zo = __fadd2_rn(f2(__uint_as_float(vv[8 * j + 6]), __uint_as_float(vv[8 * j + 7])), f2(b1.z, b1.w));
+                        hn[j] = lstm_cell_pair<false>(zi, zf, zc, zo, c2[ch * 4 + j]);
+                        hi[j] = split_pair(hn[j], lo[j]);
+                    }
+                    tmem_st4(lane_addr + COL_H2 + u0 / 2 + ch * 4, hi[0], hi[1], hi[2], hi[3]);
+                    tmem_st4(lane_addr + COL_H2 + H / 2 + u0 / 2 + ch * 4, lo[0], lo[1], lo[2], lo[3]);
+                    if (p == T && tile0 + m < n_eff) {
+                        float *hl = L2.h_last + (size_t)(A.row0 + tile0 + m) * H + u0 + ch * 8;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { hl[2 * j] = hn[j].x; hl[2 * j + 1] = hn[j].y; }
+                    }
+                }
+                tmem_st_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_h2);
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NGW) {
+        fence_after_sync();
+        tmem_dealloc(tbase, 512);
+    }
+    if (tid == 0 && s_dead && A.err) *A.err = 1;
+}
+
+template <int H>
+constexpr size_t tc_scaler2_smem_bytes() {
+    return (size_t)3 * H * 4 * H * 2 * 2 + (size_t)3 * 4 * H * sizeof(float) + 128;
+}
+
 // ---- demultiplexer head on the approximate layer-2 state -----------------------------
 // One thread per window row: Dense + softmax + decision exactly as the exact kernel does it
 // (same code, demux_head.cuh), then the margin test.  Unsafe rows are appended to the
@@ -1080,6 +1340,25 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
     if (!G || !h_last || !tstart || !rl) return PB2_ENOMEM;
     (void)rl;
     int *err = ctx->tc_err;
+    // POREPLEX_B200_SPLIT_SCALER=1: the two layers as two launches of k_lstm_tc with the first
+    // layer's sequence in HBM (verification)
+    const char *split_env = getenv("POREPLEX_B200_SPLIT_SCALER");
+    if (!(split_env && split_env[0] == '1')) {
+        if (!ctx->attr_scaler_tc2) {
+            PB_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc_scaler2<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)tc_scaler2_smem_bytes<H>()));
+            ctx->attr_scaler_tc2 = true;
+        }
+        TcArgs A = {};
+        A.dir[0] = {S.l1.recurrent, S.l1.kernel, S.l1.bias, 0, 2, 0, 0, 0, nullptr};
+        A.dir[1] = {S.l2.recurrent, S.l2.kernel, S.l2.bias, 0, 0, 0, 0, 0, h_last};
+        A.xsrc = pooled; A.xoff = xoff; A.nreal = nreal; A.padval = 0.f;
+        A.T = thead; A.n = n; A.row0 = 0;
+        A.tab = S.zero_prefix; A.tab_stride = 4 * H;
+        A.err = err;
+        PB_LAUNCH(ctx, K_SCALER_TC_L2, "k_lstm_tc_scaler2", st,
+            k_lstm_tc_scaler2<H><<<dim3((unsigned)tiles, 1), 128 * 3 + 32, tc_scaler2_smem_bytes<H>(), st>>>(A));
+    } else
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
         const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
         const int64_t r0 = t0 * TCM;

@@ -78,7 +78,7 @@ struct pb2_context {
     int device = 0;
     bool profiling = false;
     bool attr_scaler = false, attr_demux = false;   // max-dynamic-smem attributes set
-    bool attr_demux_tc = false, attr_scaler_tc = false;
+    bool attr_demux_tc = false, attr_scaler_tc = false, attr_scaler_tc2 = false;
     // tensor-core LSTM path (kernels_lstm_tc.cu): approximate outputs + margin test + exact
     // re-run of the reads whose decisions are not safe.  Off = exact kernels only.
     bool fast_lstm = true;

@@ -255,3 +255,32 @@ def test_fused_probes_equal_separate_probes(eng_stock, monkeypatch):
         assert np.array_equal(fused[5], split[5])
         for a, b in zip(fused[:5], split[:5]):
             assert np.array_equal(a, b)
+
+
+def test_fused_scaler_equals_two_kernel_scaler(eng_short, preset_short, monkeypatch):
+    """k_lstm_tc_scaler2 steps both scaler layers in one kernel (layer 2 one step behind layer 1,
+    the first layer's sequence never leaves TMEM); every output of the whole path -- the approximate
+    (scale, shift) of guard-passing reads included -- must be the bits of the two-launch version
+    whose error statistics DESIGN.md 3a validates.  Ragged lengths: tiles start at different steps
+    of the zero head, some reads are too short to be scaled at all."""
+    from poreplex_b200 import synth
+    rd = synth.to_numpy(synth.generate_reads(3000, synth.SynthSpec.for_length(4000), preset_short, seed=77))
+    n, L = rd['raw'].shape
+    rng = np.random.default_rng(5)
+    ln = np.full(n, L, np.int64)
+    ln[::3] = rng.integers(600, L, size=len(ln[::3]))
+    ln[:130] = np.sort(rng.integers(905, 1500, size=130))      # a whole tile of short heads
+    args = (rd['raw'].reshape(-1), np.arange(n, dtype=np.int64) * L, ln,
+            rd['range'], rd['digitisation'], rd['offset'])
+    fused = {k: np.array(v, copy=True) for k, v in eng_short.analyze_host(*args).items()
+             if isinstance(v, np.ndarray)}
+    reruns = eng_short.recheck_stats()
+    assert reruns[1] == 0, 'tensor-core kernel barrier time-out'
+    monkeypatch.setenv('POREPLEX_B200_SPLIT_SCALER', '1')
+    split = eng_short.analyze_host(*args)
+    monkeypatch.delenv('POREPLEX_B200_SPLIT_SCALER')
+    assert eng_short.recheck_stats() == reruns
+    assert (fused['status'] == 0).sum() > 1500 and 0 < reruns[0] < 0.5 * n
+    for k, v in fused.items():
+        assert np.array_equal(v, split[k], equal_nan=True) if v.dtype.kind == 'f' \
+            else np.array_equal(v, split[k]), k
