@@ -68,6 +68,8 @@ def algorithmic(L, stride=15, trim=300, scaler_len=30000):
         'k_lstm_tc_demux_l2_probe': ('tensor', 2 * (96 * 256 + 64 * 256) * trim),
         'k_lstm_tc_scaler_l1': ('tensor', 2 * (192 + 48 * 192) * H),
         'k_lstm_tc_scaler_l2': ('tensor', 2 * (2 * 48 * 192) * H),
+        # both scaler layers in one kernel (k_lstm_tc_scaler2)
+        'k_lstm_tc_scaler': ('tensor', 2 * (192 + 48 * 192 + 2 * 48 * 192) * H),
         # config full: poly(A) walks the raw samples of its window once (window ~ poly(A) span
         # + 2 * 200 refinement samples; here: 1/8 of the read as the per-read figure) and
         # writes one record; the chimera filter reads 14 B per event (start is implicit for
@@ -87,9 +89,10 @@ def mufu_per_read(L, stride=15, trim=300, scaler_len=30000):
     return {
         'k_lstm_tc_demux_l1': 7 * 48 * 2 * trim,
         'k_lstm_tc_demux_l2': 7 * 64 * trim,
-        'k_lstm_tc_demux_l2_probe': 5 * 64 * trim,
+        'k_lstm_tc_demux_l2_probe': 2 * 5 * 64 * trim,          # both probes (one launch, or two)
         'k_lstm_tc_scaler_l1': 7 * 48 * H,
         'k_lstm_tc_scaler_l2': 7 * 48 * H,
+        'k_lstm_tc_scaler': 2 * 7 * 48 * H,
     }
 
 

@@ -78,7 +78,8 @@ static const char *const kKernelNames[K_NUM] = {
     "k_windows", "k_demux_l1", "k_demux_l2", "k_finalize", "k_counts", "misc", "k_polya",
     "k_unsplit_windows", "k_unsplit_decide", "k_event_means", "k_lstm_tc_demux_l1",
     "k_lstm_tc_demux_l2", "k_demux_head_tc", "k_lstm_tc_scaler_l1", "k_lstm_tc_scaler_l2",
-    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe", "k_event_pos", "k_svb16_decode"};
+    "k_scaler_head_tc", "k_lstm_tc_demux_l2_probe", "k_event_pos", "k_svb16_decode",
+    "k_lstm_tc_scaler"};
 
 static void ws_free(Workspace &w)
 {

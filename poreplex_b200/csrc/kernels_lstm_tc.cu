@@ -1356,7 +1356,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         A.T = thead; A.n = n; A.row0 = 0;
         A.tab = S.zero_prefix; A.tab_stride = 4 * H;
         A.err = err;
-        PB_LAUNCH(ctx, K_SCALER_TC_L2, "k_lstm_tc_scaler2", st,
+        PB_LAUNCH(ctx, K_SCALER_TC, "k_lstm_tc_scaler2", st,
             k_lstm_tc_scaler2<H><<<dim3((unsigned)tiles, 1), 128 * 3 + 32, tc_scaler2_smem_bytes<H>(), st>>>(A));
     } else
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {

@@ -70,7 +70,8 @@ namespace pb {
 enum KernelId { K_POOL = 0, K_SCALER_PREPARE, K_SCALER_LSTM, K_SEGMENT, K_VITERBI_PATHS,
                 K_WINDOWS, K_DEMUX_L1, K_DEMUX_L2, K_FINALIZE, K_COUNTS, K_MISC, K_POLYA, K_UNSPLIT_WINDOWS,
                 K_UNSPLIT_DECIDE, K_EVENT_MEANS, K_DEMUX_TC_L1, K_DEMUX_TC_L2, K_DEMUX_TC_HEAD,
-                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_EVENT_POS, K_SVB_DECODE, K_NUM };
+                K_SCALER_TC_L1, K_SCALER_TC_L2, K_SCALER_TC_HEAD, K_DEMUX_TC_PROBE, K_EVENT_POS, K_SVB_DECODE,
+                K_SCALER_TC, K_NUM };
 struct ProfEvent { int id; cudaEvent_t a, b; };
 }
 

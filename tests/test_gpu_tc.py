@@ -284,3 +284,4 @@ def test_fused_scaler_equals_two_kernel_scaler(eng_short, preset_short, monkeypa
     for k, v in fused.items():
         assert np.array_equal(v, split[k], equal_nan=True) if v.dtype.kind == 'f' \
             else np.array_equal(v, split[k]), k
+
