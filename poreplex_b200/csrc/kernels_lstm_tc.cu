@@ -831,12 +831,15 @@ k_lstm_tc_probes(const TcArgs A)
 // Same products in the same order per accumulator column, same gate code as
 // k_lstm_tc<H,0,true> + k_lstm_tc<H,H,false>: bit-identical final states
 // (tests/test_gpu_tc.py::test_fused_scaler_equals_two_kernel_scaler).
+#ifndef PB_TC_SCALER2_NP
+#define PB_TC_SCALER2_NP 6
+#endif
 template <int H>
-__global__ void __launch_bounds__(128 * 3 + 32, 1)
+__global__ void __launch_bounds__(128 * PB_TC_SCALER2_NP + 32, 1)
 k_lstm_tc_scaler2(const TcArgs A)
 {
     constexpr int N = 4 * H;
-    constexpr int NP = 3;
+    constexpr int NP = PB_TC_SCALER2_NP;
     constexpr int NGW = 4 * NP;
     constexpr int NTHR = 128 * NP + 32;
     constexpr int UPT = H / NP;
@@ -1357,7 +1360,7 @@ int launch_scaler_tc(pb2_context *ctx, const pb2_batch &b, const float *pooled, 
         A.tab = S.zero_prefix; A.tab_stride = 4 * H;
         A.err = err;
         PB_LAUNCH(ctx, K_SCALER_TC, "k_lstm_tc_scaler2", st,
-            k_lstm_tc_scaler2<H><<<dim3((unsigned)tiles, 1), 128 * 3 + 32, tc_scaler2_smem_bytes<H>(), st>>>(A));
+            k_lstm_tc_scaler2<H><<<dim3((unsigned)tiles, 1), 128 * PB_TC_SCALER2_NP + 32, tc_scaler2_smem_bytes<H>(), st>>>(A));
     } else
     for (int64_t t0 = 0; t0 < tiles; t0 += tiles_per_pass) {
         const int64_t nt = (tiles - t0 < tiles_per_pass) ? tiles - t0 : tiles_per_pass;
