@@ -108,10 +108,13 @@ constexpr size_t tc_smem_bytes() {
     return (tc_tmem_cols<H, KX>() == 512 && need < (size_t)116 * 1024) ? (size_t)116 * 1024 : need;
 }
 
+#ifndef PB_TC_SCALAR_NP
+#define PB_TC_SCALAR_NP 2          // 3 measured: no change (46.7 vs 45.4 ms on a 2 % slower box)
+#endif
 // gate warps per lane quarter: layers alone on their SM (vector input, 512 TMEM columns) use
 // four so that 16 warps hide the MUFU / FMA latencies; scalar-input layers run two CTAs per SM
 // (units per thread must be a multiple of 8: H = 48 with a vector input uses three)
-template <int H, int KX> __host__ __device__ constexpr int tc_nparts() { return KX == 0 ? 2 : (H % 32 == 0 ? 4 : 3); }
+template <int H, int KX> __host__ __device__ constexpr int tc_nparts() { return KX == 0 ? PB_TC_SCALAR_NP : (H % 32 == 0 ? 4 : 3); }
 template <int H, int KX> __host__ __device__ constexpr int tc_threads() { return 128 * tc_nparts<H, KX>() + 32; }
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
