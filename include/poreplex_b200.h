@@ -272,7 +272,12 @@ int pb2_set_unsplit(pb2_context *ctx, const pb2_hmm_params *hmm, const pb2_unspl
  * pointers; work is enqueued on `stream` (a cudaStream_t) and not synchronised. */
 int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
                        uint32_t flags, void *stream);
-/* Same with HOST buffers: copies in, runs, copies out, synchronises. */
+/* Same with HOST buffers: copies in, runs, copies out, synchronises.  Batches of >= 65536 reads
+ * and >= 256 Mi samples whose reads lie in ascending, non-overlapping order in `raw` are uploaded
+ * in chunks that overlap the kernels (whole batch resident on the device; batches over a quarter
+ * of the device memory go through two chunk-sized arenas instead); pinned host buffers make the
+ * copies asynchronous.  Results do not depend on the chunking except for the approximate floats
+ * of the `fast` mode (pb2_set_fast_lstm). */
 int pb2_analyze_host(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
                      uint32_t flags);
 

@@ -1436,8 +1436,9 @@ static int analyze_host_pipelined(pb2_context *ctx, const pb2_batch *hb, const p
 // its upload has landed and overlap the uploads of the chunks behind it.  In `fast` mode only
 // the tensor-core half runs per chunk; the reads any chunk flagged are resolved by the exact
 // kernels as ONE sub-batch at the end (a sub-batch per chunk ends on a partly filled wave of the
-// long exact CTAs every time, which cost 20-30 ms per million reads), then label + counts run
-// over the whole batch and the results go back in one go (124 B per read).
+// long exact CTAs every time, which cost 20-30 ms per million reads) -- or as two, the first half
+// way through when the GPU is found waiting for the bus there -- then the counts run over the
+// whole batch and the results go back in one go (124 B per read).
 // Chunks are small at both ends and large in the middle (plan_chunks): a small first chunk
 // because its upload is the one nothing hides, a small last one because its kernels are what
 // nothing hides when the bus is the slower side (several GPUs sharing the host's PCIe uplinks).
@@ -1475,7 +1476,7 @@ static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb
     const size_t o_pr = take(4 * PB2_MAX_CLASSES * m), o_cnt = take(8 * n_bins);
     const size_t o_polya = take(want_polya ? sizeof(pb2_polya_result) * m : 16);
     const size_t o_pushed = take(4 * m);
-    const size_t o_unsafe = take(4 * m), o_fcnt = take(16), o_list = take(4 * m);
+    const size_t o_unsafe = take(4 * m), o_fcnt = take(64), o_list = take(4 * m);
     char *A = (char *)ws_get(ctx, ctx->ws_batch, off);
     float *pooled = (float *)ws_get(ctx, ctx->ws_pooled,
                                     sizeof(float) * ((size_t)(hb->n_raw_total / stride) + 2));
@@ -1556,6 +1557,32 @@ static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb
             PB_CUDA(ctx, cudaMemsetAsync(dr.class_probs, 0, 4 * PB2_MAX_CLASSES * m, compute));
         }
         ctx->last_rerun_reads = 0;
+        // exact re-run of the flagged reads of [r0, r1) (label included; counts come at the end)
+        int64_t resolved = 0, reruns = 0, causes[3] = {0, 0, 0};
+        auto resolve_range = [&](int64_t r0, int64_t r1, int slot) -> int {
+            if (r1 <= r0) return PB2_OK;
+            pb2_batch rb = db;
+            rb.n_reads = r1 - r0;
+            rb.raw_offsets = db.raw_offsets + r0; rb.raw_lengths = db.raw_lengths + r0;
+            rb.range = db.range + r0; rb.digitisation = db.digitisation + r0; rb.offset = db.offset + r0;
+            pb2_results rr = {};
+            rr.class_probs = dr.class_probs + (size_t)PB2_MAX_CLASSES * r0;
+            FastArrays fr = {fa.unsafe + r0, fa.pushed + r0, dr.barcode + r0, dr.barcode_guess + r0,
+                             dr.barcode_score + r0};
+            int rc2 = analyze_fast_resolve(ctx, &rb, &rr, flags, compute, pooled, dr.status + r0, dr.label + r0,
+                                           dr.scale_shift + 2 * r0, dr.segments + 2 * PB2_MAX_STATES * r0, fr,
+                                           (int *)(A + o_fcnt) + 8 * slot, (int32_t *)(A + o_list) + r0);
+            reruns += ctx->last_rerun_reads;
+            for (int i = 0; i < 3; i++) causes[i] += ctx->last_rerun_cause[i];
+            return rc2;
+        };
+        // When the bus is the slower side (several GPUs behind shared PCIe uplinks) the GPU waits for
+        // uploads in the middle of the batch and the single re-run at the end is fully exposed: half
+        // way, once the kernels of the chunks so far are done, look whether the next upload has
+        // landed; if not, the flagged reads so far are re-run now, inside that wait.
+        const char *er_env = getenv("POREPLEX_B200_HOST_EARLY_RESOLVE");       // 0 never, 1 always (tests)
+        const int early_mode = er_env ? atoi(er_env) : -1;
+        const int mid = (fast && nchunks >= 4 && early_mode != 0) ? nchunks / 2 - 1 : -1;
         for (int c = 0; c < nchunks; c++) {
             const int64_t c0 = bounds[c], nc = bounds[c + 1] - c0;
             pb2_batch cb = db;                       // a range of reads of the resident batch
@@ -1584,14 +1611,22 @@ static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb
                 return rc;
             }
             if (c + 2 < nchunks && (rc = upload(c + 2))) return rc;
+            if (c == mid) {
+                PB_CUDA(ctx, cudaStreamSynchronize(compute));
+                const cudaError_t q = cudaEventQuery(ev[(size_t)c + 1]);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return check_cuda(ctx, q, "cudaEventQuery");
+                if (q == cudaErrorNotReady || early_mode == 1) {
+                    if ((rc = resolve_range(0, bounds[c + 1], 0))) return rc;
+                    resolved = bounds[c + 1];
+                }
+            }
         }
         if (fast) {
-            if ((rc = analyze_fast_resolve(ctx, &db, &dr, flags, compute, pooled, dr.status, dr.label,
-                                           dr.scale_shift, dr.segments, fa, (int *)(A + o_fcnt),
-                                           (int32_t *)(A + o_list)))) return rc;
-        } else if ((rc = launch_counts(ctx, dr.status, dr.label, dr.barcode, n, dr.counts, compute))) {
-            return rc;
+            if ((rc = resolve_range(resolved, n, 1))) return rc;
+            ctx->last_rerun_reads = reruns;
+            for (int i = 0; i < 3; i++) ctx->last_rerun_cause[i] = causes[i];
         }
+        if ((rc = launch_counts(ctx, dr.status, dr.label, dr.barcode, n, dr.counts, compute))) return rc;
 #define PB_D2H(field, bytes)                                                                 \
         if (hr->field && (bytes) > 0)                                                        \
             PB_CUDA(ctx, cudaMemcpyAsync(hr->field, dr.field, (bytes), cudaMemcpyDeviceToHost, compute))

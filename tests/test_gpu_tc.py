@@ -128,21 +128,25 @@ def test_tc_whole_path_integer_outputs_equal_exact(eng_short, preset_short, monk
     # whole batch resident and resolves the unsafe reads of all chunks as one sub-batch at the end;
     # `arena` resolves them chunk by chunk.
     other = synth.to_numpy(synth.generate_reads(n, synth.SynthSpec.for_length(4000), preset_short, seed=32))
-    for pipeline in ('streamed', 'arena'):
+    for pipeline in ('streamed', 'streamed-early', 'arena'):
         # a different batch first: nothing may be taken from scratch a previous call left behind
         eng_short.analyze_host(other['raw'].reshape(-1), *args[1:3], other['range'], other['digitisation'],
                                other['offset'])
         monkeypatch.setenv('POREPLEX_B200_HOST_CHUNK_ELEMS', str(1_000_000))
-        monkeypatch.setenv('POREPLEX_B200_HOST_PIPELINE', pipeline)
+        monkeypatch.setenv('POREPLEX_B200_HOST_PIPELINE', pipeline.split('-')[0])
+        # streamed-early: the flagged reads of the first half are re-run half way through (what the
+        # path does on its own when it finds the GPU waiting for the bus there), the rest at the end
+        monkeypatch.setenv('POREPLEX_B200_HOST_EARLY_RESOLVE', '1' if pipeline.endswith('early') else '0')
         piped = eng_short.analyze_host(*args)
         rerun_p = eng_short.recheck_stats()[0]
         monkeypatch.delenv('POREPLEX_B200_HOST_CHUNK_ELEMS')
         monkeypatch.delenv('POREPLEX_B200_HOST_PIPELINE')
+        monkeypatch.delenv('POREPLEX_B200_HOST_EARLY_RESOLVE')
         for k in ('status', 'segments', 'barcode', 'barcode_guess', 'barcode_score', 'counts', 'label'):
             assert np.array_equal(piped[k], exact[k]), (pipeline, k)
         dp = np.abs(piped['scale_shift'].astype(np.float64) - exact['scale_shift'])
         assert dp[:, 0].max() <= 3.4e-5 and dp[:, 1].max() <= 1.5e-2
-        if pipeline == 'streamed':
+        if pipeline.startswith('streamed'):
             assert 0 < rerun_p < 0.35 * n and (dp.max(1) == 0).sum() >= rerun_p
 
 

@@ -20,8 +20,9 @@ pk, po = fast5_loader.svb16_encode(raw, off, ln, pinned=True)
 out = eng.alloc_host_results(n, pinned=True)
 res = {}
 ref = None
-for pipeline in ('streamed', 'arena', 'streamed'):
-    os.environ['POREPLEX_B200_HOST_PIPELINE'] = pipeline
+for pipeline in ('streamed', 'streamed-early', 'arena', 'streamed'):
+    os.environ['POREPLEX_B200_HOST_PIPELINE'] = pipeline.split('-')[0]
+    os.environ['POREPLEX_B200_HOST_EARLY_RESOLVE'] = '1' if pipeline.endswith('early') else '-1'
     for name, fn in (('int16', lambda: eng.analyze_host(raw, off, ln, *cal, out=out)),
                      ('packed', lambda: eng.analyze_host(None, off, ln, *cal, out=out, packed=(pk, po)))):
         r = fn()
