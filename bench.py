@@ -714,7 +714,10 @@ def main():
                                 'uploaded in 8 chunks (1 2 4 6 6 4 2 1) whose tensor-core kernels overlap the '
                                 'uploads behind them, one exact re-run over all chunks, one download)' +
                                 ('; the chimera filter of config full is not part of this call' if full else '')}
-        assert np.array_equal(res['status'], status), 'e2e and device-resident paths disagree'
+        assert np.array_equal(res['status'], status) and np.array_equal(res['segments'], seg_np), \
+            'e2e and device-resident paths disagree'
+        for k_ in ('barcode', 'barcode_guess', 'barcode_score', 'label'):
+            assert np.array_equal(res[k_], out[k_].cpu().numpy()), 'e2e and device-resident paths disagree: ' + k_
 
         # ---- the same call with the compressed upload: the streamvbyte-16 bodies of the reads
         # (what a VBZ FAST5 holds under its zstd stage) cross the bus instead of int16 samples

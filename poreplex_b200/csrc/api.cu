@@ -1502,16 +1502,15 @@ static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb
 
     std::vector<cudaEvent_t> ev((size_t)nchunks + 1, nullptr);
     for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    std::vector<int64_t> max_lens((size_t)nchunks, 0);
-    int64_t max_len_all = 0;
-    for (int c = 0; c < nchunks; c++) {
+    // longest read per chunk (sizes the grids): found chunk by chunk while earlier chunks are in flight
+    db.max_raw_length = 0;
+    auto chunk_max_len = [&](int c) {
         int64_t ml = 0;
         for (int64_t i = bounds[c]; i < bounds[c + 1]; i++)
             if (hb->raw_lengths[i] > ml) ml = hb->raw_lengths[i];
-        max_lens[c] = ml;
-        if (ml > max_len_all) max_len_all = ml;
-    }
-    db.max_raw_length = max_len_all;
+        if (ml > db.max_raw_length) db.max_raw_length = ml;
+        return ml;
+    };
 
     int svb_err = 0;
     auto run = [&]() -> int {
@@ -1586,7 +1585,7 @@ static int analyze_host_streamed(pb2_context *ctx, const pb2_batch *hb, const pb
         for (int c = 0; c < nchunks; c++) {
             const int64_t c0 = bounds[c], nc = bounds[c + 1] - c0;
             pb2_batch cb = db;                       // a range of reads of the resident batch
-            cb.n_reads = nc; cb.max_raw_length = max_lens[c];
+            cb.n_reads = nc; cb.max_raw_length = chunk_max_len(c);
             cb.raw_offsets = db.raw_offsets + c0; cb.raw_lengths = db.raw_lengths + c0;
             cb.range = db.range + c0; cb.digitisation = db.digitisation + c0; cb.offset = db.offset + c0;
             pb2_results cr = {};
