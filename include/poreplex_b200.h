@@ -424,6 +424,12 @@ int pb2_profile_enable(pb2_context *ctx, int on);
 int pb2_profile_kernel_count(void);
 const char *pb2_profile_kernel_name(int kernel_id);
 int pb2_profile_read(pb2_context *ctx, double *total_ms, int64_t *launches, int n_kernels);
+/* The same records as a time line instead of sums (and, like pb2_profile_read, consumed by the
+ * call): kernel id, start and end of every launch in milliseconds after the first launch's start,
+ * in launch order; at most `capacity` entries, *n_out = entries written.  Shows where a stream
+ * sat idle between launches (tools/host_path_profile.py). */
+int pb2_profile_timeline(pb2_context *ctx, int32_t *ids, double *start_ms, double *end_ms,
+                         int64_t capacity, int64_t *n_out);
 
 #ifdef __cplusplus
 }

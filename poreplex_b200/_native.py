@@ -138,7 +138,7 @@ EXPORTS = ['pb2_abi_version', 'pb2_create', 'pb2_destroy', 'pb2_last_error', 'pb
            'pb2_viterbi_paths', 'pb2_barcode_windows', 'pb2_demux_predict',
            'pb2_scaler_predict', 'pb2_count_results', 'pb2_kernel_launches',
            'pb2_profile_enable', 'pb2_profile_kernel_count', 'pb2_profile_kernel_name',
-           'pb2_profile_read', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
+           'pb2_profile_read', 'pb2_profile_timeline', 'pb2_set_exact_division', 'pb2_set_polya', 'pb2_measure_polya',
            'pb2_set_unsplit', 'pb2_detect_unsplit', 'pb2_detect_unsplit_host',
            'pb2_set_fast_lstm', 'pb2_demux_predict_tc', 'pb2_recheck_stats', 'pb2_debug_demux_l1', 'pb2_rerun_causes', 'pb2_set_audit_fraction',
            'pb2_audit_stats', 'pb2_detect_events', 'pb2_derive_event_tables',
@@ -232,6 +232,7 @@ def load():
     L.pb2_profile_kernel_name.argtypes = [C.c_int]
     L.pb2_profile_kernel_name.restype = C.c_char_p
     L.pb2_profile_read.argtypes = [vp, _dp, _i64p, C.c_int]
+    L.pb2_profile_timeline.argtypes = [vp, C.POINTER(C.c_int32), _dp, _dp, C.c_int64, _i64p]
     if L.pb2_abi_version() != 1:
         raise RuntimeError('poreplex_b200: ABI version mismatch')
     _lib = L

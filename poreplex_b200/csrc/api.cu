@@ -337,6 +337,30 @@ int pb2_profile_read(pb2_context *ctx, double *total_ms, int64_t *launches, int 
     return PB2_OK;
 }
 
+int pb2_profile_timeline(pb2_context *ctx, int32_t *ids, double *start_ms, double *end_ms,
+                         int64_t capacity, int64_t *n_out)
+{
+    if (!ctx || !ids || !start_ms || !end_ms || !n_out) return PB2_EINVAL;
+    DeviceGuard g(ctx->device);
+    PB_CUDA(ctx, cudaDeviceSynchronize());
+    int64_t k = 0;
+    const cudaEvent_t t0 = ctx->prof_events.empty() ? nullptr : ctx->prof_events.front().a;
+    for (const ProfEvent &pe : ctx->prof_events) {
+        float a = 0.f, b = 0.f;
+        if (k < capacity && cudaEventElapsedTime(&a, t0, pe.a) == cudaSuccess &&
+            cudaEventElapsedTime(&b, t0, pe.b) == cudaSuccess) {
+            ids[k] = pe.id; start_ms[k] = a; end_ms[k] = b;
+            k++;
+        }
+        ctx->prof_pool.push_back(pe.a);
+        ctx->prof_pool.push_back(pe.b);
+    }
+    ctx->prof_events.clear();
+    cudaGetLastError();
+    *n_out = k;
+    return PB2_OK;
+}
+
 int pb2_set_scaler(pb2_context *ctx, const pb2_scaler_params *p)
 {
     if (!ctx || !p) return PB2_EINVAL;
@@ -888,9 +912,10 @@ static int analyze_fast_tentative(pb2_context *ctx, const pb2_batch *batch, cons
     // segmentation at the three corners of the uncertainty triangle
     PB_CUDA(ctx, cudaMemcpyAsync(st1, status, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
     PB_CUDA(ctx, cudaMemcpyAsync(st2, status, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_segment(ctx, *batch, pooled, ssv, status, segments, nullptr, st))) return rc;
-    if ((rc = launch_segment(ctx, *batch, pooled, ssv + 2 * n, st1, sg1, nullptr, st))) return rc;
-    if ((rc = launch_segment(ctx, *batch, pooled, ssv + 4 * n, st2, sg2, nullptr, st))) return rc;
+    {
+        int32_t *const st3[3] = {status, st1, st2}, *const sg3[3] = {segments, sg1, sg2};
+        if ((rc = launch_segment3(ctx, *batch, pooled, ssv, st3, sg3, st))) return rc;
+    }
     if ((rc = launch_compare_corners(ctx, n, status, st1, st2, segments, sg1, sg2, unsafe, st))) return rc;
 
     if (bcd) {

@@ -32,16 +32,30 @@ constexpr uint32_t SEG_STOCK_NCOMP = 0x211112;      // mixture components: adapt
 constexpr uint64_t SEG_STOCK_EDGES =
     (0x03ull << 0) | (0x06ull << 8) | (0x14ull << 16) | (0x09ull << 24) | (0x10ull << 32) | (0x29ull << 40);
 
+// One launch decodes the same reads under up to three (scale, shift) sets -- blockIdx.y selects:
+// the tensor-core path decodes every read at the three corners of its uncertainty triangle
+// (DESIGN.md 3a), and one grid of 3 n threads fills the machine where three grids of n do not
+// (a chunk of a host batch is a fraction of a wave of this kernel).
+struct SegSets {
+    const float *scale_shift[3];
+    int32_t *status[3];
+    int32_t *segments[3];
+};
+
 template <uint64_t EDGES, int NS>
 __global__ void __launch_bounds__(VT_THREADS)
 k_segment(const HmmDev M, const HmmMask K, const int64_t *__restrict__ raw_offsets,
           const int64_t *__restrict__ raw_lengths, const float *__restrict__ pooled,
-          const float *__restrict__ scale_shift, int64_t r0, int64_t n_chunk, int stride,
-          int scan_limit, int adapter_state, uint32_t *__restrict__ bp, int32_t *status,
-          int32_t *__restrict__ segments, float *__restrict__ pooled_scaled_out)
+          const SegSets S, int64_t r0, int64_t n_chunk, int stride,
+          int scan_limit, int adapter_state, uint32_t *__restrict__ bp, int64_t bp_set_stride,
+          float *__restrict__ pooled_scaled_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chunk) return;
+    const float *__restrict__ scale_shift = S.scale_shift[blockIdx.y];
+    int32_t *status = S.status[blockIdx.y];
+    int32_t *__restrict__ segments = S.segments[blockIdx.y];
+    bp += (int64_t)blockIdx.y * bp_set_stride;
     const int64_t r = r0 + i;
     int32_t *seg = segments + r * PB2_MAX_STATES * 2;
 #pragma unroll
@@ -93,9 +107,8 @@ k_segment(const HmmDev M, const HmmMask K, const int64_t *__restrict__ raw_offse
     if (!(seen & (1u << adapter_state))) status[r] = PB2_ST_ADAPTER_NOT_DETECTED;
 }
 
-int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
-                   const float *scale_shift, int32_t *status, int32_t *segments,
-                   float *pooled_scaled_out, cudaStream_t st)
+static int launch_segment_sets(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                               const SegSets &S, int n_sets, float *pooled_scaled_out, cudaStream_t st)
 {
     if (b.n_reads <= 0) return PB2_OK;
     HmmMask K;
@@ -106,31 +119,48 @@ int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
     if (b.max_raw_length > 0 && b.max_raw_length / ctx->scaler.stride < Tmax)
         Tmax = b.max_raw_length / ctx->scaler.stride;
     if (Tmax < 1) Tmax = 1;
-    // back-pointer scratch is [Tmax][chunk] words; bound it to ~2 GiB per launch
+    // back-pointer scratch is [set][Tmax][chunk] words; bound it to ~2 GiB per set and launch
     int64_t chunk = ((int64_t)2 << 30) / (Tmax * 4);
     chunk = (chunk / VT_THREADS) * VT_THREADS;
     if (chunk < VT_THREADS) chunk = VT_THREADS;
     if (chunk > b.n_reads) chunk = b.n_reads;
-    uint32_t *bp = (uint32_t *)ws_get(ctx, ctx->ws_bp, (size_t)chunk * Tmax * 4);
+    uint32_t *bp = (uint32_t *)ws_get(ctx, ctx->ws_bp, (size_t)chunk * Tmax * 4 * n_sets);
     if (!bp) return PB2_ENOMEM;
+    const int64_t set_stride = chunk * Tmax;
     for (int64_t r0 = 0; r0 < b.n_reads; r0 += chunk) {
         const int64_t nc = (b.n_reads - r0 < chunk) ? b.n_reads - r0 : chunk;
-        const unsigned grid = (unsigned)((nc + VT_THREADS - 1) / VT_THREADS);
+        const dim3 grid((unsigned)((nc + VT_THREADS - 1) / VT_THREADS), (unsigned)n_sets);
         if (stock_topology) {
             PB_LAUNCH(ctx, K_SEGMENT, "k_segment<stock>", st,
                 k_segment<SEG_STOCK_EDGES, 6><<<grid, VT_THREADS, 0, st>>>(
-                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
-                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
-                pooled_scaled_out));
+                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, S, r0, nc,
+                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, set_stride, pooled_scaled_out));
         } else {
             PB_LAUNCH(ctx, K_SEGMENT, "k_segment", st,
                 k_segment<0, 0><<<grid, VT_THREADS, 0, st>>>(
-                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, scale_shift, r0, nc,
-                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, status, segments,
-                pooled_scaled_out));
+                ctx->seg_hmm, K, b.raw_offsets, b.raw_lengths, pooled, S, r0, nc,
+                ctx->scaler.stride, (int)Tmax, ctx->adapter_state, bp, set_stride, pooled_scaled_out));
         }
     }
     return PB2_OK;
+}
+
+int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
+                   const float *scale_shift, int32_t *status, int32_t *segments,
+                   float *pooled_scaled_out, cudaStream_t st)
+{
+    SegSets S = {{scale_shift, nullptr, nullptr}, {status, nullptr, nullptr}, {segments, nullptr, nullptr}};
+    return launch_segment_sets(ctx, b, pooled, S, 1, pooled_scaled_out, st);
+}
+
+// the three corner decodings of the tensor-core path in one launch; ss3 = [3][n][2]
+int launch_segment3(pb2_context *ctx, const pb2_batch &b, const float *pooled, const float *ss3,
+                    int32_t *const status[3], int32_t *const segments[3], cudaStream_t st)
+{
+    const int64_t n = b.n_reads;
+    SegSets S = {{ss3, ss3 + 2 * n, ss3 + 4 * n}, {status[0], status[1], status[2]},
+                 {segments[0], segments[1], segments[2]}};
+    return launch_segment_sets(ctx, b, pooled, S, 3, nullptr, st);
 }
 
 // ---------------------------------------------------------------------------

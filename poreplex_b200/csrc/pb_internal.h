@@ -191,6 +191,8 @@ int build_pad_tables(pb2_context *ctx);
 int launch_segment(pb2_context *ctx, const pb2_batch &b, const float *pooled,
                    const float *scale_shift, int32_t *status, int32_t *segments,
                    float *pooled_scaled_out, cudaStream_t st);
+int launch_segment3(pb2_context *ctx, const pb2_batch &b, const float *pooled, const float *ss3,
+                    int32_t *const status[3], int32_t *const segments[3], cudaStream_t st);
 int launch_viterbi_paths(pb2_context *ctx, const HmmDev &hmm, const float *x,
                          const int32_t *lengths, int64_t n, int32_t ld, int32_t *path,
                          double *logp, cudaStream_t st);

@@ -281,6 +281,16 @@ class SignalEngine:
         return {self.lib.pb2_profile_kernel_name(i).decode(): (ms[i], int(cnt[i]))
                 for i in range(k) if cnt[i]}
 
+    def profile_timeline(self, capacity=4096):
+        """[(kernel name, start ms, end ms)] of every launch since the last read, in launch order,
+        times relative to the first launch (synchronises; consumes the records)."""
+        ids = (C.c_int32 * capacity)()
+        a = (C.c_double * capacity)()
+        b = (C.c_double * capacity)()
+        n = C.c_int64(0)
+        self._check(self.lib.pb2_profile_timeline(self.handle, ids, a, b, capacity, C.byref(n)))
+        return [(self.lib.pb2_profile_kernel_name(ids[i]).decode(), a[i], b[i]) for i in range(n.value)]
+
     def pooled_offsets(self, raw_offsets):
         """Element offset of each read inside a pooled buffer (same rule as the kernels)."""
         return (np.asarray(raw_offsets, np.int64) + self.stride - 1) // self.stride
