@@ -269,7 +269,10 @@ int pb2_set_unsplit(pb2_context *ctx, const pb2_hmm_params *hmm, const pb2_unspl
 /* SignalAnalyzer.process stages A-D for the numeric outputs (signal_analyzer.py:82-134):
  * load_padded_signal_head -> fit_scalers -> load_signal(pool) -> detect_segments ->
  * [push_barcode_signal -> demuxer.predict] -> counts.  `batch`/`res` hold DEVICE
- * pointers; work is enqueued on `stream` (a cudaStream_t) and not synchronised. */
+ * pointers; work is enqueued on `stream` (a cudaStream_t) and not synchronised -- except in the
+ * `fast` mode (pb2_set_fast_lstm), where the call waits once on `stream` for the number of reads
+ * the guards sent to the exact re-run (it sizes the sub-batch launches from it): the kernels
+ * before that point have finished when it returns, the re-run, labels and counts have not. */
 int pb2_analyze_device(pb2_context *ctx, const pb2_batch *batch, const pb2_results *res,
                        uint32_t flags, void *stream);
 /* Same with HOST buffers: copies in, runs, copies out, synchronises.  Batches of >= 65536 reads

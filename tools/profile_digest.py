@@ -21,7 +21,8 @@ ROWS = (('k_pool', r'k_pool<', 'reads'), ('k_windows', r'k_windows\(', 'reads'),
 
 def shares(csv_path, out):
     tot, per = 0.0, {}
-    for r in csv.DictReader(open(csv_path)):
+    # ncu's --log-file starts with its own ==PROF== / ==WARNING== lines
+    for r in csv.DictReader(l for l in open(csv_path) if not l.startswith('==')):
         if r.get('Metric Name') != 'gpu__time_duration.sum':
             continue
         name = re.sub(r'\(.*', '', r['Kernel Name']).replace('void ', '').replace('pb::', '')
