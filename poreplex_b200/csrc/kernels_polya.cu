@@ -14,6 +14,9 @@ static_assert(sizeof(PolyaResult) == sizeof(pb2_polya_result), "PolyaResult mirr
 
 constexpr int POLYA_THREADS = 64;
 
+// NESTED: the literal one-loop-per-walk formulation (polya_analyze_nested), kept for comparison
+// (POREPLEX_B200_POLYA_NESTED=1); the default is the single-loop one (polya_core.cuh).
+template <bool NESTED>
 __global__ void __launch_bounds__(POLYA_THREADS)
 k_polya(const PolyaParams P, const int16_t *__restrict__ raw,
         const int64_t *__restrict__ raw_offsets, const int64_t *__restrict__ raw_lengths,
@@ -41,8 +44,12 @@ k_polya(const PolyaParams P, const int16_t *__restrict__ raw,
     }
     const double gain = pb::ddiv(range[r], digitisation[r]);
     // event replay cache: slot k of read r at cache[k * n + r] (coalesced across the warp)
-    polya_analyze(P, raw + raw_offsets[r], raw_lengths[r], gain, offset[r], scale_shift[2 * r],
-                  scale_shift[2 * r + 1], rb, re, R, cache ? cache + r : nullptr, n, cache_cap);
+    if (NESTED)
+        polya_analyze_nested(P, raw + raw_offsets[r], raw_lengths[r], gain, offset[r], scale_shift[2 * r],
+                             scale_shift[2 * r + 1], rb, re, R, cache ? cache + r : nullptr, n, cache_cap);
+    else
+        polya_analyze(P, raw + raw_offsets[r], raw_lengths[r], gain, offset[r], scale_shift[2 * r],
+                      scale_shift[2 * r + 1], rb, re, R, cache ? cache + r : nullptr, n, cache_cap);
 }
 
 int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
@@ -59,11 +66,16 @@ int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
         ? (EventCacheSlot *)ws_get(ctx, ctx->ws_polya, (size_t)cap * (size_t)b.n_reads * sizeof(EventCacheSlot))
         : nullptr;
     if (!cache) { cap = 0; cudaGetLastError(); }
-    PB_LAUNCH(ctx, K_POLYA, "k_polya", st,
-        k_polya<<<(unsigned)((b.n_reads + POLYA_THREADS - 1) / POLYA_THREADS), POLYA_THREADS, 0, st>>>(
-            P, b.raw, b.raw_offsets, b.raw_lengths, b.range, b.digitisation, b.offset, scale_shift,
-            status, segments, b.n_reads, ctx->adapter_state, ctx->polya_state,
-            reinterpret_cast<PolyaResult *>(out), cache, cap));
+    static const bool nested = [] { const char *e = getenv("POREPLEX_B200_POLYA_NESTED"); return e && e[0] == '1'; }();
+    const unsigned grid = (unsigned)((b.n_reads + POLYA_THREADS - 1) / POLYA_THREADS);
+#define PB_POLYA(NESTED)                                                                         \
+    PB_LAUNCH(ctx, K_POLYA, "k_polya", st,                                                       \
+        k_polya<NESTED><<<grid, POLYA_THREADS, 0, st>>>(                                         \
+            P, b.raw, b.raw_offsets, b.raw_lengths, b.range, b.digitisation, b.offset, scale_shift, \
+            status, segments, b.n_reads, ctx->adapter_state, ctx->polya_state,                   \
+            reinterpret_cast<PolyaResult *>(out), cache, cap))
+    if (nested) PB_POLYA(true); else PB_POLYA(false);
+#undef PB_POLYA
     return PB2_OK;
 }
 

@@ -415,7 +415,19 @@ PB_HD bool between_f32(float x, float lo, float hi) { return x >= lo && x <= hi;
 // ---- the whole of PolyASignalAnalyzer for one read --------------------------------
 // rough_begin / rough_end: pooled-sample range from the segmentation (rough_end < 0 =
 // None: no polya-tail state, polya.py:53-56,69-70).
-PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_length,
+//
+// Two formulations of the same computation.  polya_analyze_nested follows the reference's
+// control flow literally: one loop per walk over the window's events (anchors, count, sum,
+// interval search, second pass), each with its own copy of the event-stream step.  On the GPU
+// that costs a warp dearly: the reads of a warp take different routes (12 % recalibrate first,
+// some extend the window), every route runs its walks at its own code address, and the warp
+// executes the routes one after the other -- ncu: 9.9 of 32 lanes active per instruction, 37 %
+// of all instructions issued by a copy of the detector that 4 lanes were in.  polya_analyze
+// (below it) is the same computation as ONE loop with ONE event-stream step: which walk a read
+// is in is data (`walk`), so all lanes that are walking step together whatever their route, and
+// the sample loops of calc_internal_polya_stdv are two more walk kinds of the same loop.  Both
+// are kept: tests/hostcheck requires them to agree with the oracle and with each other.
+PB_HD void polya_analyze_nested(const PolyaParams &P, const int16_t *raw, int64_t full_length,
                          double gain, double offset, float scale, float shift,
                          int32_t rough_begin, int32_t rough_end_in, PolyaResult &R,
                          EventCacheSlot *cache = nullptr, int64_t cache_stride = 1,
@@ -634,6 +646,286 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
         if (!extend) return;
         rough_end_cur = rough_end + P.openend_unit;
         ext_depth++;
+    }
+}
+
+// ---- the same as one loop (see above) ------------------------------------------------
+PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_length,
+                         double gain, double offset, float scale, float shift,
+                         int32_t rough_begin, int32_t rough_end_in, PolyaResult &R,
+                         EventCacheSlot *cache = nullptr, int64_t cache_stride = 1,
+                         int cache_cap = 0)
+{
+    R.found = 0; R.n_spikes = 0; R.begin = 0; R.end = 0; R.dwell_samples = 0;
+    R.extensions = 0; R.flags = 0;
+    const int64_t stride = P.stride;
+    int64_t rough_end_cur = rough_end_in;         // < 0 : None
+    bool have_range = false;
+    float lo = P.cutoff_lo, hi = P.cutoff_hi;
+    int ext_depth = 0;
+    EvIter es;
+    es.attach(cache, cache_stride, cache_cap);
+    Event evs[2];
+
+    // what the loop does next: set up a window, start a call_polya / recalibration round, or
+    // advance the walk in progress by one event-stream step (W_ANCHORS .. W_SECOND) or by one
+    // sample (W_SD_MEAN, W_SD_VAR)
+    enum { DO_WINDOW = 0, DO_ROUND, W_ANCHORS, W_COUNT, W_SUM, W_FIND, W_SECOND, W_SD_MEAN, W_SD_VAR };
+    int walk = DO_WINDOW;
+
+    // window
+    WindowSource src;
+    src.raw = raw; src.gain = gain; src.offset = offset; src.scale = scale; src.shift = shift;
+    src.w0 = 0; src.n = 0; src.next = 0;
+    for (int k = 0; k < 7; k++) src.y[k] = 0.f;
+    int64_t rough_end = 0, insp_begin = 0, insp_end = 0, adapter_end = 0;
+    bool recal_mode = false;
+    int guard = 0;
+    // try_recalibrate_shifted_signal
+    float a_ml[64], a_len[64];
+    int na = 0;
+    int64_t npol = 0;
+    PairwiseSum sl;
+    // find_best_polya_interval
+    int64_t best = 0, best_i = -1, best_j = -1, best_npol = 0, j = 0;
+    bool alive = false;
+    int64_t Sv = 0, minP = 0, minI = -1, minCnt = 0, Pfx = 0, cnt = 0;
+    // second pass
+    PairwiseSum s_ml, s_len, s_dw;
+    uint64_t long_start = 0; float long_len = -1.0f;
+    uint64_t first_start = 0; int64_t last_end = 0;
+    int nsp = 0;
+    float prev_mean = 0.f;
+    int pending_spike = -1;
+    bool stop = false;
+    // calc_internal_polya_stdv
+    WindowSource ws = src;
+    PairwiseSum sd_sum;
+    int64_t sd_b = 0, sd_n = 0, sd_q = 0;
+    float sd_mu = 0.f;
+
+    for (;;) {
+        if (walk >= W_ANCHORS && walk <= W_SECOND) {
+            if (!es.finished() && !stop) {
+                // ---- one step of the event stream, events to the walk's consumer
+                const int ne = es.step(evs);
+                for (int q = 0; q < ne; q++) {
+                    const Event &ev = evs[q];
+                    if (walk == W_FIND) {
+                        // find_best_polya_interval as an O(E) scan (polya.py:156-187)
+                        const bool ip = between_f32(ev.mean, lo, hi);
+                        const double L = (double)ev.length;
+                        const double v = ip ? L : -L;
+                        const int64_t m = (v > 0) ? (int64_t)v : (int64_t)pb::dmul(v, P.spike_weight);
+                        const int64_t s = ip ? 1 : (int64_t)(-L);
+                        const int64_t Pprev = Pfx, cprev = cnt;
+                        Pfx += m;
+                        cnt += ip;
+                        if (alive) {
+                            Sv = (Sv < 0) ? -1 : (s > 0 ? P.spike_tolerance : Sv + s);
+                            if (Sv < 0) alive = false;
+                        }
+                        const int64_t Sjj = (s > 0) ? P.spike_tolerance : s;
+                        if (Sjj >= 0) {
+                            if (!alive) { alive = true; Sv = Sjj; minP = Pprev; minI = j; minCnt = cprev; }
+                            else if (Pprev < minP) { minP = Pprev; minI = j; minCnt = cprev; }
+                        }
+                        if (alive && Sv > 0) {
+                            const int64_t val = Pfx - minP;
+                            if (val > best) { best = val; best_i = minI; best_j = j; best_npol = cnt - minCnt; }
+                        }
+                        j++;
+                    } else if (walk == W_SECOND) {
+                        if (j > best_j) { stop = true; break; }
+                        if (j >= best_i) {
+                            const bool ip = between_f32(ev.mean, lo, hi);
+                            s_ml.push(pb::fmul(ev.mean, ev.length));
+                            s_len.push(ev.length);
+                            if (ip) s_dw.push(ev.length);
+                            if (ev.length > long_len) { long_len = ev.length; long_start = ev.start; }
+                            if (j == best_i) first_start = ev.start;
+                            if (j == best_j)
+                                last_end = (int64_t)pb::dadd((double)ev.start, (double)ev.length);
+                            if (pending_spike >= 0) {
+                                if (pending_spike < POLYA_MAX_SPIKES) R.spikes[pending_spike][3] = ev.mean;
+                                pending_spike = -1;
+                            }
+                            if (!ip) {
+                                if (nsp < POLYA_MAX_SPIKES) {
+                                    R.spikes[nsp][0] = ev.length;
+                                    R.spikes[nsp][1] = (j > best_i) ? prev_mean : NAN;
+                                    R.spikes[nsp][2] = ev.mean;
+                                    R.spikes[nsp][3] = NAN;
+                                }
+                                pending_spike = nsp;
+                                nsp++;
+                            }
+                            prev_mean = ev.mean;
+                        }
+                        j++;
+                    } else if (walk == W_ANCHORS) {
+                        // try_recalibrate_shifted_signal (polya.py:127-148): anchor events
+                        if ((int64_t)ev.start <= adapter_end + P.recal_max_dist &&
+                            ev.end > adapter_end && ev.stdv < P.recal_max_stdv) {
+                            if (na < 64) { a_ml[na] = pb::fmul(ev.mean, ev.length); a_len[na] = ev.length; }
+                            na++;
+                        }
+                    } else if (walk == W_COUNT) {
+                        npol += between_f32(ev.mean, lo, hi);
+                    } else {                      // W_SUM
+                        if (between_f32(ev.mean, lo, hi)) sl.push(ev.length);
+                    }
+                }
+                continue;
+            }
+            // ---- the walk is over: what follows it in the reference's control flow
+            if (walk == W_ANCHORS) {
+                if (na == 0) return;
+                if (na > 64) { R.flags |= 1; return; }
+                PairwiseSum s1, s2;
+                s1.begin(na); s2.begin(na);
+                for (int k = 0; k < na; k++) { s1.push(a_ml[k]); s2.push(a_len[k]); }
+                const float pm = pb::fdiv(s1.total, s2.total);
+                lo = pb::fsub(pm, P.half_range);
+                hi = pb::fadd(pm, P.half_range);
+                have_range = true;
+                // events[is_polya]['length'].sum() >= min_length: count, then sum
+                npol = 0;
+                walk = W_COUNT;
+                es.begin(src, P);
+            } else if (walk == W_COUNT) {
+                sl.begin(npol);
+                walk = W_SUM;
+                es.begin(src, P);
+            } else if (walk == W_SUM) {
+                if (!(sl.total >= P.recal_min_length)) return;
+                recal_mode = false;
+                best = 0; best_i = -1; best_j = -1; best_npol = 0; j = 0;
+                alive = false; Sv = 0; minP = 0; minI = -1; minCnt = 0; Pfx = 0; cnt = 0;
+                walk = W_FIND;
+                es.begin(src, P);
+            } else if (walk == W_FIND) {
+                const int64_t n_events = j;
+                const bool has_best = best > 0;
+                if (has_best && best_j == n_events - 1 && insp_end < full_length &&
+                    ext_depth < P.max_extension) {
+                    rough_end_cur = rough_end + P.openend_unit;      // extend the window
+                    ext_depth++;
+                    walk = DO_WINDOW;
+                } else if (!has_best) {
+                    recal_mode = true;
+                    walk = DO_ROUND;
+                } else {
+                    // second pass over the chosen interval
+                    const int64_t n_int = best_j - best_i + 1;
+                    s_ml.begin(n_int); s_len.begin(n_int); s_dw.begin(best_npol);
+                    long_start = 0; long_len = -1.0f; first_start = 0; last_end = 0;
+                    nsp = 0; prev_mean = 0.f; pending_spike = -1;
+                    j = 0; stop = false;
+                    walk = W_SECOND;
+                    es.begin(src, P);
+                }
+            } else {                              // W_SECOND
+                stop = false;
+                bool again = false;
+                if (!have_range) {
+                    // is_polya_signal_shifted (polya.py:88-93)
+                    const float lvl = pb::fdiv(s_ml.total, s_len.total);
+                    if (fabsf(pb::fsub(lvl, P.mean_loc)) > P.trigger) again = true;
+                }
+                if (again) {
+                    recal_mode = true;
+                    walk = DO_ROUND;
+                } else {
+                    // calc_internal_polya_stdv of the longest event (polya.py:150-154)
+                    const int64_t ilen = (int64_t)long_len;
+                    const int64_t sb = (int64_t)pb::dadd((double)long_start, pb::dmul((double)ilen, P.stdv_lo));
+                    const int64_t se = (int64_t)pb::dadd((double)long_start, pb::dmul((double)ilen, P.stdv_hi));
+                    sd_n = 0;
+                    if (se - sb > 2) {
+                        const int64_t b = sb < 0 ? 0 : sb, e = se > src.n ? src.n : se;   // numpy slicing clips
+                        sd_b = b;
+                        sd_n = e - b;
+                    }
+                    if (sd_n > 0) {
+                        ws = src;
+                        sd_sum.begin(sd_n);
+                        ws.seek(sd_b);
+                        sd_q = 0;
+                        walk = W_SD_MEAN;
+                    } else {
+                        // no usable stdv: not a poly(A) call
+                        if (!have_range) { recal_mode = true; walk = DO_ROUND; }
+                        else return;
+                    }
+                }
+            }
+            continue;
+        }
+        if (walk == W_SD_MEAN || walk == W_SD_VAR) {
+            if (sd_q < sd_n) {
+                // ---- one sample of the longest event
+                const float x = ws.pop();
+                if (walk == W_SD_MEAN) {
+                    sd_sum.push(x);
+                } else {
+                    const float dx = pb::fsub(x, sd_mu);
+                    sd_sum.push(pb::fmul(dx, dx));
+                }
+                sd_q++;
+                continue;
+            }
+            if (walk == W_SD_MEAN) {
+                sd_mu = pb::fdiv(sd_sum.total, (float)sd_n);
+                sd_sum.begin(sd_n);
+                ws.seek(sd_b);
+                sd_q = 0;
+                walk = W_SD_VAR;
+                continue;
+            }
+            const float sd = sqrtf(pb::fdiv(sd_sum.total, (float)sd_n));
+            if (sd < P.stdv_max) {
+                R.found = 1;
+                R.begin = (int64_t)first_start + insp_begin;
+                R.end = last_end + insp_begin;
+                R.dwell_samples = (int64_t)s_dw.total;
+                R.n_spikes = nsp;
+                R.extensions = ext_depth;
+                return;
+            }
+            if (!have_range) { recal_mode = true; walk = DO_ROUND; continue; }
+            return;
+        }
+        if (walk == DO_WINDOW) {
+            // ---- one __call__ (window)
+            rough_end = rough_end_cur;
+            if (rough_end < 0 || rough_end - rough_begin < P.openend_unit)
+                rough_end = (int64_t)rough_begin + P.openend_unit;
+            insp_begin = (int64_t)rough_begin * stride - P.refinement_expansion;
+            if (insp_begin < 0) insp_begin = 0;
+            insp_end = (rough_end + 1) * stride + P.refinement_expansion;
+            if (insp_end > full_length) insp_end = full_length;
+            adapter_end = (int64_t)rough_begin * stride - insp_begin;
+            src.w0 = insp_begin; src.n = insp_end - insp_begin;
+            if (src.n <= 0) return;                   // csupport raises on an empty signal
+            es.invalidate();                          // new window: recorded events are stale
+            if (!have_range) { lo = P.cutoff_lo; hi = P.cutoff_hi; }
+            recal_mode = rough_end_cur < 0;
+            guard = 0;
+            walk = DO_ROUND;
+        }
+        // ---- DO_ROUND: call_polya / try_recalibrate ping-pong
+        if (++guard > 8) return;                      // cannot happen; never spin
+        if (recal_mode) {
+            na = 0;
+            walk = W_ANCHORS;
+        } else {
+            best = 0; best_i = -1; best_j = -1; best_npol = 0; j = 0;
+            alive = false; Sv = 0; minP = 0; minI = -1; minCnt = 0; Pfx = 0; cnt = 0;
+            walk = W_FIND;
+        }
+        stop = false;
+        es.begin(src, P);
     }
 }
 

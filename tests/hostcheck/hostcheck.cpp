@@ -82,6 +82,17 @@ void hc_polya_cached(const pb::PolyaParams *P, const int16_t *raw, int64_t full_
     delete[] buf;
 }
 
+// the literal (one loop per walk) formulation, which the kernel's single-loop one must equal
+void hc_polya_nested(const pb::PolyaParams *P, const int16_t *raw, int64_t full_length, double gain,
+                     double offset, float scale, float shift, int32_t rough_begin, int32_t rough_end,
+                     pb::PolyaResult *R, int cap)
+{
+    pb::EventCacheSlot *buf = cap > 0 ? new pb::EventCacheSlot[cap] : nullptr;
+    pb::polya_analyze_nested(*P, raw, full_length, gain, offset, scale, shift, rough_begin, rough_end,
+                             *R, buf, 1, cap);
+    delete[] buf;
+}
+
 int hc_sizeof_params(void) { return (int)sizeof(pb::PolyaParams); }
 int hc_sizeof_result(void) { return (int)sizeof(pb::PolyaResult); }
 }

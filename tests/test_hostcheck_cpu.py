@@ -206,8 +206,45 @@ def test_polya_core_matches_restatement_and_reference(hc, oracle_mod, preset):
                                    C.c_int32(-1 if rr[1] is None else rr[1]), C.byref(R2),
                                    C.c_int(cap))
                 assert _same(want, H.result_to_dict(R2, 3012.0)), (kind, rep, cap)
+            for cap in (0, 8, 4096):       # the literal one-loop-per-walk formulation: same bytes
+                R3 = H.PolyaResultC()
+                hc.hc_polya_nested(C.byref(Pc), raw.ctypes.data_as(C.c_void_p), C.c_int64(len(raw)),
+                                   C.c_double(gain), C.c_double(off), C.c_float(scale),
+                                   C.c_float(shift), C.c_int32(rr[0]),
+                                   C.c_int32(-1 if rr[1] is None else rr[1]), C.byref(R3),
+                                   C.c_int(cap))
+                assert _same(want, H.result_to_dict(R3, 3012.0)), (kind, rep, cap, 'nested')
+                assert (R3.found, R3.n_spikes, R3.begin, R3.end, R3.dwell_samples, R3.extensions,
+                        R3.flags) == (R.found, R.n_spikes, R.begin, R.end, R.dwell_samples,
+                                      R.extensions, R.flags), (kind, rep, cap)
             found += got is not None
             none += got is None
             extended += R.extensions > 0
             spiky += bool(got and got['spikes'])
     assert found > 40 and none > 10 and extended > 5 and spiky > 15
+
+
+def test_polya_single_loop_equals_literal_formulation(hc, preset):
+    """polya_analyze (one loop, one event-stream step: what k_polya runs) against
+    polya_analyze_nested (the reference's control flow, walk by walk) on a few hundred random
+    reads of every kind, with and without the replay cache: the whole result record, byte for
+    byte (spike table, extension count and overflow flag included)."""
+    Pc = H.polya_params(preset['polya_dwell'])
+    rng = np.random.default_rng(11)
+    seen = {'found': 0, 'none': 0, 'extended': 0, 'spikes': 0}
+    for kind in ['plain', 'shift', 'noisy', 'spikes', 'open', 'short_rough', 'notail']:
+        for rep in range(60):
+            raw, gain, off, scale, shift, rr = _make_case(rng, kind)
+            args = (C.byref(Pc), raw.ctypes.data_as(C.c_void_p), C.c_int64(len(raw)), C.c_double(gain),
+                    C.c_double(off), C.c_float(scale), C.c_float(shift), C.c_int32(rr[0]),
+                    C.c_int32(-1 if rr[1] is None else rr[1]))
+            for cap in (0, 16, 4096):
+                A, B = H.PolyaResultC(), H.PolyaResultC()
+                hc.hc_polya_cached(*args, C.byref(A), C.c_int(cap))
+                hc.hc_polya_nested(*args, C.byref(B), C.c_int(cap))
+                assert bytes(A) == bytes(B), (kind, rep, cap)
+            seen['found'] += A.found
+            seen['none'] += 1 - A.found
+            seen['extended'] += A.extensions > 0
+            seen['spikes'] += A.n_spikes > 0
+    assert seen['found'] > 150 and seen['none'] > 50 and seen['extended'] > 20 and seen['spikes'] > 60, seen
