@@ -16,8 +16,11 @@ constexpr int POLYA_THREADS = 64;
 
 // NESTED: the literal one-loop-per-walk formulation (polya_analyze_nested), kept for comparison
 // (POREPLEX_B200_POLYA_NESTED=1); the default is the single-loop one (polya_core.cuh).
-template <bool NESTED>
-__global__ void __launch_bounds__(POLYA_THREADS)
+// MINB: resident blocks per SM the register allocation aims at (POREPLEX_B200_POLYA_MINB = 4, 6, 8;
+// measured per 1 M reads: 4 -> 221 registers, 8 warps per SM, 155 ms; 6 -> 168 registers and a few
+// spilled words, 12 warps, 124 ms: the default).
+template <bool NESTED, int MINB>
+__global__ void __launch_bounds__(POLYA_THREADS, MINB)
 k_polya(const PolyaParams P, const int16_t *__restrict__ raw,
         const int64_t *__restrict__ raw_offsets, const int64_t *__restrict__ raw_lengths,
         const double *__restrict__ range, const double *__restrict__ digitisation,
@@ -67,14 +70,18 @@ int launch_polya(pb2_context *ctx, const pb2_batch &b, const float *scale_shift,
         : nullptr;
     if (!cache) { cap = 0; cudaGetLastError(); }
     static const bool nested = [] { const char *e = getenv("POREPLEX_B200_POLYA_NESTED"); return e && e[0] == '1'; }();
+    static const int minb = [] { const char *e = getenv("POREPLEX_B200_POLYA_MINB"); return e ? atoi(e) : 6; }();
     const unsigned grid = (unsigned)((b.n_reads + POLYA_THREADS - 1) / POLYA_THREADS);
-#define PB_POLYA(NESTED)                                                                         \
+#define PB_POLYA(NESTED, MINB)                                                                   \
     PB_LAUNCH(ctx, K_POLYA, "k_polya", st,                                                       \
-        k_polya<NESTED><<<grid, POLYA_THREADS, 0, st>>>(                                         \
+        (k_polya<NESTED, MINB><<<grid, POLYA_THREADS, 0, st>>>(                                  \
             P, b.raw, b.raw_offsets, b.raw_lengths, b.range, b.digitisation, b.offset, scale_shift, \
             status, segments, b.n_reads, ctx->adapter_state, ctx->polya_state,                   \
-            reinterpret_cast<PolyaResult *>(out), cache, cap))
-    if (nested) PB_POLYA(true); else PB_POLYA(false);
+            reinterpret_cast<PolyaResult *>(out), cache, cap)))
+    if (nested) PB_POLYA(true, 4);
+    else if (minb == 4) PB_POLYA(false, 4);
+    else if (minb == 8) PB_POLYA(false, 8);
+    else PB_POLYA(false, 6);
 #undef PB_POLYA
     return PB2_OK;
 }
@@ -105,6 +112,8 @@ k_detect_events(const PolyaParams P, const float *__restrict__ signal,
         PlainSource src;
         src.x = signal + offsets[r]; src.n = len; src.next = 0;
         PlainEventStream<RING> es;
+        EventRings<RING> rings;
+        es.use(rings);
         es.begin(src, P);
         Event ev[2];
         const int64_t base = FILL ? event_offsets[r] : 0;

@@ -193,13 +193,21 @@ struct Detector {
 
 // RING: entries of the prefix-sum ring, a power of two >= 2 * max(window) + 2 (index i needs
 // S[i - w] .. S[i + w] and the fill runs one ahead).
+// The rings live OUTSIDE the stream object (EventRings, handed over with use()): they are indexed
+// dynamically, and an object with one dynamically indexed member is kept in local memory as a whole
+// -- with the rings as members every scalar of the detector state (indices, peak machines, window
+// source) was a local-memory load / store on each use.
+template <int RING = 64>
+struct EventRings { double S[RING], Q[RING]; };
+
 template <class Source, int RING = 64>
 struct EventStreamT {
     static constexpr int64_t MASK = RING - 1;
     Source src;
     int64_t n;
     int64_t head;                 // prefix sums S[0..head] are in the ring
-    double S[RING], Q[RING];
+    double *S, *Q;                // EventRings<RING> of the caller
+    PB_HD void use(EventRings<RING> &r) { S = r.S; Q = r.Q; }
     int64_t det_i;
     Detector d[2];
     float peak_height;
@@ -441,6 +449,8 @@ PB_HD void polya_analyze_nested(const PolyaParams &P, const int16_t *raw, int64_
     float lo = P.cutoff_lo, hi = P.cutoff_hi;
     int ext_depth = 0;
     EvIter es;
+    EventRings<64> rings;
+    es.es.use(rings);
     es.attach(cache, cache_stride, cache_cap);
     Event evs[2];
 
@@ -664,6 +674,8 @@ PB_HD void polya_analyze(const PolyaParams &P, const int16_t *raw, int64_t full_
     float lo = P.cutoff_lo, hi = P.cutoff_hi;
     int ext_depth = 0;
     EvIter es;
+    EventRings<64> rings;
+    es.es.use(rings);
     es.attach(cache, cache_stride, cache_cap);
     Event evs[2];
 

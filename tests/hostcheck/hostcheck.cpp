@@ -14,6 +14,8 @@ static int64_t detect_plain(const float *x, int64_t n, const pb::PolyaParams *P,
     pb::PlainSource src;
     src.x = x; src.n = n; src.next = 0;
     pb::PlainEventStream<RING> es;
+    pb::EventRings<RING> rings;
+    es.use(rings);
     es.begin(src, *P);
     pb::Event ev;
     int64_t k = 0;
@@ -47,6 +49,8 @@ int64_t hc_detect_events(const int16_t *raw, int64_t n, double gain, double offs
     src.raw = raw; src.gain = gain; src.offset = offset; src.scale = scale; src.shift = shift;
     src.w0 = 0; src.n = n;
     pb::EventStream es;
+    pb::EventRings<64> rings;
+    es.use(rings);
     es.begin(src, *P);
     pb::Event ev;
     int64_t k = 0;
