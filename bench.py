@@ -673,7 +673,8 @@ def main():
             return eng.analyze_host(hnp['raw'], hnp['offsets'], hnp['lengths'], hnp['range'],
                                     hnp['digitisation'], hnp['offset'], barcoding=True, out=hout,
                                     polya=full)
-        host_step()                                        # warm-up
+        host_step()                                        # warm-up (twice: the first call sizes the
+        host_step()                                        # library's device arenas and staging buffers)
         # what the box can move: the same pinned input buffer copied to the device with nothing
         # else running, every rank at the same time (N > 1: the ranks share the host's PCIe
         # uplinks) -- the floor under any host-buffer figure is h2d_bytes / this rate
@@ -691,14 +692,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             copy_rate = float(t.item())
             dist.barrier()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 8))
+        per_call = []
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            t1 = time.perf_counter()
             res = host_step()
             if world > 1:
                 c = torch.from_numpy(res['counts']).to(device)
                 dist.all_reduce(c)
                 c.cpu()
+            per_call.append(time.perf_counter() - t1)
         dt = (time.perf_counter() - t0) / e2e_steps
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=device)
@@ -708,6 +712,7 @@ def main():
         d2h = sum(v.nbytes for v in res.values())
         result['e2e'] = {'value': reads_all_ranks / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                          'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+                         'steps': e2e_steps, 'ms_per_step_fastest_this_rank': min(per_call) * 1e3,
                          'pinned_h2d_gb_per_s_per_gpu_all_ranks_copying': copy_rate,
                          'ms_per_step_floor_from_h2d': h2d / copy_rate / 1e6,
                          'api': 'pb2_analyze_host (pinned host input and result buffers; whole batch resident, '
@@ -730,6 +735,7 @@ def main():
             return eng.analyze_host(None, hnp['offsets'], hnp['lengths'], hnp['range'],
                                     hnp['digitisation'], hnp['offset'], barcoding=True, out=hout,
                                     polya=full, packed=(pk, po))
+        packed_step()
         packed_step()
         if world > 1:
             dist.barrier()
