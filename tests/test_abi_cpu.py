@@ -44,6 +44,28 @@ def test_library_is_sm100a_and_has_no_torch_types(native):
     assert 'torch' not in text.lower().replace('no python,\n * torch', '').replace('torch or cuda types', '')
 
 
+def test_library_sass_holds_tcgen05_tmem_and_tma_instructions(native):
+    """The built cubin is what the design says it is: tcgen05 products (UTCHMMA) with TMEM
+    traffic (LDTM / STTM) in every tensor-core LSTM kernel, bulk copies by the TMA unit
+    (UBLKCP + mbarrier waits) in k_pool, and no legacy HMMA tensor-core path anywhere
+    (tools/sass_histogram.py; B200_PROFILING.md's mnemonics)."""
+    import json
+    out = subprocess.run(['python', os.path.join(ROOT, 'tools', 'sass_histogram.py')], capture_output=True,
+                         text=True, check=True).stdout
+    doc = json.loads(out)
+    assert doc['totals'].get('UTCHMMA', 0) >= 100 and doc['totals'].get('STTM', 0) >= 50
+    assert doc['totals'].get('UBLKCP', 0) >= 1
+    assert 'HMMA_legacy' not in doc['totals']
+    by = {r['kernel']: r for r in doc['kernels']}
+    tc = [k for k in by if k.startswith('pb::k_lstm_tc')]
+    assert len(tc) >= 7
+    for k in tc:
+        assert by[k].get('UTCHMMA', 0) > 0 and by[k].get('LDTM', 0) > 0 and by[k].get('STTM', 0) > 0, k
+        assert by[k].get('UTCBAR', 0) > 0 and by[k].get('SYNCS', 0) > 0, k
+    pool = [k for k in by if k.startswith('pb::k_pool')]
+    assert pool and all(by[k].get('UBLKCP', 0) > 0 and by[k].get('SYNCS', 0) > 0 for k in pool)
+
+
 def test_struct_layouts_match_header_sizes(native):
     """ctypes mirrors must have the C layout (checked against a tiny C program)."""
     src = r'''
