@@ -13,7 +13,8 @@ all-reduce of the per-(label, barcode, status) counts per step when N > 1.
 
 Prints ONE JSON line (rank 0).  `value` is measured with the batch resident in HBM
 (CUDA events on the launching stream, max over ranks); `e2e` is the same metric through
-pb2_analyze_host with pinned HOST buffers, copies inside the timed region.
+pb2_analyze_host with pinned HOST buffers, copies inside the timed region (wall clock around
+min(K, 8) calls after two warm-up calls, max over ranks).
 
 The timed path is the library's default (`--mode fast`): both LSTM networks on the tensor
 cores (tcgen05 / TMEM), guards, and the exact re-run of the reads the guards flag (DESIGN.md
