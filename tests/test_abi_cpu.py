@@ -50,7 +50,8 @@ def test_library_sass_holds_tcgen05_tmem_and_tma_instructions(native):
     (UBLKCP + mbarrier waits) in k_pool, and no legacy HMMA tensor-core path anywhere
     (tools/sass_histogram.py; B200_PROFILING.md's mnemonics)."""
     import json
-    out = subprocess.run(['python', os.path.join(ROOT, 'tools', 'sass_histogram.py')], capture_output=True,
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'sass_histogram.py')], capture_output=True,
                          text=True, check=True).stdout
     doc = json.loads(out)
     assert doc['totals'].get('UTCHMMA', 0) >= 100 and doc['totals'].get('STTM', 0) >= 50
